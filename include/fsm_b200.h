@@ -1,0 +1,211 @@
+/*
+ * fsm_b200.h -- C ABI of libfsm_b200.so, the B200 (sm_100a) engine behind libfsm's
+ * fsm_exec / fsm_determinise hot path.
+ *
+ * Everything here is `extern "C"`, plain pointers and sizes: no torch types, no C++.
+ * The reference (katef/libfsm) has no FFI or plugin layer for execution -- its boundary
+ * is the exported C function
+ *
+ *     int fsm_exec(const struct fsm *, int (*fsm_getc)(void *), void *opaque,
+ *                  fsm_state_t *end, struct fsm_capture *captures);
+ *                                                  (reference include/fsm/fsm.h:560-562)
+ *
+ * plus the in-place transforms fsm_determinise / fsm_determinise_with_config
+ * (include/fsm/fsm.h:472-488).  `struct fsm` is an array of per-state heap blocks
+ * (src/libfsm/internal.h:47-85) which a GPU cannot consume, so the ABI is split in two:
+ *
+ *   1. struct fsm_b200_desc: a flat, pointer-to-array description of a `struct fsm`
+ *      (states, 256-bit-label edge groups exactly as src/adt/edgeset.c:34-41 stores them,
+ *      epsilon sets, end bits, end-id sets).  The libfsm-side shim
+ *      (libfsm_b200/shim/fsm_b200_shim.c, built inside the reference tree; see
+ *      INTEGRATION.md) produces it by walking edge_set_group_iter
+ *      (src/adt/edgeset.c:1226-1338) and calls the functions below; re(1)/fsm(1) relink
+ *      against the shim's `fsm_exec` unchanged.
+ *
+ *   2. the engine entry points below, which only see the flat description.
+ *
+ * Error convention mirrors the reference: functions returning int give -1 and set errno
+ * (EINVAL: not a DFA / no start state, as src/libfsm/exec.c:106-114; ENOMEM; EIO: CUDA
+ * failure; ENOTSUP: FSM needs a feature the engine does not accelerate).  There is NO CPU
+ * fallback: without a usable sm_100 device every compute entry point fails with EIO.
+ */
+#ifndef FSM_B200_H
+#define FSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSM_B200_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------
+ * Flat description of a `struct fsm` (reference src/libfsm/internal.h:52-85).
+ *
+ * State s owns edge groups [group_off[s], group_off[s+1]); group g carries a 256-bit
+ * label set group_symbols[4*g .. 4*g+3] (bit c of word c/64 == symbol c, the layout of
+ * `struct edge_group.symbols`, src/adt/edgeset.c:36-39) and one destination group_to[g].
+ * Groups are kept in the reference's stored order (sorted by destination), so "first
+ * group whose mask has the symbol wins" (edge_set_find, src/adt/edgeset.c:394-418) is
+ * reproducible.  eps_* is the CSR of `struct fsm_state.epsilons`; endid_* the CSR of the
+ * per-end-state sorted unique id sets (fsm_endid_get, src/libfsm/endids.c:686-755).
+ * eps_off / endid_off may be NULL (== no epsilons / no end ids).
+ * ------------------------------------------------------------------------------------ */
+struct fsm_b200_desc {
+	uint32_t nstates;            /* fsm->statecount */
+	uint32_t start;              /* fsm->start, meaningful iff hasstart */
+	uint32_t hasstart;           /* fsm->hasstart */
+	uint32_t reserved;           /* must be 0 */
+	const uint8_t  *is_end;      /* [nstates] fsm->states[s].end */
+	const uint64_t *group_off;   /* [nstates+1] */
+	const uint64_t *group_symbols; /* [4*ngroups] */
+	const uint32_t *group_to;    /* [ngroups] */
+	const uint64_t *eps_off;     /* [nstates+1] or NULL */
+	const uint32_t *eps_to;      /* [neps] */
+	const uint64_t *endid_off;   /* [nstates+1] or NULL */
+	const uint32_t *endids;      /* [nendids], sorted unique per state */
+};
+
+/* ------------------------------------------------------------------------------------
+ * Per-input result record: everything observable from one reference fsm_exec call.
+ *   ret       1 match / 0 no match                         (src/libfsm/exec.c:133-166)
+ *   end       ret==1: the accepting state index (`*end`, exec.c:165).
+ *             ret==0: the value of the reference's local `state` at return -- the final
+ *             non-end state, or the state that had no edge for the next byte.
+ *   consumed  value of exec.c's local `offset` at return (exec.c:92,150): the input
+ *             length when all input was consumed, else the index of the first byte with
+ *             no outgoing edge (the reference stops reading there, exec.c:133-138).
+ * The end-id set of a match is endids[endid_off[end] .. endid_off[end+1]) of the desc.
+ * ------------------------------------------------------------------------------------ */
+struct fsm_b200_result {
+	int32_t  ret;
+	uint32_t end;
+	uint64_t consumed;
+};
+
+/* Compiled, device-resident DFA (dense [state][256] transition table in HBM, staged to
+ * shared memory by the kernels).  Replaces the per-call fsm_all(fsm, fsm_isdfa)
+ * validation of exec.c:106: validation happens once, here. */
+typedef struct fsm_b200_dfa fsm_b200_dfa;
+
+/* Library/ABI version (FSM_B200_ABI_VERSION of the built library). */
+int fsm_b200_abi_version(void);
+
+/* Number of usable sm_100 devices (0 if none / no driver).  Never fails. */
+int fsm_b200_device_count(void);
+
+/* Human-readable description of the last error on this thread (never NULL). */
+const char *fsm_b200_last_error(void);
+
+/* Validate `desc` as a DFA exactly as fsm_all(fsm, fsm_isdfa) + fsm_getstart do
+ * (src/libfsm/exec.c:106-114, pred/isdfa.c:25-55, src/adt/edgeset.c:514-562) and build
+ * the dense table on `device`.  Returns 0 and *out on success; -1/EINVAL if `desc` is not
+ * a DFA or has no start state; -1/ENOMEM, -1/EIO otherwise. */
+int fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out);
+
+void fsm_b200_dfa_free(fsm_b200_dfa *dfa);
+
+/* Introspection of a compiled DFA. */
+struct fsm_b200_dfa_info {
+	uint32_t nstates;        /* states of the source fsm */
+	uint32_t ntable_states;  /* rows in the dense table (nstates, +1 if a dead row was added) */
+	uint32_t start;
+	uint32_t entry_bytes;    /* 1, 2 or 4 */
+	uint32_t row_pitch_bytes;/* bytes between consecutive rows of the device table */
+	uint32_t complete;       /* 1 if every state has all 256 edges (no dead row) */
+	uint32_t smem_resident;  /* 1 if the table is staged to shared memory by the kernels */
+	uint32_t device;
+	uint64_t table_bytes;
+};
+int fsm_b200_dfa_info(const fsm_b200_dfa *dfa, struct fsm_b200_dfa_info *info);
+
+/* Copy the dense table back as uint32 next-state indices, [nstates][256], with
+ * UINT32_MAX for "no edge".  For tests of the flattener; not a hot path. */
+int fsm_b200_dfa_table(const fsm_b200_dfa *dfa, uint32_t *out /* [nstates*256] */);
+
+/* --- batched execution: n independent inputs == n reference fsm_exec calls ------------
+ * Input i is bytes base[offsets[i] .. offsets[i+1]) (any byte values, including 0).
+ * `offsets` has n+1 entries, non-decreasing.  out[i] is written for every i.
+ *
+ * _host: base/offsets/out are HOST pointers; the call copies inputs to the device, runs
+ * the kernel and copies the records back (this is the end-to-end path: what a relinked
+ * re(1)/fsm(1) reaches through the shim's fsm_exec).
+ *
+ * _dev: all pointers are DEVICE pointers on the DFA's device; the kernel is enqueued on
+ * `stream` (a cudaStream_t passed as void *, NULL = legacy default stream) and the call
+ * returns without synchronising.  If d_offsets is NULL the inputs are fixed-stride:
+ * input i = d_base[i*stride .. i*stride+len).
+ */
+int fsm_b200_exec_batch_host(const fsm_b200_dfa *dfa,
+	const uint8_t *base, const uint64_t *offsets, size_t n,
+	struct fsm_b200_result *out);
+
+int fsm_b200_exec_batch_dev(const fsm_b200_dfa *dfa,
+	const uint8_t *d_base, const uint64_t *d_offsets, uint64_t stride, uint64_t len,
+	size_t n, struct fsm_b200_result *d_out, void *stream);
+
+/* Kernel variant selection for _dev/_host (0 = library default).  Exposed so that
+ * bench.py / ncu can evidence the choice; see DESIGN.md "K1 variants". */
+int fsm_b200_set_exec_variant(int variant);
+int fsm_b200_get_exec_variant(void);
+
+/* --- one long input == one reference fsm_exec call over a stream -----------------------
+ * The input is cut into chunks; each chunk computes its state->state map (DFA execution
+ * is a monoid), maps are composed by an exclusive scan, and the verdict is identical to a
+ * serial walk.  `entry_state` is the state the walk starts in (the DFA's start for a
+ * whole input; an arbitrary state for a byte-range shard, see exec_stream_map).
+ */
+int fsm_b200_exec_stream_host(const fsm_b200_dfa *dfa, const uint8_t *buf, uint64_t len,
+	struct fsm_b200_result *out);
+
+int fsm_b200_exec_stream_dev(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len,
+	struct fsm_b200_result *out /* host */, void *stream);
+
+/* Shard form for multi-GPU range sharding: computes, for the byte range d_buf[0..len),
+ * the map entry_state -> (exit_state, first_dead_offset) for EVERY entry state.
+ * map_state[s]  = state after consuming the shard from s (dead row index ntable_states-1
+ *                 when a missing edge was hit, for incomplete DFAs),
+ * map_dead[s]   = offset within the shard of the first byte with no edge, or UINT64_MAX.
+ * map_dead_state[s] = state that had no edge for that byte (UINT32_MAX if none).
+ * Ranks all-gather these [ntable_states] records and compose them in rank order. */
+int fsm_b200_exec_stream_map_dev(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len,
+	uint32_t *map_state /* host [ntable_states] */,
+	uint64_t *map_dead  /* host [ntable_states] */,
+	uint32_t *map_dead_state /* host [ntable_states] */, void *stream);
+
+/* --- determinisation: the subset-construction loop of fsm_determinise -----------------
+ * (src/libfsm/determinise.c:23-335 incl. epsilon removal, epsilons.c:121-288).
+ * Input: any NFA as a desc.  Output: a DFA as a library-owned desc (free with
+ * fsm_b200_desc_free).  State 0 of the output is the start state (determinise.c:234).
+ * The result is the reference's DFA up to state renumbering (isomorphic; the reference's
+ * numbering is an artefact of its LIFO worklist + pairwise analysis order);
+ * end bits and end-id sets are carried as determinise.c:236-266 does.
+ * state_limit: 0 = unlimited; otherwise returns 1 (and no output) as soon as more DFA
+ * states than the limit would be created (FSM_DETERMINISE_WITH_CONFIG_STATE_LIMIT_REACHED,
+ * include/fsm/fsm.h:478-488).  Returns 0 on success, -1/errno on error.
+ */
+struct fsm_b200_owned_desc {
+	struct fsm_b200_desc desc;
+	void *owner;             /* opaque; frees every array above */
+};
+int fsm_b200_determinise(const struct fsm_b200_desc *nfa, int device, size_t state_limit,
+	struct fsm_b200_owned_desc *out);
+void fsm_b200_desc_free(struct fsm_b200_owned_desc *d);
+
+/* Timing of the last determinise on this thread, milliseconds, for bench.py. */
+struct fsm_b200_det_stats {
+	double ms_total, ms_closure, ms_expand, ms_intern, ms_emit;
+	uint64_t dfa_states, dfa_groups, rounds, kernel_launches;
+};
+int fsm_b200_determinise_stats(struct fsm_b200_det_stats *st);
+
+/* Count of kernel launches issued by this library on this thread since the last reset
+ * (bench.py's "gpu_launches"). */
+uint64_t fsm_b200_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSM_B200_H */

@@ -1,0 +1,85 @@
+"""ctypes binding of libfsm_b200.so (the C ABI declared in include/fsm_b200.h).
+
+There is no CPU fallback: if the shared library has not been built this module raises at
+import, and every compute entry point fails with EIO when no sm_100 device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .desc import CDesc, COwnedDesc, CResult
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfsm_b200.so")
+
+#: every symbol include/fsm_b200.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = (
+    "fsm_b200_abi_version", "fsm_b200_device_count", "fsm_b200_last_error",
+    "fsm_b200_dfa_compile", "fsm_b200_dfa_free", "fsm_b200_dfa_info", "fsm_b200_dfa_table",
+    "fsm_b200_exec_batch_host", "fsm_b200_exec_batch_dev",
+    "fsm_b200_set_exec_variant", "fsm_b200_get_exec_variant",
+    "fsm_b200_exec_stream_host", "fsm_b200_exec_stream_dev", "fsm_b200_exec_stream_map_dev",
+    "fsm_b200_determinise", "fsm_b200_desc_free", "fsm_b200_determinise_stats",
+    "fsm_b200_launch_count",
+)
+
+
+class CDfaInfo(C.Structure):
+    _fields_ = [("nstates", C.c_uint32), ("ntable_states", C.c_uint32), ("start", C.c_uint32),
+                ("entry_bytes", C.c_uint32), ("row_pitch_bytes", C.c_uint32), ("complete", C.c_uint32),
+                ("smem_resident", C.c_uint32), ("device", C.c_uint32), ("table_bytes", C.c_uint64)]
+
+
+class CDetStats(C.Structure):
+    _fields_ = [("ms_total", C.c_double), ("ms_closure", C.c_double), ("ms_expand", C.c_double),
+                ("ms_intern", C.c_double), ("ms_emit", C.c_double),
+                ("dfa_states", C.c_uint64), ("dfa_groups", C.c_uint64), ("rounds", C.c_uint64),
+                ("kernel_launches", C.c_uint64)]
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"libfsm_b200: native library not built ({LIB_PATH} missing). "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C libfsm_b200/csrc`. "
+            "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH, use_errno=True)
+    vp, u64, sz = C.c_void_p, C.c_uint64, C.c_size_t
+    P = C.POINTER
+    lib.fsm_b200_abi_version.restype = C.c_int
+    lib.fsm_b200_device_count.restype = C.c_int
+    lib.fsm_b200_last_error.restype = C.c_char_p
+    lib.fsm_b200_dfa_compile.argtypes = [P(CDesc), C.c_int, P(vp)]
+    lib.fsm_b200_dfa_free.argtypes = [vp]
+    lib.fsm_b200_dfa_free.restype = None
+    lib.fsm_b200_dfa_info.argtypes = [vp, P(CDfaInfo)]
+    lib.fsm_b200_dfa_table.argtypes = [vp, vp]
+    lib.fsm_b200_exec_batch_host.argtypes = [vp, vp, vp, sz, vp]
+    lib.fsm_b200_exec_batch_dev.argtypes = [vp, vp, vp, u64, u64, sz, vp, vp]
+    lib.fsm_b200_set_exec_variant.argtypes = [C.c_int]
+    lib.fsm_b200_get_exec_variant.restype = C.c_int
+    lib.fsm_b200_exec_stream_host.argtypes = [vp, vp, u64, P(CResult)]
+    lib.fsm_b200_exec_stream_dev.argtypes = [vp, vp, u64, P(CResult), vp]
+    lib.fsm_b200_exec_stream_map_dev.argtypes = [vp, vp, u64, vp, vp, vp, vp]
+    lib.fsm_b200_determinise.argtypes = [P(CDesc), C.c_int, sz, P(COwnedDesc)]
+    lib.fsm_b200_desc_free.argtypes = [P(COwnedDesc)]
+    lib.fsm_b200_desc_free.restype = None
+    lib.fsm_b200_determinise_stats.argtypes = [P(CDetStats)]
+    lib.fsm_b200_launch_count.argtypes = [C.c_int]
+    lib.fsm_b200_launch_count.restype = C.c_uint64
+    return lib
+
+
+lib = _load()
+
+
+class FsmB200Error(OSError):
+    """A C-ABI call returned -1; carries errno and the library's error text."""
+
+
+def check(rc: int, what: str) -> None:
+    if rc < 0:
+        err = C.get_errno()
+        msg = lib.fsm_b200_last_error().decode("utf-8", "replace")
+        raise FsmB200Error(err, f"{what}: {msg or os.strerror(err)}")

@@ -1,0 +1,65 @@
+/*
+ * common.h -- internal helpers shared by the engine's translation units.
+ */
+#ifndef FSM_B200_COMMON_H
+#define FSM_B200_COMMON_H
+
+#include <cerrno>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#include "../../include/fsm_b200.h"
+
+namespace fsmb200 {
+
+/* thread-local error text + launch counter (api.cu) */
+void set_error(const char *fmt, ...);
+void count_launch(uint64_t n = 1);
+
+#define FSMB_CUDA(expr, fail_stmt)                                                      \
+	do {                                                                                \
+		cudaError_t e_ = (expr);                                                        \
+		if (e_ != cudaSuccess) {                                                        \
+			::fsmb200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+			    __FILE__, __LINE__);                                                    \
+			errno = (e_ == cudaErrorMemoryAllocation) ? ENOMEM : EIO;                   \
+			fail_stmt;                                                                  \
+		}                                                                               \
+	} while (0)
+
+constexpr uint32_t NO_EDGE = 0xFFFFFFFFu;
+
+/* Rows of a shared-memory table are padded by 4 bytes so that the bank of an entry
+ * depends on the state as well as on the input byte ("bank conflicts"). */
+constexpr uint32_t SMEM_ROW_PAD = 4;
+/* Largest dense table (bytes, padded) the batch kernels stage into shared memory. */
+constexpr uint32_t SMEM_TABLE_MAX = 96 * 1024;
+
+} // namespace fsmb200
+
+/* The compiled DFA. */
+struct fsm_b200_dfa {
+	int device;
+	uint32_t nstates;        /* source states */
+	uint32_t ntable;         /* table rows = nstates (+1 dead row) */
+	uint32_t start;
+	uint32_t dead;           /* dead row index or NO_EDGE when complete */
+	uint32_t entry_bytes;    /* 1/2/4 */
+	uint32_t pitch;          /* row pitch in bytes of d_table */
+	uint32_t complete;
+	uint32_t smem_resident;
+	uint64_t table_bytes;    /* ntable * pitch */
+	uint64_t blob_bytes;     /* table + is_end[ntable], padded to 16 */
+	/* device */
+	void *d_blob;            /* table rows followed by is_end bytes (u8 per row) */
+	/* host copies for introspection / stream composition */
+	uint32_t *h_table32;     /* [nstates*256], NO_EDGE for missing */
+	uint8_t *h_is_end;       /* [ntable] (dead row: 0) */
+	/* scratch for the _host entry points (grown on demand; guarded by mutex) */
+	void *scratch;
+};
+
+#endif

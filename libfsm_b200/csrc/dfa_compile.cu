@@ -1,0 +1,220 @@
+/*
+ * dfa_compile.cu -- flat description -> validated, dense, device-resident DFA.
+ *
+ * Replaces, once per DFA instead of once per fsm_exec call, the reference's
+ *   fsm_all(fsm, fsm_isdfa)            src/libfsm/exec.c:106, walk/all.c:15-31,
+ *                                      pred/isdfa.c:25-55, src/adt/edgeset.c:514-562
+ *   fsm_getstart                       src/libfsm/exec.c:111-114, start.c:34-48
+ * and turns the per-state edge groups (src/adt/edgeset.c:34-41) into the dense
+ * [state][256] table the reference never materialises (print/ir.h:98-100: IR_TABLE is
+ * "not yet implemented").  Lookup semantics = edge_set_find (edgeset.c:394-418).
+ */
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.h"
+
+using namespace fsmb200;
+
+namespace {
+
+/* fsm_isdfa for every state + fsm_getstart. */
+bool
+desc_is_dfa(const fsm_b200_desc *d)
+{
+	if (!d->hasstart || d->start >= d->nstates) {
+		return false;
+	}
+	for (uint32_t s = 0; s < d->nstates; s++) {
+		if (d->eps_off != nullptr && d->eps_off[s + 1] != d->eps_off[s]) {
+			return false;               /* pred/isdfa.c:43-45 */
+		}
+		uint64_t seen[4] = { 0, 0, 0, 0 };
+		for (uint64_t g = d->group_off[s]; g < d->group_off[s + 1]; g++) {
+			const uint64_t *sym = d->group_symbols + 4 * g;
+			for (int w = 0; w < 4; w++) {
+				if (seen[w] & sym[w]) {
+					return false;       /* edgeset.c:544-551 */
+				}
+				seen[w] |= sym[w];
+			}
+		}
+	}
+	return true;
+}
+
+} // namespace
+
+extern "C" int
+fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
+{
+	if (desc == nullptr || out == nullptr || desc->reserved != 0) {
+		set_error("dfa_compile: bad argument");
+		errno = EINVAL;
+		return -1;
+	}
+	*out = nullptr;
+	if (!desc_is_dfa(desc)) {
+		set_error("dfa_compile: not a DFA (no start state, epsilon edge or ambiguous symbol)");
+		errno = EINVAL;
+		return -1;
+	}
+
+	const uint32_t S = desc->nstates;
+	uint32_t *t32 = static_cast<uint32_t *>(malloc(sizeof(uint32_t) * (size_t) S * 256));
+	if (t32 == nullptr) {
+		errno = ENOMEM;
+		return -1;
+	}
+	bool complete = true;
+	for (uint32_t s = 0; s < S; s++) {
+		uint32_t *row = t32 + (size_t) s * 256;
+		for (int c = 0; c < 256; c++) row[c] = NO_EDGE;
+		/* groups are disjoint for a DFA, so "first group wins" needs no ordering care */
+		for (uint64_t g = desc->group_off[s]; g < desc->group_off[s + 1]; g++) {
+			const uint64_t *sym = desc->group_symbols + 4 * g;
+			const uint32_t to = desc->group_to[g];
+			if (to >= S) {
+				free(t32);
+				set_error("dfa_compile: edge to state %u out of range", to);
+				errno = EINVAL;
+				return -1;
+			}
+			for (int w = 0; w < 4; w++) {
+				uint64_t m = sym[w];
+				while (m) {
+					const int b = __builtin_ctzll(m);
+					m &= m - 1;
+					row[64 * w + b] = to;
+				}
+			}
+		}
+		for (int c = 0; c < 256 && complete; c++) {
+			if (row[c] == NO_EDGE) complete = false;
+		}
+	}
+
+	fsm_b200_dfa *dfa = new (std::nothrow) fsm_b200_dfa();
+	if (dfa == nullptr) {
+		free(t32);
+		errno = ENOMEM;
+		return -1;
+	}
+	memset(dfa, 0, sizeof *dfa);
+	dfa->device = device;
+	dfa->nstates = S;
+	dfa->start = desc->start;
+	dfa->complete = complete ? 1u : 0u;
+	dfa->ntable = S + (complete ? 0u : 1u);
+	dfa->dead = complete ? NO_EDGE : S;
+	dfa->h_table32 = t32;
+	dfa->entry_bytes = dfa->ntable <= 256 ? 1u : (dfa->ntable <= 65536 ? 2u : 4u);
+
+	/* shared-memory layout: padded rows; global layout: dense rows */
+	const uint64_t padded_pitch = 256ull * dfa->entry_bytes + SMEM_ROW_PAD;
+	const uint64_t padded_bytes = padded_pitch * dfa->ntable + ((dfa->ntable + 15u) & ~15ull);
+	dfa->smem_resident = padded_bytes <= SMEM_TABLE_MAX ? 1u : 0u;
+	dfa->pitch = dfa->smem_resident ? (uint32_t) padded_pitch : 256u * dfa->entry_bytes;
+	dfa->table_bytes = (uint64_t) dfa->pitch * dfa->ntable;
+	const uint64_t table_pad = (dfa->table_bytes + 15u) & ~15ull;
+	dfa->blob_bytes = table_pad + ((dfa->ntable + 15u) & ~15ull);
+
+	std::vector<uint8_t> blob;
+	try {
+		blob.assign(dfa->blob_bytes, 0);
+	} catch (...) {
+		fsm_b200_dfa_free(dfa);
+		errno = ENOMEM;
+		return -1;
+	}
+	dfa->h_is_end = static_cast<uint8_t *>(calloc(dfa->ntable + 1, 1));
+	if (dfa->h_is_end == nullptr) {
+		fsm_b200_dfa_free(dfa);
+		errno = ENOMEM;
+		return -1;
+	}
+	for (uint32_t s = 0; s < dfa->ntable; s++) {
+		uint8_t *row = blob.data() + (size_t) s * dfa->pitch;
+		for (int c = 0; c < 256; c++) {
+			uint32_t v = (s < S) ? t32[(size_t) s * 256 + c] : dfa->dead;   /* dead row absorbs */
+			if (v == NO_EDGE) v = dfa->dead;
+			switch (dfa->entry_bytes) {
+			case 1: row[c] = (uint8_t) v; break;
+			case 2: reinterpret_cast<uint16_t *>(row)[c] = (uint16_t) v; break;
+			default: reinterpret_cast<uint32_t *>(row)[c] = v; break;
+			}
+		}
+		const uint8_t e = (s < S && desc->is_end[s]) ? 1 : 0;
+		dfa->h_is_end[s] = e;
+		blob[table_pad + s] = e;
+	}
+
+	FSMB_CUDA(cudaSetDevice(device), { fsm_b200_dfa_free(dfa); return -1; });
+	FSMB_CUDA(cudaMalloc(&dfa->d_blob, dfa->blob_bytes), { fsm_b200_dfa_free(dfa); return -1; });
+	FSMB_CUDA(cudaMemcpy(dfa->d_blob, blob.data(), dfa->blob_bytes, cudaMemcpyHostToDevice),
+	    { fsm_b200_dfa_free(dfa); return -1; });
+	*out = dfa;
+	return 0;
+}
+
+namespace fsmb200 { void scratch_free(fsm_b200_dfa *dfa); }
+
+extern "C" void
+fsm_b200_dfa_free(fsm_b200_dfa *dfa)
+{
+	if (dfa == nullptr) return;
+	fsmb200::scratch_free(dfa);
+	if (dfa->d_blob != nullptr) {
+		cudaSetDevice(dfa->device);
+		cudaFree(dfa->d_blob);
+	}
+	free(dfa->h_table32);
+	free(dfa->h_is_end);
+	delete dfa;
+}
+
+extern "C" int
+fsm_b200_dfa_info(const fsm_b200_dfa *dfa, struct fsm_b200_dfa_info *info)
+{
+	if (dfa == nullptr || info == nullptr) {
+		errno = EINVAL;
+		return -1;
+	}
+	info->nstates = dfa->nstates;
+	info->ntable_states = dfa->ntable;
+	info->start = dfa->start;
+	info->entry_bytes = dfa->entry_bytes;
+	info->row_pitch_bytes = dfa->pitch;
+	info->complete = dfa->complete;
+	info->smem_resident = dfa->smem_resident;
+	info->device = (uint32_t) dfa->device;
+	info->table_bytes = dfa->table_bytes;
+	return 0;
+}
+
+/* Read the table back FROM THE DEVICE (so tests see what the kernels see). */
+extern "C" int
+fsm_b200_dfa_table(const fsm_b200_dfa *dfa, uint32_t *out)
+{
+	if (dfa == nullptr || out == nullptr) {
+		errno = EINVAL;
+		return -1;
+	}
+	std::vector<uint8_t> blob(dfa->blob_bytes);
+	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
+	FSMB_CUDA(cudaMemcpy(blob.data(), dfa->d_blob, dfa->blob_bytes, cudaMemcpyDeviceToHost), return -1);
+	for (uint32_t s = 0; s < dfa->nstates; s++) {
+		const uint8_t *row = blob.data() + (size_t) s * dfa->pitch;
+		for (int c = 0; c < 256; c++) {
+			uint32_t v;
+			switch (dfa->entry_bytes) {
+			case 1: v = row[c]; break;
+			case 2: v = reinterpret_cast<const uint16_t *>(row)[c]; break;
+			default: v = reinterpret_cast<const uint32_t *>(row)[c]; break;
+			}
+			out[(size_t) s * 256 + c] = (v == dfa->dead) ? NO_EDGE : v;
+		}
+	}
+	return 0;
+}

@@ -1,0 +1,591 @@
+/*
+ * k1_exec_batch.cu -- K1: batched DFA execution, one reference fsm_exec call per input.
+ *
+ * Replaces the per-byte loop of fsm_exec (src/libfsm/exec.c:132-151) and its
+ * edge_set_transition/edge_set_find group scan (src/adt/edgeset.c:565-579, 394-418)
+ * by a dense-table walk: state = T[state][byte].  One lane walks one input (inputs are
+ * independent, so this does no redundant work and needs no speculation); the serial
+ * dependence is hidden by the thousands of other lanes resident on the SM.
+ *
+ * Variants (DESIGN.md "K1 variants"; chosen by fsm_b200_set_exec_variant / auto):
+ *   LANE   k1_lane_kernel   any layout (ragged offsets, unaligned).  Table TMA-bulk-staged
+ *                           to shared memory (or read from L2 when too big); input read
+ *                           straight from HBM as 256-bit loads per lane.
+ *   TILE   k1_tile_kernel   fixed-stride, 16B-aligned batches.  Per warp a ring of
+ *                           32-row x CH-byte input tiles is fetched by 2-D TMA
+ *                           (cp.async.bulk.tensor, hardware swizzle so the lane-strided
+ *                           16-byte reads are bank-conflict free) and completed on mbarriers.
+ *
+ * Integer/byte workload: HBM- and shared-memory-lookup-bound; tensor cores do not apply.
+ */
+#include <cstring>
+#include <cuda.h>
+#include <mutex>
+
+#include "common.h"
+#include "k1_exec_batch.h"
+
+using namespace fsmb200;
+
+namespace {
+
+/* ------------------------------------------------------------------ device helpers -- */
+
+__device__ __forceinline__ uint32_t
+smem_u32(const void *p)
+{
+	return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void
+mbar_init(uint32_t bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void
+mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void
+mbar_wait(uint32_t bar, uint32_t parity)
+{
+	uint32_t done;
+	do {
+		asm volatile(
+		    "{\n\t.reg .pred p;\n\t"
+		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		    "selp.u32 %0, 1, 0, p;\n\t}"
+		    : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+	} while (!done);
+}
+
+/* 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP). */
+__device__ __forceinline__ void
+tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+	asm volatile(
+	    "cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	    :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+/* 2-D TMA tensor tile global -> shared (SASS: UTMALDG). */
+__device__ __forceinline__ void
+tma_tile_g2s(uint32_t dst, const CUtensorMap *map, uint32_t c0, uint32_t c1, uint32_t bar)
+{
+	asm volatile(
+	    "cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes"
+	    " [%0], [%1, {%2, %3}], [%4];"
+	    :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+/* Stage the DFA blob (table rows + is_end bytes) into shared memory with TMA bulk
+ * copies issued by one thread; everybody waits on the mbarrier. */
+__device__ __forceinline__ void
+stage_blob(uint8_t *smem, const uint8_t *blob, uint32_t blob_bytes, uint64_t *bar)
+{
+	const uint32_t bar_a = smem_u32(bar);
+	if (threadIdx.x == 0) {
+		mbar_init(bar_a, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		mbar_expect_tx(bar_a, blob_bytes);
+		const uint32_t dst = smem_u32(smem);
+		for (uint32_t off = 0; off < blob_bytes; off += 16384u) {
+			const uint32_t nb = min(16384u, blob_bytes - off);
+			tma_bulk_g2s(dst + off, blob + off, nb, bar_a);
+		}
+	}
+	mbar_wait(bar_a, 0);
+}
+
+/* Table lookups.  Indexing the extern shared array directly lets ptxas emit, per input
+ * byte, exactly PRMT (byte extract, off the dependent chain) + IMAD (state*pitch + byte)
+ * + LDS.U8 [R + UR] -- the dependent chain is IMAD -> LDS. */
+template <typename E> struct TableSmem {
+	const E *tbl;        /* shared memory */
+	uint32_t pitch;      /* row pitch in ELEMENTS */
+	__device__ __forceinline__ uint32_t step(uint32_t st, uint32_t b) const {
+		return (uint32_t) tbl[st * pitch + b];
+	}
+};
+
+template <typename E> struct TableGmem {
+	const E *tbl;        /* global memory (L2-resident) */
+	uint32_t pitch;      /* row pitch in ELEMENTS */
+	__device__ __forceinline__ uint32_t step(uint32_t st, uint32_t b) const {
+		return (uint32_t) __ldg(tbl + (size_t) st * pitch + b);
+	}
+};
+
+#define STEP4(T, st, w)                                    \
+	do {                                                   \
+		st = (T).step(st, __byte_perm((w), 0u, 0x4440u));  \
+		st = (T).step(st, __byte_perm((w), 0u, 0x4441u));  \
+		st = (T).step(st, __byte_perm((w), 0u, 0x4442u));  \
+		st = (T).step(st, __byte_perm((w), 0u, 0x4443u));  \
+	} while (0)
+
+__device__ __forceinline__ void
+ld256(const uint8_t *p, uint32_t (&w)[8])
+{
+	asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]),
+	      "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+	    : "l"(p));
+}
+
+__device__ __forceinline__ void
+store_result(fsm_b200_result *out, int32_t ret, uint32_t end, uint64_t consumed)
+{
+	uint4 v;
+	v.x = (uint32_t) ret;
+	v.y = end;
+	v.z = (uint32_t) consumed;
+	v.w = (uint32_t) (consumed >> 32);
+	*reinterpret_cast<uint4 *>(out) = v;
+}
+
+/* ------------------------------------------------------------------ LANE variant ---- */
+
+template <typename E, bool SMEM, bool HAS_DEAD>
+__global__ void __launch_bounds__(1024, 1)
+k1_lane_kernel(const K1Args a)
+{
+	extern __shared__ __align__(1024) uint8_t smem[];
+	__shared__ uint64_t blob_bar;
+
+	const uint8_t *is_end;
+	TableSmem<E> ts;
+	TableGmem<E> tg;
+	if (SMEM) {
+		stage_blob(smem, a.blob, a.blob_bytes, &blob_bar);
+		ts.tbl = reinterpret_cast<const E *>(smem);
+		ts.pitch = a.pitch / (uint32_t) sizeof(E);
+		is_end = smem + a.is_end_off;
+	} else {
+		tg.tbl = reinterpret_cast<const E *>(a.blob);
+		tg.pitch = a.pitch / (uint32_t) sizeof(E);
+		is_end = a.blob + a.is_end_off;
+	}
+#define TSTEP(st, b) (SMEM ? ts.step(st, b) : tg.step(st, b))
+
+	const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += nthreads) {
+		uint64_t beg, len;
+		if (a.offsets != nullptr) {
+			beg = a.offsets[i];
+			len = a.offsets[i + 1] - beg;
+		} else {
+			beg = i * a.stride;
+			len = a.len;
+		}
+		const uint8_t *p = a.base + beg;
+		uint32_t st = a.start;
+		uint64_t pos = 0;
+		bool died = false;
+
+		/* head: single bytes up to the first 32-byte boundary */
+		uint64_t head = (uint64_t) ((32u - (uint32_t) (reinterpret_cast<uintptr_t>(p) & 31u)) & 31u);
+		if (head > len) head = len;
+		for (; pos < head; pos++) {
+			const uint32_t nx = TSTEP(st, (uint32_t) __ldg(p + pos));
+			if (HAS_DEAD && nx == a.dead) { died = true; break; }
+			st = nx;
+		}
+
+		if (!died) {
+			/* body: one full 32-byte sector per 256-bit load, next sector prefetched */
+			uint64_t nchunk = (len - pos) >> 5;
+			uint32_t cur[8], nxt[8];
+			if (nchunk > 0) ld256(p + pos, cur);
+			for (uint64_t c = 0; c < nchunk; c++) {
+				if (c + 1 < nchunk) {
+					ld256(p + pos + 32, nxt);
+				} else {
+#pragma unroll
+					for (int k = 0; k < 8; k++) nxt[k] = 0;
+				}
+				const uint32_t entry = st;
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					if (SMEM) STEP4(ts, st, cur[k]); else STEP4(tg, st, cur[k]);
+				}
+				if (HAS_DEAD && st == a.dead) {
+					/* a byte of this sector had no edge: re-walk it to find which */
+					st = entry;
+					for (int k = 0; k < 32; k++) {
+						const uint32_t nx = TSTEP(st, (uint32_t) __ldg(p + pos + k));
+						if (nx == a.dead) { died = true; pos += (uint64_t) k; break; }
+						st = nx;
+					}
+					break;
+				}
+				pos += 32;
+#pragma unroll
+				for (int k = 0; k < 8; k++) cur[k] = nxt[k];
+			}
+		}
+		if (!died) {
+			for (; pos < len; pos++) {
+				const uint32_t nx = TSTEP(st, (uint32_t) __ldg(p + pos));
+				if (HAS_DEAD && nx == a.dead) { died = true; break; }
+				st = nx;
+			}
+		}
+		const int32_t ret = (!died && is_end[st]) ? 1 : 0;
+		store_result(a.out + i, ret, st, pos);
+	}
+#undef TSTEP
+}
+
+/* ------------------------------------------------------------------ TILE variant ---- */
+
+/* Shared memory: [blob, padded to 1024][per warp: NSTAGE stages of 32 x CH bytes][mbarriers] */
+template <typename E, bool HAS_DEAD, int CH, int NSTAGE>
+__global__ void __launch_bounds__(1024, 1)
+k1_tile_kernel(const K1Args a, const __grid_constant__ CUtensorMap tmap)
+{
+	extern __shared__ __align__(1024) uint8_t smem[];
+	__shared__ uint64_t blob_bar;
+	constexpr uint32_t STAGE_BYTES = 32u * CH;
+	constexpr int NVEC = CH / 16;
+
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint32_t nwarps = blockDim.x >> 5;
+	uint8_t *stage_base = smem + a.tile_stage_off + (size_t) warp * NSTAGE * STAGE_BYTES;
+	uint64_t *bars = reinterpret_cast<uint64_t *>(smem + a.tile_bar_off) + (size_t) warp * NSTAGE;
+
+	if (lane == 0) {
+#pragma unroll
+		for (int s = 0; s < NSTAGE; s++) mbar_init(smem_u32(&bars[s]), 1);
+	}
+	stage_blob(smem, a.blob, a.blob_bytes, &blob_bar);   /* fences + syncs the inits too */
+
+	TableSmem<E> ts;
+	ts.tbl = reinterpret_cast<const E *>(smem);
+	ts.pitch = a.pitch / (uint32_t) sizeof(E);
+	const uint8_t *is_end = smem + a.is_end_off;
+
+	const uint32_t ntiles = (uint32_t) ((a.n + 31) >> 5);
+	const uint32_t gw = blockIdx.x * nwarps + warp;
+	const uint32_t GW = gridDim.x * nwarps;
+	if (gw >= ntiles) return;
+	const uint32_t nst = (uint32_t) ((a.len + CH - 1) / CH);      /* stages per tile */
+
+	/* swizzle: physical 16B chunk = logical ^ f(row) (CU_TENSOR_MAP_SWIZZLE_{32,64,128}B) */
+	const uint32_t swz = (CH == 128) ? (lane & 7u) : (CH == 64) ? ((lane >> 1) & 3u) : ((lane >> 2) & 1u);
+	const uint32_t row_off = lane * CH;
+	const uint32_t stage_a = smem_u32(stage_base);
+	const uint32_t bars_a = smem_u32(bars);
+
+	/* Two cursors over this warp's sequence of (tile, stage) pairs: `ic` is the next pair
+	 * to fetch, `cc` the next to consume; ic runs NSTAGE pairs ahead.  All counters are
+	 * warp-uniform and advanced incrementally (no divisions in the loop). */
+	struct Cursor { uint32_t tile, sidx, slot, phase; };
+	Cursor cc = { gw, 0u, 0u, 0u }, ic = cc;
+	auto advance = [&](Cursor &c) {
+		if (++c.sidx == nst) { c.sidx = 0; c.tile += GW; }
+		if (++c.slot == (uint32_t) NSTAGE) { c.slot = 0; c.phase ^= 1u; }
+	};
+	auto issue = [&]() {
+		if (ic.tile < ntiles) {
+			if (lane == 0) {
+				const uint32_t bar = bars_a + ic.slot * 8u;
+				mbar_expect_tx(bar, STAGE_BYTES);
+				tma_tile_g2s(stage_a + ic.slot * STAGE_BYTES, &tmap, ic.sidx * CH, ic.tile << 5, bar);
+			}
+			advance(ic);
+		}
+	};
+#pragma unroll
+	for (int s = 0; s < NSTAGE; s++) issue();
+
+	uint32_t st = a.start;
+	uint64_t pos = 0;
+	bool died = false;
+	while (cc.tile < ntiles) {
+		const uint64_t row = ((uint64_t) cc.tile << 5) + lane;
+		if (cc.sidx == 0) { st = a.start; pos = 0; died = false; }
+
+		mbar_wait(bars_a + cc.slot * 8u, cc.phase);
+
+		const uint8_t *srow = stage_base + cc.slot * STAGE_BYTES + row_off;
+		const uint64_t remain = a.len - (uint64_t) cc.sidx * CH;  /* bytes of this input left */
+		if (!died && row < a.n) {
+			if (remain >= CH) {
+#pragma unroll
+				for (int v = 0; v < NVEC; v++) {
+					const uint4 x = *reinterpret_cast<const uint4 *>(srow + (((uint32_t) v ^ swz) << 4));
+					const uint32_t entry = st;
+					STEP4(ts, st, x.x); STEP4(ts, st, x.y); STEP4(ts, st, x.z); STEP4(ts, st, x.w);
+					if (HAS_DEAD && st == a.dead) {
+						/* a byte of this 16-byte chunk had no edge: re-walk it to find which */
+						st = entry;
+						for (uint32_t k = 0; k < 16; k++) {
+							const uint32_t b = srow[((((uint32_t) v ^ swz) << 4) | k)];
+							const uint32_t nx = ts.step(st, b);
+							if (nx == a.dead) { died = true; pos += (uint64_t) k; break; }
+							st = nx;
+						}
+						break;
+					}
+					pos += 16;
+				}
+			} else {
+				for (uint32_t k = 0; k < (uint32_t) remain; k++) {
+					const uint32_t b = srow[((((k >> 4) ^ swz) << 4) | (k & 15u))];
+					const uint32_t nx = ts.step(st, b);
+					if (HAS_DEAD && nx == a.dead) { died = true; break; }
+					st = nx;
+					pos++;
+				}
+			}
+		}
+		if (cc.sidx == nst - 1 && row < a.n) {
+			const int32_t ret = (!died && is_end[st]) ? 1 : 0;
+			store_result(a.out + row, ret, st, pos);
+		}
+		__syncwarp();       /* every lane has finished reading this slot */
+		advance(cc);
+		issue();            /* refill the slot just freed */
+	}
+}
+
+/* ------------------------------------------------------------------ host side -------- */
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_tiled_fn
+get_encode_tiled()
+{
+	static encode_tiled_fn fn = nullptr;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+		    qres == cudaDriverEntryPointSuccess) {
+			fn = reinterpret_cast<encode_tiled_fn>(p);
+		}
+	});
+	return fn;
+}
+
+int g_sm_count[64];
+int g_smem_optin[64];
+
+bool
+device_props(int device, int *sms, int *smem)
+{
+	if (device < 0 || device >= 64) return false;
+	if (g_sm_count[device] == 0) {
+		int v = 0, m = 0;
+		if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return false;
+		if (cudaDeviceGetAttribute(&m, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return false;
+		g_sm_count[device] = v;
+		g_smem_optin[device] = m;
+	}
+	*sms = g_sm_count[device];
+	*smem = g_smem_optin[device];
+	return true;
+}
+
+template <typename K>
+bool
+set_smem(K kernel, size_t bytes)
+{
+	return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes) == cudaSuccess;
+}
+
+template <typename E, bool SMEM, bool HAS_DEAD>
+int
+launch_lane(const K1Args &a, int sms, size_t smem_bytes, int block, cudaStream_t stream)
+{
+	auto kern = k1_lane_kernel<E, SMEM, HAS_DEAD>;
+	if (SMEM && !set_smem(kern, smem_bytes)) {
+		set_error("k1_lane: cannot opt in to %zu bytes of shared memory", smem_bytes);
+		errno = EIO;
+		return -1;
+	}
+	int per_sm = 1;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, SMEM ? smem_bytes : 0) != cudaSuccess || per_sm < 1) {
+		per_sm = 1;
+	}
+	uint64_t want = (a.n + (uint64_t) block - 1) / (uint64_t) block;
+	uint64_t grid = (uint64_t) sms * (uint64_t) per_sm;
+	if (want < grid) grid = want;
+	if (grid == 0) grid = 1;
+	kern<<<(unsigned) grid, block, SMEM ? smem_bytes : 0, stream>>>(a);
+	count_launch();
+	FSMB_CUDA(cudaGetLastError(), return -1);
+	return 0;
+}
+
+template <typename E, bool HAS_DEAD, int CH, int NSTAGE>
+int
+launch_tile(K1Args a, int sms, int smem_optin, cudaStream_t stream)
+{
+	auto kern = k1_tile_kernel<E, HAS_DEAD, CH, NSTAGE>;
+	encode_tiled_fn enc = get_encode_tiled();
+	if (enc == nullptr) {
+		set_error("k1_tile: cuTensorMapEncodeTiled unavailable");
+		errno = EIO;
+		return -1;
+	}
+	const uint32_t blob_pad = (a.blob_bytes + 1023u) & ~1023u;
+	const uint32_t per_warp = (uint32_t) NSTAGE * 32u * CH;
+	int nwarps = (int) (((uint32_t) smem_optin - blob_pad - 1024u) / (per_warp + 8u * NSTAGE));
+	if (nwarps > 32) nwarps = 32;
+	if (nwarps < 1) {
+		set_error("k1_tile: table too large for the tiled variant");
+		errno = ENOTSUP;
+		return -1;
+	}
+	const uint64_t ntiles = (a.n + 31) >> 5;
+	a.tile_stage_off = blob_pad;
+	a.tile_bar_off = blob_pad + (uint32_t) nwarps * per_warp;
+	const size_t smem_bytes = (size_t) a.tile_bar_off + (size_t) nwarps * NSTAGE * 8u;
+	if (!set_smem(kern, smem_bytes)) {
+		set_error("k1_tile: cannot opt in to %zu bytes of shared memory", smem_bytes);
+		errno = EIO;
+		return -1;
+	}
+
+	CUtensorMap tmap;
+	const cuuint64_t gdim[2] = { (cuuint64_t) a.stride, (cuuint64_t) a.n };
+	const cuuint64_t gstr[1] = { (cuuint64_t) a.stride };
+	const cuuint32_t box[2] = { (cuuint32_t) CH, 32u };
+	const cuuint32_t estr[2] = { 1u, 1u };
+	const CUtensorMapSwizzle sw = (CH == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+	    : (CH == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+	CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(a.base), gdim, gstr,
+	    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+	    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) {
+		set_error("k1_tile: cuTensorMapEncodeTiled failed (%d)", (int) r);
+		errno = EIO;
+		return -1;
+	}
+	uint64_t grid = (ntiles + (uint64_t) nwarps - 1) / (uint64_t) nwarps;
+	if (grid > (uint64_t) sms) grid = (uint64_t) sms;
+	if (grid == 0) grid = 1;
+	kern<<<(unsigned) grid, nwarps * 32, smem_bytes, stream>>>(a, tmap);
+	count_launch();
+	FSMB_CUDA(cudaGetLastError(), return -1);
+	return 0;
+}
+
+int g_variant = 0;
+
+} // namespace
+
+namespace fsmb200 {
+
+bool
+k1_tile_eligible(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,
+	uint64_t stride, uint64_t len, size_t n)
+{
+	return dfa->smem_resident && d_offsets == nullptr && n > 0 && len > 0 &&
+	    (reinterpret_cast<uintptr_t>(d_base) & 15u) == 0 && (stride & 15u) == 0 &&
+	    stride >= len && stride < (1ull << 32) && n < (1ull << 31) && dfa->entry_bytes <= 2;
+}
+
+int
+k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,
+	uint64_t stride, uint64_t len, size_t n, fsm_b200_result *d_out, cudaStream_t stream, int variant)
+{
+	if (n == 0) return 0;
+	int sms = 0, smem_optin = 0;
+	if (!device_props(dfa->device, &sms, &smem_optin)) {
+		set_error("k1: cannot query device %d", dfa->device);
+		errno = EIO;
+		return -1;
+	}
+	K1Args a;
+	memset(&a, 0, sizeof a);
+	a.base = d_base; a.offsets = d_offsets; a.stride = stride; a.len = len; a.n = n; a.out = d_out;
+	a.blob = static_cast<const uint8_t *>(dfa->d_blob);
+	a.blob_bytes = (uint32_t) dfa->blob_bytes;
+	a.is_end_off = (uint32_t) ((dfa->table_bytes + 15u) & ~15ull);
+	a.pitch = dfa->pitch; a.start = dfa->start; a.dead = dfa->dead;
+
+	if (variant == K1_AUTO) variant = g_variant;
+	const bool tile_ok = k1_tile_eligible(dfa, d_base, d_offsets, stride, len, n);
+	if (variant == K1_AUTO) {
+		variant = (tile_ok && n >= 4096) ? K1_TILE64 : K1_LANE;
+	}
+	const bool dead = !dfa->complete;
+
+	if (variant == K1_LANE) {
+		int block = 1024;
+		if (const char *e = getenv("FSM_B200_LANE_BLOCK")) {
+			int v = atoi(e);
+			if (v >= 32 && v <= 1024 && (v % 32) == 0) block = v;
+		}
+		if (dfa->smem_resident) {
+			const size_t smem_bytes = (a.blob_bytes + 127u) & ~127u;
+			if (dfa->entry_bytes == 1)
+				return dead ? launch_lane<uint8_t, true, true>(a, sms, smem_bytes, block, stream)
+				            : launch_lane<uint8_t, true, false>(a, sms, smem_bytes, block, stream);
+			return dead ? launch_lane<uint16_t, true, true>(a, sms, smem_bytes, block, stream)
+			            : launch_lane<uint16_t, true, false>(a, sms, smem_bytes, block, stream);
+		}
+		if (block > 256 && getenv("FSM_B200_LANE_BLOCK") == nullptr) block = 256;
+		if (dfa->entry_bytes == 2)
+			return dead ? launch_lane<uint16_t, false, true>(a, sms, 0, block, stream)
+			            : launch_lane<uint16_t, false, false>(a, sms, 0, block, stream);
+		if (dfa->entry_bytes == 4)
+			return dead ? launch_lane<uint32_t, false, true>(a, sms, 0, block, stream)
+			            : launch_lane<uint32_t, false, false>(a, sms, 0, block, stream);
+		return dead ? launch_lane<uint8_t, false, true>(a, sms, 0, block, stream)
+		            : launch_lane<uint8_t, false, false>(a, sms, 0, block, stream);
+	}
+
+	if (!tile_ok) {
+		set_error("k1: tiled variant needs a shared-memory-resident table and a fixed-stride, 16-byte aligned batch");
+		errno = ENOTSUP;
+		return -1;
+	}
+#define TILE_CASE(V, CH, NS)                                                                       \
+	if (variant == (V)) {                                                                          \
+		if (dfa->entry_bytes == 1)                                                                 \
+			return dead ? launch_tile<uint8_t, true, CH, NS>(a, sms, smem_optin, stream)           \
+			            : launch_tile<uint8_t, false, CH, NS>(a, sms, smem_optin, stream);         \
+		return dead ? launch_tile<uint16_t, true, CH, NS>(a, sms, smem_optin, stream)              \
+		            : launch_tile<uint16_t, false, CH, NS>(a, sms, smem_optin, stream);            \
+	}
+	TILE_CASE(K1_TILE64, 64, 2)
+	TILE_CASE(K1_TILE32, 32, 4)
+	TILE_CASE(K1_TILE128, 128, 2)
+	TILE_CASE(K1_TILE64x3, 64, 3)
+#undef TILE_CASE
+	set_error("k1: unknown variant %d", variant);
+	errno = EINVAL;
+	return -1;
+}
+
+} // namespace fsmb200
+
+extern "C" int
+fsm_b200_set_exec_variant(int variant)
+{
+	if (variant < 0 || variant >= K1_VARIANT_COUNT) {
+		errno = EINVAL;
+		return -1;
+	}
+	g_variant = variant;
+	return 0;
+}
+
+extern "C" int
+fsm_b200_get_exec_variant(void)
+{
+	return g_variant;
+}

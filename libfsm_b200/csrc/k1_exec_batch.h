@@ -1,0 +1,42 @@
+/* k1_exec_batch.h -- internal interface of the K1 batch kernels. */
+#ifndef FSM_B200_K1_H
+#define FSM_B200_K1_H
+
+#include "common.h"
+
+namespace fsmb200 {
+
+enum K1Variant {
+	K1_AUTO = 0,
+	K1_LANE = 1,       /* lane-per-input, 256-bit global loads */
+	K1_TILE64 = 2,     /* warp tile 32 x 64 B, 2-stage TMA ring */
+	K1_TILE32 = 3,     /* warp tile 32 x 32 B, 4-stage TMA ring */
+	K1_TILE128 = 4,    /* warp tile 32 x 128 B, 2-stage TMA ring (fewer warps) */
+	K1_TILE64x3 = 5,   /* warp tile 32 x 64 B, 3-stage TMA ring (fewer warps) */
+	K1_VARIANT_COUNT
+};
+
+struct K1Args {
+	const uint8_t *base;
+	const uint64_t *offsets;    /* n+1 entries, or nullptr for fixed stride */
+	uint64_t stride, len;
+	uint64_t n;
+	fsm_b200_result *out;
+	const uint8_t *blob;        /* table rows then is_end bytes */
+	uint32_t blob_bytes;
+	uint32_t is_end_off;
+	uint32_t pitch;
+	uint32_t start;
+	uint32_t dead;
+	uint32_t tile_stage_off;    /* TILE variants: shared-memory carve-up */
+	uint32_t tile_bar_off;
+};
+
+bool k1_tile_eligible(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,
+	uint64_t stride, uint64_t len, size_t n);
+
+int k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,
+	uint64_t stride, uint64_t len, size_t n, fsm_b200_result *d_out, cudaStream_t stream, int variant);
+
+} // namespace fsmb200
+#endif

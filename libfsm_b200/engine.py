@@ -1,0 +1,169 @@
+"""Host-side mirror of the reference interface for the hot path.
+
+``Dfa`` plays the role of a determinised ``struct fsm`` handed to ``fsm_exec``
+(reference include/fsm/fsm.h:560-562): it is compiled once (DFA-ness validated as
+src/libfsm/exec.c:106-114 does per call) and then executes batches of inputs on the GPU.
+``determinise`` mirrors ``fsm_determinise_with_config`` (include/fsm/fsm.h:472-488).
+
+numpy arrays are host buffers (end-to-end path, copies inside the call); torch CUDA
+tensors are device buffers (resident path, asynchronous on the current stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import errno as _errno
+
+import numpy as np
+
+from . import _native
+from ._native import lib, check, CDfaInfo, CDetStats
+from .desc import FlatFsm, COwnedDesc, CResult, RESULT_DTYPE
+
+VARIANTS = {"auto": 0, "lane": 1, "tile64": 2, "tile32": 3, "tile128": 4, "tile64x3": 5}
+
+
+def device_count() -> int:
+    return int(lib.fsm_b200_device_count())
+
+
+def set_exec_variant(name_or_id) -> None:
+    v = VARIANTS[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
+    check(lib.fsm_b200_set_exec_variant(v), "set_exec_variant")
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib.fsm_b200_launch_count(1 if reset else 0))
+
+
+def _is_torch_cuda(x) -> bool:
+    return hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+def _stream_ptr() -> int:
+    import torch
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+class Dfa:
+    """A compiled, device-resident DFA (``fsm_b200_dfa``)."""
+
+    def __init__(self, fsm: FlatFsm, device: int = 0):
+        self.fsm = fsm
+        self.device = device
+        self._h = C.c_void_p()
+        cdesc = fsm.as_c()
+        check(lib.fsm_b200_dfa_compile(C.byref(cdesc), device, C.byref(self._h)), "dfa_compile")
+        info = CDfaInfo()
+        check(lib.fsm_b200_dfa_info(self._h, C.byref(info)), "dfa_info")
+        self.info = {k: int(getattr(info, k)) for k, _ in CDfaInfo._fields_}
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.fsm_b200_dfa_free(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def table(self) -> np.ndarray:
+        """Dense [nstates, 256] table as read back from the device (0xFFFFFFFF = no edge)."""
+        out = np.empty((self.info["nstates"], 256), dtype=np.uint32)
+        check(lib.fsm_b200_dfa_table(self._h, out.ctypes.data), "dfa_table")
+        return out
+
+    # ---- batched execution -----------------------------------------------------------
+    def exec_batch(self, base, offsets=None, *, stride=None, length=None, n=None, out=None):
+        """n independent fsm_exec calls.
+
+        host:   ``base`` uint8 numpy array, ``offsets`` uint64 numpy array [n+1]
+                -> numpy structured array (ret, end, consumed)
+        device: ``base`` torch.uint8 CUDA tensor; either ``offsets`` (torch int64 CUDA
+                tensor [n+1]) or fixed ``stride``/``length``/``n``
+                -> torch.uint8 CUDA tensor [n, 16] (view with ``results_from_torch``)
+        """
+        if _is_torch_cuda(base):
+            import torch
+            if offsets is not None:
+                n = int(offsets.numel()) - 1
+                off_ptr, stride, length = offsets.data_ptr(), 0, 0
+            else:
+                off_ptr = None
+                if length is None:
+                    length = stride
+                if n is None:
+                    n = int(base.numel()) // int(stride) if stride else 0
+            if out is None:
+                out = torch.empty((max(n, 0), 16), dtype=torch.uint8, device=base.device)
+            check(lib.fsm_b200_exec_batch_dev(self._h, base.data_ptr(), off_ptr, int(stride), int(length),
+                                              n, out.data_ptr(), _stream_ptr()), "exec_batch_dev")
+            return out
+        base = np.ascontiguousarray(base, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = offsets.shape[0] - 1
+        if out is None:
+            out = np.empty(max(n, 0), dtype=RESULT_DTYPE)
+        bptr = base.ctypes.data if base.size else np.zeros(16, np.uint8).ctypes.data
+        check(lib.fsm_b200_exec_batch_host(self._h, bptr, offsets.ctypes.data, n, out.ctypes.data),
+              "exec_batch_host")
+        return out
+
+    def exec_batch_hostptr(self, base_ptr: int, offsets_ptr: int, n: int, out_ptr: int) -> None:
+        """Raw-pointer form of the host path (pinned buffers owned by the caller)."""
+        check(lib.fsm_b200_exec_batch_host(self._h, base_ptr, offsets_ptr, n, out_ptr), "exec_batch_host")
+
+    # ---- one long input -----------------------------------------------------------------
+    def exec_stream(self, buf):
+        """One fsm_exec call over a single long input -> (ret, end, consumed)."""
+        r = CResult()
+        if _is_torch_cuda(buf):
+            check(lib.fsm_b200_exec_stream_dev(self._h, buf.data_ptr(), int(buf.numel()), C.byref(r),
+                                               _stream_ptr()), "exec_stream_dev")
+        else:
+            buf = np.ascontiguousarray(buf, dtype=np.uint8)
+            ptr = buf.ctypes.data if buf.size else np.zeros(16, np.uint8).ctypes.data
+            check(lib.fsm_b200_exec_stream_host(self._h, ptr, int(buf.size), C.byref(r)), "exec_stream_host")
+        return int(r.ret), int(r.end), int(r.consumed)
+
+    def exec_stream_map(self, dbuf):
+        """Shard form: per entry state the (exit state, first dead offset, dead-from state)
+        of the byte range ``dbuf`` (torch CUDA uint8).  See include/fsm_b200.h."""
+        nt = self.info["ntable_states"]
+        ms = np.empty(nt, np.uint32); md = np.empty(nt, np.uint64); mf = np.empty(nt, np.uint32)
+        check(lib.fsm_b200_exec_stream_map_dev(self._h, dbuf.data_ptr(), int(dbuf.numel()),
+                                               ms.ctypes.data, md.ctypes.data, mf.ctypes.data,
+                                               _stream_ptr()), "exec_stream_map_dev")
+        return ms, md, mf
+
+
+def results_from_torch(t) -> np.ndarray:
+    """[n,16] uint8 CUDA/CPU tensor of result records -> numpy structured array."""
+    return t.detach().cpu().numpy().reshape(-1).view(RESULT_DTYPE)
+
+
+class StateLimitReached(Exception):
+    """FSM_DETERMINISE_WITH_CONFIG_STATE_LIMIT_REACHED (reference include/fsm/fsm.h:481-488)."""
+
+
+def determinise(nfa: FlatFsm, device: int = 0, state_limit: int = 0) -> FlatFsm:
+    """GPU subset construction; the reference's DFA up to state renumbering."""
+    od = COwnedDesc()
+    cdesc = nfa.as_c()
+    rc = lib.fsm_b200_determinise(C.byref(cdesc), device, state_limit, C.byref(od))
+    if rc == 1:
+        raise StateLimitReached()
+    check(rc, "determinise")
+    try:
+        return FlatFsm.from_c(od.desc)
+    finally:
+        lib.fsm_b200_desc_free(C.byref(od))
+
+
+def determinise_stats() -> dict:
+    st = CDetStats()
+    lib.fsm_b200_determinise_stats(C.byref(st))
+    return {k: getattr(st, k) for k, _ in CDetStats._fields_}

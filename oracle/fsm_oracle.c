@@ -1,0 +1,624 @@
+/*
+ * fsm_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.  See fsm_oracle.h.
+ *
+ * A from-scratch CPU restatement of the katef/libfsm hot path over the flat
+ * `struct fsm_b200_desc`.  No reference source is included or copied; each function cites
+ * the reference file:line whose observable behaviour it restates.  Parity PINNED against
+ * the compiled reference (oracle/_ref/libfsm_ref.so) by tests/test_oracle_vs_reference.py
+ * and against tests/golden/ fixtures generated from the reference.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include <errno.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "fsm_oracle.h"
+
+#define NO_EDGE UINT32_MAX
+
+static inline int
+sym_get(const uint64_t *symbols, unsigned c)
+{
+	return (int) ((symbols[c >> 6] >> (c & 63)) & 1u);
+}
+
+/* ---------------------------------------------------------------------------------
+ * fsm_all(fsm, fsm_isdfa) followed by fsm_getstart, as fsm_exec does before touching
+ * the input (src/libfsm/exec.c:106-114).
+ *  - pred/isdfa.c:36-38: no start state => not a DFA (for every state, so also for an
+ *    fsm with states but no start; with zero states fsm_all is vacuously true and the
+ *    following fsm_getstart fails: same verdict)
+ *  - pred/isdfa.c:43-45: any epsilon edge => not a DFA
+ *  - src/adt/edgeset.c:514-562: a symbol present in two groups of one state => not a DFA
+ * --------------------------------------------------------------------------------- */
+int
+oracle_isdfa(const struct fsm_b200_desc *d)
+{
+	uint32_t s;
+
+	if (!d->hasstart || d->start >= d->nstates) {
+		return 0;
+	}
+	for (s = 0; s < d->nstates; s++) {
+		uint64_t seen[4] = { 0, 0, 0, 0 };
+		uint64_t g;
+
+		if (d->eps_off != NULL && d->eps_off[s + 1] != d->eps_off[s]) {
+			return 0;
+		}
+		for (g = d->group_off[s]; g < d->group_off[s + 1]; g++) {
+			const uint64_t *sym = &d->group_symbols[4 * g];
+			int w;
+			for (w = 0; w < 4; w++) {
+				if (seen[w] & sym[w]) {
+					return 0;
+				}
+				seen[w] |= sym[w];
+			}
+		}
+	}
+	return 1;
+}
+
+/* edge_set_find (src/adt/edgeset.c:394-418): linear scan of the state's groups in stored
+ * order, first group whose mask contains the symbol wins. */
+static inline uint32_t
+group_scan(const struct fsm_b200_desc *d, uint32_t state, unsigned c)
+{
+	uint64_t g;
+	for (g = d->group_off[state]; g < d->group_off[state + 1]; g++) {
+		if (sym_get(&d->group_symbols[4 * g], c)) {
+			return d->group_to[g];
+		}
+	}
+	return NO_EDGE;
+}
+
+/* fsm_exec (src/libfsm/exec.c:85-167) without captures / eager outputs (neither is
+ * produced by re_comp). */
+int
+oracle_exec(const struct fsm_b200_desc *d, const uint8_t *buf, uint64_t len,
+	int validate, struct fsm_b200_result *out)
+{
+	uint32_t state;
+	uint64_t offset = 0;
+
+	if (validate && !oracle_isdfa(d)) {       /* exec.c:106-109 */
+		errno = EINVAL;
+		return -1;
+	}
+	if (!d->hasstart) {                       /* exec.c:111-114 */
+		errno = EINVAL;
+		return -1;
+	}
+	state = d->start;
+
+	while (offset < len) {                    /* exec.c:132 (getc != EOF) */
+		uint32_t next = group_scan(d, state, buf[offset]);
+		if (next == NO_EDGE) {                /* exec.c:133-138: stop, input not drained */
+			out->ret = 0;
+			out->end = state;
+			out->consumed = offset;
+			return 0;
+		}
+		state = next;
+		offset++;                             /* exec.c:150 */
+	}
+
+	out->end = state;
+	out->consumed = offset;
+	out->ret = d->is_end[state] ? 1 : 0;      /* exec.c:153-166 */
+	return out->ret;
+}
+
+struct batch_job {
+	const struct fsm_b200_desc *d;
+	const uint8_t *base;
+	const uint64_t *offsets;
+	size_t lo, hi;
+	int validate_each;
+	struct fsm_b200_result *out;
+};
+
+static void *
+batch_worker(void *opaque)
+{
+	struct batch_job *j = opaque;
+	size_t i;
+	for (i = j->lo; i < j->hi; i++) {
+		(void) oracle_exec(j->d, j->base + j->offsets[i],
+		    j->offsets[i + 1] - j->offsets[i], j->validate_each, &j->out[i]);
+	}
+	return NULL;
+}
+
+int
+oracle_exec_batch(const struct fsm_b200_desc *d, const uint8_t *base,
+	const uint64_t *offsets, size_t n, int validate_each, int nthreads,
+	struct fsm_b200_result *out)
+{
+	pthread_t *tids;
+	struct batch_job *jobs;
+	int t, started = 0;
+
+	if (!oracle_isdfa(d)) {
+		errno = EINVAL;
+		return -1;
+	}
+	if (nthreads < 1) {
+		nthreads = 1;
+	}
+	if ((size_t) nthreads > n && n > 0) {
+		nthreads = (int) n;
+	}
+	tids = malloc(sizeof *tids * (size_t) nthreads);
+	jobs = malloc(sizeof *jobs * (size_t) nthreads);
+	if (tids == NULL || jobs == NULL) {
+		free(tids); free(jobs);
+		errno = ENOMEM;
+		return -1;
+	}
+	for (t = 0; t < nthreads; t++) {
+		jobs[t].d = d; jobs[t].base = base; jobs[t].offsets = offsets;
+		jobs[t].lo = n * (size_t) t / (size_t) nthreads;
+		jobs[t].hi = n * (size_t) (t + 1) / (size_t) nthreads;
+		jobs[t].validate_each = validate_each;
+		jobs[t].out = out;
+		if (nthreads == 1) {
+			batch_worker(&jobs[t]);
+		} else if (pthread_create(&tids[t], NULL, batch_worker, &jobs[t]) != 0) {
+			batch_worker(&jobs[t]);
+			tids[t] = (pthread_t) 0;
+			continue;
+		} else {
+			started++;
+		}
+	}
+	if (nthreads > 1) {
+		for (t = 0; t < nthreads; t++) {
+			if (tids[t] != (pthread_t) 0) {
+				pthread_join(tids[t], NULL);
+			}
+		}
+	}
+	(void) started;
+	free(tids); free(jobs);
+	return 0;
+}
+
+void
+oracle_flatten(const struct fsm_b200_desc *d, uint32_t *table)
+{
+	uint32_t s;
+	unsigned c;
+	for (s = 0; s < d->nstates; s++) {
+		for (c = 0; c < 256; c++) {
+			table[(size_t) s * 256 + c] = group_scan(d, s, c);
+		}
+	}
+}
+
+/* ---------------------------------------------------------------------------------
+ * Epsilon closure (src/libfsm/closure.c:130-190, :24-128): for every state the set of
+ * states reachable by zero or more epsilon edges, itself included, ascending.
+ * --------------------------------------------------------------------------------- */
+static int
+cmp_u32(const void *a, const void *b)
+{
+	uint32_t x = *(const uint32_t *) a, y = *(const uint32_t *) b;
+	return (x > y) - (x < y);
+}
+
+int
+oracle_epsilon_closure(const struct fsm_b200_desc *d, uint64_t **off_out, uint32_t **to_out)
+{
+	const uint32_t n = d->nstates;
+	uint64_t *off = malloc(sizeof *off * ((size_t) n + 1));
+	uint32_t *to = NULL, *stack = malloc(sizeof *stack * ((size_t) n + 1));
+	uint32_t *mark = calloc((size_t) n + 1, sizeof *mark);   /* generation stamps */
+	size_t used = 0, cap = 0;
+	uint32_t s;
+
+	if (off == NULL || stack == NULL || mark == NULL) {
+		goto oom;
+	}
+	for (s = 0; s < n; s++) {
+		size_t sp = 0, begin = used;
+		off[s] = used;
+		stack[sp++] = s;
+		mark[s] = s + 1;
+		while (sp > 0) {
+			uint32_t u = stack[--sp];
+			uint64_t e;
+			if (used == cap) {
+				size_t ncap = cap ? cap * 2 : 1024;
+				uint32_t *nt = realloc(to, sizeof *nt * ncap);
+				if (nt == NULL) goto oom;
+				to = nt; cap = ncap;
+			}
+			to[used++] = u;
+			if (d->eps_off == NULL) continue;
+			for (e = d->eps_off[u]; e < d->eps_off[u + 1]; e++) {
+				uint32_t v = d->eps_to[e];
+				if (mark[v] != s + 1) {
+					mark[v] = s + 1;
+					stack[sp++] = v;
+				}
+			}
+		}
+		qsort(to + begin, used - begin, sizeof *to, cmp_u32);
+	}
+	off[n] = used;
+	free(stack); free(mark);
+	if (to == NULL) {
+		to = malloc(sizeof *to);
+		if (to == NULL) { free(off); errno = ENOMEM; return -1; }
+	}
+	*off_out = off; *to_out = to;
+	return 0;
+oom:
+	free(off); free(to); free(stack); free(mark);
+	errno = ENOMEM;
+	return -1;
+}
+
+/* ---------------------------------------------------------------------------------
+ * Subset construction.
+ *
+ * The reference first folds epsilon closures into the labelled edges
+ * (fsm_remove_epsilons, src/libfsm/epsilons.c:180-254): state s gets the union of the
+ * edge groups, the end bit and the end ids of every state in closure(s).  It then runs
+ * the subset construction on that epsilon-free NFA starting from the set {start}
+ * (determinise.c:88-104): a DFA state is a set of NFA states that is NOT re-closed, so
+ * two different sets with equal closures stay distinct states.  This restatement keeps
+ * exactly that formulation so that state counts agree with the reference; only the
+ * numbering differs (BFS over symbols here; LIFO worklist + analysis order there).
+ * --------------------------------------------------------------------------------- */
+struct vec32 { uint32_t *a; size_t n, cap; };
+
+static int
+vec32_push(struct vec32 *v, uint32_t x)
+{
+	if (v->n == v->cap) {
+		size_t ncap = v->cap ? v->cap * 2 : 16;
+		uint32_t *na = realloc(v->a, sizeof *na * ncap);
+		if (na == NULL) return 0;
+		v->a = na; v->cap = ncap;
+	}
+	v->a[v->n++] = x;
+	return 1;
+}
+
+struct vec64 { uint64_t *a; size_t n, cap; };
+
+static int
+vec64_push(struct vec64 *v, uint64_t x)
+{
+	if (v->n == v->cap) {
+		size_t ncap = v->cap ? v->cap * 2 : 16;
+		uint64_t *na = realloc(v->a, sizeof *na * ncap);
+		if (na == NULL) return 0;
+		v->a = na; v->cap = ncap;
+	}
+	v->a[v->n++] = x;
+	return 1;
+}
+
+/* interning pool of sorted u32 sets */
+struct pool {
+	struct vec32 buf;        /* concatenated sets */
+	struct vec64 off;        /* set i = buf[off[i] .. off[i+1]) */
+	uint32_t *htab;          /* open addressing, value = set id + 1 */
+	size_t hcap;             /* power of two */
+};
+
+static uint64_t
+hash_set(const uint32_t *a, size_t n)
+{
+	uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t) n;
+	size_t i;
+	for (i = 0; i < n; i++) {
+		h ^= a[i];
+		h *= 0x100000001b3ull;
+		h ^= h >> 29;
+	}
+	return h;
+}
+
+static int
+pool_grow(struct pool *p)
+{
+	size_t ncap = p->hcap ? p->hcap * 2 : 1024, i;
+	uint32_t *nt = calloc(ncap, sizeof *nt);
+	if (nt == NULL) return 0;
+	for (i = 0; i + 1 < p->off.n; i++) {
+		const uint32_t *a = p->buf.a + p->off.a[i];
+		size_t n = (size_t) (p->off.a[i + 1] - p->off.a[i]);
+		size_t h = (size_t) hash_set(a, n) & (ncap - 1);
+		while (nt[h] != 0) h = (h + 1) & (ncap - 1);
+		nt[h] = (uint32_t) i + 1;
+	}
+	free(p->htab);
+	p->htab = nt; p->hcap = ncap;
+	return 1;
+}
+
+/* returns id, sets *isnew; (uint32_t)-1 on OOM */
+static uint32_t
+pool_intern(struct pool *p, const uint32_t *a, size_t n, int *isnew)
+{
+	size_t h, count = p->off.n ? p->off.n - 1 : 0, i;
+	if (p->off.n == 0 && !vec64_push(&p->off, 0)) return (uint32_t) -1;
+	if ((count + 1) * 2 > p->hcap && !pool_grow(p)) return (uint32_t) -1;
+	h = (size_t) hash_set(a, n) & (p->hcap - 1);
+	while (p->htab[h] != 0) {
+		uint32_t id = p->htab[h] - 1;
+		size_t m = (size_t) (p->off.a[id + 1] - p->off.a[id]);
+		if (m == n && memcmp(p->buf.a + p->off.a[id], a, n * sizeof *a) == 0) {
+			*isnew = 0;
+			return id;
+		}
+		h = (h + 1) & (p->hcap - 1);
+	}
+	for (i = 0; i < n; i++) {
+		if (!vec32_push(&p->buf, a[i])) return (uint32_t) -1;
+	}
+	if (!vec64_push(&p->off, p->buf.n)) return (uint32_t) -1;
+	p->htab[h] = (uint32_t) count + 1;
+	*isnew = 1;
+	return (uint32_t) count;
+}
+
+
+static size_t
+sort_unique(uint32_t *a, size_t n)
+{
+	size_t i, w = 0;
+	if (n < 2) return n;
+	qsort(a, n, sizeof *a, cmp_u32);
+	for (i = 0; i < n; i++) {
+		if (w == 0 || a[w - 1] != a[i]) a[w++] = a[i];
+	}
+	return w;
+}
+
+int
+oracle_determinise(const struct fsm_b200_desc *nfa, size_t state_limit,
+	struct oracle_owned_desc *out)
+{
+	const uint32_t n = nfa->nstates;
+	uint64_t *cl_off = NULL; uint32_t *cl_to = NULL;
+	uint64_t *adj_off = NULL;          /* per NFA state: expanded (symbol,to) edges */
+	uint8_t *adj_sym = NULL; uint32_t *adj_to = NULL;
+	uint8_t *aend = NULL;              /* augmented end bit */
+	struct vec32 symlist[256];
+	struct pool pool;
+	struct vec64 o_goff = {0}, o_gsym = {0}, o_eoff = {0};
+	struct vec32 o_gto = {0}, o_eid = {0}, o_end = {0}, tmp = {0};
+	int rc = -1;
+	uint32_t s;
+	size_t c;
+	uint8_t *reach = NULL;
+
+	memset(out, 0, sizeof *out);
+	memset(symlist, 0, sizeof symlist);
+	memset(&pool, 0, sizeof pool);
+
+	if (oracle_epsilon_closure(nfa, &cl_off, &cl_to) != 0) return -1;
+
+	/* determinise.c:65-68 */
+	if (state_limit != 0 && n > state_limit) { rc = 1; goto done; }
+
+	/* mark_states_reachable_by_label (epsilons.c:296-323) */
+	reach = calloc((size_t) n + 1, 1);
+	aend = calloc((size_t) n + 1, 1);
+	adj_off = calloc((size_t) n + 2, sizeof *adj_off);
+	if (!reach || !aend || !adj_off) goto oom;
+	for (s = 0; s < n; s++) {
+		uint64_t g;
+		for (g = nfa->group_off[s]; g < nfa->group_off[s + 1]; g++) {
+			reach[nfa->group_to[g]] = 1;
+		}
+	}
+	if (nfa->hasstart) reach[nfa->start] = 1;
+
+	/* augmented, symbol-expanded adjacency: two passes (count, fill) */
+	for (int pass = 0; pass < 2; pass++) {
+		uint64_t total = 0;
+		for (s = 0; s < n; s++) {
+			uint64_t k;
+			if (pass == 1) total = adj_off[s];
+			else adj_off[s] = total;
+			if (!reach[s]) continue;
+			for (k = cl_off[s]; k < cl_off[s + 1]; k++) {
+				uint32_t es = cl_to[k];
+				uint64_t g;
+				if (nfa->is_end[es]) aend[s] = 1;
+				for (g = nfa->group_off[es]; g < nfa->group_off[es + 1]; g++) {
+					const uint64_t *sym = &nfa->group_symbols[4 * g];
+					for (c = 0; c < 256; c++) {
+						if (!sym_get(sym, (unsigned) c)) continue;
+						if (pass == 1) {
+							adj_sym[total] = (uint8_t) c;
+							adj_to[total] = nfa->group_to[g];
+						}
+						total++;
+					}
+				}
+			}
+		}
+		if (pass == 0) {
+			adj_off[n] = total;
+			adj_sym = malloc(total + 1);
+			adj_to = malloc(sizeof *adj_to * (total + 1));
+			if (!adj_sym || !adj_to) goto oom;
+		}
+	}
+	/* states not reachable by label keep their own end bit (they are garbage) */
+	for (s = 0; s < n; s++) if (!reach[s]) aend[s] = nfa->is_end[s];
+
+	if (!nfa->hasstart) {   /* determinise.c:88-91: nothing to do, fsm left as is */
+		rc = 0;
+		out->desc.nstates = 0;
+		goto done;
+	}
+
+	{
+		int isnew;
+		uint32_t st = nfa->start;
+		if (pool_intern(&pool, &st, 1, &isnew) == (uint32_t) -1) goto oom;
+	}
+	if (!vec64_push(&o_goff, 0) || !vec64_push(&o_eoff, 0)) goto oom;
+
+	/* BFS: DFA state id == interned set id (discovery order) */
+	for (uint32_t cur = 0; cur + 1 < pool.off.n; cur++) {
+		const size_t mb = (size_t) pool.off.a[cur], me = (size_t) pool.off.a[cur + 1];
+		uint32_t dst_of_sym[256];
+		uint8_t used[256];
+		int is_end = 0;
+		size_t i;
+
+		memset(used, 0, sizeof used);
+		for (c = 0; c < 256; c++) symlist[c].n = 0;
+		tmp.n = 0;
+
+		for (i = mb; i < me; i++) {
+			uint32_t m = pool.buf.a[i];
+			uint64_t e, k;
+			if (aend[m]) {
+				is_end = 1;
+				/* end ids: union over closure members that are end states
+				 * (epsilons.c:529-569 then endids.c:782-826) */
+				for (k = cl_off[m]; k < cl_off[m + 1]; k++) {
+					uint32_t es = cl_to[k];
+					uint64_t q;
+					if (!nfa->is_end[es] || nfa->endid_off == NULL) continue;
+					for (q = nfa->endid_off[es]; q < nfa->endid_off[es + 1]; q++) {
+						if (!vec32_push(&tmp, nfa->endids[q])) goto oom;
+					}
+				}
+			}
+			for (e = adj_off[m]; e < adj_off[m + 1]; e++) {
+				if (!vec32_push(&symlist[adj_sym[e]], adj_to[e])) goto oom;
+				used[adj_sym[e]] = 1;
+			}
+		}
+		if (!vec32_push(&o_end, (uint32_t) is_end)) goto oom;
+		tmp.n = sort_unique(tmp.a, tmp.n);
+		for (i = 0; i < tmp.n; i++) if (!vec32_push(&o_eid, tmp.a[i])) goto oom;
+		if (!vec64_push(&o_eoff, o_eid.n)) goto oom;
+
+		for (c = 0; c < 256; c++) {
+			int isnew;
+			dst_of_sym[c] = NO_EDGE;
+			if (!used[c]) continue;
+			symlist[c].n = sort_unique(symlist[c].a, symlist[c].n);
+			dst_of_sym[c] = pool_intern(&pool, symlist[c].a, symlist[c].n, &isnew);
+			if (dst_of_sym[c] == (uint32_t) -1) goto oom;
+			if (isnew && state_limit != 0 && (pool.off.n - 2) > state_limit) {
+				/* determinise.c:166-169: checked with the count BEFORE adding */
+				rc = 1;
+				goto done;
+			}
+		}
+		/* groups: one per distinct destination, ascending destination
+		 * (edge_set keeps groups sorted by .to, src/adt/edgeset.c:283-373) */
+		{
+			uint32_t dsts[256]; size_t nd = 0, j;
+			for (c = 0; c < 256; c++) if (dst_of_sym[c] != NO_EDGE) dsts[nd++] = dst_of_sym[c];
+			nd = sort_unique(dsts, nd);
+			for (j = 0; j < nd; j++) {
+				uint64_t sym[4] = {0, 0, 0, 0};
+				for (c = 0; c < 256; c++) {
+					if (dst_of_sym[c] == dsts[j]) sym[c >> 6] |= 1ull << (c & 63);
+				}
+				if (!vec64_push(&o_gsym, sym[0]) || !vec64_push(&o_gsym, sym[1]) ||
+				    !vec64_push(&o_gsym, sym[2]) || !vec64_push(&o_gsym, sym[3]) ||
+				    !vec32_push(&o_gto, dsts[j])) goto oom;
+			}
+			if (!vec64_push(&o_goff, o_gto.n)) goto oom;
+		}
+	}
+
+	{
+		const uint32_t nd = (uint32_t) (pool.off.n - 1);
+		uint8_t *is_end = malloc((size_t) nd + 1);
+		uint32_t i;
+		if (!is_end) goto oom;
+		for (i = 0; i < nd; i++) is_end[i] = (uint8_t) o_end.a[i];
+		out->desc.nstates = nd;
+		out->desc.start = 0;
+		out->desc.hasstart = 1;
+		out->desc.is_end = is_end;
+		out->desc.group_off = o_goff.a;
+		out->desc.group_symbols = o_gsym.a ? o_gsym.a : calloc(4, sizeof(uint64_t));
+		out->desc.group_to = o_gto.a ? o_gto.a : calloc(1, sizeof(uint32_t));
+		out->desc.eps_off = NULL;
+		out->desc.eps_to = NULL;
+		out->desc.endid_off = o_eoff.a;
+		out->desc.endids = o_eid.a ? o_eid.a : calloc(1, sizeof(uint32_t));
+		out->blocks[0] = is_end;
+		out->blocks[1] = (void *) out->desc.group_off;
+		out->blocks[2] = (void *) out->desc.group_symbols;
+		out->blocks[3] = (void *) out->desc.group_to;
+		out->blocks[4] = (void *) out->desc.endid_off;
+		out->blocks[5] = (void *) out->desc.endids;
+		o_goff.a = NULL; o_gsym.a = NULL; o_gto.a = NULL; o_eoff.a = NULL; o_eid.a = NULL;
+		rc = 0;
+	}
+	goto done;
+oom:
+	errno = ENOMEM;
+	rc = -1;
+done:
+	free(cl_off); free(cl_to); free(adj_off); free(adj_sym); free(adj_to);
+	free(aend); free(reach);
+	for (c = 0; c < 256; c++) free(symlist[c].a);
+	free(pool.buf.a); free(pool.off.a); free(pool.htab);
+	free(o_goff.a); free(o_gsym.a); free(o_gto.a); free(o_eoff.a); free(o_eid.a);
+	free(o_end.a); free(tmp.a);
+	return rc;
+}
+
+void
+oracle_desc_free(struct oracle_owned_desc *d)
+{
+	size_t i;
+	for (i = 0; i < sizeof d->blocks / sizeof d->blocks[0]; i++) {
+		free(d->blocks[i]);
+		d->blocks[i] = NULL;
+	}
+	memset(&d->desc, 0, sizeof d->desc);
+}
+
+uint32_t
+oracle_canonicalise(const struct fsm_b200_desc *d, uint32_t *canon_table,
+	uint32_t *canon_of_state)
+{
+	const uint32_t n = d->nstates;
+	uint32_t *order, ncanon = 0, head = 0, s;
+	unsigned c;
+
+	if (!oracle_isdfa(d)) return (uint32_t) -1;
+	order = malloc(sizeof *order * ((size_t) n + 1));
+	if (order == NULL) return (uint32_t) -1;
+	for (s = 0; s < n; s++) canon_of_state[s] = NO_EDGE;
+	canon_of_state[d->start] = ncanon;
+	order[ncanon++] = d->start;
+	while (head < ncanon) {
+		uint32_t u = order[head];
+		for (c = 0; c < 256; c++) {
+			uint32_t v = group_scan(d, u, c);
+			if (v != NO_EDGE && canon_of_state[v] == NO_EDGE) {
+				canon_of_state[v] = ncanon;
+				order[ncanon++] = v;
+			}
+			canon_table[(size_t) head * 256 + c] = (v == NO_EDGE) ? NO_EDGE : canon_of_state[v];
+		}
+		head++;
+	}
+	free(order);
+	return ncanon;
+}

@@ -1,0 +1,320 @@
+/*
+ * ref_harness.c -- TEST INFRASTRUCTURE.  See ref_harness.h.
+ *
+ * Compiled against the reference's headers where they lie (/root/reference/include and
+ * its private src/libfsm/internal.h, include/adt/edgeset.h, include/adt/stateset.h) and
+ * linked to oracle/_ref/libfsm_ref.so.  All automaton logic here is the reference's own;
+ * this file only marshals between `struct fsm` and the flat description.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include <assert.h>
+#include <errno.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <fsm/fsm.h>
+#include <fsm/bool.h>
+#include <fsm/pred.h>
+#include <fsm/walk.h>
+#include <re/re.h>
+
+#include <adt/set.h>
+#include <adt/stateset.h>
+#include <adt/edgeset.h>
+
+#include "libfsm/internal.h"
+
+#include "ref_harness.h"
+
+struct strcur { const char *p; size_t left; };
+
+static int
+str_getc(void *opaque)
+{
+	struct strcur *c = opaque;
+	if (c->left == 0) return EOF;
+	c->left--;
+	return (unsigned char) *c->p++;
+}
+
+void *
+refh_re_comp(const char *pattern, size_t len, int dialect, int flags)
+{
+	struct strcur c = { pattern, len };
+	struct re_err err;
+	return re_comp((enum re_dialect) dialect, str_getc, &c, NULL, (enum re_flags) flags, &err);
+}
+
+int refh_determinise(void *fsm) { return fsm_determinise(fsm); }
+
+int
+refh_determinise_limit(void *fsm, size_t state_limit)
+{
+	struct fsm_determinise_config cfg = { state_limit };
+	return (int) fsm_determinise_with_config(fsm, &cfg);
+}
+
+int refh_minimise(void *fsm) { return fsm_minimise(fsm); }
+int refh_setendid(void *fsm, unsigned id) { return fsm_setendid(fsm, id); }
+void *refh_union_array(size_t n, void **fsms) { return fsm_union_array(n, (struct fsm **) fsms, NULL); }
+void *refh_clone(const void *fsm) { return fsm_clone(fsm); }
+void refh_free(void *fsm) { fsm_free(fsm); }
+unsigned refh_countstates(const void *fsm) { return fsm_countstates(fsm); }
+int refh_equal(const void *a, const void *b) { return fsm_equal(a, b); }
+int refh_remove_epsilons(void *fsm) { return fsm_remove_epsilons(fsm); }
+
+void *
+refh_from_desc(const struct fsm_b200_desc *d)
+{
+	struct fsm *fsm = fsm_new(NULL);
+	uint32_t s;
+	if (fsm == NULL) return NULL;
+	if (d->nstates > 0 && !fsm_addstate_bulk(fsm, d->nstates)) goto fail;
+	for (s = 0; s < d->nstates; s++) {
+		uint64_t g, e;
+		for (g = d->group_off[s]; g < d->group_off[s + 1]; g++) {
+			unsigned c;
+			for (c = 0; c < 256; c++) {
+				if ((d->group_symbols[4 * g + (c >> 6)] >> (c & 63)) & 1u) {
+					if (!fsm_addedge_literal(fsm, s, d->group_to[g], (char) c)) goto fail;
+				}
+			}
+		}
+		if (d->eps_off != NULL) {
+			for (e = d->eps_off[s]; e < d->eps_off[s + 1]; e++) {
+				if (!fsm_addedge_epsilon(fsm, s, d->eps_to[e])) goto fail;
+			}
+		}
+		if (d->is_end[s]) {
+			fsm_setend(fsm, s, 1);
+			if (d->endid_off != NULL) {
+				for (e = d->endid_off[s]; e < d->endid_off[s + 1]; e++) {
+					if (!fsm_endid_set(fsm, s, d->endids[e])) goto fail;
+				}
+			}
+		}
+	}
+	if (d->hasstart) fsm_setstart(fsm, d->start);
+	return fsm;
+fail:
+	fsm_free(fsm);
+	return NULL;
+}
+
+int
+refh_flatten(const void *vfsm, struct refh_flat *out)
+{
+	const struct fsm *fsm = vfsm;
+	const size_t n = fsm->statecount;
+	size_t ngroups = 0, neps = 0, nids = 0, s;
+	uint8_t *is_end; uint64_t *goff, *gsym, *eoff, *ioff; uint32_t *gto, *eto, *ids;
+	fsm_state_t st;
+
+	memset(out, 0, sizeof *out);
+	for (s = 0; s < n; s++) {
+		struct edge_group_iter egi;
+		struct edge_group_iter_info info;
+		edge_set_group_iter_reset(fsm->states[s].edges, EDGE_GROUP_ITER_ALL, &egi);
+		while (edge_set_group_iter_next(&egi, &info)) ngroups++;
+		neps += state_set_count(fsm->states[s].epsilons);
+		if (fsm->states[s].end) nids += fsm_endid_count(fsm, (fsm_state_t) s);
+	}
+	is_end = calloc(n + 1, 1);
+	goff = calloc(n + 1, sizeof *goff);
+	gsym = calloc(4 * ngroups + 4, sizeof *gsym);
+	gto  = calloc(ngroups + 1, sizeof *gto);
+	eoff = calloc(n + 1, sizeof *eoff);
+	eto  = calloc(neps + 1, sizeof *eto);
+	ioff = calloc(n + 1, sizeof *ioff);
+	ids  = calloc(nids + 1, sizeof *ids);
+	if (!is_end || !goff || !gsym || !gto || !eoff || !eto || !ioff || !ids) {
+		free(is_end); free(goff); free(gsym); free(gto); free(eoff); free(eto); free(ioff); free(ids);
+		errno = ENOMEM;
+		return -1;
+	}
+	ngroups = neps = nids = 0;
+	for (s = 0; s < n; s++) {
+		struct edge_group_iter egi;
+		struct edge_group_iter_info info;
+		struct state_iter si;
+		fsm_state_t es;
+
+		goff[s] = ngroups; eoff[s] = neps; ioff[s] = nids;
+		is_end[s] = (uint8_t) fsm->states[s].end;
+		edge_set_group_iter_reset(fsm->states[s].edges, EDGE_GROUP_ITER_ALL, &egi);
+		while (edge_set_group_iter_next(&egi, &info)) {
+			memcpy(&gsym[4 * ngroups], info.symbols, 4 * sizeof(uint64_t));
+			gto[ngroups] = info.to;
+			ngroups++;
+		}
+		for (state_set_reset(fsm->states[s].epsilons, &si); state_set_next(&si, &es); ) {
+			eto[neps++] = es;
+		}
+		if (fsm->states[s].end) {
+			size_t c = fsm_endid_count(fsm, (fsm_state_t) s);
+			if (c > 0) {
+				int ok = fsm_endid_get(fsm, (fsm_state_t) s, c, &ids[nids]);
+				assert(ok); (void) ok;
+				nids += c;
+			}
+		}
+	}
+	goff[n] = ngroups; eoff[n] = neps; ioff[n] = nids;
+
+	out->desc.nstates = (uint32_t) n;
+	out->desc.hasstart = (uint32_t) fsm_getstart(fsm, &st);
+	out->desc.start = out->desc.hasstart ? st : 0;
+	out->desc.is_end = is_end;
+	out->desc.group_off = goff; out->desc.group_symbols = gsym; out->desc.group_to = gto;
+	out->desc.eps_off = eoff; out->desc.eps_to = eto;
+	out->desc.endid_off = ioff; out->desc.endids = ids;
+	out->blocks[0] = is_end; out->blocks[1] = goff; out->blocks[2] = gsym; out->blocks[3] = gto;
+	out->blocks[4] = eoff; out->blocks[5] = eto; out->blocks[6] = ioff; out->blocks[7] = ids;
+	return 0;
+}
+
+void
+refh_flat_free(struct refh_flat *f)
+{
+	size_t i;
+	for (i = 0; i < 8; i++) { free(f->blocks[i]); f->blocks[i] = NULL; }
+	memset(&f->desc, 0, sizeof f->desc);
+}
+
+int
+refh_epsilon_closure(void *vfsm, uint64_t **off_out, uint32_t **to_out)
+{
+	struct fsm *fsm = vfsm;
+	const size_t n = fsm->statecount;
+	struct state_set **cl = epsilon_closure(fsm);
+	uint64_t *off; uint32_t *to; size_t total = 0, s;
+	if (cl == NULL) return -1;
+	for (s = 0; s < n; s++) total += state_set_count(cl[s]);
+	off = calloc(n + 1, sizeof *off);
+	to = calloc(total + 1, sizeof *to);
+	if (!off || !to) { free(off); free(to); closure_free(fsm, cl, n); errno = ENOMEM; return -1; }
+	total = 0;
+	for (s = 0; s < n; s++) {
+		struct state_iter si; fsm_state_t es;
+		off[s] = total;
+		for (state_set_reset(cl[s], &si); state_set_next(&si, &es); ) to[total++] = es;
+	}
+	off[n] = total;
+	closure_free(fsm, cl, n);
+	*off_out = off; *to_out = to;
+	return 0;
+}
+
+struct bufcur { const uint8_t *p; uint64_t len, nread; int hit_eof; };
+
+static int
+buf_getc(void *opaque)
+{
+	struct bufcur *c = opaque;
+	if (c->nread == c->len) { c->hit_eof = 1; return EOF; }
+	return c->p[c->nread++];
+}
+
+int
+refh_exec(const void *fsm, const uint8_t *buf, uint64_t len, struct fsm_b200_result *out)
+{
+	struct bufcur c = { buf, len, 0, 0 };
+	fsm_state_t end = (fsm_state_t) -1;
+	int r = fsm_exec(fsm, buf_getc, &c, &end, NULL);
+	out->ret = r;
+	out->end = (r == 1) ? end : UINT32_MAX;
+	/* offset at return == bytes successfully transitioned: every byte read, unless the
+	 * walk stopped on a byte without an edge (that byte was read but not consumed) */
+	out->consumed = c.hit_eof ? c.nread : (c.nread > 0 ? c.nread - 1 : 0);
+	if (r < 0) out->consumed = 0;
+	return r;
+}
+
+struct job {
+	const struct fsm *fsm; const uint8_t *base; const uint64_t *offsets;
+	size_t lo, hi; int mode; struct fsm_b200_result *out;
+};
+
+static void *
+worker(void *opaque)
+{
+	struct job *j = opaque;
+	size_t i;
+	for (i = j->lo; i < j->hi; i++) {
+		const uint8_t *buf = j->base + j->offsets[i];
+		const uint64_t len = j->offsets[i + 1] - j->offsets[i];
+		if (j->mode == 0) {
+			refh_exec(j->fsm, buf, len, &j->out[i]);
+		} else {
+			/* validation hoisted; the reference's own per-byte transition */
+			fsm_state_t state = j->fsm->start;
+			uint64_t off = 0;
+			int dead = 0;
+			while (off < len) {
+				fsm_state_t next;
+				if (!edge_set_transition(j->fsm->states[state].edges, buf[off], &next)) {
+					dead = 1;
+					break;
+				}
+				state = next;
+				off++;
+			}
+			j->out[i].ret = (!dead && fsm_isend(j->fsm, state)) ? 1 : 0;
+			j->out[i].end = state;
+			j->out[i].consumed = off;
+		}
+	}
+	return NULL;
+}
+
+int
+refh_exec_batch(const void *vfsm, const uint8_t *base, const uint64_t *offsets, size_t n,
+	int mode, int nthreads, struct fsm_b200_result *out)
+{
+	const struct fsm *fsm = vfsm;
+	pthread_t tids[256];
+	struct job jobs[256];
+	int t;
+	fsm_state_t st;
+
+	if (mode == 1) {
+		if (!fsm_all(fsm, fsm_isdfa) || !fsm_getstart(fsm, &st)) { errno = EINVAL; return -1; }
+	}
+	if (nthreads < 1) nthreads = 1;
+	if (nthreads > 256) nthreads = 256;
+	for (t = 0; t < nthreads; t++) {
+		jobs[t].fsm = fsm; jobs[t].base = base; jobs[t].offsets = offsets;
+		jobs[t].lo = n * (size_t) t / (size_t) nthreads;
+		jobs[t].hi = n * (size_t) (t + 1) / (size_t) nthreads;
+		jobs[t].mode = mode; jobs[t].out = out;
+	}
+	if (nthreads == 1) {
+		worker(&jobs[0]);
+		return 0;
+	}
+	for (t = 0; t < nthreads; t++) {
+		if (pthread_create(&tids[t], NULL, worker, &jobs[t]) != 0) {
+			int k;
+			for (k = 0; k < t; k++) pthread_join(tids[k], NULL);
+			errno = EAGAIN;
+			return -1;
+		}
+	}
+	for (t = 0; t < nthreads; t++) pthread_join(tids[t], NULL);
+	return 0;
+}
+
+size_t
+refh_endids(const void *fsm, unsigned state, unsigned *ids, size_t cap)
+{
+	size_t c;
+	if (!fsm_isend(fsm, state)) return 0;
+	c = fsm_endid_count(fsm, state);
+	if (c > 0 && c <= cap) {
+		int ok = fsm_endid_get(fsm, state, c, ids);
+		(void) ok;
+	}
+	return c;
+}
