@@ -1,0 +1,261 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container,
+where /root/reference exists and `make -C oracle` has produced oracle/_ref/).
+
+Everything recorded here is an output of the reference's own code:
+  * automata: re_comp -> fsm_determinise -> fsm_minimise (-> fsm_setendid, fsm_union_array)
+  * expectations: fsm_exec (mode 0, the real entry point incl. its per-call validation) and
+    the reference's per-byte edge_set_transition walk (mode 1, gives the stop state too)
+  * vectors: the reference's own conformance vectors tests/retest/*.tst ('+' must match,
+    '-' must not), plus seeded synthetic inputs.
+
+Usage: python tests/golden/make_golden.py
+"""
+from __future__ import annotations
+
+import glob
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import reflib  # noqa: E402
+import goldenio  # noqa: E402
+from libfsm_b200.desc import FlatFsm  # noqa: E402
+
+REF_TESTS = "/root/reference/tests"
+DIALECTS = {"pcre": reflib.RE_PCRE, "glob": reflib.RE_GLOB, "native": reflib.RE_NATIVE,
+            "sql": reflib.RE_SQL, "like": reflib.RE_LIKE, "literal": reflib.RE_LITERAL}
+FLAGS = {"i": 1 << 0, "t": 1 << 1, "m": 1 << 2, "r": 1 << 3, "s": 1 << 4, "z": 1 << 5, "a": 1 << 6, "x": 1 << 7}
+
+
+def unescape(s: bytes) -> bytes | None:
+    """parse_escapes of the reference's retest driver (src/retest/main.c:299-)."""
+    out, i = bytearray(), 0
+    simple = {ord('a'): 7, ord('b'): 8, ord('e'): 27, ord('f'): 12, ord('n'): 10, ord('r'): 13,
+              ord('t'): 9, ord('v'): 11, ord('"'): 34, ord('\\'): 92}
+    while i < len(s):
+        c = s[i]
+        if c != 92:
+            out.append(c); i += 1; continue
+        i += 1
+        if i >= len(s):
+            return None
+        c = s[i]
+        if c in simple:
+            out.append(simple[c]); i += 1
+        elif 48 <= c <= 55:
+            v, nd = 0, 0
+            while i < len(s) and nd < 3 and 48 <= s[i] <= 55:
+                v = v * 8 + (s[i] - 48); nd += 1; i += 1
+            out.append(v & 0xFF)
+        elif c == ord('x'):
+            i += 1
+            curly = i < len(s) and s[i] == ord('{')
+            if curly:
+                i += 1
+            v, nd = 0, 0
+            while i < len(s) and chr(s[i]) in "0123456789abcdefABCDEF" and (curly or nd < 2):
+                v = v * 16 + int(chr(s[i]), 16); nd += 1; i += 1
+            if nd == 0:
+                return None
+            if curly:
+                if i >= len(s) or s[i] != ord('}'):
+                    return None
+                i += 1
+            out.append(v & 0xFF)
+        else:
+            return None
+    return bytes(out)
+
+
+def parse_tst(path: str):
+    """Yield (dialect, flags, regexp bytes, [(should_match, input bytes), ...])."""
+    dialect, flags, opts_e = "pcre", 0, False
+    saved, restore = False, False
+    regexp, vecs = None, []
+    with open(path, "rb") as fh:
+        lines = fh.read().split(b"\n")
+    for raw in lines + [b""]:
+        s = raw
+        if len(s) == 0:
+            if regexp is not None:
+                yield dialect, rflags, regexp, vecs
+            regexp, vecs, flags = None, [], 0
+            if restore:
+                opts_e = saved
+            continue
+        if s[:1] == b"#":
+            continue
+        if s[:1] == b"R" and (len(s) == 1 or s[1:2] == b" "):
+            dialect = "pcre" if len(s) == 1 else s[2:].decode().strip()
+            continue
+        if s[:2] == b"O ":
+            if s[2:3] == b"&":
+                restore, saved = True, opts_e
+                continue
+            has_e = b"e" in s[3:]
+            if s[2:3] == b"=":
+                opts_e = has_e
+            elif s[2:3] == b"+":
+                opts_e = opts_e or has_e
+            elif s[2:3] == b"-":
+                opts_e = opts_e and not has_e
+            continue
+        if s[:2] == b"M ":
+            for ch in s[2:].decode():
+                if ch == "0":
+                    flags = 0
+                elif ch in FLAGS:
+                    flags |= FLAGS[ch]
+            continue
+        if regexp is None:
+            if s[:1] == b"~":
+                s = s[1:]
+            if opts_e:
+                s = unescape(s)
+                if s is None:
+                    regexp = None
+                    continue
+            regexp, rflags, vecs = s, flags, []
+            continue
+        if s[:1] in (b"+", b"-"):
+            t = unescape(s[1:])
+            if t is not None:
+                vecs.append((s[:1] == b"+", t))
+
+
+def run_case(R, name, h, strings, tst=None, note=""):
+    f = R.flatten(h)
+    base, offsets = reflib.offsets_for(strings)
+    exp = R.exec_batch(h, base, offsets, mode=0)
+    is_dfa = not (len(strings) and exp["ret"][0] < 0)
+    am = R.exec_batch(h, base, offsets, mode=1) if is_dfa else None
+    if am is not None:
+        m = exp["ret"] == 1
+        assert (am["ret"] == exp["ret"]).all() and (am["consumed"] == exp["consumed"]).all()
+        assert (am["end"][m] == exp["end"][m]).all()
+    return {"name": name, "fsm": f, "base": base, "offsets": offsets, "expect": exp,
+            "expect_amortised": am, "tst_expect": tst, "is_dfa": is_dfa, "note": note}
+
+
+def rand_strings(rng, n, maxlen, alphabet):
+    alphabet = np.frombuffer(alphabet, dtype=np.uint8)
+    out = []
+    for _ in range(n):
+        ln = int(rng.integers(0, maxlen + 1))
+        out.append(alphabet[rng.integers(0, len(alphabet), ln)].tobytes())
+    return out
+
+
+def cfg2_strings(rng, n, length, adversarial):
+    """BASELINE config 2 input distributions."""
+    a = rng.integers(0x20, 0x7F, size=(n, length), dtype=np.uint8)
+    if adversarial:
+        a[rng.random((n, length)) < 0.5] = ord("a")
+    return [row.tobytes() for row in a]
+
+
+UTF8_RE = (r"^([\x00-\x7F]|[\xC2-\xDF][\x80-\xBF]|\xE0[\xA0-\xBF][\x80-\xBF]|[\xE1-\xEC\xEE\xEF][\x80-\xBF]{2}"
+           r"|\xED[\x80-\x9F][\x80-\xBF]|\xF0[\x90-\xBF][\x80-\xBF]{2}|[\xF1-\xF3][\x80-\xBF]{3}"
+           r"|\xF4[\x80-\x8F][\x80-\xBF]{2})*$")
+
+
+def main():
+    R = reflib.Ref()
+    rng = np.random.default_rng(20260922)
+    cases = []
+
+    # 1. the reference's own conformance vectors
+    nvec = 0
+    for path in sorted(glob.glob(os.path.join(REF_TESTS, "retest", "*.tst"))):
+        for k, (dialect, flags, regexp, vecs) in enumerate(parse_tst(path)):
+            if dialect not in DIALECTS or not vecs:
+                continue
+            try:
+                h = R.compile_dfa(regexp, DIALECTS[dialect], flags, minimise=True)
+            except ValueError:
+                continue
+            strings = [v for _, v in vecs]
+            tst = np.array([1 if m else 0 for m, _ in vecs], dtype=np.int8)
+            c = run_case(R, f"retest:{os.path.basename(path)}:{k}", h, strings, tst,
+                         note=f"{dialect} /{regexp.decode('latin-1')}/ flags={flags}")
+            # the reference's own expectation must hold for the reference's fsm_exec
+            assert ((c["expect"]["ret"] == 1) == (tst == 1)).all(), c["name"]
+            cases.append(c); nvec += len(vecs)
+            R.free(h)
+    print(f"retest: {len(cases)} regexps, {nvec} vectors")
+
+    # 2. BASELINE config DFAs with seeded inputs (small samples of the bench workloads)
+    h = R.compile_dfa(r"a[ -~]{7}\z")
+    assert R.countstates(h) == 256
+    cases.append(run_case(R, "cfg2:uniform", h, cfg2_strings(rng, 256, 1024, False)))
+    cases.append(run_case(R, "cfg2:adversarial", h, cfg2_strings(rng, 256, 1024, True)))
+    cases.append(run_case(R, "cfg2:ragged", h, rand_strings(rng, 700, 300, b"a" * 20 + bytes(range(0x20, 0x7F)) + b"\x00\n\xff")))
+    cases.append(run_case(R, "cfg2:edge", h, [b"", b"a", b"a1234567", b"\x00a1234567", b"a" * 4097, b"a1234567\n"]))
+    R.free(h)
+
+    h = R.compile_dfa(r"[0-9]+\.[0-9]+")
+    cases.append(run_case(R, "cfg1:digits", h, rand_strings(rng, 400, 200, b"0123456789....abc ")))
+    R.free(h)
+
+    # 3. anchored / incomplete DFAs: inputs die at assorted offsets (exec.c:133-138)
+    for pat in (r"^abc[0-9]+x$", r"^(GET|POST) /[a-z]+ HTTP/1\.[01]$", r"^[a-f0-9]{32}$"):
+        h = R.compile_dfa(pat)
+        strs = rand_strings(rng, 300, 80, b"abcx0123456789GETPOS /HTP1.\nf")
+        strs += [b"abc123x", b"abc1x", b"abcx", b"abc123", b"GET /index HTTP/1.1", b"POST /a HTTP/1.0",
+                 b"GET /index HTTP/1.2", b"0123456789abcdef0123456789abcdef", b"0123456789abcdef0123456789abcdeg",
+                 b"0123456789abcdef0123456789abcdef0", b""]
+        cases.append(run_case(R, f"anchored:{pat}", h, strs))
+        R.free(h)
+
+    # 4. unions with end ids (tests/endids/endids2_union_many_endids.c: 6 patterns x 5 ids)
+    pats = ["abc", "def", "abc.def", "abc_def", "foo", "bar"]
+    hs = []
+    for i, p in enumerate(pats):
+        hh = R.compile_dfa(p)
+        for j in range(5):
+            R.setendid(hh, 1 + 5 * i + j)
+        hs.append(hh)
+    u = R.union_array(hs)
+    R.determinise(u)
+    strs = [b"abc", b"def", b"abcxdef", b"abc_def", b"foo", b"bar", b"foobar", b"xxabc_defyy", b"nothing", b"",
+            b"abcdef", b"barfoo abc def"] + rand_strings(rng, 300, 40, b"abcdef_xforb ")
+    cases.append(run_case(R, "endids:union6x5", u, strs))
+    R.minimise(u)
+    cases.append(run_case(R, "endids:union6x5:minimised", u, strs))
+    R.free(u)
+
+    # 5. a DFA with more than 256 states (16-bit table entries) built the rx(1) way, no minimise
+    words = ["error", "warning", "failed", "id=[0-9]{4}", "[A-Z]{3}-[0-9]{3}", "x[0-9a-f]{3}y"]
+    u = R.union_dfa(words, state_limit=20000)
+    n_u = R.countstates(u)
+    assert n_u > 256, n_u
+    strs = rand_strings(rng, 500, 120, b"erowaningfldtmuspcby=0123456789.ABCxyf -") + \
+        [b"connection failed", b"user=bob id=1234", b"warning: error", b"ABC-123", b"x0a1y", b"failed error id=0000 XYZ-999 xfffy warning"]
+    cases.append(run_case(R, f"union6:{n_u}states", u, strs))
+    R.free(u)
+
+    # 6. UTF-8 validator (BASELINE config 4's automaton, as a PCRE over raw bytes)
+    h = R.compile_dfa(UTF8_RE)
+    good = "héllo wörld ∑ 😀 ascii".encode()
+    strs = [good, good[:-1], good + b"\xff", b"\xc0\x80", b"\xed\xa0\x80", b"\xf4\x90\x80\x80", b"", b"\xf0\x9f\x98\x80" * 50,
+            b"\xe2\x82", b"a" * 100 + b"\x80"] + rand_strings(rng, 200, 60, bytes(range(256)))
+    cases.append(run_case(R, f"utf8:{R.countstates(h)}states", h, strs))
+    R.free(h)
+
+    # 7. not a DFA: fsm_exec must refuse with -1/EINVAL (exec.c:106-114)
+    h = R.re_comp(r"ab*c|abd")            # NFA with epsilons, never determinised
+    cases.append(run_case(R, "notdfa:nfa", h, [b"abc", b"abd"]))
+    R.free(h)
+
+    goldenio.save_exec_cases(os.path.join(HERE, "golden_exec.npz"), cases)
+    tot = sum(len(c["offsets"]) - 1 for c in cases)
+    print(f"wrote golden_exec.npz: {len(cases)} cases, {tot} inputs, "
+          f"{os.path.getsize(os.path.join(HERE, 'golden_exec.npz')) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,66 @@
+"""Load/save the golden fixture bundles under tests/golden/ (plain npz, no pickles)."""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from libfsm_b200.desc import FlatFsm, RESULT_DTYPE  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+FSM_KEYS = ("is_end", "group_off", "group_symbols", "group_to", "eps_off", "eps_to", "endid_off", "endids")
+
+
+def pack_fsm(prefix: str, f: FlatFsm, out: dict) -> None:
+    out[prefix + "hdr"] = np.array([f.nstates, f.start, int(f.hasstart)], dtype=np.int64)
+    for k in FSM_KEYS:
+        out[prefix + k] = getattr(f, k)
+
+
+def unpack_fsm(prefix: str, z) -> FlatFsm:
+    n, start, has = (int(x) for x in z[prefix + "hdr"])
+    return FlatFsm(nstates=n, start=start, hasstart=bool(has), **{k: z[prefix + k] for k in FSM_KEYS})
+
+
+def save_exec_cases(path: str, cases: list[dict]) -> None:
+    """case: name, fsm, base(u8), offsets(u64), expect(RESULT_DTYPE; end valid where ret==1),
+    expect_amortised (RESULT_DTYPE, end valid everywhere) or None, tst_expect (i8: 1 '+', 0 '-', -1 n/a),
+    is_dfa (bool)."""
+    out, meta = {}, []
+    for i, c in enumerate(cases):
+        p = f"c{i}_"
+        pack_fsm(p, c["fsm"], out)
+        out[p + "base"] = c["base"]
+        out[p + "offsets"] = c["offsets"]
+        out[p + "expect"] = c["expect"].view(np.uint8)
+        if c.get("expect_amortised") is not None:
+            out[p + "expect_am"] = c["expect_amortised"].view(np.uint8)
+        tst = c.get("tst_expect")
+        if tst is None:
+            tst = np.full(len(c["offsets"]) - 1, -1)
+        out[p + "tst"] = np.asarray(tst, dtype=np.int8)
+        meta.append({"name": c["name"], "is_dfa": bool(c.get("is_dfa", True)), "note": c.get("note", "")})
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(path, **out)
+
+
+def load_exec_cases(path: str) -> list[dict]:
+    z = np.load(path)
+    meta = json.loads(bytes(z["meta"]).decode())
+    cases = []
+    for i, m in enumerate(meta):
+        p = f"c{i}_"
+        c = dict(m)
+        c["fsm"] = unpack_fsm(p, z)
+        c["base"] = z[p + "base"]
+        c["offsets"] = z[p + "offsets"]
+        c["expect"] = z[p + "expect"].view(RESULT_DTYPE)
+        c["expect_amortised"] = z[p + "expect_am"].view(RESULT_DTYPE) if (p + "expect_am") in z.files else None
+        c["tst_expect"] = z[p + "tst"]
+        cases.append(c)
+    return cases

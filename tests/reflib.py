@@ -257,12 +257,19 @@ class Ref:
             self.setendid(h, endid)
         return h
 
-    def union_dfa(self, patterns, dialect: int = RE_PCRE, flags: int = 0, minimise_each: bool = True):
+    def union_dfa(self, patterns, dialect: int = RE_PCRE, flags: int = 0, minimise_each: bool = True,
+                  state_limit: int = 0):
         """The rx(1)/re(1) recipe (reference src/rx/main.c:487-566,1353,1371): per pattern
         re_comp+determinise+minimise+setendid(index), fsm_union_array, fsm_determinise."""
         hs = [self.compile_dfa(p, dialect, flags, minimise_each, endid=i) for i, p in enumerate(patterns)]
         u = self.union_array(hs)
-        self.determinise(u)
+        if state_limit:
+            res = self.determinise_limit(u, state_limit)
+            if res != 0:
+                self.free(u)
+                raise RuntimeError(f"union determinise: result {res} (1 = state limit {state_limit} reached)")
+        else:
+            self.determinise(u)
         return u
 
     # -- execution --------------------------------------------------------------------
