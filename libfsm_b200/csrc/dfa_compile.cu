@@ -112,7 +112,12 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa 
 	dfa->entry_bytes = dfa->ntable <= 256 ? 1u : (dfa->ntable <= 65536 ? 2u : 4u);
 
 	/* shared-memory layout: padded rows; global layout: dense rows */
-	const uint64_t padded_pitch = 256ull * dfa->entry_bytes + SMEM_ROW_PAD;
+	uint32_t row_pad = SMEM_ROW_PAD;
+	if (const char *e = getenv("FSM_B200_ROW_PAD")) {      /* tuning knob, see DESIGN.md */
+		const int v = atoi(e);
+		if (v >= 0 && v <= 64 && (v % 4) == 0) row_pad = (uint32_t) v;
+	}
+	const uint64_t padded_pitch = 256ull * dfa->entry_bytes + row_pad;
 	const uint64_t padded_bytes = padded_pitch * dfa->ntable + ((dfa->ntable + 15u) & ~15ull);
 	dfa->smem_resident = padded_bytes <= SMEM_TABLE_MAX ? 1u : 0u;
 	dfa->pitch = dfa->smem_resident ? (uint32_t) padded_pitch : 256u * dfa->entry_bytes;

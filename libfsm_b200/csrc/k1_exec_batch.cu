@@ -519,7 +519,14 @@ k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offs
 	if (variant == K1_AUTO) variant = g_variant;
 	const bool tile_ok = k1_tile_eligible(dfa, d_base, d_offsets, stride, len, n);
 	if (variant == K1_AUTO) {
-		variant = (tile_ok && n >= 4096) ? K1_TILE64 : K1_LANE;
+		/* Measured on B200 (profiles/r1_k1_variants.jsonl): LANE >= TILE64 on both config-2
+		 * distributions -- both saturate the L1TEX data pipe (ncu: l1tex 97 %), and LANE also
+		 * takes ragged/unaligned batches.  FSM_B200_K1_VARIANT overrides. */
+		variant = K1_LANE;
+		if (const char *e = getenv("FSM_B200_K1_VARIANT")) {
+			const int v = atoi(e);
+			if (v > K1_AUTO && v < K1_VARIANT_COUNT && (v == K1_LANE || tile_ok)) variant = v;
+		}
 	}
 	const bool dead = !dfa->complete;
 
