@@ -60,6 +60,8 @@ struct fsm_b200_dfa {
 	uint8_t *h_is_end;       /* [ntable] (dead row: 0) */
 	/* scratch for the _host entry points (grown on demand; guarded by mutex) */
 	void *scratch;
+	/* scratch of the stream (K1b) entry points */
+	void *stream_scratch;
 };
 
 #endif

@@ -163,13 +163,14 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa 
 	return 0;
 }
 
-namespace fsmb200 { void scratch_free(fsm_b200_dfa *dfa); }
+namespace fsmb200 { void scratch_free(fsm_b200_dfa *dfa); void stream_scratch_free(fsm_b200_dfa *dfa); }
 
 extern "C" void
 fsm_b200_dfa_free(fsm_b200_dfa *dfa)
 {
 	if (dfa == nullptr) return;
 	fsmb200::scratch_free(dfa);
+	fsmb200::stream_scratch_free(dfa);
 	if (dfa->d_blob != nullptr) {
 		cudaSetDevice(dfa->device);
 		cudaFree(dfa->d_blob);

@@ -179,13 +179,13 @@ k1_lane_kernel(const K1Args a)
 		uint64_t beg, len;
 		if (a.offsets != nullptr) {
 			beg = a.offsets[i];
-			len = a.offsets[i + 1] - beg;
+			len = (a.ends != nullptr ? a.ends[i] : a.offsets[i + 1]) - beg;
 		} else {
 			beg = i * a.stride;
 			len = a.len;
 		}
 		const uint8_t *p = a.base + beg;
-		uint32_t st = a.start;
+		uint32_t st = a.entry != nullptr ? a.entry[i] : a.start;
 		uint64_t pos = 0;
 		bool died = false;
 
@@ -497,6 +497,62 @@ k1_tile_eligible(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t 
 	    stride >= len && stride < (1ull << 32) && n < (1ull << 31) && dfa->entry_bytes <= 2;
 }
 
+static void
+fill_args(K1Args &a, const fsm_b200_dfa *dfa)
+{
+	memset(&a, 0, sizeof a);
+	a.blob = static_cast<const uint8_t *>(dfa->d_blob);
+	a.blob_bytes = (uint32_t) dfa->blob_bytes;
+	a.is_end_off = (uint32_t) ((dfa->table_bytes + 15u) & ~15ull);
+	a.pitch = dfa->pitch; a.start = dfa->start; a.dead = dfa->dead;
+}
+
+static int
+dispatch_lane(const fsm_b200_dfa *dfa, const K1Args &a, int sms, cudaStream_t stream)
+{
+	const bool dead = !dfa->complete;
+	int block = 1024;
+	const char *e = getenv("FSM_B200_LANE_BLOCK");
+	if (e != nullptr) {
+		int v = atoi(e);
+		if (v >= 32 && v <= 1024 && (v % 32) == 0) block = v;
+	}
+	if (dfa->smem_resident) {
+		const size_t smem_bytes = (a.blob_bytes + 127u) & ~127u;
+		if (dfa->entry_bytes == 1)
+			return dead ? launch_lane<uint8_t, true, true>(a, sms, smem_bytes, block, stream)
+			            : launch_lane<uint8_t, true, false>(a, sms, smem_bytes, block, stream);
+		return dead ? launch_lane<uint16_t, true, true>(a, sms, smem_bytes, block, stream)
+		            : launch_lane<uint16_t, true, false>(a, sms, smem_bytes, block, stream);
+	}
+	if (block > 256 && e == nullptr) block = 256;
+	if (dfa->entry_bytes == 2)
+		return dead ? launch_lane<uint16_t, false, true>(a, sms, 0, block, stream)
+		            : launch_lane<uint16_t, false, false>(a, sms, 0, block, stream);
+	if (dfa->entry_bytes == 4)
+		return dead ? launch_lane<uint32_t, false, true>(a, sms, 0, block, stream)
+		            : launch_lane<uint32_t, false, false>(a, sms, 0, block, stream);
+	return dead ? launch_lane<uint8_t, false, true>(a, sms, 0, block, stream)
+	            : launch_lane<uint8_t, false, false>(a, sms, 0, block, stream);
+}
+
+int
+k1_launch_jobs(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_begs,
+	const uint64_t *d_ends, const uint32_t *d_entry, size_t n, fsm_b200_result *d_out, cudaStream_t stream)
+{
+	if (n == 0) return 0;
+	int sms = 0, smem_optin = 0;
+	if (!device_props(dfa->device, &sms, &smem_optin)) {
+		set_error("k1: cannot query device %d", dfa->device);
+		errno = EIO;
+		return -1;
+	}
+	K1Args a;
+	fill_args(a, dfa);
+	a.base = d_base; a.offsets = d_begs; a.ends = d_ends; a.entry = d_entry; a.n = n; a.out = d_out;
+	return dispatch_lane(dfa, a, sms, stream);
+}
+
 int
 k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,
 	uint64_t stride, uint64_t len, size_t n, fsm_b200_result *d_out, cudaStream_t stream, int variant)
@@ -509,12 +565,8 @@ k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offs
 		return -1;
 	}
 	K1Args a;
-	memset(&a, 0, sizeof a);
+	fill_args(a, dfa);
 	a.base = d_base; a.offsets = d_offsets; a.stride = stride; a.len = len; a.n = n; a.out = d_out;
-	a.blob = static_cast<const uint8_t *>(dfa->d_blob);
-	a.blob_bytes = (uint32_t) dfa->blob_bytes;
-	a.is_end_off = (uint32_t) ((dfa->table_bytes + 15u) & ~15ull);
-	a.pitch = dfa->pitch; a.start = dfa->start; a.dead = dfa->dead;
 
 	if (variant == K1_AUTO) variant = g_variant;
 	const bool tile_ok = k1_tile_eligible(dfa, d_base, d_offsets, stride, len, n);
@@ -531,28 +583,7 @@ k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offs
 	const bool dead = !dfa->complete;
 
 	if (variant == K1_LANE) {
-		int block = 1024;
-		if (const char *e = getenv("FSM_B200_LANE_BLOCK")) {
-			int v = atoi(e);
-			if (v >= 32 && v <= 1024 && (v % 32) == 0) block = v;
-		}
-		if (dfa->smem_resident) {
-			const size_t smem_bytes = (a.blob_bytes + 127u) & ~127u;
-			if (dfa->entry_bytes == 1)
-				return dead ? launch_lane<uint8_t, true, true>(a, sms, smem_bytes, block, stream)
-				            : launch_lane<uint8_t, true, false>(a, sms, smem_bytes, block, stream);
-			return dead ? launch_lane<uint16_t, true, true>(a, sms, smem_bytes, block, stream)
-			            : launch_lane<uint16_t, true, false>(a, sms, smem_bytes, block, stream);
-		}
-		if (block > 256 && getenv("FSM_B200_LANE_BLOCK") == nullptr) block = 256;
-		if (dfa->entry_bytes == 2)
-			return dead ? launch_lane<uint16_t, false, true>(a, sms, 0, block, stream)
-			            : launch_lane<uint16_t, false, false>(a, sms, 0, block, stream);
-		if (dfa->entry_bytes == 4)
-			return dead ? launch_lane<uint32_t, false, true>(a, sms, 0, block, stream)
-			            : launch_lane<uint32_t, false, false>(a, sms, 0, block, stream);
-		return dead ? launch_lane<uint8_t, false, true>(a, sms, 0, block, stream)
-		            : launch_lane<uint8_t, false, false>(a, sms, 0, block, stream);
+		return dispatch_lane(dfa, a, sms, stream);
 	}
 
 	if (!tile_ok) {

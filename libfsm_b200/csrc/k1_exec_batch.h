@@ -19,6 +19,8 @@ enum K1Variant {
 struct K1Args {
 	const uint8_t *base;
 	const uint64_t *offsets;    /* n+1 entries, or nullptr for fixed stride */
+	const uint64_t *ends;       /* optional: input i = [offsets[i], ends[i]) (K1b jobs) */
+	const uint32_t *entry;      /* optional: per-input entry state (K1b jobs), else `start` */
 	uint64_t stride, len;
 	uint64_t n;
 	fsm_b200_result *out;
@@ -37,6 +39,10 @@ bool k1_tile_eligible(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint
 
 int k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,
 	uint64_t stride, uint64_t len, size_t n, fsm_b200_result *d_out, cudaStream_t stream, int variant);
+
+/* K1b jobs: input i = d_base[d_begs[i] .. d_ends[i]) walked from state d_entry[i] (LANE variant). */
+int k1_launch_jobs(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_begs,
+	const uint64_t *d_ends, const uint32_t *d_entry, size_t n, fsm_b200_result *d_out, cudaStream_t stream);
 
 } // namespace fsmb200
 #endif

@@ -1,15 +1,523 @@
-/* k1b_stream.cu -- K1b: one long input (placeholder until the chunk-map kernels land). */
+/*
+ * k1b_stream.cu -- K1b: ONE long input == one reference fsm_exec call over a stream
+ * (src/libfsm/exec.c:132-151 is strictly serial: O(1) state carried byte to byte).
+ *
+ * DFA execution is a monoid: a byte range maps every entry state to an exit state, and maps
+ * compose associatively.  The stream is cut into chunks of C bytes and processed in five
+ * data-parallel steps, exact for ANY DFA (no reliance on self-synchronisation):
+ *
+ *   1. prefix   thread (chunk c, state s): walk the first W bytes of c from s
+ *               -> img[c][s] (or "died": offset + state it died in).  Chains from wrong entry
+ *               states die or merge within a few bytes for practical DFAs, so few distinct
+ *               live images survive per chunk (1 for the config-2 and UTF-8 DFAs).
+ *   2. reps     one job per DISTINCT live image (c, v): the rest of chunk c walked from v.
+ *   3. body     the K1 LANE kernel over the jobs (one lane per job, 256-bit loads, table in
+ *               shared memory) -- this is where the bytes are scanned, at K1 speed.
+ *   4. cmap     next[c][s] = exit of job(c, img[c][s]), plus first-dead offset / state.
+ *   5. compose  two-level composition of the chunk maps in chunk order (level 1: groups of G
+ *               maps in shared memory, one thread per entry state; level 2: over groups).
+ *
+ * The result is the map entry-state -> (exit state | first dead offset + dead-from state)
+ * of the whole range: exec_stream uses entry = start; the multi-GPU shard form all-gathers
+ * the maps of the ranks' byte ranges and composes them in rank order (sharding.py).
+ *
+ * Applies to tables with <= 256 rows (8-bit entries, shared-memory resident).  Larger DFAs,
+ * and inputs too short to cut, run as a K1 batch of one (a serial walk on one lane).
+ */
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
 #include "common.h"
+#include "k1_exec_batch.h"
+
 using namespace fsmb200;
 
-extern "C" int
-fsm_b200_exec_stream_host(const fsm_b200_dfa *, const uint8_t *, uint64_t, struct fsm_b200_result *)
-{ set_error("exec_stream_host: not implemented yet"); errno = ENOTSUP; return -1; }
+namespace {
+
+constexpr uint32_t DEADMARK = 0xFFFFFFFFu;
+constexpr uint16_t DEAD16 = 0xFFFFu;
+constexpr uint32_t PREFIX_W = 64;
+
+struct StreamArgs {
+	const uint8_t *buf;
+	uint64_t len;
+	uint64_t C;            /* chunk bytes */
+	uint32_t nchunks;
+	uint32_t T;            /* real states (entry states considered) */
+	const uint8_t *blob;
+	uint32_t blob_bytes, pitch, dead;
+	/* per (chunk, state) */
+	uint32_t *img, *pdo, *pdf;
+	uint8_t *live;
+	uint32_t *job_of;
+	uint16_t *next;
+	uint64_t *dead_off;
+	uint32_t *dead_from;
+	/* jobs */
+	uint64_t *job_beg, *job_end;
+	uint32_t *job_entry;
+	uint32_t *njobs;
+	const fsm_b200_result *rec;
+};
+
+__device__ __forceinline__ uint32_t
+smem_u32(const void *p)
+{
+	return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+/* Stage the table blob with TMA bulk copies (same scheme as K1). */
+__device__ __forceinline__ void
+stage_blob(uint8_t *smem, const uint8_t *blob, uint32_t blob_bytes, uint64_t *bar)
+{
+	const uint32_t bar_a = smem_u32(bar);
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_a));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(blob_bytes) : "memory");
+		const uint32_t dst = smem_u32(smem);
+		for (uint32_t off = 0; off < blob_bytes; off += 16384u) {
+			const uint32_t nb = min(16384u, blob_bytes - off);
+			asm volatile(
+			    "cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			    :: "r"(dst + off), "l"(blob + off), "r"(nb), "r"(bar_a) : "memory");
+		}
+	}
+	uint32_t done;
+	do {
+		asm volatile(
+		    "{\n\t.reg .pred p;\n\t"
+		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		    "selp.u32 %0, 1, 0, p;\n\t}"
+		    : "=r"(done) : "r"(bar_a), "r"(0) : "memory");
+	} while (!done);
+}
+
+/* 1. prefix: thread per (chunk, entry state).  Lanes of a warp share the chunk (same bytes:
+ * broadcast loads) and hold consecutive states (row pitch 260 B: distinct banks). */
+__global__ void __launch_bounds__(1024, 1)
+k1b_prefix_kernel(const StreamArgs a)
+{
+	extern __shared__ __align__(1024) uint8_t smem[];
+	__shared__ uint64_t blob_bar;
+	stage_blob(smem, a.blob, a.blob_bytes, &blob_bar);
+
+	const uint64_t total = (uint64_t) a.nchunks * a.T;
+	const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
+	for (uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+		const uint32_t c = (uint32_t) (idx / a.T), s = (uint32_t) (idx % a.T);
+		const uint64_t beg = (uint64_t) c * a.C;
+		const uint64_t clen = min(a.C, a.len - beg);
+		const uint32_t w = (uint32_t) min((uint64_t) PREFIX_W, clen);
+		const uint8_t *p = a.buf + beg;
+		uint32_t st = s, k = 0;
+		bool died = false;
+		for (; k < w; k++) {
+			const uint32_t nx = smem[st * a.pitch + __ldg(p + k)];
+			if (nx == a.dead) { died = true; break; }
+			st = nx;
+		}
+		if (died) {
+			a.img[idx] = DEADMARK; a.pdo[idx] = k; a.pdf[idx] = st;
+		} else {
+			a.img[idx] = st;
+			a.live[(uint64_t) c * a.T + st] = 1;      /* benign race: all writers store 1 */
+		}
+	}
+}
+
+/* 2. reps: one job per distinct live image. */
+__global__ void
+k1b_reps_kernel(const StreamArgs a)
+{
+	const uint64_t total = (uint64_t) a.nchunks * a.T;
+	const uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= total || !a.live[idx]) return;
+	const uint32_t c = (uint32_t) (idx / a.T), v = (uint32_t) (idx % a.T);
+	const uint64_t beg = (uint64_t) c * a.C;
+	const uint64_t clen = min(a.C, a.len - beg);
+	const uint64_t w = min((uint64_t) PREFIX_W, clen);
+	const uint32_t j = atomicAdd(a.njobs, 1u);
+	a.job_of[idx] = j;
+	a.job_beg[j] = beg + w;
+	a.job_end[j] = beg + clen;
+	a.job_entry[j] = v;
+}
+
+/* 4. cmap: the chunk's full map, with first-dead bookkeeping. */
+__global__ void
+k1b_cmap_kernel(const StreamArgs a)
+{
+	const uint64_t total = (uint64_t) a.nchunks * a.T;
+	const uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= total) return;
+	const uint32_t c = (uint32_t) (idx / a.T);
+	const uint64_t beg = (uint64_t) c * a.C;
+	const uint32_t v = a.img[idx];
+	if (v == DEADMARK) {
+		a.next[idx] = DEAD16;
+		a.dead_off[idx] = beg + a.pdo[idx];
+		a.dead_from[idx] = a.pdf[idx];
+		return;
+	}
+	const uint32_t j = a.job_of[(uint64_t) c * a.T + v];
+	const fsm_b200_result r = a.rec[j];
+	const uint64_t jlen = a.job_end[j] - a.job_beg[j];
+	if (r.consumed < jlen) {                 /* the body walk hit a missing edge */
+		a.next[idx] = DEAD16;
+		a.dead_off[idx] = a.job_beg[j] + r.consumed;
+		a.dead_from[idx] = r.end;
+	} else {
+		a.next[idx] = (uint16_t) r.end;
+	}
+}
+
+/* 5. compose, level 1: block b folds chunks [b*G, b*G+G) for every entry state.
+ * gnext[b][s] = exit or DEAD16; on death gchunk/gstate say where (chunk, state entering it). */
+__global__ void
+k1b_compose1_kernel(const uint16_t *next, uint32_t nchunks, uint32_t T, uint32_t G,
+	uint16_t *gnext, uint32_t *gchunk, uint32_t *gstate)
+{
+	extern __shared__ __align__(16) uint16_t sm[];
+	const uint32_t c0 = blockIdx.x * G;
+	const uint32_t cn = min(G, nchunks - c0);
+	const uint64_t base = (uint64_t) c0 * T;
+	for (uint32_t i = threadIdx.x; i < cn * T; i += blockDim.x) sm[i] = next[base + i];
+	__syncthreads();
+	for (uint32_t s = threadIdx.x; s < T; s += blockDim.x) {
+		uint32_t st = s, dc = 0xFFFFFFFFu, ds = 0;
+		for (uint32_t k = 0; k < cn; k++) {
+			const uint16_t nx = sm[k * T + st];
+			if (nx == DEAD16) { dc = c0 + k; ds = st; st = DEAD16; break; }
+			st = nx;
+		}
+		gnext[(uint64_t) blockIdx.x * T + s] = (uint16_t) st;
+		gchunk[(uint64_t) blockIdx.x * T + s] = dc;
+		gstate[(uint64_t) blockIdx.x * T + s] = ds;
+	}
+}
+
+struct StreamOut {          /* per entry state, [T] */
+	uint32_t state;         /* exit state, or dead-from state when died */
+	uint32_t died;
+	uint64_t dead_off;      /* offset within the range of the first byte without an edge */
+};
+
+/* 5. compose, level 2: one thread per entry state folds the group maps in order. */
+__global__ void
+k1b_compose2_kernel(const uint16_t *gnext, const uint32_t *gchunk, const uint32_t *gstate,
+	uint32_t ngroups, uint32_t T, const uint64_t *dead_off, const uint32_t *dead_from, StreamOut *out)
+{
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= T) return;
+	uint32_t st = s;
+	for (uint32_t g = 0; g < ngroups; g++) {
+		const uint64_t i = (uint64_t) g * T + st;
+		const uint16_t nx = gnext[i];
+		if (nx == DEAD16) {
+			const uint64_t at = (uint64_t) gchunk[i] * T + gstate[i];
+			out[s].state = dead_from[at];
+			out[s].died = 1;
+			out[s].dead_off = dead_off[at];
+			return;
+		}
+		st = nx;
+	}
+	out[s].state = st;
+	out[s].died = 0;
+	out[s].dead_off = 0xFFFFFFFFFFFFFFFFull;
+}
+
+/* ------------------------------------------------------------------ host side -------- */
+
+struct Arena {
+	uint8_t *base = nullptr;
+	size_t cap = 0, used = 0;
+	template <typename T> T *take(size_t n) {
+		used = (used + 255) & ~(size_t) 255;
+		T *p = reinterpret_cast<T *>(base + used);
+		used += n * sizeof(T);
+		return p;
+	}
+};
+
+struct StreamScratch {
+	std::mutex mu;
+	Arena arena;
+	uint8_t *d_in = nullptr; size_t in_cap = 0;       /* for the _host entry point */
+	cudaStream_t stream = nullptr;
+};
+
+std::mutex g_ss_mu;
+
+StreamScratch *
+ss_get(const fsm_b200_dfa *cdfa)
+{
+	fsm_b200_dfa *dfa = const_cast<fsm_b200_dfa *>(cdfa);
+	std::lock_guard<std::mutex> g(g_ss_mu);
+	if (dfa->stream_scratch == nullptr) dfa->stream_scratch = new (std::nothrow) StreamScratch();
+	return static_cast<StreamScratch *>(dfa->stream_scratch);
+}
+
+size_t
+pick_chunk(uint32_t T, uint64_t len, int sms)
+{
+	/* One body job per lane and about two waves of lanes (measured on B200, 2 GiB of UTF-8:
+	 * 2 KiB chunks 1.39 TB/s, 8 KiB 2.07 TB/s, 32 KiB 0.99 TB/s -- profiles/r1_k1b_stream.jsonl);
+	 * never so small that the T x W prefix walks outweigh the body. */
+	const uint64_t lanes = 2ull * (uint64_t) (sms > 0 ? sms : 148) * 1024ull;
+	uint64_t lo = 2048;
+	while (lo < 2ull * T * PREFIX_W) lo <<= 1;
+	uint64_t c = lo;
+	while (c < (1ull << 22) && len / c > lanes) c <<= 1;
+	if (const char *e = getenv("FSM_B200_STREAM_CHUNK")) {
+		const long v = atol(e);
+		if (v >= 64 && v <= (1l << 30)) c = (uint64_t) v & ~31ull;
+	}
+	while (len / c > (1ull << 22)) c <<= 1;           /* bound the number of chunks */
+	return (size_t) c;
+}
+
+/* Run steps 1-5 over d_buf[0..len); leaves StreamOut[T] in h_out. */
+int
+stream_map(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStream_t stream,
+	StreamScratch *ss, std::vector<StreamOut> &h_out)
+{
+	const uint32_t T = dfa->nstates;
+	int sms = 0;
+	FSMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dfa->device), return -1);
+	const uint64_t C = pick_chunk(T, len, sms);
+	const uint32_t nchunks = (uint32_t) ((len + C - 1) / C);
+	const uint64_t cs = (uint64_t) nchunks * T;
+	uint32_t G = 32768u / T;
+	if (G > 1024) G = 1024;
+	if (G < 1) G = 1;
+	const uint32_t ngroups = (nchunks + G - 1) / G;
+
+	const size_t need = cs * (4 + 4 + 4 + 1 + 4 + 2 + 8 + 4) + cs * (8 + 8 + 4 + 16) +
+	    (size_t) ngroups * T * (2 + 4 + 4) + T * sizeof(StreamOut) + 64 * 256 + 4096;
+	if (ss->arena.cap < need) {
+		if (ss->arena.base) cudaFree(ss->arena.base);
+		ss->arena.base = nullptr; ss->arena.cap = 0;
+		void *p = nullptr;
+		FSMB_CUDA(cudaMalloc(&p, need), return -1);
+		ss->arena.base = static_cast<uint8_t *>(p);
+		ss->arena.cap = need;
+	}
+	Arena &ar = ss->arena;
+	ar.used = 0;
+
+	StreamArgs a;
+	memset(&a, 0, sizeof a);
+	a.buf = d_buf; a.len = len; a.C = C; a.nchunks = nchunks; a.T = T;
+	a.blob = static_cast<const uint8_t *>(dfa->d_blob);
+	a.blob_bytes = (uint32_t) dfa->blob_bytes; a.pitch = dfa->pitch; a.dead = dfa->dead;
+	a.img = ar.take<uint32_t>(cs); a.pdo = ar.take<uint32_t>(cs); a.pdf = ar.take<uint32_t>(cs);
+	a.live = ar.take<uint8_t>(cs); a.job_of = ar.take<uint32_t>(cs); a.next = ar.take<uint16_t>(cs);
+	a.dead_off = ar.take<uint64_t>(cs); a.dead_from = ar.take<uint32_t>(cs);
+	a.job_beg = ar.take<uint64_t>(cs); a.job_end = ar.take<uint64_t>(cs); a.job_entry = ar.take<uint32_t>(cs);
+	fsm_b200_result *rec = ar.take<fsm_b200_result>(cs);
+	a.rec = rec;
+	a.njobs = ar.take<uint32_t>(64);
+	uint16_t *gnext = ar.take<uint16_t>((size_t) ngroups * T);
+	uint32_t *gchunk = ar.take<uint32_t>((size_t) ngroups * T);
+	uint32_t *gstate = ar.take<uint32_t>((size_t) ngroups * T);
+	StreamOut *d_out = ar.take<StreamOut>(T);
+
+	FSMB_CUDA(cudaMemsetAsync(a.live, 0, cs, stream), return -1);
+	FSMB_CUDA(cudaMemsetAsync(a.njobs, 0, sizeof(uint32_t), stream), return -1);
+
+	const size_t smem_bytes = (dfa->blob_bytes + 127u) & ~(size_t) 127u;
+	FSMB_CUDA(cudaFuncSetAttribute(k1b_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes), return -1);
+	{
+		uint64_t want = (cs + 1023) / 1024;
+		unsigned grid = (unsigned) (want < (uint64_t) sms ? want : (uint64_t) sms);
+		k1b_prefix_kernel<<<grid, 1024, smem_bytes, stream>>>(a);
+		count_launch();
+	}
+	k1b_reps_kernel<<<(unsigned) ((cs + 255) / 256), 256, 0, stream>>>(a);
+	count_launch();
+	uint32_t njobs = 0;
+	FSMB_CUDA(cudaMemcpyAsync(&njobs, a.njobs, sizeof njobs, cudaMemcpyDeviceToHost, stream), return -1);
+	FSMB_CUDA(cudaStreamSynchronize(stream), return -1);
+	if (k1_launch_jobs(dfa, d_buf, a.job_beg, a.job_end, a.job_entry, njobs, rec, stream) != 0) return -1;
+	k1b_cmap_kernel<<<(unsigned) ((cs + 255) / 256), 256, 0, stream>>>(a);
+	count_launch();
+	const size_t sm1 = (size_t) G * T * sizeof(uint16_t);
+	FSMB_CUDA(cudaFuncSetAttribute(k1b_compose1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm1), return -1);
+	k1b_compose1_kernel<<<ngroups, 256, sm1, stream>>>(a.next, nchunks, T, G, gnext, gchunk, gstate);
+	count_launch();
+	k1b_compose2_kernel<<<(T + 255) / 256, 256, 0, stream>>>(gnext, gchunk, gstate, ngroups, T, a.dead_off, a.dead_from, d_out);
+	count_launch();
+	FSMB_CUDA(cudaGetLastError(), return -1);
+	h_out.resize(T);
+	FSMB_CUDA(cudaMemcpyAsync(h_out.data(), d_out, T * sizeof(StreamOut), cudaMemcpyDeviceToHost, stream), return -1);
+	FSMB_CUDA(cudaStreamSynchronize(stream), return -1);
+	return 0;
+}
+
+bool
+parallel_ok(const fsm_b200_dfa *dfa, uint64_t len)
+{
+	if (!(dfa->smem_resident && dfa->entry_bytes == 1)) return false;
+	uint64_t min_len = 4096;
+	if (const char *e = getenv("FSM_B200_STREAM_MIN")) {
+		const long v = atol(e);
+		if (v >= 0) min_len = (uint64_t) v;
+	}
+	return len >= min_len && len >= 2 * PREFIX_W;
+}
+
+/* Serial form: a K1 batch of one (correct for any table size). */
+int
+stream_serial(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStream_t stream,
+	StreamScratch *ss, fsm_b200_result *out)
+{
+	if (ss->arena.cap < 4096) {
+		if (ss->arena.base) cudaFree(ss->arena.base);
+		ss->arena.base = nullptr; ss->arena.cap = 0;
+		void *p = nullptr;
+		FSMB_CUDA(cudaMalloc(&p, 1 << 20), return -1);
+		ss->arena.base = static_cast<uint8_t *>(p);
+		ss->arena.cap = 1 << 20;
+	}
+	fsm_b200_result *d_rec = reinterpret_cast<fsm_b200_result *>(ss->arena.base);
+	if (k1_launch(dfa, d_buf, nullptr, len, len, 1, d_rec, stream, K1_LANE) != 0) return -1;
+	FSMB_CUDA(cudaMemcpyAsync(out, d_rec, sizeof *out, cudaMemcpyDeviceToHost, stream), return -1);
+	FSMB_CUDA(cudaStreamSynchronize(stream), return -1);
+	return 0;
+}
+
+} // namespace
+
+namespace fsmb200 {
+void
+stream_scratch_free(fsm_b200_dfa *dfa)
+{
+	StreamScratch *ss = static_cast<StreamScratch *>(dfa->stream_scratch);
+	if (ss == nullptr) return;
+	cudaSetDevice(dfa->device);
+	if (ss->stream) { cudaStreamSynchronize(ss->stream); cudaStreamDestroy(ss->stream); }
+	cudaFree(ss->arena.base);
+	cudaFree(ss->d_in);
+	delete ss;
+	dfa->stream_scratch = nullptr;
+}
+}
 
 extern "C" int
-fsm_b200_exec_stream_dev(const fsm_b200_dfa *, const uint8_t *, uint64_t, struct fsm_b200_result *, void *)
-{ set_error("exec_stream_dev: not implemented yet"); errno = ENOTSUP; return -1; }
+fsm_b200_exec_stream_dev(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len,
+	struct fsm_b200_result *out, void *stream)
+{
+	if (dfa == nullptr || out == nullptr || (len > 0 && d_buf == nullptr)) {
+		set_error("exec_stream_dev: bad argument");
+		errno = EINVAL;
+		return -1;
+	}
+	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
+	StreamScratch *ss = ss_get(dfa);
+	if (ss == nullptr) { errno = ENOMEM; return -1; }
+	std::lock_guard<std::mutex> g(ss->mu);
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if (len == 0) {
+		out->ret = dfa->h_is_end[dfa->start] ? 1 : 0;
+		out->end = dfa->start;
+		out->consumed = 0;
+		return 0;
+	}
+	if (!parallel_ok(dfa, len)) {
+		return stream_serial(dfa, d_buf, len, st, ss, out);
+	}
+	std::vector<StreamOut> m;
+	if (stream_map(dfa, d_buf, len, st, ss, m) != 0) return -1;
+	const StreamOut &r = m[dfa->start];
+	out->end = r.state;
+	if (r.died) {
+		out->ret = 0;
+		out->consumed = r.dead_off;
+	} else {
+		out->ret = dfa->h_is_end[r.state] ? 1 : 0;
+		out->consumed = len;
+	}
+	return 0;
+}
 
 extern "C" int
-fsm_b200_exec_stream_map_dev(const fsm_b200_dfa *, const uint8_t *, uint64_t, uint32_t *, uint64_t *, uint32_t *, void *)
-{ set_error("exec_stream_map_dev: not implemented yet"); errno = ENOTSUP; return -1; }
+fsm_b200_exec_stream_map_dev(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len,
+	uint32_t *map_state, uint64_t *map_dead, uint32_t *map_dead_state, void *stream)
+{
+	if (dfa == nullptr || map_state == nullptr || map_dead == nullptr || map_dead_state == nullptr ||
+	    (len > 0 && d_buf == nullptr)) {
+		set_error("exec_stream_map_dev: bad argument");
+		errno = EINVAL;
+		return -1;
+	}
+	if (!(dfa->smem_resident && dfa->entry_bytes == 1)) {
+		set_error("exec_stream_map_dev: needs a table with <= 256 rows");
+		errno = ENOTSUP;
+		return -1;
+	}
+	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
+	StreamScratch *ss = ss_get(dfa);
+	if (ss == nullptr) { errno = ENOMEM; return -1; }
+	std::lock_guard<std::mutex> g(ss->mu);
+	const uint32_t T = dfa->nstates;
+	if (len == 0) {
+		for (uint32_t s = 0; s < T; s++) { map_state[s] = s; map_dead[s] = UINT64_MAX; map_dead_state[s] = UINT32_MAX; }
+	} else {
+		std::vector<StreamOut> m;
+		if (stream_map(dfa, d_buf, len, static_cast<cudaStream_t>(stream), ss, m) != 0) return -1;
+		for (uint32_t s = 0; s < T; s++) {
+			if (m[s].died) {
+				map_state[s] = dfa->dead; map_dead[s] = m[s].dead_off; map_dead_state[s] = m[s].state;
+			} else {
+				map_state[s] = m[s].state; map_dead[s] = UINT64_MAX; map_dead_state[s] = UINT32_MAX;
+			}
+		}
+	}
+	if (!dfa->complete) {                 /* the dead row maps to itself, dying at offset 0 */
+		map_state[dfa->dead] = dfa->dead; map_dead[dfa->dead] = 0; map_dead_state[dfa->dead] = dfa->dead;
+	}
+	return 0;
+}
+
+extern "C" int
+fsm_b200_exec_stream_host(const fsm_b200_dfa *dfa, const uint8_t *buf, uint64_t len,
+	struct fsm_b200_result *out)
+{
+	if (dfa == nullptr || out == nullptr || (len > 0 && buf == nullptr)) {
+		set_error("exec_stream_host: bad argument");
+		errno = EINVAL;
+		return -1;
+	}
+	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
+	StreamScratch *ss = ss_get(dfa);
+	if (ss == nullptr) { errno = ENOMEM; return -1; }
+	cudaStream_t st;
+	const uint8_t *d_in;
+	{
+		std::lock_guard<std::mutex> g(ss->mu);
+		if (ss->stream == nullptr) {
+			FSMB_CUDA(cudaStreamCreateWithFlags(&ss->stream, cudaStreamNonBlocking), return -1);
+		}
+		if (ss->in_cap < len + 64) {
+			if (ss->d_in) cudaFree(ss->d_in);
+			ss->d_in = nullptr; ss->in_cap = 0;
+			void *p = nullptr;
+			FSMB_CUDA(cudaMalloc(&p, len + len / 8 + 4096), return -1);
+			ss->d_in = static_cast<uint8_t *>(p);
+			ss->in_cap = len + len / 8 + 4096;
+		}
+		st = ss->stream;
+		d_in = ss->d_in;
+		if (len > 0) {
+			FSMB_CUDA(cudaMemcpyAsync(ss->d_in, buf, len, cudaMemcpyHostToDevice, st), return -1);
+		}
+	}
+	return fsm_b200_exec_stream_dev(dfa, d_in, len, out, st);
+}
