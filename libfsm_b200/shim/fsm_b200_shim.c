@@ -1,0 +1,314 @@
+/*
+ * fsm_b200_shim.c -- libfsm's fsm_exec, re-implemented over libfsm_b200.so.
+ *
+ * Replaces src/libfsm/exec.c of the reference.  What it keeps, bit for bit:
+ *   - signature and return convention: 1 match (+ *end), 0 no match, -1/errno
+ *     (EINVAL when the fsm is not a DFA or has no start state, exec.c:106-114);
+ *   - `*end` is written only on success (exec.c:165);
+ *   - the input is read through the caller's getc callback; after a failed match on a
+ *     missing edge the cursor of an fsm_sgetc string is left where the reference leaves it
+ *     (one past the byte that had no edge, exec.c:132-138).  A FILE* is rewound the same way
+ *     when it is seekable.
+ * What it does differently, on purpose:
+ *   - DFA-ness is validated once per (fsm, content fingerprint), not on every call: the
+ *     reference's per-call fsm_all(fsm, fsm_isdfa) (exec.c:106) costs O(edges) per input;
+ *   - the walk runs on the GPU (one long input: K1b chunk maps; a batch: K1).  There is no
+ *     CPU walk in here: without a usable device the call fails with -1/EIO.
+ * Not accelerated (returns -1/ENOTSUP): FSMs with capture actions when `captures` is
+ * non-NULL (exec.c:41-44,157-163) and FSMs with eager outputs (exec.c:126-144) -- neither
+ * is produced by re_comp or used by any CLI.
+ */
+#include <assert.h>
+#include <errno.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <fsm/fsm.h>
+#include <fsm/capture.h>
+#include <fsm/pred.h>
+
+#include <adt/set.h>
+#include <adt/stateset.h>
+#include <adt/edgeset.h>
+
+#include "libfsm/internal.h"
+
+#include "fsm_b200_shim.h"
+
+/* ------------------------------------------------------------------ flattening ------- */
+
+int
+fsm_b200_flatten(const struct fsm *fsm, struct fsm_b200_flat *out)
+{
+	const size_t n = fsm->statecount;
+	size_t ngroups = 0, neps = 0, nids = 0, s;
+	uint8_t *is_end; uint64_t *goff, *gsym, *eoff, *ioff; uint32_t *gto, *eto, *ids;
+	fsm_state_t start;
+
+	memset(out, 0, sizeof *out);
+	for (s = 0; s < n; s++) {
+		struct edge_group_iter it;
+		struct edge_group_iter_info info;
+		edge_set_group_iter_reset(fsm->states[s].edges, EDGE_GROUP_ITER_ALL, &it);
+		while (edge_set_group_iter_next(&it, &info)) ngroups++;
+		neps += state_set_count(fsm->states[s].epsilons);
+		if (fsm->states[s].end) nids += fsm_endid_count(fsm, (fsm_state_t) s);
+	}
+	is_end = calloc(n + 1, 1);
+	goff = calloc(n + 1, sizeof *goff);
+	gsym = calloc(4 * ngroups + 4, sizeof *gsym);
+	gto = calloc(ngroups + 1, sizeof *gto);
+	eoff = calloc(n + 1, sizeof *eoff);
+	eto = calloc(neps + 1, sizeof *eto);
+	ioff = calloc(n + 1, sizeof *ioff);
+	ids = calloc(nids + 1, sizeof *ids);
+	if (!is_end || !goff || !gsym || !gto || !eoff || !eto || !ioff || !ids) {
+		free(is_end); free(goff); free(gsym); free(gto); free(eoff); free(eto); free(ioff); free(ids);
+		errno = ENOMEM;
+		return -1;
+	}
+	ngroups = neps = nids = 0;
+	for (s = 0; s < n; s++) {
+		struct edge_group_iter it;
+		struct edge_group_iter_info info;
+		struct state_iter si;
+		fsm_state_t es;
+
+		goff[s] = ngroups; eoff[s] = neps; ioff[s] = nids;
+		is_end[s] = (uint8_t) fsm->states[s].end;
+		edge_set_group_iter_reset(fsm->states[s].edges, EDGE_GROUP_ITER_ALL, &it);
+		while (edge_set_group_iter_next(&it, &info)) {
+			memcpy(&gsym[4 * ngroups], info.symbols, sizeof info.symbols);
+			gto[ngroups++] = info.to;
+		}
+		for (state_set_reset(fsm->states[s].epsilons, &si); state_set_next(&si, &es); ) {
+			eto[neps++] = es;
+		}
+		if (fsm->states[s].end) {
+			const size_t c = fsm_endid_count(fsm, (fsm_state_t) s);
+			if (c > 0 && fsm_endid_get(fsm, (fsm_state_t) s, c, &ids[nids])) nids += c;
+		}
+	}
+	goff[n] = ngroups; eoff[n] = neps; ioff[n] = nids;
+	out->desc.nstates = (uint32_t) n;
+	out->desc.hasstart = (uint32_t) fsm_getstart(fsm, &start);
+	out->desc.start = out->desc.hasstart ? start : 0;
+	out->desc.is_end = is_end;
+	out->desc.group_off = goff; out->desc.group_symbols = gsym; out->desc.group_to = gto;
+	out->desc.eps_off = eoff; out->desc.eps_to = eto;
+	out->desc.endid_off = ioff; out->desc.endids = ids;
+	out->blocks[0] = is_end; out->blocks[1] = goff; out->blocks[2] = gsym; out->blocks[3] = gto;
+	out->blocks[4] = eoff; out->blocks[5] = eto; out->blocks[6] = ioff; out->blocks[7] = ids;
+	return 0;
+}
+
+void
+fsm_b200_flat_free(struct fsm_b200_flat *flat)
+{
+	size_t i;
+	for (i = 0; i < 8; i++) { free(flat->blocks[i]); flat->blocks[i] = NULL; }
+	memset(&flat->desc, 0, sizeof flat->desc);
+}
+
+/* ------------------------------------------------------------------ device-table cache */
+
+/* Content fingerprint: everything fsm_exec can observe (start, end bits, epsilon presence,
+ * edge groups).  O(groups), allocation-free; the reference spends O(edges) per call on
+ * validation alone. */
+static uint64_t
+fingerprint(const struct fsm *fsm)
+{
+	uint64_t h = 0x9e3779b97f4a7c15ull ^ (uint64_t) fsm->statecount;
+	size_t s;
+#define MIX(v) do { h ^= (uint64_t) (v); h *= 0xff51afd7ed558ccdull; h ^= h >> 32; } while (0)
+	MIX(fsm->hasstart); MIX(fsm->start);
+	for (s = 0; s < fsm->statecount; s++) {
+		struct edge_group_iter it;
+		struct edge_group_iter_info info;
+		MIX(fsm->states[s].end);
+		MIX(state_set_count(fsm->states[s].epsilons));
+		MIX(fsm->states[s].has_eager_outputs);
+		edge_set_group_iter_reset(fsm->states[s].edges, EDGE_GROUP_ITER_ALL, &it);
+		while (edge_set_group_iter_next(&it, &info)) {
+			MIX(info.to); MIX(info.symbols[0]); MIX(info.symbols[1]); MIX(info.symbols[2]); MIX(info.symbols[3]);
+		}
+		MIX(0x5bd1e995u);
+	}
+#undef MIX
+	return h;
+}
+
+#define CACHE_SLOTS 16
+static struct cache_entry {
+	const struct fsm *fsm;
+	uint64_t fp;
+	fsm_b200_dfa *dfa;        /* NULL: known not to be a DFA (errno_val says why) */
+	int errno_val;
+	unsigned long stamp;
+} cache[CACHE_SLOTS];
+static unsigned long cache_clock;
+static pthread_mutex_t cache_mu = PTHREAD_MUTEX_INITIALIZER;   /* lx(1) calls from threads */
+
+static int
+device_index(void)
+{
+	const char *e = getenv("FSM_B200_DEVICE");
+	return e != NULL ? atoi(e) : 0;
+}
+
+/* Returns the compiled DFA for `fsm` (cached), or NULL with errno set. */
+static fsm_b200_dfa *
+get_dfa(const struct fsm *fsm)
+{
+	const uint64_t fp = fingerprint(fsm);
+	struct cache_entry *victim = &cache[0];
+	fsm_b200_dfa *dfa = NULL;
+	struct fsm_b200_flat flat;
+	int i, err = 0;
+
+	pthread_mutex_lock(&cache_mu);
+	for (i = 0; i < CACHE_SLOTS; i++) {
+		if (cache[i].fsm == fsm && cache[i].fp == fp && cache[i].stamp != 0) {
+			cache[i].stamp = ++cache_clock;
+			dfa = cache[i].dfa;
+			err = cache[i].errno_val;
+			pthread_mutex_unlock(&cache_mu);
+			if (dfa == NULL) errno = err;
+			return dfa;
+		}
+		if (cache[i].stamp < victim->stamp) victim = &cache[i];
+	}
+	/* miss: validate + build (the engine restates fsm_all(fsm_isdfa) + fsm_getstart) */
+	if (fsm_b200_flatten(fsm, &flat) != 0) {
+		pthread_mutex_unlock(&cache_mu);
+		return NULL;
+	}
+	if (fsm_b200_dfa_compile(&flat.desc, device_index(), &dfa) != 0) {
+		err = errno;
+		dfa = NULL;
+	}
+	fsm_b200_flat_free(&flat);
+	if (dfa != NULL || err == EINVAL) {      /* remember DFAs and definite non-DFAs */
+		if (victim->stamp != 0 && victim->dfa != NULL) fsm_b200_dfa_free(victim->dfa);
+		victim->fsm = fsm; victim->fp = fp; victim->dfa = dfa; victim->errno_val = err;
+		victim->stamp = ++cache_clock;
+	}
+	pthread_mutex_unlock(&cache_mu);
+	if (dfa == NULL) errno = err;
+	return dfa;
+}
+
+void
+fsm_b200_invalidate(const struct fsm *fsm)
+{
+	int i;
+	pthread_mutex_lock(&cache_mu);
+	for (i = 0; i < CACHE_SLOTS; i++) {
+		if (cache[i].fsm == fsm && cache[i].stamp != 0) {
+			if (cache[i].dfa != NULL) fsm_b200_dfa_free(cache[i].dfa);
+			memset(&cache[i], 0, sizeof cache[i]);
+		}
+	}
+	pthread_mutex_unlock(&cache_mu);
+}
+
+static int
+unsupported(const struct fsm *fsm, const struct fsm_capture *captures)
+{
+	size_t s;
+	if (captures != NULL && fsm_countcaptures(fsm) > 0) return 1;
+	for (s = 0; s < fsm->statecount; s++) {
+		if (fsm->states[s].has_eager_outputs) return 1;
+	}
+	return 0;
+}
+
+/* ------------------------------------------------------------------ fsm_exec ---------- */
+
+int
+fsm_exec(const struct fsm *fsm,
+	int (*fsm_getc)(void *opaque), void *opaque,
+	fsm_state_t *end, struct fsm_capture *captures)
+{
+	fsm_b200_dfa *dfa;
+	struct fsm_b200_result r;
+	unsigned char *buf = NULL;
+	size_t len = 0, cap = 0;
+	const char *sgetc_start = NULL;
+	long file_start = -1;
+	int c;
+
+	assert(fsm != NULL);
+	assert(fsm_getc != NULL);
+	assert(end != NULL);
+
+	if (unsupported(fsm, captures)) {
+		errno = ENOTSUP;
+		return -1;
+	}
+	dfa = get_dfa(fsm);                 /* -1/EINVAL: not a DFA, no start (exec.c:106-114) */
+	if (dfa == NULL) {
+		return -1;
+	}
+
+	if (fsm_getc == fsm_sgetc) {
+		sgetc_start = *(const char **) opaque;
+	} else if (fsm_getc == fsm_fgetc) {
+		file_start = ftell((FILE *) opaque);
+	}
+
+	/* drain the callback (exec.c:132) */
+	while (c = fsm_getc(opaque), c != EOF) {
+		if (len == cap) {
+			size_t ncap = cap ? cap * 2 : 4096;
+			unsigned char *nb = realloc(buf, ncap);
+			if (nb == NULL) {
+				free(buf);
+				errno = ENOMEM;
+				return -1;
+			}
+			buf = nb; cap = ncap;
+		}
+		buf[len++] = (unsigned char) c;
+	}
+
+	if (fsm_b200_exec_stream_host(dfa, buf, len, &r) != 0) {
+		free(buf);
+		return -1;                      /* errno from the engine (EIO: no device) */
+	}
+	free(buf);
+
+	if (r.ret == 0 && r.consumed < len) {
+		/* the reference stopped reading right after the byte with no edge (exec.c:133-138) */
+		if (sgetc_start != NULL) {
+			*(const char **) opaque = sgetc_start + r.consumed + 1;
+		} else if (file_start >= 0) {
+			(void) fseek((FILE *) opaque, file_start + (long) r.consumed + 1, SEEK_SET);
+		}
+	}
+	if (r.ret != 1) {
+		return 0;
+	}
+	*end = r.end;
+	return 1;
+}
+
+int
+fsm_exec_batch(const struct fsm *fsm, const unsigned char *base, const uint64_t *offsets,
+	size_t n, struct fsm_b200_result *out)
+{
+	fsm_b200_dfa *dfa;
+
+	assert(fsm != NULL);
+	if (unsupported(fsm, NULL)) {
+		errno = ENOTSUP;
+		return -1;
+	}
+	dfa = get_dfa(fsm);
+	if (dfa == NULL) {
+		return -1;
+	}
+	return fsm_b200_exec_batch_host(dfa, base, offsets, n, out);
+}
