@@ -81,3 +81,46 @@ def utf8_host(nbytes: int, seed: int = 4) -> np.ndarray:
     out[starts[m]] = 0xF0 | (cp[m] >> 18); out[starts[m] + 1] = 0x80 | ((cp[m] >> 12) & 0x3F)
     out[starts[m] + 2] = 0x80 | ((cp[m] >> 6) & 0x3F); out[starts[m] + 3] = 0x80 | (cp[m] & 0x3F)
     return out
+
+
+def config5_nfa(words: int = 2000, length: int = 50, seed: int = 12345):
+    """BASELINE config 5's synthetic NFA: start state with a /./ self-loop plus
+    `words` chains of `length` random a-z literals from start; the last state of chain w is an
+    end state with end id w.  2000 x 50 -> 100 001 states (reference: 96 538 DFA states)."""
+    from .desc import FlatFsm
+    rng = np.random.default_rng(seed)
+    letters = rng.integers(ord("a"), ord("z") + 1, size=(words, length))
+    n = 1 + words * length
+    nedges = 1 + words * length
+    group_off = np.zeros(n + 1, dtype=np.uint64)
+    sym = np.zeros((nedges, 4), dtype=np.uint64)
+    to = np.zeros(nedges, dtype=np.uint32)
+    # start: groups sorted by destination: self-loop (to 0) first, then chain heads ascending
+    sym[0, :] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    to[0] = 0
+    heads = 1 + np.arange(words) * length
+    for w in range(words):
+        c = int(letters[w, 0])
+        sym[1 + w, c >> 6] = np.uint64(1) << np.uint64(c & 63)
+        to[1 + w] = heads[w]
+    group_off[1] = 1 + words
+    g = 1 + words
+    is_end = np.zeros(n, dtype=np.uint8)
+    endid_off = np.zeros(n + 1, dtype=np.uint64)
+    endids = []
+    for w in range(words):
+        for j in range(length):
+            s = 1 + w * length + j
+            if j + 1 < length:
+                c = int(letters[w, j + 1])
+                sym[g, c >> 6] = np.uint64(1) << np.uint64(c & 63)
+                to[g] = s + 1
+                g += 1
+            else:
+                is_end[s] = 1
+                endids.append(w)
+            group_off[s + 1] = g
+            endid_off[s + 1] = len(endids)
+    return FlatFsm(nstates=n, start=0, hasstart=True, is_end=is_end, group_off=group_off,
+                   group_symbols=sym[:g], group_to=to[:g], eps_off=None, eps_to=None,
+                   endid_off=endid_off, endids=np.array(endids, dtype=np.uint32))

@@ -18,6 +18,7 @@
 #include <fsm/bool.h>
 #include <fsm/pred.h>
 #include <fsm/walk.h>
+#include <fsm/parser.h>
 #include <re/re.h>
 
 #include <adt/set.h>
@@ -45,6 +46,17 @@ refh_re_comp(const char *pattern, size_t len, int dialect, int flags)
 	struct strcur c = { pattern, len };
 	struct re_err err;
 	return re_comp((enum re_dialect) dialect, str_getc, &c, NULL, (enum re_flags) flags, &err);
+}
+
+void *
+refh_parse_file(const char *path)
+{
+	FILE *f = fopen(path, "r");
+	struct fsm *fsm;
+	if (f == NULL) return NULL;
+	fsm = fsm_parse(f, NULL);
+	fclose(f);
+	return fsm;
 }
 
 int refh_determinise(void *fsm) { return fsm_determinise(fsm); }

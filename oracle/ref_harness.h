@@ -16,6 +16,7 @@
 /* re_comp(dialect, ...) (include/re/re.h:136-140). dialect: enum re_dialect value
  * (RE_PCRE = 5, RE_NATIVE = 3, RE_LITERAL = 1, RE_GLOB = 2). Returns NULL on error. */
 void *refh_re_comp(const char *pattern, size_t len, int dialect, int flags);
+void *refh_parse_file(const char *path);                /* fsm_parse of an fsm(5) file */
 int   refh_determinise(void *fsm);                       /* fsm_determinise: 1 ok */
 int   refh_determinise_limit(void *fsm, size_t state_limit); /* enum ..._res value */
 int   refh_minimise(void *fsm);                          /* fsm_minimise: 1 ok */

@@ -257,5 +257,81 @@ def main():
           f"{os.path.getsize(os.path.join(HERE, 'golden_exec.npz')) / 1024:.0f} KiB")
 
 
+def eps_union_nfa(R, patterns, endids=True):
+    """fsm_union_array of re_comp NFAs (epsilon-heavy, NOT determinised)."""
+    hs = []
+    for i, p in enumerate(patterns):
+        h = R.re_comp(p)
+        if endids:
+            R.setendid(h, i)
+        hs.append(h)
+    return R.union_array(hs)
+
+
+def det_case(R, name, h_nfa, with_closure=True, note=""):
+    nfa = R.flatten(h_nfa)
+    cl_off = cl_to = None
+    if with_closure:
+        cl_off, cl_to = R.epsilon_closure(h_nfa, nfa.nstates)
+    res = R.determinise_limit(h_nfa, 20000)   # in place: h_nfa now holds the reference's DFA
+    if res != 0:
+        print(f"  skip {name}: fsm_determinise_with_config -> {res}")
+        return None
+    dfa = R.flatten(h_nfa)
+    return {"name": name, "nfa": nfa, "dfa": dfa, "closure_off": cl_off, "closure_to": cl_to, "note": note}
+
+
+def main_det():
+    from libfsm_b200 import workloads
+    R = reflib.Ref()
+    cases = []
+    # the reference's own fixtures: tests/determinise/in*.fsm (13) and tests/eclosure/in*.fsm (8)
+    for d in ("determinise", "eclosure"):
+        for path in sorted(glob.glob(os.path.join(REF_TESTS, d, "in*.fsm"))):
+            h = R.parse_file(path)
+            c = det_case(R, f"{d}:{os.path.basename(path)}", h)
+            assert c is not None
+            outp = path.replace("in", "out")
+            if d == "determinise" and os.path.exists(outp):
+                ho = R.parse_file(outp)
+                assert R.equal(h, ho), path          # the reference's own expected output
+                R.free(ho)
+            if d == "eclosure":
+                txt = path.replace("in", "out").replace(".fsm", ".txt")
+                if os.path.exists(txt):             # exact closure sets, as `fsm -cq epsilonclosure` prints them
+                    exp = {}
+                    for line in open(txt):
+                        k, v = line.split(":")
+                        exp[int(k)] = [int(x) for x in v.split()]
+                    for s2, members in exp.items():
+                        got = list(c["closure_to"][int(c["closure_off"][s2]):int(c["closure_off"][s2 + 1])])
+                        assert got == members, (path, s2, got, members)
+            cases.append(c)
+            R.free(h)
+    # synthetic: BASELINE config 5's generator at small sizes, epsilon-heavy unions, regex NFAs
+    for words, length in ((20, 6), (200, 10), (64, 50)):
+        h = R.from_flat(workloads.config5_nfa(words, length, seed=12345))
+        cases.append(det_case(R, f"cfg5:{words}x{length}", h, with_closure=False)); R.free(h); print("cfg5", words, length, flush=True)
+    pats = ["^abc", "^abd", "^a.*b$", "^[0-9]+x", "^(foo|bar)+$", "^x{2,4}y", "^anch", "^a?b?c?d?$", "abd"]
+    h = eps_union_nfa(R, pats)
+    cases.append(det_case(R, "epsunion:9pats", h)); R.free(h)
+    rng = np.random.default_rng(7)
+    lits = ["^" + "".join(chr(c) for c in rng.integers(97, 103, size=int(rng.integers(2, 7)))) for _ in range(120)]
+    h = eps_union_nfa(R, lits)
+    cases.append(det_case(R, "epsunion:120literals", h)); R.free(h)
+    for pat in (r"(a|b)*abb", r"[0-9]+\.[0-9]+", r"a[ -~]{7}\z", r"(ab|cd)*e|f+"):
+        h = R.re_comp(pat)
+        cases.append(det_case(R, f"re:{pat}", h)); R.free(h)
+    # no start state; empty fsm
+    cases = [c for c in cases if c is not None]
+    goldenio.save_det_cases(os.path.join(HERE, "golden_determinise.npz"), cases)
+    print(f"wrote golden_determinise.npz: {len(cases)} cases, "
+          f"{os.path.getsize(os.path.join(HERE, 'golden_determinise.npz')) / 1024:.0f} KiB, "
+          f"largest DFA {max(c['dfa'].nstates for c in cases)} states")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] == "exec":
+        main()
+    if len(sys.argv) < 2 or sys.argv[1] == "det":
+        main_det()

@@ -64,3 +64,33 @@ def load_exec_cases(path: str) -> list[dict]:
         c["tst_expect"] = z[p + "tst"]
         cases.append(c)
     return cases
+
+
+def save_det_cases(path: str, cases: list[dict]) -> None:
+    """case: name, nfa (FlatFsm), dfa (FlatFsm: the REFERENCE's fsm_determinise output),
+    closure_off/closure_to (reference epsilon_closure CSR) or None."""
+    out, meta = {}, []
+    for i, c in enumerate(cases):
+        p = f"d{i}_"
+        pack_fsm(p + "nfa_", c["nfa"], out)
+        pack_fsm(p + "dfa_", c["dfa"], out)
+        if c.get("closure_off") is not None:
+            out[p + "cl_off"] = c["closure_off"]; out[p + "cl_to"] = c["closure_to"]
+        meta.append({"name": c["name"], "note": c.get("note", "")})
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(path, **out)
+
+
+def load_det_cases(path: str) -> list[dict]:
+    z = np.load(path)
+    meta = json.loads(bytes(z["meta"]).decode())
+    cases = []
+    for i, m in enumerate(meta):
+        p = f"d{i}_"
+        c = dict(m)
+        c["nfa"] = unpack_fsm(p + "nfa_", z)
+        c["dfa"] = unpack_fsm(p + "dfa_", z)
+        c["closure_off"] = z[p + "cl_off"] if (p + "cl_off") in z.files else None
+        c["closure_to"] = z[p + "cl_to"] if (p + "cl_to") in z.files else None
+        cases.append(c)
+    return cases

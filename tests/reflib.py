@@ -171,6 +171,7 @@ class Ref:
         self.lib = C.CDLL(HARNESS_SO, use_errno=True)
         L, vp, P = self.lib, C.c_void_p, C.POINTER
         L.refh_re_comp.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int]; L.refh_re_comp.restype = vp
+        L.refh_parse_file.argtypes = [C.c_char_p]; L.refh_parse_file.restype = vp
         L.refh_determinise.argtypes = [vp]
         L.refh_determinise_limit.argtypes = [vp, C.c_size_t]
         L.refh_minimise.argtypes = [vp]
@@ -197,6 +198,12 @@ class Ref:
         h = self.lib.refh_re_comp(p, len(p), dialect, flags)
         if not h:
             raise ValueError(f"re_comp failed for {pattern!r}")
+        return h
+
+    def parse_file(self, path: str):
+        h = self.lib.refh_parse_file(path.encode())
+        if not h:
+            raise ValueError(f"fsm_parse failed for {path}")
         return h
 
     def determinise(self, h) -> None:
