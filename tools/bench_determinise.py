@@ -1,0 +1,29 @@
+#!/usr/bin/env python3
+"""BASELINE config 5: fsm_determinise of the 100 001-state synthetic NFA, GPU (K2) vs the
+reference's fsm_determinise on this box's CPU (oracle/_ref, single thread: the reference is
+single-threaded)."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import reflib, libfsm_b200 as L
+from libfsm_b200 import workloads
+
+words = int(os.environ.get("WORDS", 2000)); length = int(os.environ.get("LENGTH", 50))
+nfa = workloads.config5_nfa(words, length, seed=12345)
+L.determinise(workloads.config5_nfa(50, 10))          # warm up: context, module load
+ts = []
+for _ in range(3):
+    t0 = time.perf_counter(); dfa = L.determinise(nfa); ts.append(time.perf_counter() - t0)
+st = L.determinise_stats()
+edges = dfa.nstates * 256
+out = {"nfa_states": nfa.nstates, "dfa_states": dfa.nstates, "dfa_groups": int(dfa.group_to.size),
+       "gpu_s": min(ts), "gpu_s_all": ts, "stats": st, "dfa_edges_per_s_gpu": edges / min(ts)}
+if reflib.have_ref():
+    R = reflib.Ref()
+    h = R.from_flat(nfa)
+    t0 = time.perf_counter(); R.determinise(h); t1 = time.perf_counter()
+    out["cpu_reference_s"] = t1 - t0
+    out["cpu_reference_dfa_states"] = R.countstates(h)
+    out["speedup"] = (t1 - t0) / min(ts)
+    R.free(h)
+print(json.dumps(out))
