@@ -53,19 +53,24 @@ thread_local fsm_b200_det_stats tl_stats;
 
 /* ------------------------------------------------------------------ device buffers ---- */
 
+/* Stream-ordered allocations from the device's default memory pool (release threshold raised
+ * in fsm_b200_determinise so memory is retained across calls: no cudaMalloc/cudaFree
+ * synchronisation inside the frontier loop). */
 template <typename T> struct DBuf {
 	T *p = nullptr;
 	size_t cap = 0;
-	~DBuf() { if (p) cudaFree(p); }
+	cudaStream_t owner = nullptr;
+	~DBuf() { if (p) cudaFreeAsync(p, owner); }
 	int reserve(size_t n, bool keep, cudaStream_t st) {
 		if (n <= cap) return 0;
+		owner = st;
 		size_t ncap = std::max(n, cap + cap / 2 + 1024);
 		T *q = nullptr;
-		cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+		cudaError_t e = cudaMallocAsync(&q, ncap * sizeof(T), st);
 		if (e != cudaSuccess) {
 			cudaGetLastError();
 			ncap = n;
-			e = cudaMalloc(&q, ncap * sizeof(T));
+			e = cudaMallocAsync(&q, ncap * sizeof(T), st);
 			if (e != cudaSuccess) {
 				set_error("determinise: cudaMalloc(%zu bytes) failed: %s", ncap * sizeof(T), cudaGetErrorString(e));
 				errno = ENOMEM;
@@ -73,15 +78,14 @@ template <typename T> struct DBuf {
 			}
 		}
 		if (keep && p && cap) {
-			if (cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
-			    cudaStreamSynchronize(st) != cudaSuccess) {
-				cudaFree(q);
+			if (cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+				cudaFreeAsync(q, st);
 				set_error("determinise: device copy failed");
 				errno = EIO;
 				return -1;
 			}
 		}
-		if (p) cudaFree(p);
+		if (p) cudaFreeAsync(p, st);
 		p = q; cap = ncap;
 		return 0;
 	}
@@ -540,6 +544,56 @@ k2_rehash_kernel(Table tab, Pool pool, uint32_t nsets)
 	}
 }
 
+/* emit: per DFA state, one group per distinct destination, ascending (edge_set keeps groups
+ * sorted by .to, src/adt/edgeset.c:283-373); label set = union of the classes' symbols */
+__global__ void
+k2_emit_count_kernel(const uint32_t *trans, uint32_t D, uint32_t K, uint32_t *ngroups)
+{
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= D) return;
+	const uint32_t *row = trans + (size_t) s * K;
+	uint32_t cnt = 0;
+	for (uint32_t k = 0; k < K; k++) {
+		const uint32_t to = row[k];
+		if (to == NONE32) continue;
+		bool seen = false;
+		for (uint32_t j = 0; j < k && !seen; j++) seen = row[j] == to;
+		cnt += seen ? 0u : 1u;
+	}
+	ngroups[s] = cnt;
+}
+
+__global__ void
+k2_emit_fill_kernel(const uint32_t *trans, uint32_t D, uint32_t K, const uint64_t *class_mask,
+	const uint64_t *goff, uint32_t *gto, uint64_t *gsym)
+{
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= D) return;
+	const uint32_t *row = trans + (size_t) s * K;
+	uint64_t o = goff[s];
+	const uint64_t e = goff[s + 1];
+	uint32_t last = 0;
+	bool first = true;
+	for (; o < e; o++) {
+		uint32_t best = NONE32;                       /* next destination in ascending order */
+		for (uint32_t k = 0; k < K; k++) {
+			const uint32_t to = row[k];
+			if (to != NONE32 && (first || to > last) && to < best) best = to;
+		}
+		uint64_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+		for (uint32_t k = 0; k < K; k++) {
+			if (row[k] == best) {
+				m0 |= class_mask[4 * k]; m1 |= class_mask[4 * k + 1];
+				m2 |= class_mask[4 * k + 2]; m3 |= class_mask[4 * k + 3];
+			}
+		}
+		gto[o] = best;
+		gsym[4 * o] = m0; gsym[4 * o + 1] = m1; gsym[4 * o + 2] = m2; gsym[4 * o + 3] = m3;
+		last = best;
+		first = false;
+	}
+}
+
 inline unsigned
 blocks_for(uint64_t n, unsigned t = 256)
 {
@@ -656,9 +710,17 @@ fsm_b200_determinise(const struct fsm_b200_desc *nfa, int device, size_t state_l
 	if (G == 0) { rep[0] = 0; memset(class_of, 0, sizeof class_of); }
 
 	CK(cudaSetDevice(device));
+	{
+		cudaMemPool_t mp;
+		uint64_t keep_all = UINT64_MAX;
+		if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
+			cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep_all);
+		}
+	}
 	cudaStream_t st;
 	CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-	struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sguard{ st };
+	/* declared before every DBuf so that it is destroyed after their cudaFreeAsync calls */
+	struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } sguard{ st };
 	Scanner scan; scan.st = st;
 
 	/* ---- upload the NFA ---- */
@@ -829,47 +891,42 @@ fsm_b200_determinise(const struct fsm_b200_desc *nfa, int device, size_t state_l
 	tl_stats.ms_expand = ms_since(t_exp);
 	tl_stats.rounds = rounds;
 
-	/* ---- emit: groups, end bits, end ids (host; O(states x classes + pool)) ---- */
+	/* ---- emit: groups on the device; end bits + end ids on the host (O(pool)) ---- */
 	const auto t_emit = std::chrono::steady_clock::now();
 	const uint32_t D = nsets;
-	std::vector<uint32_t> h_trans((size_t) D * K), h_pooldata(pool_used);
+	uint64_t class_mask[256][4];
+	memset(class_mask, 0, sizeof class_mask);
+	for (int c = 0; c < 256; c++) class_mask[class_of[c]][c >> 6] |= 1ull << (c & 63);
+	DBuf<uint64_t> d_cmask, d_ogoff, d_ogsym;
+	DBuf<uint32_t> d_ng, d_ogto;
+	if (d_cmask.reserve(1024, false, st) || d_ng.reserve(D + 1, false, st) || d_ogoff.reserve(D + 2, false, st)) return -1;
+	CK(cudaMemcpyAsync(d_cmask.p, class_mask, sizeof class_mask, cudaMemcpyHostToDevice, st));
+	k2_emit_count_kernel<<<blocks_for(D, 128), 128, 0, st>>>(d_trans.p, D, K, d_ng.p); count_launch();
+	if (scan.run<uint32_t>(d_ng.p, d_ogoff.p, D) != 0) return -1;
+	own->group_off.assign(D + 1, 0);
+	CK(cudaMemcpyAsync(own->group_off.data(), d_ogoff.p, (D + 1) * 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	const uint64_t NG = own->group_off[D];
+	if (d_ogto.reserve(NG + 1, false, st) || d_ogsym.reserve(4 * NG + 4, false, st)) return -1;
+	k2_emit_fill_kernel<<<blocks_for(D, 128), 128, 0, st>>>(d_trans.p, D, K, d_cmask.p, d_ogoff.p, d_ogto.p, d_ogsym.p); count_launch();
+	own->group_to.resize(NG);
+	own->group_sym.resize(4 * NG);
+	std::vector<uint32_t> h_pooldata(pool_used);
 	std::vector<uint64_t> h_pooloff(D + 1);
 	std::vector<uint8_t> h_aend(n);
-	CK(cudaMemcpyAsync(h_trans.data(), d_trans.p, (size_t) D * K * 4, cudaMemcpyDeviceToHost, st));
+	if (NG) {
+		CK(cudaMemcpyAsync(own->group_to.data(), d_ogto.p, NG * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(own->group_sym.data(), d_ogsym.p, NG * 32, cudaMemcpyDeviceToHost, st));
+	}
 	CK(cudaMemcpyAsync(h_pooloff.data(), d_pooloff.p, (D + 1) * 8, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(h_pooldata.data(), d_pooldata.p, pool_used * 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(h_aend.data(), d_aend.p, n, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 
-	uint64_t class_mask[256][4];
-	memset(class_mask, 0, sizeof class_mask);
-	for (int c = 0; c < 256; c++) class_mask[class_of[c]][c >> 6] |= 1ull << (c & 63);
-
 	own->is_end.assign(D, 0);
-	own->group_off.assign(D + 1, 0);
 	own->endid_off.assign(D + 1, 0);
-	own->group_to.reserve((size_t) D * 2);
-	own->group_sym.reserve((size_t) D * 8);
-	std::vector<std::pair<uint32_t, uint32_t>> pairs(K);
 	std::vector<uint32_t> ids;
 	for (uint32_t s = 0; s < D; s++) {
-		uint32_t np = 0;
-		for (uint32_t k = 0; k < K; k++) {
-			const uint32_t to = h_trans[(size_t) s * K + k];
-			if (to != NONE32) pairs[np++] = { to, k };
-		}
-		std::sort(pairs.begin(), pairs.begin() + np);
-		for (uint32_t i = 0; i < np; ) {
-			uint64_t sym[4] = { 0, 0, 0, 0 };
-			uint32_t j = i;
-			for (; j < np && pairs[j].first == pairs[i].first; j++) {
-				for (int w = 0; w < 4; w++) sym[w] |= class_mask[pairs[j].second][w];
-			}
-			own->group_to.push_back(pairs[i].first);
-			own->group_sym.insert(own->group_sym.end(), sym, sym + 4);
-			i = j;
-		}
-		own->group_off[s + 1] = own->group_to.size();
 		/* end bit + end ids: determinise.c:236-266 over the epsilon-folded members */
 		ids.clear();
 		bool end = false;
@@ -886,8 +943,10 @@ fsm_b200_determinise(const struct fsm_b200_desc *nfa, int device, size_t state_l
 			}
 		}
 		own->is_end[s] = end ? 1 : 0;
-		std::sort(ids.begin(), ids.end());
-		ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+		if (ids.size() > 1) {
+			std::sort(ids.begin(), ids.end());
+			ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+		}
 		own->endids.insert(own->endids.end(), ids.begin(), ids.end());
 		own->endid_off[s + 1] = own->endids.size();
 	}
