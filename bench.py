@@ -157,6 +157,9 @@ def main():
     ap.add_argument("--dist", default="uniform", choices=["uniform", "adversarial"])
     ap.add_argument("--variant", default="auto")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N>1: fused = scanning lanes store records into every peer's buffer over NVLink P2P; "
+                         "nccl = one NCCL all-gather per step on a side stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -186,22 +189,37 @@ def main():
     # range shard `rank` of the global batch: its own seeded 2^20 x 1 KiB slice
     d_in = workloads.cfg2_device(n, LENGTH, adversarial, seed=42 + 1000 * rank, device=dev)
     nbuf = 2
+    fused = world > 1 and args.gather == "fused"
     d_out = [torch.empty((n, 16), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
     gathered = [torch.empty((world * n, 16), dtype=torch.uint8, device=dev) for _ in range(nbuf)] if world > 1 else None
     side = torch.cuda.Stream(device=dev) if world > 1 else None
     main_stream = torch.cuda.current_stream()
     gather_done = [None] * nbuf
+    ring = None
+    token = torch.zeros(1, dtype=torch.int32, device=dev)
+    if fused:
+        from libfsm_b200.peer import GatherRing
+        ring = GatherRing(n, world, rank, local, nbuf)
+        peer_args = [ring.peer_slot_ptrs(b) for b in range(nbuf)]
 
     def step(i):
         b = i % nbuf
         if world > 1 and gather_done[b] is not None:
             main_stream.wait_event(gather_done[b])         # buffer free again
-        dfa.exec_batch(d_in, stride=LENGTH, length=LENGTH, n=n, out=d_out[b])
+        if fused:
+            # ONE kernel: scan + P2P stores of every record into every peer's gathered buffer
+            dfa.exec_batch_gather(d_in, stride=LENGTH, length=LENGTH, n=n, out_ptr=ring.local_slot_ptr(b),
+                                  peer_ptrs=peer_args[b][0], npeers=peer_args[b][1])
+        else:
+            dfa.exec_batch(d_in, stride=LENGTH, length=LENGTH, n=n, out=d_out[b])
         if world > 1:
             ev = torch.cuda.Event(); ev.record(main_stream)
             side.wait_event(ev)
             with torch.cuda.stream(side):
-                dist.all_gather_into_tensor(gathered[b], d_out[b])
+                if fused:
+                    dist.all_reduce(token)                  # 4-byte completion handshake, off the data path
+                else:
+                    dist.all_gather_into_tensor(gathered[b], d_out[b])
                 gather_done[b] = torch.cuda.Event(); gather_done[b].record(side)
 
     def sync_all():
@@ -218,11 +236,21 @@ def main():
     sample_host = d_in[idx].cpu().numpy()
     off = np.arange(sample_host.shape[0] + 1, dtype=np.uint64) * np.uint64(LENGTH)
     want = oracle.exec_batch(fsm, sample_host.reshape(-1), off, nthreads=min(16, os.cpu_count() or 1))
-    got = L.results_from_torch(d_out[0][idx])
-    assert (got == want).all(), "bench: GPU results differ from the oracle"
-    if world > 1:
-        mine = gathered[0][rank * n:(rank + 1) * n]
-        assert torch.equal(mine, d_out[0]), "bench: all-gather slot mismatch"
+    if fused:
+        everything = ring.read(0)                          # this rank's gathered buffer: all ranks' records
+        got = everything[rank * n:(rank + 1) * n][::64]
+        assert (got == want).all(), "bench: GPU results differ from the oracle"
+        # cross-check the P2P-gathered buffer against an NCCL all-gather of the same records
+        mine_t = torch.from_numpy(everything[rank * n:(rank + 1) * n].view(np.uint8).reshape(n, 16).copy()).to(dev)
+        dist.all_gather_into_tensor(gathered[0], mine_t)
+        torch.cuda.synchronize(dev)
+        assert (L.results_from_torch(gathered[0]) == everything).all(), "bench: fused gather != NCCL all-gather"
+    else:
+        got = L.results_from_torch(d_out[0][idx])
+        assert (got == want).all(), "bench: GPU results differ from the oracle"
+        if world > 1:
+            mine = gathered[0][rank * n:(rank + 1) * n]
+            assert torch.equal(mine, d_out[0]), "bench: all-gather slot mismatch"
 
     # ---- device-resident timing ----------------------------------------------------------
     for i in range(args.warmup):
@@ -290,7 +318,9 @@ def main():
             "config": {"workload": "configs[1]: 256-state DFA a[ -~]{7}\\z, 2^20 x 1 KiB ASCII per GPU",
                        "distribution": args.dist, "variant": args.variant, "table": dfa.info,
                        "l2": "1 GiB input per step > 126 MB L2: no flush needed",
-                       "multi_gpu": "range-sharded batch, one NCCL all-gather of 16 B result records per step" if world > 1 else "single GPU"},
+                       "multi_gpu": ("single GPU" if world == 1 else
+                                     "range-sharded batch; scan fused with the gather: lanes store the 16 B records into every peer's buffer over NVLink P2P; 4-byte NCCL handshake per step on a side stream"
+                                     if fused else "range-sharded batch, one NCCL all-gather of 16 B result records per step on a side stream")},
             "clocks": sampler.result(),
             "e2e": {"value": e2e_value, "unit": "GB/s", "steps": e2e_steps,
                     "h2d_bytes_per_step": int(h_in.numel() + h_off.numel() * 8),
@@ -309,6 +339,8 @@ def main():
     dfa.close()
     if world > 1:
         dist.barrier()
+        if ring is not None:
+            ring.close()
         dist.destroy_process_group()
     return 0
 

@@ -146,6 +146,25 @@ int fsm_b200_exec_batch_dev(const fsm_b200_dfa *dfa,
 	const uint8_t *d_base, const uint64_t *d_offsets, uint64_t stride, uint64_t len,
 	size_t n, struct fsm_b200_result *d_out, void *stream);
 
+/* --- multi-GPU: scan fused with the result gather over NVLink peer memory -------------------
+ * As _dev, but every record is ALSO stored into npeers (<= 7) peer buffers: peer_outs[r]
+ * points at the slot of THIS rank's range inside rank r's gathered buffer (device memory
+ * of another GPU of the node, mapped with fsm_b200_ipc_open).  The stores are issued by the
+ * scanning lanes themselves (P2P over NVLink/NVSwitch), so the gather overlaps the scan
+ * tile by tile and no collective kernel competes for SMs.  After the kernels of all ranks
+ * have completed (any cross-rank barrier), every gathered buffer holds every rank's records.
+ * Helper entry points: plain cudaMalloc'd buffers (IPC needs whole allocations), handle
+ * export/open, and a synchronous read-back for checks. */
+int fsm_b200_exec_batch_dev_gather(const fsm_b200_dfa *dfa,
+	const uint8_t *d_base, const uint64_t *d_offsets, uint64_t stride, uint64_t len, size_t n,
+	struct fsm_b200_result *d_out, struct fsm_b200_result *const *peer_outs, int npeers, void *stream);
+int fsm_b200_dev_alloc(int device, size_t bytes, void **out);
+int fsm_b200_dev_free(int device, void *p);
+int fsm_b200_dev_read(int device, void *host_dst, const void *dev_src, size_t bytes);
+int fsm_b200_ipc_export(const void *dev_ptr, void *handle64 /* 64 bytes */);
+int fsm_b200_ipc_open(int device, const void *handle64, void **out);
+int fsm_b200_ipc_close(int device, void *p);
+
 /* Kernel variant selection for _dev/_host (0 = library default).  Exposed so that
  * bench.py / ncu can evidence the choice; see DESIGN.md "K1 variants". */
 int fsm_b200_set_exec_variant(int variant);

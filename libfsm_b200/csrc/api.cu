@@ -268,3 +268,75 @@ fsm_b200_exec_batch_host(const fsm_b200_dfa *dfa,
 	}
 	return rc;
 }
+
+
+/* ---- fused scan + gather over NVLink peer memory ------------------------------------------ */
+
+extern "C" int
+fsm_b200_exec_batch_dev_gather(const fsm_b200_dfa *dfa,
+	const uint8_t *d_base, const uint64_t *d_offsets, uint64_t stride, uint64_t len, size_t n,
+	struct fsm_b200_result *d_out, struct fsm_b200_result *const *peer_outs, int npeers, void *stream)
+{
+	if (dfa == nullptr || (n > 0 && (d_base == nullptr || d_out == nullptr)) || (npeers > 0 && peer_outs == nullptr)) {
+		set_error("exec_batch_dev_gather: bad argument");
+		errno = EINVAL;
+		return -1;
+	}
+	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
+	return k1_launch(dfa, d_base, d_offsets, stride, len, n, d_out, static_cast<cudaStream_t>(stream), K1_AUTO,
+	    peer_outs, npeers);
+}
+
+extern "C" int
+fsm_b200_dev_alloc(int device, size_t bytes, void **out)
+{
+	if (out == nullptr) { errno = EINVAL; return -1; }
+	FSMB_CUDA(cudaSetDevice(device), return -1);
+	FSMB_CUDA(cudaMalloc(out, bytes), return -1);
+	return 0;
+}
+
+extern "C" int
+fsm_b200_dev_free(int device, void *p)
+{
+	FSMB_CUDA(cudaSetDevice(device), return -1);
+	FSMB_CUDA(cudaFree(p), return -1);
+	return 0;
+}
+
+extern "C" int
+fsm_b200_dev_read(int device, void *host_dst, const void *dev_src, size_t bytes)
+{
+	FSMB_CUDA(cudaSetDevice(device), return -1);
+	FSMB_CUDA(cudaMemcpy(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost), return -1);
+	return 0;
+}
+
+extern "C" int
+fsm_b200_ipc_export(const void *dev_ptr, void *handle64)
+{
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	cudaIpcMemHandle_t h;
+	FSMB_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)), return -1);
+	memcpy(handle64, &h, 64);
+	return 0;
+}
+
+extern "C" int
+fsm_b200_ipc_open(int device, const void *handle64, void **out)
+{
+	cudaIpcMemHandle_t h;
+	if (out == nullptr) { errno = EINVAL; return -1; }
+	memcpy(&h, handle64, 64);
+	FSMB_CUDA(cudaSetDevice(device), return -1);
+	FSMB_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess), return -1);
+	return 0;
+}
+
+extern "C" int
+fsm_b200_ipc_close(int device, void *p)
+{
+	FSMB_CUDA(cudaSetDevice(device), return -1);
+	FSMB_CUDA(cudaIpcCloseMemHandle(p), return -1);
+	return 0;
+}

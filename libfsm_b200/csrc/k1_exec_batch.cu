@@ -139,15 +139,20 @@ ld256(const uint8_t *p, uint32_t (&w)[8])
 	    : "l"(p));
 }
 
+/* One 16-byte record per input; with the fused gather the same record is also stored into
+ * every peer GPU's gathered buffer (P2P stores over NVLink, posted: they overlap the scan). */
 __device__ __forceinline__ void
-store_result(fsm_b200_result *out, int32_t ret, uint32_t end, uint64_t consumed)
+store_result(const K1Args &a, uint64_t i, int32_t ret, uint32_t end, uint64_t consumed)
 {
 	uint4 v;
 	v.x = (uint32_t) ret;
 	v.y = end;
 	v.z = (uint32_t) consumed;
 	v.w = (uint32_t) (consumed >> 32);
-	*reinterpret_cast<uint4 *>(out) = v;
+	*reinterpret_cast<uint4 *>(a.out + i) = v;
+	for (uint32_t r = 0; r < a.npeers; r++) {
+		*reinterpret_cast<uint4 *>(a.peer_out[r] + i) = v;
+	}
 }
 
 /* ------------------------------------------------------------------ LANE variant ---- */
@@ -238,7 +243,7 @@ k1_lane_kernel(const K1Args a)
 			}
 		}
 		const int32_t ret = (!died && is_end[st]) ? 1 : 0;
-		store_result(a.out + i, ret, st, pos);
+		store_result(a, i, ret, st, pos);
 	}
 #undef TSTEP
 }
@@ -348,7 +353,7 @@ k1_tile_kernel(const K1Args a, const __grid_constant__ CUtensorMap tmap)
 		}
 		if (cc.sidx == nst - 1 && row < a.n) {
 			const int32_t ret = (!died && is_end[st]) ? 1 : 0;
-			store_result(a.out + row, ret, st, pos);
+			store_result(a, row, ret, st, pos);
 		}
 		__syncwarp();       /* every lane has finished reading this slot */
 		advance(cc);
@@ -555,7 +560,8 @@ k1_launch_jobs(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d
 
 int
 k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,
-	uint64_t stride, uint64_t len, size_t n, fsm_b200_result *d_out, cudaStream_t stream, int variant)
+	uint64_t stride, uint64_t len, size_t n, fsm_b200_result *d_out, cudaStream_t stream, int variant,
+	fsm_b200_result *const *peer_outs, int npeers)
 {
 	if (n == 0) return 0;
 	int sms = 0, smem_optin = 0;
@@ -567,6 +573,13 @@ k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offs
 	K1Args a;
 	fill_args(a, dfa);
 	a.base = d_base; a.offsets = d_offsets; a.stride = stride; a.len = len; a.n = n; a.out = d_out;
+	if (npeers < 0 || npeers > 7) {
+		set_error("k1: at most 7 peers (8 GPUs of one node)");
+		errno = EINVAL;
+		return -1;
+	}
+	for (int r = 0; r < npeers; r++) a.peer_out[r] = peer_outs[r];
+	a.npeers = (uint32_t) npeers;
 
 	if (variant == K1_AUTO) variant = g_variant;
 	const bool tile_ok = k1_tile_eligible(dfa, d_base, d_offsets, stride, len, n);

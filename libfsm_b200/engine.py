@@ -112,6 +112,12 @@ class Dfa:
               "exec_batch_host")
         return out
 
+    def exec_batch_gather(self, base, *, stride: int, length: int, n: int, out_ptr: int, peer_ptrs, npeers: int) -> None:
+        """Fixed-stride device batch whose records go to out_ptr AND to npeers peer buffers
+        (fused scan + gather over NVLink peer memory; see libfsm_b200.peer.GatherRing)."""
+        check(lib.fsm_b200_exec_batch_dev_gather(self._h, base.data_ptr(), None, int(stride), int(length), n,
+                                                 out_ptr, peer_ptrs, npeers, _stream_ptr()), "exec_batch_dev_gather")
+
     def exec_batch_hostptr(self, base_ptr: int, offsets_ptr: int, n: int, out_ptr: int) -> None:
         """Raw-pointer form of the host path (pinned buffers owned by the caller)."""
         check(lib.fsm_b200_exec_batch_host(self._h, base_ptr, offsets_ptr, n, out_ptr), "exec_batch_host")
