@@ -5,8 +5,10 @@ metric : GB/s of input scanned with bit-exact match ids (fsm_exec semantics)
 workload (N=1): configs[1] -- one 256-state DFA (PCRE a[ -~]{7}\\z, built by the reference:
          re_comp -> fsm_determinise -> fsm_minimise; shipped as a golden fixture), 2^20 inputs
          x 1 KiB synthetic ASCII.  N>1: the batch is range-sharded, every rank scans its own
-         2^20 x 1 KiB shard (weak scaling) and the per-shard result records are exchanged by
-         ONE NCCL all-gather per step, overlapped with the next step's scan on a side stream.
+         2^20 x 1 KiB shard (weak scaling).  The per-shard result records reach every rank
+         either FUSED with the scan (default: the scanning lanes store each 16 B record into
+         every peer's gathered buffer over NVLink P2P; only a 4-byte NCCL handshake per step,
+         on a side stream) or by ONE NCCL all-gather per step on a side stream (--gather nccl).
 
 A "step" is one pass of the hot path over one batch.  `value` has inputs resident in HBM;
 `e2e` goes through the host entry point of the C ABI (fsm_b200_exec_batch_host) with pinned
@@ -151,8 +153,8 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dist", default="uniform", choices=["uniform", "adversarial"])
     ap.add_argument("--variant", default="auto")
@@ -217,7 +219,8 @@ def main():
             side.wait_event(ev)
             with torch.cuda.stream(side):
                 if fused:
-                    dist.all_reduce(token)                  # 4-byte completion handshake, off the data path
+                    if not os.environ.get("BENCH_NO_HANDSHAKE"):
+                        dist.all_reduce(token)              # 4-byte completion handshake, off the data path
                 else:
                     dist.all_gather_into_tensor(gathered[b], d_out[b])
                 gather_done[b] = torch.cuda.Event(); gather_done[b].record(side)
@@ -271,9 +274,15 @@ def main():
 
     # kernel-only duration (CUDA events around each launch, on the launching stream)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
     for a, b in kev:
         a.record(main_stream)
-        dfa.exec_batch(d_in, stride=LENGTH, length=LENGTH, n=n, out=d_out[0])
+        if fused:
+            dfa.exec_batch_gather(d_in, stride=LENGTH, length=LENGTH, n=n, out_ptr=ring.local_slot_ptr(0),
+                                  peer_ptrs=peer_args[0][0], npeers=peer_args[0][1])
+        else:
+            dfa.exec_batch(d_in, stride=LENGTH, length=LENGTH, n=n, out=d_out[0])
         b.record(main_stream)
     torch.cuda.synchronize(dev)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
