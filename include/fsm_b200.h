@@ -118,6 +118,8 @@ struct fsm_b200_dfa_info {
 	uint32_t smem_resident;  /* 1 if the table is staged to shared memory by the kernels */
 	uint32_t device;
 	uint64_t table_bytes;
+	uint32_t nclasses;       /* 0: rows indexed by byte; else by byte class (compressed rows) */
+	uint32_t reserved;
 };
 int fsm_b200_dfa_info(const fsm_b200_dfa *dfa, struct fsm_b200_dfa_info *info);
 

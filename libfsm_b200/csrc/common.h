@@ -37,6 +37,11 @@ constexpr uint32_t NO_EDGE = 0xFFFFFFFFu;
 constexpr uint32_t SMEM_ROW_PAD = 4;
 /* Largest dense table (bytes, padded) the batch kernels stage into shared memory. */
 constexpr uint32_t SMEM_TABLE_MAX = 96 * 1024;
+/* Largest byte-class-compressed table staged into shared memory (LANE kernel only: it has
+ * no input staging buffers, so nearly all of the 227 KB opt-in limit is available). */
+constexpr uint32_t SMEM_CLASS_TABLE_MAX = 200 * 1024;
+/* Above this many byte classes the indirection is not worth it for an L2-resident table. */
+constexpr uint32_t CLASS_GLOBAL_MAX = 192;
 
 } // namespace fsmb200
 
@@ -51,8 +56,12 @@ struct fsm_b200_dfa {
 	uint32_t pitch;          /* row pitch in bytes of d_table */
 	uint32_t complete;
 	uint32_t smem_resident;
+	uint32_t nclasses;       /* 0: rows indexed by byte; else rows indexed by byte class */
+	uint32_t is_end_off;     /* blob offsets */
+	uint32_t cls_off;
 	uint64_t table_bytes;    /* ntable * pitch */
-	uint64_t blob_bytes;     /* table + is_end[ntable], padded to 16 */
+	uint64_t blob_bytes;     /* table | is_end[ntable] | class LUT[256], each padded to 16 */
+	uint8_t class_of[256];
 	/* device */
 	void *d_blob;            /* table rows followed by is_end bytes (u8 per row) */
 	/* host copies for introspection / stream composition */

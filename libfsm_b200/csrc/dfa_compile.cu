@@ -111,19 +111,60 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa 
 	dfa->h_table32 = t32;
 	dfa->entry_bytes = dfa->ntable <= 256 ? 1u : (dfa->ntable <= 65536 ? 2u : 4u);
 
-	/* shared-memory layout: padded rows; global layout: dense rows */
+	/* Layout choice:
+	 *   dense + shared memory   rows of 256 entries, padded by 4 B      (small DFAs: K1, K1b)
+	 *   classed + shared memory rows of C entries, C = byte classes      (mid-size DFAs)
+	 *   classed + global (L2)   same rows, read with ld.global.nc        (large DFAs)
+	 *   dense + global          when there are too many classes to gain */
 	uint32_t row_pad = SMEM_ROW_PAD;
 	if (const char *e = getenv("FSM_B200_ROW_PAD")) {      /* tuning knob, see DESIGN.md */
 		const int v = atoi(e);
 		if (v >= 0 && v <= 64 && (v % 4) == 0) row_pad = (uint32_t) v;
 	}
-	const uint64_t padded_pitch = 256ull * dfa->entry_bytes + row_pad;
-	const uint64_t padded_bytes = padded_pitch * dfa->ntable + ((dfa->ntable + 15u) & ~15ull);
-	dfa->smem_resident = padded_bytes <= SMEM_TABLE_MAX ? 1u : 0u;
-	dfa->pitch = dfa->smem_resident ? (uint32_t) padded_pitch : 256u * dfa->entry_bytes;
+	const uint32_t eb = dfa->entry_bytes;
+	const uint64_t end_pad = (dfa->ntable + 15u) & ~15ull;
+	const uint64_t dense_pitch = 256ull * eb + row_pad;
+	uint32_t C = 0;
+	for (int c = 0; c < 256; c++) dfa->class_of[c] = (uint8_t) c;
+	if (dense_pitch * dfa->ntable + end_pad <= SMEM_TABLE_MAX && getenv("FSM_B200_FORCE_CLASSED") == nullptr) {
+		dfa->smem_resident = 1;
+		dfa->pitch = (uint32_t) dense_pitch;
+	} else {
+		/* byte classes: symbols whose columns are identical in every row */
+		uint8_t rep[256];
+		for (int c = 0; c < 256; c++) {
+			int found = -1;
+			for (uint32_t k = 0; k < C && found < 0; k++) {
+				bool same = true;
+				for (uint32_t s = 0; s < S && same; s++) {
+					same = t32[(size_t) s * 256 + c] == t32[(size_t) s * 256 + rep[k]];
+				}
+				if (same) found = (int) k;
+			}
+			if (found < 0) { rep[C] = (uint8_t) c; found = (int) C; C++; }
+			dfa->class_of[c] = (uint8_t) found;
+		}
+		uint64_t cpitch = ((uint64_t) C * eb + 3u) & ~3ull;
+		if (((cpitch >> 2) & 1u) == 0) cpitch += 4;          /* odd word pitch spreads rows over banks */
+		if (cpitch * dfa->ntable + end_pad + 256 <= SMEM_CLASS_TABLE_MAX) {
+			dfa->smem_resident = 1;
+			dfa->nclasses = C;
+			dfa->pitch = (uint32_t) cpitch;
+		} else if (C <= CLASS_GLOBAL_MAX) {
+			dfa->smem_resident = 0;
+			dfa->nclasses = C;
+			dfa->pitch = (uint32_t) (((uint64_t) C * eb + 3u) & ~3ull);
+		} else {
+			dfa->smem_resident = 0;
+			dfa->pitch = 256u * eb;
+		}
+	}
+	const uint32_t ncols = dfa->nclasses ? dfa->nclasses : 256u;
 	dfa->table_bytes = (uint64_t) dfa->pitch * dfa->ntable;
 	const uint64_t table_pad = (dfa->table_bytes + 15u) & ~15ull;
-	dfa->blob_bytes = table_pad + ((dfa->ntable + 15u) & ~15ull);
+	dfa->is_end_off = (uint32_t) table_pad;
+	dfa->cls_off = (uint32_t) (table_pad + end_pad);
+	dfa->blob_bytes = table_pad + end_pad + (dfa->nclasses ? 256u : 0u);
 
 	std::vector<uint8_t> blob;
 	try {
@@ -139,21 +180,24 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa 
 		errno = ENOMEM;
 		return -1;
 	}
+	int col_byte[256];                       /* a representative byte of every column */
+	for (int c = 255; c >= 0; c--) col_byte[dfa->nclasses ? dfa->class_of[c] : c] = c;
 	for (uint32_t s = 0; s < dfa->ntable; s++) {
 		uint8_t *row = blob.data() + (size_t) s * dfa->pitch;
-		for (int c = 0; c < 256; c++) {
-			uint32_t v = (s < S) ? t32[(size_t) s * 256 + c] : dfa->dead;   /* dead row absorbs */
+		for (uint32_t k = 0; k < ncols; k++) {
+			uint32_t v = (s < S) ? t32[(size_t) s * 256 + col_byte[k]] : dfa->dead;   /* dead row absorbs */
 			if (v == NO_EDGE) v = dfa->dead;
 			switch (dfa->entry_bytes) {
-			case 1: row[c] = (uint8_t) v; break;
-			case 2: reinterpret_cast<uint16_t *>(row)[c] = (uint16_t) v; break;
-			default: reinterpret_cast<uint32_t *>(row)[c] = v; break;
+			case 1: row[k] = (uint8_t) v; break;
+			case 2: reinterpret_cast<uint16_t *>(row)[k] = (uint16_t) v; break;
+			default: reinterpret_cast<uint32_t *>(row)[k] = v; break;
 			}
 		}
 		const uint8_t e = (s < S && desc->is_end[s]) ? 1 : 0;
 		dfa->h_is_end[s] = e;
-		blob[table_pad + s] = e;
+		blob[dfa->is_end_off + s] = e;
 	}
+	if (dfa->nclasses) memcpy(blob.data() + dfa->cls_off, dfa->class_of, 256);
 
 	FSMB_CUDA(cudaSetDevice(device), { fsm_b200_dfa_free(dfa); return -1; });
 	FSMB_CUDA(cudaMalloc(&dfa->d_blob, dfa->blob_bytes), { fsm_b200_dfa_free(dfa); return -1; });
@@ -196,6 +240,8 @@ fsm_b200_dfa_info(const fsm_b200_dfa *dfa, struct fsm_b200_dfa_info *info)
 	info->smem_resident = dfa->smem_resident;
 	info->device = (uint32_t) dfa->device;
 	info->table_bytes = dfa->table_bytes;
+	info->nclasses = dfa->nclasses;
+	info->reserved = 0;
 	return 0;
 }
 
@@ -212,12 +258,14 @@ fsm_b200_dfa_table(const fsm_b200_dfa *dfa, uint32_t *out)
 	FSMB_CUDA(cudaMemcpy(blob.data(), dfa->d_blob, dfa->blob_bytes, cudaMemcpyDeviceToHost), return -1);
 	for (uint32_t s = 0; s < dfa->nstates; s++) {
 		const uint8_t *row = blob.data() + (size_t) s * dfa->pitch;
+		const uint8_t *cls = dfa->nclasses ? blob.data() + dfa->cls_off : nullptr;
 		for (int c = 0; c < 256; c++) {
+			const uint32_t k = cls ? cls[c] : (uint32_t) c;
 			uint32_t v;
 			switch (dfa->entry_bytes) {
-			case 1: v = row[c]; break;
-			case 2: v = reinterpret_cast<const uint16_t *>(row)[c]; break;
-			default: v = reinterpret_cast<const uint32_t *>(row)[c]; break;
+			case 1: v = row[k]; break;
+			case 2: v = reinterpret_cast<const uint16_t *>(row)[k]; break;
+			default: v = reinterpret_cast<const uint32_t *>(row)[k]; break;
 			}
 			out[(size_t) s * 256 + c] = (v == dfa->dead) ? NO_EDGE : v;
 		}

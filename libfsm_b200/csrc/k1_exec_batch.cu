@@ -157,7 +157,7 @@ store_result(const K1Args &a, uint64_t i, int32_t ret, uint32_t end, uint64_t co
 
 /* ------------------------------------------------------------------ LANE variant ---- */
 
-template <typename E, bool SMEM, bool HAS_DEAD>
+template <typename E, bool SMEM, bool HAS_DEAD, bool CLS>
 __global__ void __launch_bounds__(1024, 1)
 k1_lane_kernel(const K1Args a)
 {
@@ -165,6 +165,7 @@ k1_lane_kernel(const K1Args a)
 	__shared__ uint64_t blob_bar;
 
 	const uint8_t *is_end;
+	const uint8_t *cls = nullptr;      /* CLS: byte -> class LUT; rows are indexed by class */
 	TableSmem<E> ts;
 	TableGmem<E> tg;
 	if (SMEM) {
@@ -172,12 +173,22 @@ k1_lane_kernel(const K1Args a)
 		ts.tbl = reinterpret_cast<const E *>(smem);
 		ts.pitch = a.pitch / (uint32_t) sizeof(E);
 		is_end = smem + a.is_end_off;
+		if (CLS) cls = smem + a.cls_off;
 	} else {
 		tg.tbl = reinterpret_cast<const E *>(a.blob);
 		tg.pitch = a.pitch / (uint32_t) sizeof(E);
 		is_end = a.blob + a.is_end_off;
+		if (CLS) cls = a.blob + a.cls_off;       /* 256 B, L1-resident */
 	}
-#define TSTEP(st, b) (SMEM ? ts.step(st, b) : tg.step(st, b))
+#define COL(b) (CLS ? (uint32_t) (SMEM ? cls[(b)] : __ldg(cls + (b))) : (uint32_t) (b))
+#define TSTEP(st, b) (SMEM ? ts.step(st, COL(b)) : tg.step(st, COL(b)))
+#define WSTEP4(st, w)                                          \
+	do {                                                       \
+		st = TSTEP(st, __byte_perm((w), 0u, 0x4440u));         \
+		st = TSTEP(st, __byte_perm((w), 0u, 0x4441u));         \
+		st = TSTEP(st, __byte_perm((w), 0u, 0x4442u));         \
+		st = TSTEP(st, __byte_perm((w), 0u, 0x4443u));         \
+	} while (0)
 
 	const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
 	for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += nthreads) {
@@ -217,9 +228,7 @@ k1_lane_kernel(const K1Args a)
 				}
 				const uint32_t entry = st;
 #pragma unroll
-				for (int k = 0; k < 8; k++) {
-					if (SMEM) STEP4(ts, st, cur[k]); else STEP4(tg, st, cur[k]);
-				}
+				for (int k = 0; k < 8; k++) WSTEP4(st, cur[k]);
 				if (HAS_DEAD && st == a.dead) {
 					/* a byte of this sector had no edge: re-walk it to find which */
 					st = entry;
@@ -246,6 +255,185 @@ k1_lane_kernel(const K1Args a)
 		store_result(a, i, ret, st, pos);
 	}
 #undef TSTEP
+#undef WSTEP4
+#undef COL
+}
+
+/* First byte of a sector (within `mask`) whose transition enters the dead row, and the state
+ * it was taken from.  Returns (from_state, byte index). */
+template <typename T, bool CLS, bool SMEM>
+__device__ __noinline__ uint2
+rewalk_sector(const T tab, const uint8_t *cls, uint32_t entry, uint32_t mask, uint32_t dead, const uint32_t (&w)[8])
+{
+	uint32_t st = entry, at = 0, from = entry;
+	bool found = false;
+#pragma unroll 1
+	for (int k = 0; k < 8; k++) {
+		const uint32_t word = w[k];
+#pragma unroll
+		for (int t = 0; t < 4; t++) {
+			const uint32_t j = 4 * k + t;
+			const uint32_t b = (word >> (8 * t)) & 0xFFu;
+			const uint32_t col = CLS ? (uint32_t) (SMEM ? cls[b] : __ldg(cls + b)) : b;
+			const uint32_t nx = tab.step(st, col);
+			const bool in = ((mask >> j) & 1u) != 0u;
+			const bool hit = in && !found && nx == dead;
+			at = hit ? j : at;
+			from = hit ? st : from;
+			found = found || hit;
+			st = (in && !found) ? nx : st;
+		}
+	}
+	return make_uint2(from, at);
+}
+
+/* ------------------------------------------------------------------ RAGGED variant -- */
+
+/*
+ * Ragged batches (offsets array, arbitrary alignment, lines of 10..1000 bytes that may die
+ * after a few bytes: BASELINE config 3).  Lane l of a warp walks lines l, l+32, l+64, ... of
+ * the warp's contiguous range, ONE aligned 32-byte sector per loop iteration:
+ *   - every load is a full aligned sector (256-bit), also for unaligned line starts/ends:
+ *     bytes outside [lo, hi) of the sector are walked too but their result is discarded
+ *     with a select (a lookup with any byte value is in bounds), so there is no byte-wise
+ *     head/tail path and no dependent global load in the chain;
+ *   - three sector buffers: A (being walked), B (next sector of the same line) and N (first
+ *     sector of the lane's NEXT line, fetched when the current line starts), so a lane that
+ *     finishes -- or dies in -- a line continues immediately with a prefetched sector;
+ *   - a died line is re-walked from registers (same select scheme) to find the exact offset.
+ * Sectors that would reach outside [base+offsets[0], base+offsets[n]) (only the first and the
+ * last line of a batch can) are assembled from byte loads instead.
+ */
+template <typename E, bool SMEM, bool HAS_DEAD, bool CLS>
+__global__ void __launch_bounds__(768, 1)      /* three sector buffers: 85 registers per lane */
+k1_ragged_kernel(const K1Args a)
+{
+	extern __shared__ __align__(1024) uint8_t smem[];
+	__shared__ uint64_t blob_bar;
+
+	const uint8_t *is_end;
+	const uint8_t *cls = nullptr;
+	TableSmem<E> ts;
+	TableGmem<E> tg;
+	if (SMEM) {
+		stage_blob(smem, a.blob, a.blob_bytes, &blob_bar);
+		ts.tbl = reinterpret_cast<const E *>(smem);
+		ts.pitch = a.pitch / (uint32_t) sizeof(E);
+		is_end = smem + a.is_end_off;
+		if (CLS) cls = smem + a.cls_off;
+	} else {
+		tg.tbl = reinterpret_cast<const E *>(a.blob);
+		tg.pitch = a.pitch / (uint32_t) sizeof(E);
+		is_end = a.blob + a.is_end_off;
+		if (CLS) cls = a.blob + a.cls_off;
+	}
+#define COL(b) (CLS ? (uint32_t) (SMEM ? cls[(b)] : __ldg(cls + (b))) : (uint32_t) (b))
+#define TSTEP(st, b) (SMEM ? ts.step(st, COL(b)) : tg.step(st, COL(b)))
+
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint64_t nwarps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
+	const uint64_t gw = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	/* contiguous range of lines per warp, in multiples of 32 */
+	const uint64_t per = (((a.n + nwarps - 1) / nwarps) + 31u) & ~31ull;
+	const uint64_t wbeg = gw * per;
+	const uint64_t wend = min(a.n, wbeg + per);
+	const uintptr_t lo_ptr = reinterpret_cast<uintptr_t>(a.base) + a.offsets[0];
+	const uintptr_t hi_ptr = reinterpret_cast<uintptr_t>(a.base) + a.offsets[a.n];
+
+	auto load_sector = [&](uintptr_t saddr, uint32_t (&w)[8]) {
+		if (saddr >= lo_ptr && saddr + 32 <= hi_ptr) {
+			ld256(reinterpret_cast<const uint8_t *>(saddr), w);
+		} else {                                     /* batch edge: assemble from byte loads */
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				uint32_t v = 0;
+#pragma unroll
+				for (int t = 0; t < 4; t++) {
+					const uintptr_t p = saddr + 4 * k + t;
+					if (p >= lo_ptr && p < hi_ptr) v |= (uint32_t) __ldg(reinterpret_cast<const uint8_t *>(p)) << (8 * t);
+				}
+				w[k] = v;
+			}
+		}
+	};
+
+	uint64_t i = wbeg + lane;
+	bool have = i < wend;
+	uintptr_t cur = 0, end = 0, nbeg = 0, nend = 0;
+	uint32_t A[8], B[8], N[8];
+#pragma unroll
+	for (int k = 0; k < 8; k++) { A[k] = 0; B[k] = 0; N[k] = 0; }
+	bool have_next = false;
+	if (have) {
+		cur = reinterpret_cast<uintptr_t>(a.base) + a.offsets[i];
+		end = reinterpret_cast<uintptr_t>(a.base) + (a.ends != nullptr ? a.ends[i] : a.offsets[i + 1]);
+		load_sector(cur & ~(uintptr_t) 31, A);
+		have_next = i + 32 < wend;
+		if (have_next) {
+			nbeg = reinterpret_cast<uintptr_t>(a.base) + a.offsets[i + 32];
+			nend = reinterpret_cast<uintptr_t>(a.base) + (a.ends != nullptr ? a.ends[i + 32] : a.offsets[i + 33]);
+			load_sector(nbeg & ~(uintptr_t) 31, N);
+		}
+	}
+	uint32_t st = a.entry != nullptr && have ? a.entry[i] : a.start;
+	uintptr_t line_beg = cur;
+
+	while (have) {
+		const uintptr_t saddr = cur & ~(uintptr_t) 31;
+		const uint32_t lo = (uint32_t) (cur - saddr);
+		const uint32_t hi = (end - saddr) >= 32 ? 32u : (uint32_t) (end - saddr);
+		const bool more = saddr + 32 < end;              /* the line continues in the next sector */
+		if (more) load_sector(saddr + 32, B);
+
+		/* walk the 32 bytes; keep the new state only for bytes inside [lo, hi) */
+		const uint32_t mask = (hi > lo) ? ((0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (32u - hi))) : 0u;
+		const uint32_t entry = st;
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+#pragma unroll
+			for (int t = 0; t < 4; t++) {
+				const uint32_t nx = TSTEP(st, __byte_perm(A[k], 0u, 0x4440u + t));
+				st = ((mask >> (4 * k + t)) & 1u) ? nx : st;
+			}
+		}
+		bool died = false;
+		uint32_t consumed_here = hi - lo;
+		if (HAS_DEAD && st == a.dead) {
+			/* re-walk from registers to find the first byte without an edge (out of line: keeps
+			 * its temporaries out of the main loop's register budget) */
+			died = true;
+			const uint2 r = SMEM ? rewalk_sector<TableSmem<E>, CLS, SMEM>(ts, cls, entry, mask, a.dead, A)
+			                     : rewalk_sector<TableGmem<E>, CLS, SMEM>(tg, cls, entry, mask, a.dead, A);
+			st = r.x;
+			consumed_here = r.y - lo;
+		}
+		cur += consumed_here;
+		if (died || !more) {
+			/* line done */
+			const int32_t ret = (!died && is_end[st]) ? 1 : 0;
+			store_result(a, i, ret, st, (uint64_t) (cur - line_beg));
+			i += 32;
+			have = have_next;
+			if (have) {
+				cur = nbeg; end = nend; line_beg = cur;
+				st = a.entry != nullptr ? a.entry[i] : a.start;
+#pragma unroll
+				for (int k = 0; k < 8; k++) A[k] = N[k];
+				have_next = i + 32 < wend;
+				if (have_next) {
+					nbeg = reinterpret_cast<uintptr_t>(a.base) + a.offsets[i + 32];
+					nend = reinterpret_cast<uintptr_t>(a.base) + (a.ends != nullptr ? a.ends[i + 32] : a.offsets[i + 33]);
+					load_sector(nbeg & ~(uintptr_t) 31, N);
+				}
+			}
+		} else {
+			cur = saddr + 32;
+#pragma unroll
+			for (int k = 0; k < 8; k++) A[k] = B[k];
+		}
+	}
+#undef TSTEP
+#undef COL
 }
 
 /* ------------------------------------------------------------------ TILE variant ---- */
@@ -409,11 +597,11 @@ set_smem(K kernel, size_t bytes)
 	return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes) == cudaSuccess;
 }
 
-template <typename E, bool SMEM, bool HAS_DEAD>
+template <typename E, bool SMEM, bool HAS_DEAD, bool CLS>
 int
 launch_lane(const K1Args &a, int sms, size_t smem_bytes, int block, cudaStream_t stream)
 {
-	auto kern = k1_lane_kernel<E, SMEM, HAS_DEAD>;
+	auto kern = k1_lane_kernel<E, SMEM, HAS_DEAD, CLS>;
 	if (SMEM && !set_smem(kern, smem_bytes)) {
 		set_error("k1_lane: cannot opt in to %zu bytes of shared memory", smem_bytes);
 		errno = EIO;
@@ -497,7 +685,7 @@ bool
 k1_tile_eligible(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,
 	uint64_t stride, uint64_t len, size_t n)
 {
-	return dfa->smem_resident && d_offsets == nullptr && n > 0 && len > 0 &&
+	return dfa->smem_resident && dfa->nclasses == 0 && d_offsets == nullptr && n > 0 && len > 0 &&
 	    (reinterpret_cast<uintptr_t>(d_base) & 15u) == 0 && (stride & 15u) == 0 &&
 	    stride >= len && stride < (1ull << 32) && n < (1ull << 31) && dfa->entry_bytes <= 2;
 }
@@ -508,14 +696,60 @@ fill_args(K1Args &a, const fsm_b200_dfa *dfa)
 	memset(&a, 0, sizeof a);
 	a.blob = static_cast<const uint8_t *>(dfa->d_blob);
 	a.blob_bytes = (uint32_t) dfa->blob_bytes;
-	a.is_end_off = (uint32_t) ((dfa->table_bytes + 15u) & ~15ull);
+	a.is_end_off = dfa->is_end_off;
+	a.cls_off = dfa->cls_off;
 	a.pitch = dfa->pitch; a.start = dfa->start; a.dead = dfa->dead;
+}
+
+template <typename E, bool SMEM, bool HAS_DEAD, bool CLS>
+int
+launch_ragged(const K1Args &a, int sms, size_t smem_bytes, int block, cudaStream_t stream)
+{
+	auto kern = k1_ragged_kernel<E, SMEM, HAS_DEAD, CLS>;
+	if (block > 768) block = 768;
+	if (SMEM && !set_smem(kern, smem_bytes)) {
+		set_error("k1_ragged: cannot opt in to %zu bytes of shared memory", smem_bytes);
+		errno = EIO;
+		return -1;
+	}
+	int per_sm = 1;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, SMEM ? smem_bytes : 0) != cudaSuccess || per_sm < 1) {
+		per_sm = 1;
+	}
+	uint64_t want = (a.n + (uint64_t) block - 1) / (uint64_t) block;
+	uint64_t grid = (uint64_t) sms * (uint64_t) per_sm;
+	if (want < grid) grid = want;
+	if (grid == 0) grid = 1;
+	kern<<<(unsigned) grid, block, SMEM ? smem_bytes : 0, stream>>>(a);
+	count_launch();
+	FSMB_CUDA(cudaGetLastError(), return -1);
+	return 0;
+}
+
+template <typename E, bool SMEM>
+static int
+dispatch_lane2(const fsm_b200_dfa *dfa, const K1Args &a, int sms, size_t smem_bytes, int block, cudaStream_t stream)
+{
+	const bool dead = !dfa->complete, cls = dfa->nclasses != 0;
+	if (a.offsets != nullptr && !a.prefer_lane && getenv("FSM_B200_NO_RAGGED") == nullptr) {
+		if (dead) {
+			return cls ? launch_ragged<E, SMEM, true, true>(a, sms, smem_bytes, block, stream)
+			           : launch_ragged<E, SMEM, true, false>(a, sms, smem_bytes, block, stream);
+		}
+		return cls ? launch_ragged<E, SMEM, false, true>(a, sms, smem_bytes, block, stream)
+		           : launch_ragged<E, SMEM, false, false>(a, sms, smem_bytes, block, stream);
+	}
+	if (dead) {
+		return cls ? launch_lane<E, SMEM, true, true>(a, sms, smem_bytes, block, stream)
+		           : launch_lane<E, SMEM, true, false>(a, sms, smem_bytes, block, stream);
+	}
+	return cls ? launch_lane<E, SMEM, false, true>(a, sms, smem_bytes, block, stream)
+	           : launch_lane<E, SMEM, false, false>(a, sms, smem_bytes, block, stream);
 }
 
 static int
 dispatch_lane(const fsm_b200_dfa *dfa, const K1Args &a, int sms, cudaStream_t stream)
 {
-	const bool dead = !dfa->complete;
 	int block = 1024;
 	const char *e = getenv("FSM_B200_LANE_BLOCK");
 	if (e != nullptr) {
@@ -524,21 +758,14 @@ dispatch_lane(const fsm_b200_dfa *dfa, const K1Args &a, int sms, cudaStream_t st
 	}
 	if (dfa->smem_resident) {
 		const size_t smem_bytes = (a.blob_bytes + 127u) & ~127u;
-		if (dfa->entry_bytes == 1)
-			return dead ? launch_lane<uint8_t, true, true>(a, sms, smem_bytes, block, stream)
-			            : launch_lane<uint8_t, true, false>(a, sms, smem_bytes, block, stream);
-		return dead ? launch_lane<uint16_t, true, true>(a, sms, smem_bytes, block, stream)
-		            : launch_lane<uint16_t, true, false>(a, sms, smem_bytes, block, stream);
+		if (dfa->entry_bytes == 1) return dispatch_lane2<uint8_t, true>(dfa, a, sms, smem_bytes, block, stream);
+		if (dfa->entry_bytes == 2) return dispatch_lane2<uint16_t, true>(dfa, a, sms, smem_bytes, block, stream);
+		return dispatch_lane2<uint32_t, true>(dfa, a, sms, smem_bytes, block, stream);
 	}
 	if (block > 256 && e == nullptr) block = 256;
-	if (dfa->entry_bytes == 2)
-		return dead ? launch_lane<uint16_t, false, true>(a, sms, 0, block, stream)
-		            : launch_lane<uint16_t, false, false>(a, sms, 0, block, stream);
-	if (dfa->entry_bytes == 4)
-		return dead ? launch_lane<uint32_t, false, true>(a, sms, 0, block, stream)
-		            : launch_lane<uint32_t, false, false>(a, sms, 0, block, stream);
-	return dead ? launch_lane<uint8_t, false, true>(a, sms, 0, block, stream)
-	            : launch_lane<uint8_t, false, false>(a, sms, 0, block, stream);
+	if (dfa->entry_bytes == 1) return dispatch_lane2<uint8_t, false>(dfa, a, sms, 0, block, stream);
+	if (dfa->entry_bytes == 2) return dispatch_lane2<uint16_t, false>(dfa, a, sms, 0, block, stream);
+	return dispatch_lane2<uint32_t, false>(dfa, a, sms, 0, block, stream);
 }
 
 int
@@ -555,6 +782,7 @@ k1_launch_jobs(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d
 	K1Args a;
 	fill_args(a, dfa);
 	a.base = d_base; a.offsets = d_begs; a.ends = d_ends; a.entry = d_entry; a.n = n; a.out = d_out;
+	a.prefer_lane = 1;
 	return dispatch_lane(dfa, a, sms, stream);
 }
 

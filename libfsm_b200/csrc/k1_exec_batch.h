@@ -29,9 +29,11 @@ struct K1Args {
 	const uint8_t *blob;        /* table rows then is_end bytes */
 	uint32_t blob_bytes;
 	uint32_t is_end_off;
+	uint32_t cls_off;           /* class LUT (CLS kernels) */
 	uint32_t pitch;
 	uint32_t start;
 	uint32_t dead;
+	uint32_t prefer_lane;       /* K1b jobs: long inputs, keep the 3-instructions-per-byte LANE kernel */
 	uint32_t tile_stage_off;    /* TILE variants: shared-memory carve-up */
 	uint32_t tile_bar_off;
 };

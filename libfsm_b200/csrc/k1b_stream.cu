@@ -364,7 +364,7 @@ stream_map(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStre
 bool
 parallel_ok(const fsm_b200_dfa *dfa, uint64_t len)
 {
-	if (!(dfa->smem_resident && dfa->entry_bytes == 1)) return false;
+	if (!(dfa->smem_resident && dfa->nclasses == 0 && dfa->entry_bytes == 1)) return false;
 	uint64_t min_len = 4096;
 	if (const char *e = getenv("FSM_B200_STREAM_MIN")) {
 		const long v = atol(e);
@@ -457,7 +457,7 @@ fsm_b200_exec_stream_map_dev(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint
 		errno = EINVAL;
 		return -1;
 	}
-	if (!(dfa->smem_resident && dfa->entry_bytes == 1)) {
+	if (!(dfa->smem_resident && dfa->nclasses == 0 && dfa->entry_bytes == 1)) {
 		set_error("exec_stream_map_dev: needs a table with <= 256 rows");
 		errno = ENOTSUP;
 		return -1;

@@ -1,7 +1,8 @@
 /*
  * fsm_b200_shim.c -- libfsm's fsm_exec, re-implemented over libfsm_b200.so.
  *
- * Replaces src/libfsm/exec.c of the reference.  What it keeps, bit for bit:
+ * Replaces src/libfsm/exec.c (and, further down, src/libfsm/determinise.c's two entry
+ * points) of the reference.  What fsm_exec keeps, bit for bit:
  *   - signature and return convention: 1 match (+ *end), 0 no match, -1/errno
  *     (EINVAL when the fsm is not a DFA or has no start state, exec.c:106-114);
  *   - `*end` is written only on success (exec.c:165);
@@ -28,6 +29,7 @@
 #include <fsm/fsm.h>
 #include <fsm/capture.h>
 #include <fsm/pred.h>
+#include <fsm/walk.h>
 
 #include <adt/set.h>
 #include <adt/stateset.h>
@@ -293,6 +295,114 @@ fsm_exec(const struct fsm *fsm,
 	}
 	*end = r.end;
 	return 1;
+}
+
+/* ------------------------------------------------------------------ fsm_determinise --- */
+
+/*
+ * fsm_determinise_with_config / fsm_determinise (include/fsm/fsm.h:472-488), replacing
+ * src/libfsm/determinise.c.  Same contract: in place -- afterwards the same `struct fsm *`
+ * holds the DFA, state 0 is the start state (determinise.c:234), the allocator is kept,
+ * end bits and end ids are carried (determinise.c:236-266), linkage_info is gone
+ * (determinise.c:284).  The subset construction itself (incl. the epsilon removal the
+ * reference runs first, determinise.c:48-52) happens in the engine (K2); this function
+ * only marshals: struct fsm -> flat NFA -> [GPU] -> flat DFA -> struct fsm -> fsm_move.
+ * State NUMBERS are BFS order instead of the reference's LIFO/analysis order (DESIGN.md
+ * section 5): an isomorphic DFA.
+ * Not accelerated: capture actions and eager outputs (determinise.c:268-274 remaps them);
+ * such FSMs fail with ERRNO/ENOTSUP rather than silently taking another path.
+ */
+enum fsm_determinise_with_config_res
+fsm_determinise_with_config(struct fsm *nfa, const struct fsm_determinise_config *config)
+{
+	const size_t state_limit = config == NULL ? 0 : config->state_limit;
+	struct fsm_b200_flat flat;
+	struct fsm_b200_owned_desc out;
+	struct fsm *dfa;
+	uint32_t s;
+	int rc;
+
+	assert(nfa != NULL);
+	if (fsm_countcaptures(nfa) > 0 || unsupported(nfa, NULL)) {
+		errno = ENOTSUP;
+		return FSM_DETERMINISE_WITH_CONFIG_ERRNO;
+	}
+	if (fsm_b200_flatten(nfa, &flat) != 0) {
+		return FSM_DETERMINISE_WITH_CONFIG_ERRNO;
+	}
+	rc = fsm_b200_determinise(&flat.desc, device_index(), state_limit, &out);
+	if (rc == 1) {
+		fsm_b200_flat_free(&flat);
+		return FSM_DETERMINISE_WITH_CONFIG_STATE_LIMIT_REACHED;
+	}
+	if (rc != 0) {
+		fsm_b200_flat_free(&flat);
+		return FSM_DETERMINISE_WITH_CONFIG_ERRNO;
+	}
+	if (!flat.desc.hasstart) {
+		/* determinise.c:88-91: no start state => OK, and the fsm only loses its epsilons */
+		fsm_b200_flat_free(&flat);
+		fsm_b200_desc_free(&out);
+		if (fsm_has(nfa, fsm_hasepsilons) && !fsm_remove_epsilons(nfa)) {
+			return FSM_DETERMINISE_WITH_CONFIG_ERRNO;
+		}
+		return FSM_DETERMINISE_WITH_CONFIG_OK;
+	}
+	fsm_b200_flat_free(&flat);
+
+	dfa = fsm_new_statealloc(nfa->alloc, out.desc.nstates > 0 ? out.desc.nstates : 1);
+	if (dfa == NULL) {
+		goto fail;
+	}
+	if (out.desc.nstates > 0 && !fsm_addstate_bulk(dfa, out.desc.nstates)) {
+		goto fail_dfa;
+	}
+	for (s = 0; s < out.desc.nstates; s++) {
+		uint64_t g, e;
+		const uint64_t g0 = out.desc.group_off[s], g1 = out.desc.group_off[s + 1];
+		if (g1 > g0 && !edge_set_advise_growth(&dfa->states[s].edges, dfa->alloc, (size_t) (g1 - g0))) {
+			goto fail_dfa;
+		}
+		for (g = g0; g < g1; g++) {      /* groups arrive sorted by destination: pure appends */
+			uint64_t sym[4];
+			memcpy(sym, &out.desc.group_symbols[4 * g], sizeof sym);
+			if (!edge_set_add_bulk(&dfa->states[s].edges, dfa->alloc, sym, out.desc.group_to[g])) {
+				goto fail_dfa;
+			}
+		}
+		if (out.desc.is_end[s]) {
+			fsm_setend(dfa, s, 1);
+			for (e = out.desc.endid_off[s]; e < out.desc.endid_off[s + 1]; e++) {
+				if (!fsm_endid_set(dfa, s, out.desc.endids[e])) {
+					goto fail_dfa;
+				}
+			}
+		}
+	}
+	fsm_setstart(dfa, 0);
+	fsm_b200_desc_free(&out);
+	fsm_b200_invalidate(nfa);
+	fsm_move(nfa, dfa);
+	return FSM_DETERMINISE_WITH_CONFIG_OK;
+
+fail_dfa:
+	fsm_free(dfa);
+fail:
+	fsm_b200_desc_free(&out);
+	return FSM_DETERMINISE_WITH_CONFIG_ERRNO;
+}
+
+int
+fsm_determinise(struct fsm *nfa)
+{
+	switch (fsm_determinise_with_config(nfa, NULL)) {
+	case FSM_DETERMINISE_WITH_CONFIG_OK:
+		return 1;
+	case FSM_DETERMINISE_WITH_CONFIG_STATE_LIMIT_REACHED:
+	case FSM_DETERMINISE_WITH_CONFIG_ERRNO:
+	default:
+		return 0;
+	}
 }
 
 int

@@ -57,6 +57,19 @@ def test_golden_host_path(case):
             assert (got["ret"] == case["expect"]["ret"]).all()
 
 
+@pytest.mark.parametrize("case", [c for c in CASES if c["is_dfa"]], ids=lambda c: c["name"])
+def test_golden_host_path_byte_class_tables(case, monkeypatch):
+    """Same golden records through the byte-class-compressed table layout (rows indexed by
+    class; normally used for DFAs too big for dense shared-memory rows), forced here."""
+    monkeypatch.setenv("FSM_B200_FORCE_CLASSED", "1")
+    with L.Dfa(case["fsm"]) as dfa:
+        assert dfa.info["nclasses"] >= 1
+        got = dfa.exec_batch(case["base"], case["offsets"])
+        assert_records_equal(got, case["expect_amortised"], case["name"])
+        import reflib
+        assert (dfa.table() == reflib.Oracle().flatten(case["fsm"])).all()
+
+
 @pytest.mark.parametrize("case", [c for c in CASES if c["is_dfa"]][::3], ids=lambda c: c["name"])
 def test_device_table_matches_oracle_flatten(oracle, case):
     with L.Dfa(case["fsm"]) as dfa:
@@ -126,7 +139,7 @@ def test_dead_states_and_wide_tables_fixed_stride(torch_cuda, oracle, name, vari
     with L.Dfa(fsm) as dfa:
         L.set_exec_variant(variant)
         dev = torch.from_numpy(host).cuda()
-        if variant != "lane" and not dfa.info["smem_resident"]:
+        if variant != "lane" and (not dfa.info["smem_resident"] or dfa.info["nclasses"]):
             with pytest.raises(L.FsmB200Error) as ei:
                 dfa.exec_batch(dev, stride=length, length=length, n=n)
             assert ei.value.errno == errno.ENOTSUP

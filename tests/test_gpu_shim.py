@@ -61,3 +61,58 @@ def test_multi_pattern_prints_matching_pattern():
     args = ["-r", "pcre", "-z", "abc", "def", "xyz"]
     got, want = run(RE_B200, args), run(RE_REF, args)
     assert got[0] == want[0] and got[1] == want[1]
+
+
+FSM_B200 = os.path.join(ROOT, "build", "shim", "fsm_b200")
+FSM_REF = os.path.join(ROOT, "oracle", "_ref", "fsm_ref")
+
+
+def to_fsm5(f) -> str | None:
+    """A FlatFsm as fsm(5) text (printable labels only; None if it has others)."""
+    lines = []
+    for s in range(f.nstates):
+        for g in range(int(f.group_off[s]), int(f.group_off[s + 1])):
+            for c in range(256):
+                if (int(f.group_symbols[g][c >> 6]) >> (c & 63)) & 1:
+                    if not (0x20 <= c < 0x7F) or chr(c) in "'\\":
+                        return None
+                    lines.append(f"{s} -> {int(f.group_to[g])} '{chr(c)}';")
+        for e in range(int(f.eps_off[s]), int(f.eps_off[s + 1])):
+            lines.append(f"{s} -> {int(f.eps_to[e])};")
+    if f.hasstart:
+        lines.append(f"start: {f.start};")
+    ends = [str(s) for s in range(f.nstates) if f.is_end[s]]
+    if ends:
+        lines.append("end: " + ", ".join(ends) + ";")
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.skipif(not (os.path.exists(FSM_B200) and os.path.exists(FSM_REF)), reason="relinked fsm(1) not built")
+def test_fsm_cli_determinise_like_the_reference_tests(tmp_path):
+    """The reference's own test method for determinise (tests/determinise/Makefile:11-20):
+    `fsm -pd in.fsm` then `fsm -t equal` against the expected automaton -- here with the
+    relinked fsm(1) (fsm_determinise -> K2 on the GPU) against the reference's fsm(1)."""
+    import goldenio
+    cases = goldenio.load_det_cases(os.path.join(goldenio.GOLDEN_DIR, "golden_determinise.npz"))
+    ran = 0
+    for c in cases:
+        if not (c["name"].startswith("determinise:") or c["name"].startswith("eclosure:") or c["name"] == "cfg5:20x6"):
+            continue
+        txt = to_fsm5(c["nfa"])
+        if txt is None:
+            continue
+        inp = tmp_path / "in.fsm"
+        inp.write_text(txt)
+        outs = {}
+        for tag, binary in (("b200", FSM_B200), ("ref", FSM_REF)):
+            p = subprocess.run([binary, "-pd"], stdin=open(inp), capture_output=True, timeout=120)
+            assert p.returncode == 0, (c["name"], tag, p.stderr)
+            outs[tag] = tmp_path / f"out_{tag}.fsm"
+            outs[tag].write_bytes(p.stdout)
+        eq = subprocess.run([FSM_REF, "-t", "equal", str(outs["b200"]), str(outs["ref"])], capture_output=True, timeout=120)
+        assert eq.returncode == 0, (c["name"], eq.stdout, eq.stderr)
+        # same number of states too (subset construction without minimisation is canonical)
+        cnt = [subprocess.run([FSM_REF, "-q", "count"], stdin=open(outs[t]), capture_output=True).stdout for t in ("b200", "ref")]
+        assert cnt[0] == cnt[1], c["name"]
+        ran += 1
+    assert ran >= 10
