@@ -119,7 +119,7 @@ struct fsm_b200_dfa_info {
 	uint32_t device;
 	uint64_t table_bytes;
 	uint32_t nclasses;       /* 0: rows indexed by byte; else by byte class (compressed rows) */
-	uint32_t reserved;
+	uint32_t kstride;        /* 0, or K in {2,4}: a K-bytes-per-lookup table is also resident */
 };
 int fsm_b200_dfa_info(const fsm_b200_dfa *dfa, struct fsm_b200_dfa_info *info);
 

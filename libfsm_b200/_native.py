@@ -31,7 +31,7 @@ class CDfaInfo(C.Structure):
     _fields_ = [("nstates", C.c_uint32), ("ntable_states", C.c_uint32), ("start", C.c_uint32),
                 ("entry_bytes", C.c_uint32), ("row_pitch_bytes", C.c_uint32), ("complete", C.c_uint32),
                 ("smem_resident", C.c_uint32), ("device", C.c_uint32), ("table_bytes", C.c_uint64),
-                ("nclasses", C.c_uint32), ("reserved", C.c_uint32)]
+                ("nclasses", C.c_uint32), ("kstride", C.c_uint32)]
 
 
 class CDetStats(C.Structure):

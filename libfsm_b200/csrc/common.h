@@ -62,6 +62,13 @@ struct fsm_b200_dfa {
 	uint64_t table_bytes;    /* ntable * pitch */
 	uint64_t blob_bytes;     /* table | is_end[ntable] | class LUT[256], each padded to 16 */
 	uint8_t class_of[256];
+	/* k-stride form (tables with <= 256 rows and few byte classes): one lookup per K bytes */
+	void *d_kblob;           /* stepK rows | step1 rows | is_end | K class LUTs of 256 B */
+	uint32_t kstride;        /* 0 (none), 2 or 4 */
+	uint32_t kclasses;
+	uint32_t kpitch, k1pitch;            /* row pitches (bytes) of stepK / step1 */
+	uint32_t k1_off, kend_off, klut_off; /* blob offsets */
+	uint32_t kblob_bytes;
 	/* device */
 	void *d_blob;            /* table rows followed by is_end bytes (u8 per row) */
 	/* host copies for introspection / stream composition */

@@ -203,6 +203,64 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa 
 	FSMB_CUDA(cudaMalloc(&dfa->d_blob, dfa->blob_bytes), { fsm_b200_dfa_free(dfa); return -1; });
 	FSMB_CUDA(cudaMemcpy(dfa->d_blob, blob.data(), dfa->blob_bytes, cudaMemcpyHostToDevice),
 	    { fsm_b200_dfa_free(dfa); return -1; });
+
+	/* ---- k-stride form: with C byte classes and C^K <= 256, index rows by the class tuple of
+	 * K consecutive bytes: ONE dependent table lookup per K input bytes.  The K class lookups
+	 * (256-byte LUTs, pre-multiplied by C^j) are independent of the state, conflict-free for
+	 * ASCII and off the dependent chain; the shared-memory wavefronts per byte drop from
+	 * 1 + conflicts to (K + 1 + conflicts) / K. */
+	if (dfa->ntable <= 256 && getenv("FSM_B200_NO_KSTRIDE") == nullptr) {
+		uint8_t kcls[256], rep[256];
+		uint32_t KC = 0;
+		for (int c = 0; c < 256; c++) {
+			int found = -1;
+			for (uint32_t k = 0; k < KC && found < 0; k++) {
+				bool same = true;
+				for (uint32_t st = 0; st < S && same; st++) same = t32[(size_t) st * 256 + c] == t32[(size_t) st * 256 + rep[k]];
+				if (same) found = (int) k;
+			}
+			if (found < 0) { rep[KC] = (uint8_t) c; found = (int) KC; KC++; }
+			kcls[c] = (uint8_t) found;
+		}
+		uint32_t K = 0;
+		if (KC * KC * KC * KC <= 256) K = 4; else if (KC * KC <= 256) K = 2;
+		if (const char *e = getenv("FSM_B200_KSTRIDE")) { const int v = atoi(e); if ((v == 2 && KC * KC <= 256) || v == 0) K = (uint32_t) v; }
+		if (K != 0) {
+			const uint32_t T = dfa->ntable;
+			uint32_t W = 1;
+			for (uint32_t j = 0; j < K; j++) W *= KC;
+			auto odd_pitch = [](uint32_t nbytes) { uint32_t p = (nbytes + 3u) & ~3u; if (((p >> 2) & 1u) == 0) p += 4; return p; };
+			const uint32_t kpitch = odd_pitch(W), k1pitch = odd_pitch(KC);
+			const uint32_t k1_off = (T * kpitch + 15u) & ~15u;
+			const uint32_t kend_off = (k1_off + T * k1pitch + 15u) & ~15u;
+			const uint32_t klut_off = (kend_off + T + 15u) & ~15u;
+			const uint32_t kbytes = klut_off + 256u * K;
+			std::vector<uint8_t> kb(kbytes, 0);
+			auto step1 = [&](uint32_t st, uint32_t cls) -> uint32_t {
+				if (st >= S) return dfa->dead;
+				const uint32_t v = t32[(size_t) st * 256 + rep[cls]];
+				return v == NO_EDGE ? dfa->dead : v;
+			};
+			for (uint32_t st = 0; st < T; st++) {
+				for (uint32_t c = 0; c < KC; c++) kb[k1_off + st * k1pitch + c] = (uint8_t) step1(st, c);
+				for (uint32_t idx = 0; idx < W; idx++) {
+					uint32_t cur = st, rem = idx;
+					for (uint32_t j = 0; j < K; j++) { cur = step1(cur, rem % KC); rem /= KC; }   /* byte j has weight C^j */
+					kb[st * kpitch + idx] = (uint8_t) cur;
+				}
+				kb[kend_off + st] = dfa->h_is_end[st];
+			}
+			uint32_t wgt = 1;
+			for (uint32_t j = 0; j < K; j++) {
+				for (int c = 0; c < 256; c++) kb[klut_off + 256u * j + c] = (uint8_t) (kcls[c] * wgt);
+				wgt *= KC;
+			}
+			FSMB_CUDA(cudaMalloc(&dfa->d_kblob, kbytes), { fsm_b200_dfa_free(dfa); return -1; });
+			FSMB_CUDA(cudaMemcpy(dfa->d_kblob, kb.data(), kbytes, cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
+			dfa->kstride = K; dfa->kclasses = KC; dfa->kpitch = kpitch; dfa->k1pitch = k1pitch;
+			dfa->k1_off = k1_off; dfa->kend_off = kend_off; dfa->klut_off = klut_off; dfa->kblob_bytes = kbytes;
+		}
+	}
 	*out = dfa;
 	return 0;
 }
@@ -219,6 +277,7 @@ fsm_b200_dfa_free(fsm_b200_dfa *dfa)
 		cudaSetDevice(dfa->device);
 		cudaFree(dfa->d_blob);
 	}
+	if (dfa->d_kblob != nullptr) cudaFree(dfa->d_kblob);
 	free(dfa->h_table32);
 	free(dfa->h_is_end);
 	delete dfa;
@@ -241,7 +300,7 @@ fsm_b200_dfa_info(const fsm_b200_dfa *dfa, struct fsm_b200_dfa_info *info)
 	info->device = (uint32_t) dfa->device;
 	info->table_bytes = dfa->table_bytes;
 	info->nclasses = dfa->nclasses;
-	info->reserved = 0;
+	info->kstride = dfa->kstride;
 	return 0;
 }
 

@@ -436,6 +436,104 @@ k1_ragged_kernel(const K1Args a)
 #undef COL
 }
 
+/* ------------------------------------------------------------------ K-STRIDE variant -- */
+
+/*
+ * Lane-per-input like LANE, but the dependent chain advances K bytes per lookup:
+ *   idx = L0[b0] + L1[b1] (+ L2[b2] + L3[b3])     K independent 256-byte class LUT reads
+ *   st  = stepK[st * pitch + idx]                  one dependent read per K bytes
+ * Heads, tails and the re-walk of a sector that died use the single-byte class table.
+ * 8-bit entries, everything in shared memory (a few KB to a few tens of KB).
+ */
+template <int K, bool HAS_DEAD>
+__global__ void __launch_bounds__(1024, 1)
+k1_kstride_kernel(const K1Args a)
+{
+	extern __shared__ __align__(1024) uint8_t smem[];
+	__shared__ uint64_t blob_bar;
+	stage_blob(smem, a.kblob, a.kblob_bytes, &blob_bar);
+
+	const uint8_t *tk = smem;
+	const uint8_t *t1 = smem + a.k1_off;
+	const uint8_t *is_end = smem + a.kend_off;
+	const uint8_t *L0 = smem + a.klut_off, *L1 = L0 + 256, *L2 = L0 + 512, *L3 = L0 + 768;
+	const uint32_t kp = a.kpitch, p1 = a.k1pitch;
+#define STEP1(st, b) ((uint32_t) t1[(st) * p1 + L0[(b)]])
+
+	const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += nthreads) {
+		uint64_t beg, len;
+		if (a.offsets != nullptr) {
+			beg = a.offsets[i];
+			len = (a.ends != nullptr ? a.ends[i] : a.offsets[i + 1]) - beg;
+		} else {
+			beg = i * a.stride;
+			len = a.len;
+		}
+		const uint8_t *p = a.base + beg;
+		uint32_t st = a.entry != nullptr ? a.entry[i] : a.start;
+		uint64_t pos = 0;
+		bool died = false;
+
+		uint64_t head = (uint64_t) ((32u - (uint32_t) (reinterpret_cast<uintptr_t>(p) & 31u)) & 31u);
+		if (head > len) head = len;
+		for (; pos < head; pos++) {
+			const uint32_t nx = STEP1(st, (uint32_t) __ldg(p + pos));
+			if (HAS_DEAD && nx == a.dead) { died = true; break; }
+			st = nx;
+		}
+		if (!died) {
+			uint64_t nchunk = (len - pos) >> 5;
+			uint32_t cur[8], nxt[8];
+			if (nchunk > 0) ld256(p + pos, cur);
+			for (uint64_t c = 0; c < nchunk; c++) {
+				if (c + 1 < nchunk) {
+					ld256(p + pos + 32, nxt);
+				} else {
+#pragma unroll
+					for (int k = 0; k < 8; k++) nxt[k] = 0;
+				}
+				const uint32_t entry = st;
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					const uint32_t w = cur[k];
+					const uint32_t c0 = L0[__byte_perm(w, 0u, 0x4440u)], c1 = L1[__byte_perm(w, 0u, 0x4441u)];
+					if (K == 4) {
+						const uint32_t c2 = L2[__byte_perm(w, 0u, 0x4442u)], c3 = L3[__byte_perm(w, 0u, 0x4443u)];
+						st = tk[st * kp + (c0 + c1 + c2 + c3)];
+					} else {
+						const uint32_t d0 = L0[__byte_perm(w, 0u, 0x4442u)], d1 = L1[__byte_perm(w, 0u, 0x4443u)];
+						st = tk[st * kp + (c0 + c1)];
+						st = tk[st * kp + (d0 + d1)];
+					}
+				}
+				if (HAS_DEAD && st == a.dead) {
+					st = entry;
+					for (int k = 0; k < 32; k++) {
+						const uint32_t nx = STEP1(st, (uint32_t) __ldg(p + pos + k));
+						if (nx == a.dead) { died = true; pos += (uint64_t) k; break; }
+						st = nx;
+					}
+					break;
+				}
+				pos += 32;
+#pragma unroll
+				for (int k = 0; k < 8; k++) cur[k] = nxt[k];
+			}
+		}
+		if (!died) {
+			for (; pos < len; pos++) {
+				const uint32_t nx = STEP1(st, (uint32_t) __ldg(p + pos));
+				if (HAS_DEAD && nx == a.dead) { died = true; break; }
+				st = nx;
+			}
+		}
+		const int32_t ret = (!died && is_end[st]) ? 1 : 0;
+		store_result(a, i, ret, st, pos);
+	}
+#undef STEP1
+}
+
 /* ------------------------------------------------------------------ TILE variant ---- */
 
 /* Shared memory: [blob, padded to 1024][per warp: NSTAGE stages of 32 x CH bytes][mbarriers] */
@@ -621,6 +719,28 @@ launch_lane(const K1Args &a, int sms, size_t smem_bytes, int block, cudaStream_t
 	return 0;
 }
 
+template <int K, bool HAS_DEAD>
+int
+launch_kstride(const K1Args &a, int sms, cudaStream_t stream)
+{
+	auto kern = k1_kstride_kernel<K, HAS_DEAD>;
+	const size_t smem_bytes = (a.kblob_bytes + 127u) & ~127u;
+	if (!set_smem(kern, smem_bytes)) {
+		set_error("k1_kstride: cannot opt in to %zu bytes of shared memory", smem_bytes);
+		errno = EIO;
+		return -1;
+	}
+	const int block = 1024;
+	uint64_t want = (a.n + (uint64_t) block - 1) / (uint64_t) block;
+	uint64_t grid = (uint64_t) sms;
+	if (want < grid) grid = want;
+	if (grid == 0) grid = 1;
+	kern<<<(unsigned) grid, block, smem_bytes, stream>>>(a);
+	count_launch();
+	FSMB_CUDA(cudaGetLastError(), return -1);
+	return 0;
+}
+
 template <typename E, bool HAS_DEAD, int CH, int NSTAGE>
 int
 launch_tile(K1Args a, int sms, int smem_optin, cudaStream_t stream)
@@ -699,6 +819,9 @@ fill_args(K1Args &a, const fsm_b200_dfa *dfa)
 	a.is_end_off = dfa->is_end_off;
 	a.cls_off = dfa->cls_off;
 	a.pitch = dfa->pitch; a.start = dfa->start; a.dead = dfa->dead;
+	a.kblob = static_cast<const uint8_t *>(dfa->d_kblob);
+	a.kblob_bytes = dfa->kblob_bytes; a.kpitch = dfa->kpitch; a.k1pitch = dfa->k1pitch;
+	a.k1_off = dfa->k1_off; a.kend_off = dfa->kend_off; a.klut_off = dfa->klut_off;
 }
 
 template <typename E, bool SMEM, bool HAS_DEAD, bool CLS>
@@ -783,6 +906,11 @@ k1_launch_jobs(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d
 	fill_args(a, dfa);
 	a.base = d_base; a.offsets = d_begs; a.ends = d_ends; a.entry = d_entry; a.n = n; a.out = d_out;
 	a.prefer_lane = 1;
+	if (dfa->kstride != 0 && getenv("FSM_B200_STREAM_NO_KSTRIDE") == nullptr) {
+		const bool dead = !dfa->complete;
+		if (dfa->kstride == 4) return dead ? launch_kstride<4, true>(a, sms, stream) : launch_kstride<4, false>(a, sms, stream);
+		return dead ? launch_kstride<2, true>(a, sms, stream) : launch_kstride<2, false>(a, sms, stream);
+	}
 	return dispatch_lane(dfa, a, sms, stream);
 }
 
@@ -816,15 +944,27 @@ k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offs
 		 * distributions -- both saturate the L1TEX data pipe (ncu: l1tex 97 %), and LANE also
 		 * takes ragged/unaligned batches.  FSM_B200_K1_VARIANT overrides. */
 		variant = K1_LANE;
+		/* fixed-stride batches on DFAs with few byte classes: one lookup per K bytes */
+		if (dfa->kstride != 0 && d_offsets == nullptr) variant = K1_KSTRIDE;
 		if (const char *e = getenv("FSM_B200_K1_VARIANT")) {
 			const int v = atoi(e);
-			if (v > K1_AUTO && v < K1_VARIANT_COUNT && (v == K1_LANE || tile_ok)) variant = v;
+			if (v > K1_AUTO && v < K1_VARIANT_COUNT &&
+			    (v == K1_LANE || (v == K1_KSTRIDE && dfa->kstride != 0) || (v != K1_KSTRIDE && tile_ok))) variant = v;
 		}
 	}
 	const bool dead = !dfa->complete;
 
 	if (variant == K1_LANE) {
 		return dispatch_lane(dfa, a, sms, stream);
+	}
+	if (variant == K1_KSTRIDE) {
+		if (dfa->kstride == 0) {
+			set_error("k1: this DFA has no k-stride table (more than 16 byte classes or more than 256 rows)");
+			errno = ENOTSUP;
+			return -1;
+		}
+		if (dfa->kstride == 4) return dead ? launch_kstride<4, true>(a, sms, stream) : launch_kstride<4, false>(a, sms, stream);
+		return dead ? launch_kstride<2, true>(a, sms, stream) : launch_kstride<2, false>(a, sms, stream);
 	}
 
 	if (!tile_ok) {

@@ -13,6 +13,7 @@ enum K1Variant {
 	K1_TILE32 = 3,     /* warp tile 32 x 32 B, 4-stage TMA ring */
 	K1_TILE128 = 4,    /* warp tile 32 x 128 B, 2-stage TMA ring (fewer warps) */
 	K1_TILE64x3 = 5,   /* warp tile 32 x 64 B, 3-stage TMA ring (fewer warps) */
+	K1_KSTRIDE = 6,    /* lane-per-input, one table lookup per K bytes via byte-class tuples */
 	K1_VARIANT_COUNT
 };
 
@@ -33,6 +34,9 @@ struct K1Args {
 	uint32_t pitch;
 	uint32_t start;
 	uint32_t dead;
+	/* k-stride kernels */
+	const uint8_t *kblob;
+	uint32_t kblob_bytes, kpitch, k1pitch, k1_off, kend_off, klut_off;
 	uint32_t prefer_lane;       /* K1b jobs: long inputs, keep the 3-instructions-per-byte LANE kernel */
 	uint32_t tile_stage_off;    /* TILE variants: shared-memory carve-up */
 	uint32_t tile_bar_off;

@@ -19,7 +19,7 @@ from . import _native
 from ._native import lib, check, CDfaInfo, CDetStats
 from .desc import FlatFsm, COwnedDesc, CResult, RESULT_DTYPE
 
-VARIANTS = {"auto": 0, "lane": 1, "tile64": 2, "tile32": 3, "tile128": 4, "tile64x3": 5}
+VARIANTS = {"auto": 0, "lane": 1, "tile64": 2, "tile32": 3, "tile128": 4, "tile64x3": 5, "kstride": 6}
 
 
 def device_count() -> int:

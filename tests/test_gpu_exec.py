@@ -78,7 +78,7 @@ def test_device_table_matches_oracle_flatten(oracle, case):
 
 
 @pytest.mark.parametrize("adversarial", [False, True])
-@pytest.mark.parametrize("variant", ("lane",) + TILE_VARIANTS)
+@pytest.mark.parametrize("variant", ("lane", "kstride") + TILE_VARIANTS)
 def test_cfg2_fixed_stride_all_variants(torch_cuda, oracle, variant, adversarial):
     torch = torch_cuda
     fsm = BY_NAME["cfg2:uniform"]["fsm"]
@@ -94,7 +94,7 @@ def test_cfg2_fixed_stride_all_variants(torch_cuda, oracle, variant, adversarial
         assert_records_equal(L.results_from_torch(out), want, variant)
 
 
-@pytest.mark.parametrize("variant", ("lane",) + TILE_VARIANTS)
+@pytest.mark.parametrize("variant", ("lane", "kstride") + TILE_VARIANTS)
 @pytest.mark.parametrize("length,stride", [(1, 16), (15, 16), (16, 16), (17, 32), (63, 64), (64, 64), (65, 80),
                                            (127, 128), (200, 208), (1000, 1008), (4096 + 48, 4096 + 48)])
 def test_odd_lengths_and_strides(torch_cuda, oracle, variant, length, stride):
@@ -118,7 +118,7 @@ def test_odd_lengths_and_strides(torch_cuda, oracle, variant, length, stride):
 
 
 @pytest.mark.parametrize("name", ["anchored:^abc[0-9]+x$", "anchored:^[a-f0-9]{32}$", "utf8:", "union6:", "cfg1:digits"])
-@pytest.mark.parametrize("variant", ("lane", "tile64", "tile32"))
+@pytest.mark.parametrize("variant", ("lane", "tile64", "tile32", "kstride", "auto"))
 def test_dead_states_and_wide_tables_fixed_stride(torch_cuda, oracle, name, variant):
     """Incomplete DFAs (inputs die mid-way: consumed offset + stop state), the 16-bit-entry
     table (>256 states: L2-resident, lane variant only) and the UTF-8 validator."""
@@ -139,7 +139,9 @@ def test_dead_states_and_wide_tables_fixed_stride(torch_cuda, oracle, name, vari
     with L.Dfa(fsm) as dfa:
         L.set_exec_variant(variant)
         dev = torch.from_numpy(host).cuda()
-        if variant != "lane" and (not dfa.info["smem_resident"] or dfa.info["nclasses"]):
+        unsupported = (variant.startswith("tile") and (not dfa.info["smem_resident"] or dfa.info["nclasses"])) or \
+            (variant == "kstride" and dfa.info["kstride"] == 0)
+        if unsupported:
             with pytest.raises(L.FsmB200Error) as ei:
                 dfa.exec_batch(dev, stride=length, length=length, n=n)
             assert ei.value.errno == errno.ENOTSUP
@@ -148,6 +150,14 @@ def test_dead_states_and_wide_tables_fixed_stride(torch_cuda, oracle, name, vari
         torch.cuda.synchronize()
         assert_records_equal(L.results_from_torch(out), want, f"{name} {variant}")
         assert (want["consumed"] < length).any() or fsm.nstates > 256 or name in ("utf8:", "cfg1:digits")
+
+
+def test_kstride_tables_exist_where_expected():
+    expect = {"cfg2:uniform": 4, "cfg1:digits": 4, "anchored:^[a-f0-9]{32}$": 4, "anchored:^abc[0-9]+x$": 2, "union6:": 0}
+    for name, k in expect.items():
+        case = next(c for c in CASES if c["name"].startswith(name))
+        with L.Dfa(case["fsm"]) as dfa:
+            assert dfa.info["kstride"] == k, (name, dfa.info)
 
 
 def test_ragged_offsets_device_path(torch_cuda, oracle):

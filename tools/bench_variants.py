@@ -20,7 +20,7 @@ def main():
     cases = {c["name"]: c for c in goldenio.load_exec_cases(os.path.join(goldenio.GOLDEN_DIR, "golden_exec.npz"))}
     fsm = cases["cfg2:uniform"]["fsm"]
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
-    variants = os.environ.get("VARIANTS", "lane,tile64,tile32,tile128,tile64x3").split(",")
+    variants = os.environ.get("VARIANTS", "kstride,lane,tile64,tile32,tile128,tile64x3").split(",")
     pads = os.environ.get("PADS", "4,0").split(",")
     for adversarial in (False, True):
         dev = workloads.cfg2_device(n, length, adversarial, seed=42)
