@@ -315,6 +315,12 @@ def main():
     peaks, peak_src = measured_peaks()
     achieved = bytes_step / (kernel_ms / 1e3) / 1e9
 
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_k1_traffic.json")
+    if os.path.exists(tp) and args.dist == "uniform":
+        tj = json.load(open(tp))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        traffic_src = f"{tj['source']}: dram__bytes_read.sum + dram__bytes_write.sum per launch of {tj['kernel']}"
     line = None
     if rank == 0:
         threads = os.cpu_count() or 1
@@ -339,7 +345,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src,
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_step,
-                         "traffic": 1.0918e9, "traffic_source": "profiles/r1_k1_lane_uniform_ncu_full.txt (dram read+write per launch)"},
+                         "traffic": traffic, "traffic_source": traffic_src},
             "cpu_baseline": {"value": cpu["asis_gbs"], "unit": "GB/s", "cores": threads, "kind": cpu["kind"],
                              "sample": f"{sample_n} x {LENGTH} B inputs, same distribution; reference fsm_exec per input (as-is)",
                              "amortised_value": cpu["amortised_gbs"]},

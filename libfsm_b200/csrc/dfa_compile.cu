@@ -231,10 +231,12 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa 
 			for (uint32_t j = 0; j < K; j++) W *= KC;
 			auto odd_pitch = [](uint32_t nbytes) { uint32_t p = (nbytes + 3u) & ~3u; if (((p >> 2) & 1u) == 0) p += 4; return p; };
 			const uint32_t kpitch = odd_pitch(W), k1pitch = odd_pitch(KC);
-			const uint32_t k1_off = (T * kpitch + 15u) & ~15u;
+			/* blob: [K class LUTs of 256 B][stepK rows][step1 rows][is_end]; the LUTs and stepK sit
+			 * at compile-time offsets so every lookup is LDS [reg + uniform base + immediate] */
+			const uint32_t klut_off = 0, ktab_off = 256u * K;
+			const uint32_t k1_off = (ktab_off + T * kpitch + 15u) & ~15u;
 			const uint32_t kend_off = (k1_off + T * k1pitch + 15u) & ~15u;
-			const uint32_t klut_off = (kend_off + T + 15u) & ~15u;
-			const uint32_t kbytes = klut_off + 256u * K;
+			const uint32_t kbytes = (kend_off + T + 15u) & ~15u;
 			std::vector<uint8_t> kb(kbytes, 0);
 			auto step1 = [&](uint32_t st, uint32_t cls) -> uint32_t {
 				if (st >= S) return dfa->dead;
@@ -246,7 +248,7 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa 
 				for (uint32_t idx = 0; idx < W; idx++) {
 					uint32_t cur = st, rem = idx;
 					for (uint32_t j = 0; j < K; j++) { cur = step1(cur, rem % KC); rem /= KC; }   /* byte j has weight C^j */
-					kb[st * kpitch + idx] = (uint8_t) cur;
+					kb[ktab_off + st * kpitch + idx] = (uint8_t) cur;
 				}
 				kb[kend_off + st] = dfa->h_is_end[st];
 			}

@@ -453,10 +453,11 @@ k1_kstride_kernel(const K1Args a)
 	__shared__ uint64_t blob_bar;
 	stage_blob(smem, a.kblob, a.kblob_bytes, &blob_bar);
 
-	const uint8_t *tk = smem;
+	/* blob layout: [K LUTs][stepK rows][step1 rows][is_end] (dfa_compile.cu) */
+	const uint8_t *L0 = smem, *L1 = smem + 256, *L2 = smem + 512, *L3 = smem + 768;
+	const uint8_t *tk = smem + 256 * K;
 	const uint8_t *t1 = smem + a.k1_off;
 	const uint8_t *is_end = smem + a.kend_off;
-	const uint8_t *L0 = smem + a.klut_off, *L1 = L0 + 256, *L2 = L0 + 512, *L3 = L0 + 768;
 	const uint32_t kp = a.kpitch, p1 = a.k1pitch;
 #define STEP1(st, b) ((uint32_t) t1[(st) * p1 + L0[(b)]])
 
