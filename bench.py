@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def result(self):
         if not self.samples:

@@ -191,7 +191,8 @@ k1_lane_kernel(const K1Args a)
 	} while (0)
 
 	const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
-	for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += nthreads) {
+	const uint64_t n_inputs = a.n_dev != nullptr ? (uint64_t) *a.n_dev : a.n;
+	for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_inputs; i += nthreads) {
 		uint64_t beg, len;
 		if (a.offsets != nullptr) {
 			beg = a.offsets[i];
@@ -462,7 +463,8 @@ k1_kstride_kernel(const K1Args a)
 #define STEP1(st, b) ((uint32_t) t1[(st) * p1 + L0[(b)]])
 
 	const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
-	for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += nthreads) {
+	const uint64_t n_inputs = a.n_dev != nullptr ? (uint64_t) *a.n_dev : a.n;
+	for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_inputs; i += nthreads) {
 		uint64_t beg, len;
 		if (a.offsets != nullptr) {
 			beg = a.offsets[i];
@@ -894,7 +896,8 @@ dispatch_lane(const fsm_b200_dfa *dfa, const K1Args &a, int sms, cudaStream_t st
 
 int
 k1_launch_jobs(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_begs,
-	const uint64_t *d_ends, const uint32_t *d_entry, size_t n, fsm_b200_result *d_out, cudaStream_t stream)
+	const uint64_t *d_ends, const uint32_t *d_entry, size_t n, const uint32_t *d_n,
+	fsm_b200_result *d_out, cudaStream_t stream)
 {
 	if (n == 0) return 0;
 	int sms = 0, smem_optin = 0;
@@ -905,7 +908,7 @@ k1_launch_jobs(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d
 	}
 	K1Args a;
 	fill_args(a, dfa);
-	a.base = d_base; a.offsets = d_begs; a.ends = d_ends; a.entry = d_entry; a.n = n; a.out = d_out;
+	a.base = d_base; a.offsets = d_begs; a.ends = d_ends; a.entry = d_entry; a.n = n; a.n_dev = d_n; a.out = d_out;
 	a.prefer_lane = 1;
 	if (dfa->kstride != 0 && getenv("FSM_B200_STREAM_NO_KSTRIDE") == nullptr) {
 		const bool dead = !dfa->complete;

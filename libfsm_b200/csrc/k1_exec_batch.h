@@ -24,6 +24,7 @@ struct K1Args {
 	const uint32_t *entry;      /* optional: per-input entry state (K1b jobs), else `start` */
 	uint64_t stride, len;
 	uint64_t n;
+	const uint32_t *n_dev;      /* optional: actual input count lives on the device (<= n) */
 	fsm_b200_result *out;        /* result i -> out[i] ... */
 	fsm_b200_result *peer_out[7]; /* ... and, fused gather, -> peer_out[r][i] over NVLink P2P */
 	uint32_t npeers;
@@ -51,7 +52,8 @@ int k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_
 
 /* K1b jobs: input i = d_base[d_begs[i] .. d_ends[i]) walked from state d_entry[i] (LANE variant). */
 int k1_launch_jobs(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_begs,
-	const uint64_t *d_ends, const uint32_t *d_entry, size_t n, fsm_b200_result *d_out, cudaStream_t stream);
+	const uint64_t *d_ends, const uint32_t *d_entry, size_t n_max, const uint32_t *d_n,
+	fsm_b200_result *d_out, cudaStream_t stream);
 
 } // namespace fsmb200
 #endif

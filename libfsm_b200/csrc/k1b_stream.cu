@@ -9,13 +9,16 @@
  *   1. prefix   thread (chunk c, state s): walk the first W bytes of c from s
  *               -> img[c][s] (or "died": offset + state it died in).  Chains from wrong entry
  *               states die or merge within a few bytes for practical DFAs, so few distinct
- *               live images survive per chunk (1 for the config-2 and UTF-8 DFAs).
- *   2. reps     one job per DISTINCT live image (c, v): the rest of chunk c walked from v.
- *   3. body     the K1 LANE kernel over the jobs (one lane per job, 256-bit loads, table in
- *               shared memory) -- this is where the bytes are scanned, at K1 speed.
- *   4. cmap     next[c][s] = exit of job(c, img[c][s]), plus first-dead offset / state.
- *   5. compose  two-level composition of the chunk maps in chunk order (level 1: groups of G
- *               maps in shared memory, one thread per entry state; level 2: over groups).
+ *               live images survive per chunk (1 for the config-2 and UTF-8 DFAs).  The first
+ *               thread to reach a live image (c, v) claims it (atomicCAS) and appends ONE job:
+ *               the rest of chunk c walked from v.
+ *   2. body     the K1 kernels over the jobs (one lane per job, 256-bit loads, table in shared
+ *               memory; k-stride when the DFA has one) -- this is where the bytes are scanned,
+ *               at K1 speed.  The job count stays on the device (no host round trip).
+ *   3. compose  two-level composition of the chunk maps in chunk order.  Level 1 (one block
+ *               per group of G chunks) builds next[c][s] = exit of job(c, img[c][s]) on the fly
+ *               in shared memory and folds the group, one thread per entry state; level 2
+ *               folds the groups.  First-dead offset / dead-from state are resolved lazily.
  *
  * The result is the map entry-state -> (exit state | first dead offset + dead-from state)
  * of the whole range: exec_stream uses entry = start; the multi-GPU shard form all-gathers
@@ -39,6 +42,7 @@ namespace {
 constexpr uint32_t DEADMARK = 0xFFFFFFFFu;
 constexpr uint16_t DEAD16 = 0xFFFFu;
 constexpr uint32_t PREFIX_W = 64;
+constexpr uint32_t NOJOB = 0xFFFFFFFFu;
 
 struct StreamArgs {
 	const uint8_t *buf;
@@ -50,11 +54,7 @@ struct StreamArgs {
 	uint32_t blob_bytes, pitch, dead;
 	/* per (chunk, state) */
 	uint32_t *img, *pdo, *pdf;
-	uint8_t *live;
-	uint32_t *job_of;
-	uint16_t *next;
-	uint64_t *dead_off;
-	uint32_t *dead_from;
+	uint32_t *job_of;      /* [chunk][image state] -> job index; NOJOB / PENDING while unclaimed */
 	/* jobs */
 	uint64_t *job_beg, *job_end;
 	uint32_t *job_entry;
@@ -99,8 +99,10 @@ stage_blob(uint8_t *smem, const uint8_t *blob, uint32_t blob_bytes, uint64_t *ba
 }
 
 /* 1. prefix: thread per (chunk, entry state).  Lanes of a warp share the chunk (same bytes:
- * broadcast loads) and hold consecutive states (row pitch 260 B: distinct banks). */
-__global__ void __launch_bounds__(1024, 1)
+ * broadcast loads, independent of the state so the unrolled loop batches them) and hold
+ * consecutive states (row pitch 260 B: distinct banks).  The dead row absorbs, so there is
+ * no early exit; the first death is recorded with selects. */
+__global__ void __launch_bounds__(1024, 2)
 k1b_prefix_kernel(const StreamArgs a)
 {
 	extern __shared__ __align__(1024) uint8_t smem[];
@@ -115,79 +117,75 @@ k1b_prefix_kernel(const StreamArgs a)
 		const uint64_t clen = min(a.C, a.len - beg);
 		const uint32_t w = (uint32_t) min((uint64_t) PREFIX_W, clen);
 		const uint8_t *p = a.buf + beg;
-		uint32_t st = s, k = 0;
+		uint32_t st = s, dk = 0, df = s;
 		bool died = false;
-		for (; k < w; k++) {
-			const uint32_t nx = smem[st * a.pitch + __ldg(p + k)];
-			if (nx == a.dead) { died = true; break; }
-			st = nx;
+		if (w == PREFIX_W) {
+#pragma unroll 16
+			for (uint32_t k = 0; k < PREFIX_W; k++) {
+				const uint32_t nx = smem[st * a.pitch + __ldg(p + k)];
+				const bool hit = !died && nx == a.dead;
+				dk = hit ? k : dk;
+				df = hit ? st : df;
+				died = died || hit;
+				st = nx;
+			}
+		} else {
+			for (uint32_t k = 0; k < w; k++) {
+				const uint32_t nx = smem[st * a.pitch + __ldg(p + k)];
+				if (nx == a.dead) { died = true; dk = k; df = st; break; }
+				st = nx;
+			}
 		}
 		if (died) {
-			a.img[idx] = DEADMARK; a.pdo[idx] = k; a.pdf[idx] = st;
+			a.img[idx] = DEADMARK; a.pdo[idx] = dk; a.pdf[idx] = df;
 		} else {
 			a.img[idx] = st;
-			a.live[(uint64_t) c * a.T + st] = 1;      /* benign race: all writers store 1 */
+			/* first thread to produce the live image (c, st) appends its job */
+			uint32_t *slot = &a.job_of[(uint64_t) c * a.T + st];
+			if (atomicCAS(slot, NOJOB, NOJOB - 1u) == NOJOB) {
+				const uint32_t j = atomicAdd(a.njobs, 1u);
+				a.job_beg[j] = beg + w;
+				a.job_end[j] = beg + clen;
+				a.job_entry[j] = st;
+				*slot = j;                      /* read by the compose kernels (later launches) */
+			}
 		}
 	}
 }
 
-/* 2. reps: one job per distinct live image. */
-__global__ void
-k1b_reps_kernel(const StreamArgs a)
+/* The chunk map, evaluated lazily: where does chunk c take entry state s?
+ * Returns the exit state, or DEAD16 with the global first-dead offset and dead-from state. */
+__device__ __forceinline__ uint16_t
+chunk_next(const StreamArgs &a, uint32_t c, uint32_t s, uint64_t *dead_off, uint32_t *dead_from)
 {
-	const uint64_t total = (uint64_t) a.nchunks * a.T;
-	const uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= total || !a.live[idx]) return;
-	const uint32_t c = (uint32_t) (idx / a.T), v = (uint32_t) (idx % a.T);
-	const uint64_t beg = (uint64_t) c * a.C;
-	const uint64_t clen = min(a.C, a.len - beg);
-	const uint64_t w = min((uint64_t) PREFIX_W, clen);
-	const uint32_t j = atomicAdd(a.njobs, 1u);
-	a.job_of[idx] = j;
-	a.job_beg[j] = beg + w;
-	a.job_end[j] = beg + clen;
-	a.job_entry[j] = v;
-}
-
-/* 4. cmap: the chunk's full map, with first-dead bookkeeping. */
-__global__ void
-k1b_cmap_kernel(const StreamArgs a)
-{
-	const uint64_t total = (uint64_t) a.nchunks * a.T;
-	const uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= total) return;
-	const uint32_t c = (uint32_t) (idx / a.T);
-	const uint64_t beg = (uint64_t) c * a.C;
+	const uint64_t idx = (uint64_t) c * a.T + s;
 	const uint32_t v = a.img[idx];
 	if (v == DEADMARK) {
-		a.next[idx] = DEAD16;
-		a.dead_off[idx] = beg + a.pdo[idx];
-		a.dead_from[idx] = a.pdf[idx];
-		return;
+		if (dead_off) { *dead_off = (uint64_t) c * a.C + a.pdo[idx]; *dead_from = a.pdf[idx]; }
+		return DEAD16;
 	}
 	const uint32_t j = a.job_of[(uint64_t) c * a.T + v];
 	const fsm_b200_result r = a.rec[j];
-	const uint64_t jlen = a.job_end[j] - a.job_beg[j];
+	const uint64_t jb = a.job_beg[j], jlen = a.job_end[j] - jb;
 	if (r.consumed < jlen) {                 /* the body walk hit a missing edge */
-		a.next[idx] = DEAD16;
-		a.dead_off[idx] = a.job_beg[j] + r.consumed;
-		a.dead_from[idx] = r.end;
-	} else {
-		a.next[idx] = (uint16_t) r.end;
+		if (dead_off) { *dead_off = jb + r.consumed; *dead_from = r.end; }
+		return DEAD16;
 	}
+	return (uint16_t) r.end;
 }
 
-/* 5. compose, level 1: block b folds chunks [b*G, b*G+G) for every entry state.
+/* 3. compose, level 1: block b folds chunks [b*G, b*G+G) for every entry state.
  * gnext[b][s] = exit or DEAD16; on death gchunk/gstate say where (chunk, state entering it). */
 __global__ void
-k1b_compose1_kernel(const uint16_t *next, uint32_t nchunks, uint32_t T, uint32_t G,
-	uint16_t *gnext, uint32_t *gchunk, uint32_t *gstate)
+k1b_compose1_kernel(const StreamArgs a, uint32_t G, uint16_t *gnext, uint32_t *gchunk, uint32_t *gstate)
 {
 	extern __shared__ __align__(16) uint16_t sm[];
+	const uint32_t T = a.T;
 	const uint32_t c0 = blockIdx.x * G;
-	const uint32_t cn = min(G, nchunks - c0);
-	const uint64_t base = (uint64_t) c0 * T;
-	for (uint32_t i = threadIdx.x; i < cn * T; i += blockDim.x) sm[i] = next[base + i];
+	const uint32_t cn = min(G, a.nchunks - c0);
+	for (uint32_t i = threadIdx.x; i < cn * T; i += blockDim.x) {
+		sm[i] = chunk_next(a, c0 + i / T, i % T, nullptr, nullptr);
+	}
 	__syncthreads();
 	for (uint32_t s = threadIdx.x; s < T; s += blockDim.x) {
 		uint32_t st = s, dc = 0xFFFFFFFFu, ds = 0;
@@ -208,22 +206,30 @@ struct StreamOut {          /* per entry state, [T] */
 	uint64_t dead_off;      /* offset within the range of the first byte without an edge */
 };
 
-/* 5. compose, level 2: one thread per entry state folds the group maps in order. */
+/* 3. compose, level 2: one thread per entry state folds the group maps in order. */
 __global__ void
-k1b_compose2_kernel(const uint16_t *gnext, const uint32_t *gchunk, const uint32_t *gstate,
-	uint32_t ngroups, uint32_t T, const uint64_t *dead_off, const uint32_t *dead_from, StreamOut *out)
+k1b_compose2_kernel(const StreamArgs a, const uint16_t *gnext, const uint32_t *gchunk, const uint32_t *gstate,
+	uint32_t ngroups, uint32_t smem_groups, StreamOut *out)
 {
+	extern __shared__ __align__(16) uint16_t sm[];
+	const uint32_t T = a.T;
+	const bool staged = smem_groups != 0;            /* single block: group maps fit shared memory */
+	if (staged) {
+		for (uint64_t i = threadIdx.x; i < (uint64_t) ngroups * T; i += blockDim.x) sm[i] = gnext[i];
+		__syncthreads();
+	}
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= T) return;
 	uint32_t st = s;
 	for (uint32_t g = 0; g < ngroups; g++) {
 		const uint64_t i = (uint64_t) g * T + st;
-		const uint16_t nx = gnext[i];
+		const uint16_t nx = staged ? sm[i] : gnext[i];
 		if (nx == DEAD16) {
-			const uint64_t at = (uint64_t) gchunk[i] * T + gstate[i];
-			out[s].state = dead_from[at];
+			uint64_t off = 0; uint32_t from = 0;
+			(void) chunk_next(a, gchunk[i], gstate[i], &off, &from);
+			out[s].state = from;
 			out[s].died = 1;
-			out[s].dead_off = dead_off[at];
+			out[s].dead_off = off;
 			return;
 		}
 		st = nx;
@@ -294,13 +300,14 @@ stream_map(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStre
 	const uint64_t C = pick_chunk(T, len, sms);
 	const uint32_t nchunks = (uint32_t) ((len + C - 1) / C);
 	const uint64_t cs = (uint64_t) nchunks * T;
-	uint32_t G = 32768u / T;
-	if (G > 1024) G = 1024;
+	/* level-1 groups: small enough that many blocks run (G <= 256) and G*T*2 B fits 32 KB */
+	uint32_t G = 16384u / T;
+	if (G > 256) G = 256;
 	if (G < 1) G = 1;
 	const uint32_t ngroups = (nchunks + G - 1) / G;
 
-	const size_t need = cs * (4 + 4 + 4 + 1 + 4 + 2 + 8 + 4) + cs * (8 + 8 + 4 + 16) +
-	    (size_t) ngroups * T * (2 + 4 + 4) + T * sizeof(StreamOut) + 64 * 256 + 4096;
+	const size_t need = cs * (4 + 4 + 4 + 4) + cs * (8 + 8 + 4 + 16) +
+	    (size_t) ngroups * T * (2 + 4 + 4) + T * sizeof(StreamOut) + 64 * 256 + 8192;
 	if (ss->arena.cap < need) {
 		if (ss->arena.base) cudaFree(ss->arena.base);
 		ss->arena.base = nullptr; ss->arena.cap = 0;
@@ -318,8 +325,7 @@ stream_map(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStre
 	a.blob = static_cast<const uint8_t *>(dfa->d_blob);
 	a.blob_bytes = (uint32_t) dfa->blob_bytes; a.pitch = dfa->pitch; a.dead = dfa->dead;
 	a.img = ar.take<uint32_t>(cs); a.pdo = ar.take<uint32_t>(cs); a.pdf = ar.take<uint32_t>(cs);
-	a.live = ar.take<uint8_t>(cs); a.job_of = ar.take<uint32_t>(cs); a.next = ar.take<uint16_t>(cs);
-	a.dead_off = ar.take<uint64_t>(cs); a.dead_from = ar.take<uint32_t>(cs);
+	a.job_of = ar.take<uint32_t>(cs);
 	a.job_beg = ar.take<uint64_t>(cs); a.job_end = ar.take<uint64_t>(cs); a.job_entry = ar.take<uint32_t>(cs);
 	fsm_b200_result *rec = ar.take<fsm_b200_result>(cs);
 	a.rec = rec;
@@ -329,31 +335,37 @@ stream_map(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStre
 	uint32_t *gstate = ar.take<uint32_t>((size_t) ngroups * T);
 	StreamOut *d_out = ar.take<StreamOut>(T);
 
-	FSMB_CUDA(cudaMemsetAsync(a.live, 0, cs, stream), return -1);
+	FSMB_CUDA(cudaMemsetAsync(a.job_of, 0xFF, cs * sizeof(uint32_t), stream), return -1);
 	FSMB_CUDA(cudaMemsetAsync(a.njobs, 0, sizeof(uint32_t), stream), return -1);
 
 	const size_t smem_bytes = (dfa->blob_bytes + 127u) & ~(size_t) 127u;
 	FSMB_CUDA(cudaFuncSetAttribute(k1b_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes), return -1);
 	{
+		int per_sm = 1;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1b_prefix_kernel, 1024, smem_bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
 		uint64_t want = (cs + 1023) / 1024;
-		unsigned grid = (unsigned) (want < (uint64_t) sms ? want : (uint64_t) sms);
+		const uint64_t cap = (uint64_t) sms * (uint64_t) per_sm;
+		unsigned grid = (unsigned) (want < cap ? want : cap);
 		k1b_prefix_kernel<<<grid, 1024, smem_bytes, stream>>>(a);
 		count_launch();
 	}
-	k1b_reps_kernel<<<(unsigned) ((cs + 255) / 256), 256, 0, stream>>>(a);
-	count_launch();
-	uint32_t njobs = 0;
-	FSMB_CUDA(cudaMemcpyAsync(&njobs, a.njobs, sizeof njobs, cudaMemcpyDeviceToHost, stream), return -1);
-	FSMB_CUDA(cudaStreamSynchronize(stream), return -1);
-	if (k1_launch_jobs(dfa, d_buf, a.job_beg, a.job_end, a.job_entry, njobs, rec, stream) != 0) return -1;
-	k1b_cmap_kernel<<<(unsigned) ((cs + 255) / 256), 256, 0, stream>>>(a);
-	count_launch();
+	/* body: at most one job per (chunk, state); the actual count is read on the device */
+	if (k1_launch_jobs(dfa, d_buf, a.job_beg, a.job_end, a.job_entry, cs, a.njobs, rec, stream) != 0) return -1;
 	const size_t sm1 = (size_t) G * T * sizeof(uint16_t);
 	FSMB_CUDA(cudaFuncSetAttribute(k1b_compose1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm1), return -1);
-	k1b_compose1_kernel<<<ngroups, 256, sm1, stream>>>(a.next, nchunks, T, G, gnext, gchunk, gstate);
+	k1b_compose1_kernel<<<ngroups, 256, sm1, stream>>>(a, G, gnext, gchunk, gstate);
 	count_launch();
-	k1b_compose2_kernel<<<(T + 255) / 256, 256, 0, stream>>>(gnext, gchunk, gstate, ngroups, T, a.dead_off, a.dead_from, d_out);
-	count_launch();
+	{
+		const size_t sm2 = (size_t) ngroups * T * sizeof(uint16_t);
+		const bool staged = sm2 <= 160 * 1024 && T <= 1024;
+		if (staged) {
+			FSMB_CUDA(cudaFuncSetAttribute(k1b_compose2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm2), return -1);
+			k1b_compose2_kernel<<<1, T < 32 ? 256 : ((T + 31) / 32) * 32 < 256 ? 256 : ((T + 31) / 32) * 32, sm2, stream>>>(a, gnext, gchunk, gstate, ngroups, 1u, d_out);
+		} else {
+			k1b_compose2_kernel<<<(T + 255) / 256, 256, 0, stream>>>(a, gnext, gchunk, gstate, ngroups, 0u, d_out);
+		}
+		count_launch();
+	}
 	FSMB_CUDA(cudaGetLastError(), return -1);
 	h_out.resize(T);
 	FSMB_CUDA(cudaMemcpyAsync(h_out.data(), d_out, T * sizeof(StreamOut), cudaMemcpyDeviceToHost, stream), return -1);

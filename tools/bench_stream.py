@@ -11,7 +11,7 @@ cases = goldenio.load_exec_cases(os.path.join(goldenio.GOLDEN_DIR, "golden_exec.
 def case(p): return next(c for c in cases if c["name"].startswith(p))
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 nbytes = int(os.environ.get("NBYTES", 1 << 31))
-for name in ("utf8:", "cfg2:uniform", "cfg1:digits"):
+for name in os.environ.get("DFAS", "utf8:,cfg2:uniform,cfg1:digits").split(","):
     fsm = case(name)["fsm"]
     if name == "utf8:":
         block = workloads.utf8_host(1 << 24, seed=6)
