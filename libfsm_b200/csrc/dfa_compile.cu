@@ -204,6 +204,21 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa 
 	FSMB_CUDA(cudaMemcpy(dfa->d_blob, blob.data(), dfa->blob_bytes, cudaMemcpyHostToDevice),
 	    { fsm_b200_dfa_free(dfa); return -1; });
 
+	{   /* absorbing states (all 256 edges are self-loops; also the dead row): a stream chunk entered
+	     * in such a state leaves in it, so K1b needs no scan job for it */
+		std::vector<uint8_t> ab(dfa->ntable, 0);
+		for (uint32_t st = 0; st < dfa->ntable; st++) {
+			bool self = true;
+			for (int c = 0; c < 256 && self; c++) {
+				const uint32_t v = st < S ? t32[(size_t) st * 256 + c] : dfa->dead;
+				self = (v == st);
+			}
+			ab[st] = self ? 1 : 0;
+		}
+		FSMB_CUDA(cudaMalloc(&dfa->d_absorb, dfa->ntable), { fsm_b200_dfa_free(dfa); return -1; });
+		FSMB_CUDA(cudaMemcpy(dfa->d_absorb, ab.data(), dfa->ntable, cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
+	}
+
 	/* ---- k-stride form: with C byte classes and C^K <= 256, index rows by the class tuple of
 	 * K consecutive bytes: ONE dependent table lookup per K input bytes.  The K class lookups
 	 * (256-byte LUTs, pre-multiplied by C^j) are independent of the state, conflict-free for
@@ -283,6 +298,7 @@ fsm_b200_dfa_free(fsm_b200_dfa *dfa)
 		cudaFree(dfa->d_blob);
 	}
 	if (dfa->d_kblob != nullptr) cudaFree(dfa->d_kblob);
+	if (dfa->d_absorb != nullptr) cudaFree(dfa->d_absorb);
 	free(dfa->h_table32);
 	free(dfa->h_is_end);
 	delete dfa;

@@ -41,8 +41,9 @@ namespace {
 
 constexpr uint32_t DEADMARK = 0xFFFFFFFFu;
 constexpr uint16_t DEAD16 = 0xFFFFu;
-constexpr uint32_t PREFIX_W = 64;
+constexpr uint32_t PREFIX_W_MAX = 64;
 constexpr uint32_t NOJOB = 0xFFFFFFFFu;
+constexpr uint32_t ABSORBED = 0xFFFFFFFDu;     /* job_of marker: image state is absorbing, no scan needed */
 
 struct StreamArgs {
 	const uint8_t *buf;
@@ -50,6 +51,8 @@ struct StreamArgs {
 	uint64_t C;            /* chunk bytes */
 	uint32_t nchunks;
 	uint32_t T;            /* real states (entry states considered) */
+	uint32_t W;            /* prefix window (bytes) */
+	const uint8_t *absorb; /* [ntable] */
 	const uint8_t *blob;
 	uint32_t blob_bytes, pitch, dead;
 	/* per (chunk, state) */
@@ -115,13 +118,13 @@ k1b_prefix_kernel(const StreamArgs a)
 		const uint32_t c = (uint32_t) (idx / a.T), s = (uint32_t) (idx % a.T);
 		const uint64_t beg = (uint64_t) c * a.C;
 		const uint64_t clen = min(a.C, a.len - beg);
-		const uint32_t w = (uint32_t) min((uint64_t) PREFIX_W, clen);
+		const uint32_t w = (uint32_t) min((uint64_t) a.W, clen);
 		const uint8_t *p = a.buf + beg;
 		uint32_t st = s, dk = 0, df = s;
 		bool died = false;
-		if (w == PREFIX_W) {
+		if (w == a.W) {
 #pragma unroll 16
-			for (uint32_t k = 0; k < PREFIX_W; k++) {
+			for (uint32_t k = 0; k < a.W; k++) {
 				const uint32_t nx = smem[st * a.pitch + __ldg(p + k)];
 				const bool hit = !died && nx == a.dead;
 				dk = hit ? k : dk;
@@ -142,7 +145,9 @@ k1b_prefix_kernel(const StreamArgs a)
 			a.img[idx] = st;
 			/* first thread to produce the live image (c, st) appends its job */
 			uint32_t *slot = &a.job_of[(uint64_t) c * a.T + st];
-			if (atomicCAS(slot, NOJOB, NOJOB - 1u) == NOJOB) {
+			if (a.absorb[st]) {
+				*slot = ABSORBED;               /* leaves the chunk as it entered: no job */
+			} else if (atomicCAS(slot, NOJOB, NOJOB - 1u) == NOJOB) {
 				const uint32_t j = atomicAdd(a.njobs, 1u);
 				a.job_beg[j] = beg + w;
 				a.job_end[j] = beg + clen;
@@ -165,6 +170,7 @@ chunk_next(const StreamArgs &a, uint32_t c, uint32_t s, uint64_t *dead_off, uint
 		return DEAD16;
 	}
 	const uint32_t j = a.job_of[(uint64_t) c * a.T + v];
+	if (j == ABSORBED) return (uint16_t) v;
 	const fsm_b200_result r = a.rec[j];
 	const uint64_t jb = a.job_beg[j], jlen = a.job_end[j] - jb;
 	if (r.consumed < jlen) {                 /* the body walk hit a missing edge */
@@ -270,15 +276,30 @@ ss_get(const fsm_b200_dfa *cdfa)
 	return static_cast<StreamScratch *>(dfa->stream_scratch);
 }
 
+uint32_t
+pick_window(uint32_t T)
+{
+	/* chains from wrong entry states merge or die within a few bytes for practical DFAs; a
+	 * shorter window for big tables keeps the T x W prefix walks cheap (a chain that has not
+	 * merged yet only costs an extra job, never exactness) */
+	uint32_t w = T <= 16 ? 64u : (T <= 64 ? 32u : 16u);
+	if (const char *e = getenv("FSM_B200_STREAM_WINDOW")) {
+		const int v = atoi(e);
+		if (v >= 1 && v <= (int) PREFIX_W_MAX) w = (uint32_t) v;
+	}
+	return w;
+}
+
 size_t
-pick_chunk(uint32_t T, uint64_t len, int sms)
+pick_chunk(uint32_t T, uint32_t W, uint64_t len, int sms)
 {
 	/* One body job per lane and about two waves of lanes (measured on B200, 2 GiB of UTF-8:
 	 * 2 KiB chunks 1.39 TB/s, 8 KiB 2.07 TB/s, 32 KiB 0.99 TB/s -- profiles/r1_k1b_stream.jsonl);
 	 * never so small that the T x W prefix walks outweigh the body. */
 	const uint64_t lanes = 2ull * (uint64_t) (sms > 0 ? sms : 148) * 1024ull;
 	uint64_t lo = 2048;
-	while (lo < 2ull * T * PREFIX_W) lo <<= 1;
+	(void) W;
+	while (lo < 128ull * T) lo <<= 1;      /* per-chunk bookkeeping (T map entries) must stay small next to the chunk */
 	uint64_t c = lo;
 	while (c < (1ull << 22) && len / c > lanes) c <<= 1;
 	if (const char *e = getenv("FSM_B200_STREAM_CHUNK")) {
@@ -297,7 +318,8 @@ stream_map(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStre
 	const uint32_t T = dfa->nstates;
 	int sms = 0;
 	FSMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dfa->device), return -1);
-	const uint64_t C = pick_chunk(T, len, sms);
+	const uint32_t W = pick_window(T);
+	const uint64_t C = pick_chunk(T, W, len, sms);
 	const uint32_t nchunks = (uint32_t) ((len + C - 1) / C);
 	const uint64_t cs = (uint64_t) nchunks * T;
 	/* level-1 groups: small enough that many blocks run (G <= 256) and G*T*2 B fits 32 KB */
@@ -321,7 +343,7 @@ stream_map(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStre
 
 	StreamArgs a;
 	memset(&a, 0, sizeof a);
-	a.buf = d_buf; a.len = len; a.C = C; a.nchunks = nchunks; a.T = T;
+	a.buf = d_buf; a.len = len; a.C = C; a.nchunks = nchunks; a.T = T; a.W = W; a.absorb = dfa->d_absorb;
 	a.blob = static_cast<const uint8_t *>(dfa->d_blob);
 	a.blob_bytes = (uint32_t) dfa->blob_bytes; a.pitch = dfa->pitch; a.dead = dfa->dead;
 	a.img = ar.take<uint32_t>(cs); a.pdo = ar.take<uint32_t>(cs); a.pdf = ar.take<uint32_t>(cs);
@@ -382,7 +404,7 @@ parallel_ok(const fsm_b200_dfa *dfa, uint64_t len)
 		const long v = atol(e);
 		if (v >= 0) min_len = (uint64_t) v;
 	}
-	return len >= min_len && len >= 2 * PREFIX_W;
+	return len >= min_len && len >= 2 * PREFIX_W_MAX;
 }
 
 /* Serial form: a K1 batch of one (correct for any table size). */
