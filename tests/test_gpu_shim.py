@@ -116,3 +116,16 @@ def test_fsm_cli_determinise_like_the_reference_tests(tmp_path):
         assert cnt[0] == cnt[1], c["name"]
         ran += 1
     assert ran >= 10
+
+
+SELFTEST = os.path.join(ROOT, "build", "shim", "shim_selftest")
+
+
+@pytest.mark.skipif(not os.path.exists(SELFTEST), reason="shim selftest not built")
+def test_shim_selftest_c_program():
+    """A C program using only libfsm's API (re_comp, fsm_determinise, fsm_minimise,
+    fsm_union_array, fsm_exec, fsm_endid_get) plus the additive fsm_exec_batch, linked to the
+    shim: determinise runs through K2, exec through K1/K1b; see libfsm_b200/shim/shim_selftest.c."""
+    p = subprocess.run([SELFTEST], capture_output=True, timeout=300)
+    assert p.returncode == 0, (p.stdout.decode(), p.stderr.decode())
+    assert b"shim selftest ok" in p.stdout
