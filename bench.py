@@ -159,6 +159,8 @@ def main():
     ap.add_argument("--dist", default="uniform", choices=["uniform", "adversarial"])
     ap.add_argument("--variant", default="auto")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--gather-records", default="compact", choices=["compact", "full"],
+                    help="fused gather payload: compact = 4-byte match ids ((ret==1)<<31 | end), full = 16-byte records")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N>1: fused = scanning lanes store records into every peer's buffer over NVLink P2P; "
                          "nccl = one NCCL all-gather per step on a side stream")
@@ -198,11 +200,18 @@ def main():
     main_stream = torch.cuda.current_stream()
     gather_done = [None] * nbuf
     ring = None
+    compact = False
     token = torch.zeros(1, dtype=torch.int32, device=dev)
     if fused:
         from libfsm_b200.peer import GatherRing
-        ring = GatherRing(n, world, rank, local, nbuf)
+        compact = args.gather_records == "compact"
+        ring = GatherRing(n, world, rank, local, nbuf, elem_bytes=4 if compact else 16)
         peer_args = [ring.peer_slot_ptrs(b) for b in range(nbuf)]
+        own_out = [torch.empty((n, 16), dtype=torch.uint8, device=dev) for _ in range(nbuf)] if compact else None
+
+    def local_out_ptr(b):
+        # full records of this rank's own range: inside its gathered buffer (full) or beside it (compact)
+        return own_out[b].data_ptr() if (fused and args.gather_records == "compact") else ring.local_slot_ptr(b)
 
     def step(i):
         b = i % nbuf
@@ -210,8 +219,8 @@ def main():
             main_stream.wait_event(gather_done[b])         # buffer free again
         if fused:
             # ONE kernel: scan + P2P stores of every record into every peer's gathered buffer
-            dfa.exec_batch_gather(d_in, stride=LENGTH, length=LENGTH, n=n, out_ptr=ring.local_slot_ptr(b),
-                                  peer_ptrs=peer_args[b][0], npeers=peer_args[b][1])
+            dfa.exec_batch_gather(d_in, stride=LENGTH, length=LENGTH, n=n, out_ptr=local_out_ptr(b),
+                                  peer_ptrs=peer_args[b][0], npeers=peer_args[b][1], compact=compact)
         else:
             dfa.exec_batch(d_in, stride=LENGTH, length=LENGTH, n=n, out=d_out[b])
         if world > 1:
@@ -239,7 +248,20 @@ def main():
     sample_host = d_in[idx].cpu().numpy()
     off = np.arange(sample_host.shape[0] + 1, dtype=np.uint64) * np.uint64(LENGTH)
     want = oracle.exec_batch(fsm, sample_host.reshape(-1), off, nthreads=min(16, os.cpu_count() or 1))
-    if fused:
+    if fused and compact:
+        mine = L.results_from_torch(own_out[0])
+        assert (mine[::64] == want).all(), "bench: GPU results differ from the oracle"
+        ids = ((mine["ret"] == 1).astype(np.uint32) << np.uint32(31)) | mine["end"]
+        everything = ring.read(0)                          # peers' match ids (own slot is not written)
+        ids_t = torch.from_numpy(ids.view(np.int32).copy()).to(dev)
+        allids = torch.empty(world * n, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allids, ids_t)         # NCCL reference for the P2P-gathered ids
+        torch.cuda.synchronize(dev)
+        ref_ids = allids.cpu().numpy().view(np.uint32)
+        for r in range(world):
+            if r != rank:
+                assert (everything[r * n:(r + 1) * n] == ref_ids[r * n:(r + 1) * n]).all(), "bench: fused gather != NCCL all-gather"
+    elif fused:
         everything = ring.read(0)                          # this rank's gathered buffer: all ranks' records
         got = everything[rank * n:(rank + 1) * n][::64]
         assert (got == want).all(), "bench: GPU results differ from the oracle"
@@ -279,8 +301,8 @@ def main():
     for a, b in kev:
         a.record(main_stream)
         if fused:
-            dfa.exec_batch_gather(d_in, stride=LENGTH, length=LENGTH, n=n, out_ptr=ring.local_slot_ptr(0),
-                                  peer_ptrs=peer_args[0][0], npeers=peer_args[0][1])
+            dfa.exec_batch_gather(d_in, stride=LENGTH, length=LENGTH, n=n, out_ptr=local_out_ptr(0),
+                                  peer_ptrs=peer_args[0][0], npeers=peer_args[0][1], compact=compact)
         else:
             dfa.exec_batch(d_in, stride=LENGTH, length=LENGTH, n=n, out=d_out[0])
         b.record(main_stream)
@@ -334,7 +356,7 @@ def main():
                        "distribution": args.dist, "variant": args.variant, "table": dfa.info,
                        "l2": "1 GiB input per step > 126 MB L2: no flush needed",
                        "multi_gpu": ("single GPU" if world == 1 else
-                                     "range-sharded batch; scan fused with the gather: lanes store the 16 B records into every peer's buffer over NVLink P2P; 4-byte NCCL handshake per step on a side stream"
+                                     f"range-sharded batch; scan fused with the gather: lanes store {'4 B match ids ((ret==1)<<31|end)' if args.gather_records == 'compact' else '16 B records'} into every peer's buffer over NVLink P2P; 4-byte NCCL handshake per step on a side stream"
                                      if fused else "range-sharded batch, one NCCL all-gather of 16 B result records per step on a side stream")},
             "clocks": sampler.result(),
             "e2e": {"value": e2e_value, "unit": "GB/s", "steps": e2e_steps,

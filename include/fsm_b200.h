@@ -155,11 +155,14 @@ int fsm_b200_exec_batch_dev(const fsm_b200_dfa *dfa,
  * scanning lanes themselves (P2P over NVLink/NVSwitch), so the gather overlaps the scan
  * tile by tile and no collective kernel competes for SMs.  After the kernels of all ranks
  * have completed (any cross-rank barrier), every gathered buffer holds every rank's records.
+ * compact = 0: peers receive the full 16-byte records (peer_outs[r] is a record array);
+ * compact = 1: peers receive 4-byte match ids, (ret == 1) << 31 | end (peer_outs[r] is a
+ * uint32_t array) -- a quarter of the NVLink volume; `consumed` stays on the owning rank.
  * Helper entry points: plain cudaMalloc'd buffers (IPC needs whole allocations), handle
  * export/open, and a synchronous read-back for checks. */
 int fsm_b200_exec_batch_dev_gather(const fsm_b200_dfa *dfa,
 	const uint8_t *d_base, const uint64_t *d_offsets, uint64_t stride, uint64_t len, size_t n,
-	struct fsm_b200_result *d_out, struct fsm_b200_result *const *peer_outs, int npeers, void *stream);
+	struct fsm_b200_result *d_out, void *const *peer_outs, int npeers, int compact, void *stream);
 int fsm_b200_dev_alloc(int device, size_t bytes, void **out);
 int fsm_b200_dev_free(int device, void *p);
 int fsm_b200_dev_read(int device, void *host_dst, const void *dev_src, size_t bytes);

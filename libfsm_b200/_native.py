@@ -60,7 +60,7 @@ def _load() -> C.CDLL:
     lib.fsm_b200_dfa_table.argtypes = [vp, vp]
     lib.fsm_b200_exec_batch_host.argtypes = [vp, vp, vp, sz, vp]
     lib.fsm_b200_exec_batch_dev.argtypes = [vp, vp, vp, u64, u64, sz, vp, vp]
-    lib.fsm_b200_exec_batch_dev_gather.argtypes = [vp, vp, vp, u64, u64, sz, vp, P(vp), C.c_int, vp]
+    lib.fsm_b200_exec_batch_dev_gather.argtypes = [vp, vp, vp, u64, u64, sz, vp, P(vp), C.c_int, C.c_int, vp]
     lib.fsm_b200_dev_alloc.argtypes = [C.c_int, sz, P(vp)]
     lib.fsm_b200_dev_free.argtypes = [C.c_int, vp]
     lib.fsm_b200_dev_read.argtypes = [C.c_int, vp, vp, sz]

@@ -150,8 +150,15 @@ store_result(const K1Args &a, uint64_t i, int32_t ret, uint32_t end, uint64_t co
 	v.z = (uint32_t) consumed;
 	v.w = (uint32_t) (consumed >> 32);
 	*reinterpret_cast<uint4 *>(a.out + i) = v;
-	for (uint32_t r = 0; r < a.npeers; r++) {
-		*reinterpret_cast<uint4 *>(a.peer_out[r] + i) = v;
+	if (a.peer_compact) {
+		const uint32_t id = (ret == 1 ? 0x80000000u : 0u) | end;      /* the match id: 4 B on the wire */
+		for (uint32_t r = 0; r < a.npeers; r++) {
+			reinterpret_cast<uint32_t *>(a.peer_out[r])[i] = id;
+		}
+	} else {
+		for (uint32_t r = 0; r < a.npeers; r++) {
+			*reinterpret_cast<uint4 *>(a.peer_out[r] + i) = v;
+		}
 	}
 }
 
@@ -921,7 +928,7 @@ k1_launch_jobs(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d
 int
 k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,
 	uint64_t stride, uint64_t len, size_t n, fsm_b200_result *d_out, cudaStream_t stream, int variant,
-	fsm_b200_result *const *peer_outs, int npeers)
+	fsm_b200_result *const *peer_outs, int npeers, int peer_compact)
 {
 	if (n == 0) return 0;
 	int sms = 0, smem_optin = 0;
@@ -940,6 +947,7 @@ k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offs
 	}
 	for (int r = 0; r < npeers; r++) a.peer_out[r] = peer_outs[r];
 	a.npeers = (uint32_t) npeers;
+	a.peer_compact = peer_compact ? 1u : 0u;
 
 	if (variant == K1_AUTO) variant = g_variant;
 	const bool tile_ok = k1_tile_eligible(dfa, d_base, d_offsets, stride, len, n);

@@ -18,11 +18,12 @@ from .desc import RESULT_DTYPE
 class GatherRing:
     """`nbuf` gathered buffers of world*n result records on every rank, peer-mapped."""
 
-    def __init__(self, n: int, world: int, rank: int, device: int, nbuf: int = 2):
+    def __init__(self, n: int, world: int, rank: int, device: int, nbuf: int = 2, elem_bytes: int = 16):
         import torch
         import torch.distributed as dist
         self.n, self.world, self.rank, self.device, self.nbuf = n, world, rank, device, nbuf
-        self.bytes = world * n * 16
+        self.elem = elem_bytes                  # 16: full records; 4: compact match ids
+        self.bytes = world * n * elem_bytes
         self.local = []
         for _ in range(nbuf):
             p = C.c_void_p()
@@ -47,7 +48,7 @@ class GatherRing:
                     check(lib.fsm_b200_ipc_open(device, h.ctypes.data, C.byref(p)), "ipc_open")
                     self.peer[b][r] = p.value
                     self._opened.append(p.value)
-        self.slot = rank * n * 16
+        self.slot = rank * n * elem_bytes
 
     def local_slot_ptr(self, b: int) -> int:
         """Where this rank's own records live inside its own gathered buffer b."""
@@ -59,7 +60,7 @@ class GatherRing:
         return (C.c_void_p * len(ptrs))(*ptrs), len(ptrs)
 
     def read(self, b: int) -> np.ndarray:
-        out = np.empty(self.world * self.n, dtype=RESULT_DTYPE)
+        out = np.empty(self.world * self.n, dtype=RESULT_DTYPE if self.elem == 16 else np.uint32)
         check(lib.fsm_b200_dev_read(self.device, out.ctypes.data, self.local[b], self.bytes), "dev_read")
         return out
 
