@@ -192,7 +192,10 @@ def main():
     n = N_INPUTS
     # range shard `rank` of the global batch: its own seeded 2^20 x 1 KiB slice
     d_in = workloads.cfg2_device(n, LENGTH, adversarial, seed=42 + 1000 * rank, device=dev)
-    nbuf = 2
+    # buffers in flight: the completion handshake / all-gather of step i is only waited for when its
+    # buffer is reused at step i+nbuf, so a few steps of slack hide the collective's latency (its
+    # kernel cannot co-reside with the persistent scan kernel and runs between scan launches)
+    nbuf = int(os.environ.get("BENCH_NBUF", "4"))
     fused = world > 1 and args.gather == "fused"
     d_out = [torch.empty((n, 16), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
     gathered = [torch.empty((world * n, 16), dtype=torch.uint8, device=dev) for _ in range(nbuf)] if world > 1 else None
