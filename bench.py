@@ -161,6 +161,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--gather-records", default="compact", choices=["compact", "full"],
                     help="fused gather payload: compact = 4-byte match ids ((ret==1)<<31 | end), full = 16-byte records")
+    ap.add_argument("--handshake", default="flags", choices=["flags", "nccl", "none"],
+                    help="fused gather completion signal: flags = the kernel's last CTA stores a step number into "
+                         "every peer's memory; nccl = 4-byte NCCL all-reduce per step on a side stream")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N>1: fused = scanning lanes store records into every peer's buffer over NVLink P2P; "
                          "nccl = one NCCL all-gather per step on a side stream")
@@ -210,6 +213,7 @@ def main():
         compact = args.gather_records == "compact"
         ring = GatherRing(n, world, rank, local, nbuf, elem_bytes=4 if compact else 16)
         peer_args = [ring.peer_slot_ptrs(b) for b in range(nbuf)]
+        sig_args = [ring.signal_args(b) for b in range(nbuf)]
         own_out = [torch.empty((n, 16), dtype=torch.uint8, device=dev) for _ in range(nbuf)] if compact else None
 
     def local_out_ptr(b):
@@ -222,17 +226,20 @@ def main():
             main_stream.wait_event(gather_done[b])         # buffer free again
         if fused:
             # ONE kernel: scan + P2P stores of every record into every peer's gathered buffer
+            # (+ with --handshake flags the completion flag, value = step number + 1)
+            use_flags = args.handshake == "flags"
             dfa.exec_batch_gather(d_in, stride=LENGTH, length=LENGTH, n=n, out_ptr=local_out_ptr(b),
-                                  peer_ptrs=peer_args[b][0], npeers=peer_args[b][1], compact=compact)
+                                  peer_ptrs=peer_args[b][0], npeers=peer_args[b][1], compact=compact,
+                                  sig_counter=sig_args[b][0] if use_flags else None,
+                                  sig_flags=sig_args[b][1] if use_flags else None, sig_value=i + 1)
         else:
             dfa.exec_batch(d_in, stride=LENGTH, length=LENGTH, n=n, out=d_out[b])
-        if world > 1:
+        if world > 1 and (not fused or args.handshake == "nccl"):
             ev = torch.cuda.Event(); ev.record(main_stream)
             side.wait_event(ev)
             with torch.cuda.stream(side):
                 if fused:
-                    if not os.environ.get("BENCH_NO_HANDSHAKE"):
-                        dist.all_reduce(token)              # 4-byte completion handshake, off the data path
+                    dist.all_reduce(token)                  # 4-byte completion handshake, off the data path
                 else:
                     dist.all_gather_into_tensor(gathered[b], d_out[b])
                 gather_done[b] = torch.cuda.Event(); gather_done[b].record(side)
@@ -251,6 +258,9 @@ def main():
     sample_host = d_in[idx].cpu().numpy()
     off = np.arange(sample_host.shape[0] + 1, dtype=np.uint64) * np.uint64(LENGTH)
     want = oracle.exec_batch(fsm, sample_host.reshape(-1), off, nthreads=min(16, os.cpu_count() or 1))
+    if fused and args.handshake == "flags":
+        flags = ring.read_flags(0)                         # step 0 was launched with sig_value 1
+        assert (flags == 1).all(), f"bench: completion flags {flags} != 1 after step 0"
     if fused and compact:
         mine = L.results_from_torch(own_out[0])
         assert (mine[::64] == want).all(), "bench: GPU results differ from the oracle"
@@ -359,7 +369,7 @@ def main():
                        "distribution": args.dist, "variant": args.variant, "table": dfa.info,
                        "l2": "1 GiB input per step > 126 MB L2: no flush needed",
                        "multi_gpu": ("single GPU" if world == 1 else
-                                     f"range-sharded batch; scan fused with the gather: lanes store {'4 B match ids ((ret==1)<<31|end)' if args.gather_records == 'compact' else '16 B records'} into every peer's buffer over NVLink P2P; 4-byte NCCL handshake per step on a side stream"
+                                     f"range-sharded batch; scan fused with the gather: lanes store {'4 B match ids ((ret==1)<<31|end)' if args.gather_records == 'compact' else '16 B records'} into every peer's buffer over NVLink P2P; completion signal: {args.handshake}"
                                      if fused else "range-sharded batch, one NCCL all-gather of 16 B result records per step on a side stream")},
             "clocks": sampler.result(),
             "e2e": {"value": e2e_value, "unit": "GB/s", "steps": e2e_steps,

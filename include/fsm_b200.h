@@ -158,13 +158,21 @@ int fsm_b200_exec_batch_dev(const fsm_b200_dfa *dfa,
  * compact = 0: peers receive the full 16-byte records (peer_outs[r] is a record array);
  * compact = 1: peers receive 4-byte match ids, (ret == 1) << 31 | end (peer_outs[r] is a
  * uint32_t array) -- a quarter of the NVLink volume; `consumed` stays on the owning rank.
+ * Completion signal (optional, sig_counter != NULL): sig_counter is a zeroed uint32 in local
+ * device memory; sig_flags[0..npeers-1] point at one uint32 flag word in each peer's memory,
+ * sig_flags[npeers] at this rank's own.  When the last CTA of the kernel has finished (all
+ * CTAs' peer stores fenced at system scope) it stores sig_value into every flag: a consumer
+ * that reads flag == sig_value knows this rank's records of that step are complete -- the
+ * handshake costs no collective kernel (which could not co-reside with the persistent scan).
  * Helper entry points: plain cudaMalloc'd buffers (IPC needs whole allocations), handle
  * export/open, and a synchronous read-back for checks. */
 int fsm_b200_exec_batch_dev_gather(const fsm_b200_dfa *dfa,
 	const uint8_t *d_base, const uint64_t *d_offsets, uint64_t stride, uint64_t len, size_t n,
-	struct fsm_b200_result *d_out, void *const *peer_outs, int npeers, int compact, void *stream);
+	struct fsm_b200_result *d_out, void *const *peer_outs, int npeers, int compact,
+	void *sig_counter, void *const *sig_flags, uint32_t sig_value, void *stream);
 int fsm_b200_dev_alloc(int device, size_t bytes, void **out);
 int fsm_b200_dev_free(int device, void *p);
+int fsm_b200_dev_zero(int device, void *p, size_t bytes);
 int fsm_b200_dev_read(int device, void *host_dst, const void *dev_src, size_t bytes);
 int fsm_b200_ipc_export(const void *dev_ptr, void *handle64 /* 64 bytes */);
 int fsm_b200_ipc_open(int device, const void *handle64, void **out);

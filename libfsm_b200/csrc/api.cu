@@ -275,7 +275,8 @@ fsm_b200_exec_batch_host(const fsm_b200_dfa *dfa,
 extern "C" int
 fsm_b200_exec_batch_dev_gather(const fsm_b200_dfa *dfa,
 	const uint8_t *d_base, const uint64_t *d_offsets, uint64_t stride, uint64_t len, size_t n,
-	struct fsm_b200_result *d_out, void *const *peer_outs, int npeers, int compact, void *stream)
+	struct fsm_b200_result *d_out, void *const *peer_outs, int npeers, int compact,
+	void *sig_counter, void *const *sig_flags, uint32_t sig_value, void *stream)
 {
 	if (dfa == nullptr || (n > 0 && (d_base == nullptr || d_out == nullptr)) || (npeers > 0 && peer_outs == nullptr)) {
 		set_error("exec_batch_dev_gather: bad argument");
@@ -284,7 +285,8 @@ fsm_b200_exec_batch_dev_gather(const fsm_b200_dfa *dfa,
 	}
 	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
 	return k1_launch(dfa, d_base, d_offsets, stride, len, n, d_out, static_cast<cudaStream_t>(stream), K1_AUTO,
-	    reinterpret_cast<fsm_b200_result *const *>(peer_outs), npeers, compact);
+	    reinterpret_cast<fsm_b200_result *const *>(peer_outs), npeers, compact,
+	    static_cast<uint32_t *>(sig_counter), reinterpret_cast<uint32_t *const *>(sig_flags), sig_value);
 }
 
 extern "C" int
@@ -301,6 +303,14 @@ fsm_b200_dev_free(int device, void *p)
 {
 	FSMB_CUDA(cudaSetDevice(device), return -1);
 	FSMB_CUDA(cudaFree(p), return -1);
+	return 0;
+}
+
+extern "C" int
+fsm_b200_dev_zero(int device, void *p, size_t bytes)
+{
+	FSMB_CUDA(cudaSetDevice(device), return -1);
+	FSMB_CUDA(cudaMemset(p, 0, bytes), return -1);
 	return 0;
 }
 

@@ -162,6 +162,29 @@ store_result(const K1Args &a, uint64_t i, int32_t ret, uint32_t end, uint64_t co
 	}
 }
 
+/* Fused-gather completion signal.  Every CTA: all its P2P stores issued -> __threadfence_system
+ * -> count itself done.  The last CTA resets the counter and publishes sig_value into the flag
+ * word of every peer (and its own): a consumer that sees flag == value from rank r knows all of
+ * r's records for that step have landed in its gathered buffer.  No collective kernel needed. */
+__device__ __forceinline__ void
+signal_done(const K1Args &a)
+{
+	if (a.sig_counter == nullptr) return;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence_system();
+		const uint32_t old = atomicAdd(a.sig_counter, 1u);
+		if (old == gridDim.x - 1) {
+			atomicExch(a.sig_counter, 0u);
+			__threadfence_system();
+			for (uint32_t r = 0; r <= a.npeers; r++) {
+				*reinterpret_cast<volatile uint32_t *>(a.sig_flags[r]) = a.sig_value;
+			}
+			__threadfence_system();
+		}
+	}
+}
+
 /* ------------------------------------------------------------------ LANE variant ---- */
 
 template <typename E, bool SMEM, bool HAS_DEAD, bool CLS>
@@ -262,6 +285,7 @@ k1_lane_kernel(const K1Args a)
 		const int32_t ret = (!died && is_end[st]) ? 1 : 0;
 		store_result(a, i, ret, st, pos);
 	}
+	signal_done(a);
 #undef TSTEP
 #undef WSTEP4
 #undef COL
@@ -541,6 +565,7 @@ k1_kstride_kernel(const K1Args a)
 		const int32_t ret = (!died && is_end[st]) ? 1 : 0;
 		store_result(a, i, ret, st, pos);
 	}
+	signal_done(a);
 #undef STEP1
 }
 
@@ -928,7 +953,8 @@ k1_launch_jobs(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d
 int
 k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,
 	uint64_t stride, uint64_t len, size_t n, fsm_b200_result *d_out, cudaStream_t stream, int variant,
-	fsm_b200_result *const *peer_outs, int npeers, int peer_compact)
+	fsm_b200_result *const *peer_outs, int npeers, int peer_compact,
+	uint32_t *sig_counter, uint32_t *const *sig_flags, uint32_t sig_value)
 {
 	if (n == 0) return 0;
 	int sms = 0, smem_optin = 0;
@@ -948,6 +974,11 @@ k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offs
 	for (int r = 0; r < npeers; r++) a.peer_out[r] = peer_outs[r];
 	a.npeers = (uint32_t) npeers;
 	a.peer_compact = peer_compact ? 1u : 0u;
+	if (sig_counter != nullptr && sig_flags != nullptr) {
+		a.sig_counter = sig_counter;
+		for (int r = 0; r <= npeers; r++) a.sig_flags[r] = sig_flags[r];
+		a.sig_value = sig_value;
+	}
 
 	if (variant == K1_AUTO) variant = g_variant;
 	const bool tile_ok = k1_tile_eligible(dfa, d_base, d_offsets, stride, len, n);

@@ -28,7 +28,12 @@ struct K1Args {
 	fsm_b200_result *out;        /* result i -> out[i] ... */
 	fsm_b200_result *peer_out[7]; /* ... and, fused gather, -> peer_out[r][i] over NVLink P2P */
 	uint32_t npeers;
-	uint32_t peer_compact;        /* 1: peers receive 4-byte match ids (ret << 31 | end) instead of 16-byte records */
+	uint32_t peer_compact;
+	/* completion signal of the fused gather: the last CTA to finish (after a system-scope fence
+	 * in every CTA) stores sig_value into one flag word in every peer's memory */
+	uint32_t *sig_counter;        /* local, zero between launches */
+	uint32_t *sig_flags[8];       /* [npeers + 1]: peers' flag words, then this rank's own */
+	uint32_t sig_value;        /* 1: peers receive 4-byte match ids (ret << 31 | end) instead of 16-byte records */
 	const uint8_t *blob;        /* table rows then is_end bytes */
 	uint32_t blob_bytes;
 	uint32_t is_end_off;
@@ -49,7 +54,8 @@ bool k1_tile_eligible(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint
 
 int k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,
 	uint64_t stride, uint64_t len, size_t n, fsm_b200_result *d_out, cudaStream_t stream, int variant,
-	fsm_b200_result *const *peer_outs = nullptr, int npeers = 0, int peer_compact = 0);
+	fsm_b200_result *const *peer_outs = nullptr, int npeers = 0, int peer_compact = 0,
+	uint32_t *sig_counter = nullptr, uint32_t *const *sig_flags = nullptr, uint32_t sig_value = 0);
 
 /* K1b jobs: input i = d_base[d_begs[i] .. d_ends[i]) walked from state d_entry[i] (LANE variant). */
 int k1_launch_jobs(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_begs,

@@ -113,12 +113,14 @@ class Dfa:
         return out
 
     def exec_batch_gather(self, base, *, stride: int, length: int, n: int, out_ptr: int, peer_ptrs, npeers: int,
-                          compact: bool = False) -> None:
+                          compact: bool = False, sig_counter: int | None = None, sig_flags=None, sig_value: int = 0) -> None:
         """Fixed-stride device batch whose records go to out_ptr AND to npeers peer buffers
         (fused scan + gather over NVLink peer memory; see libfsm_b200.peer.GatherRing).
-        compact: peers receive 4-byte match ids ((ret == 1) << 31 | end) instead of records."""
+        compact: peers receive 4-byte match ids ((ret == 1) << 31 | end) instead of records.
+        sig_*: optional completion flags written into every peer's memory by the last CTA."""
         check(lib.fsm_b200_exec_batch_dev_gather(self._h, base.data_ptr(), None, int(stride), int(length), n,
-                                                 out_ptr, peer_ptrs, npeers, 1 if compact else 0, _stream_ptr()),
+                                                 out_ptr, peer_ptrs, npeers, 1 if compact else 0,
+                                                 sig_counter, sig_flags, int(sig_value) & 0xFFFFFFFF, _stream_ptr()),
               "exec_batch_dev_gather")
 
     def exec_batch_hostptr(self, base_ptr: int, offsets_ptr: int, n: int, out_ptr: int) -> None:
