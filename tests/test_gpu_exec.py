@@ -242,12 +242,13 @@ def test_full_size_config2_properties(torch_cuda, oracle, adversarial):
     dev = workloads.cfg2_device(n, length, adversarial, seed=42)
     with L.Dfa(fsm) as dfa:
         results = {}
-        for variant in ("lane", "tile64"):
+        for variant in ("lane", "tile64", "kstride", "auto"):
             L.set_exec_variant(variant)
             out = dfa.exec_batch(dev, stride=length, length=length, n=n)
             torch.cuda.synchronize()
             results[variant] = out
         assert torch.equal(results["lane"], results["tile64"])
+        assert torch.equal(results["lane"], results["kstride"]) and torch.equal(results["lane"], results["auto"])
         rec = results["tile64"].view(torch.int32).reshape(n, 4)
         ret, end = rec[:, 0], rec[:, 1]
         consumed = rec[:, 2].to(torch.int64) | (rec[:, 3].to(torch.int64) << 32)
