@@ -153,7 +153,10 @@ def test_dead_states_and_wide_tables_fixed_stride(torch_cuda, oracle, name, vari
 
 
 def test_kstride_tables_exist_where_expected():
-    expect = {"cfg2:uniform": 4, "cfg1:digits": 4, "anchored:^[a-f0-9]{32}$": 4, "anchored:^abc[0-9]+x$": 2, "union6:": 0}
+    # K = 4 for <= 4 byte classes; K = 2 for <= 16 classes on tables with more than 32 rows
+    # (small tables stay on the one-byte kernel); none for > 256 rows
+    expect = {"cfg2:uniform": 4, "cfg1:digits": 4, "anchored:^[a-f0-9]{32}$": 4, "anchored:^abc[0-9]+x$": 0,
+              "endids:union6x5": 2, "union6:": 0}
     for name, k in expect.items():
         case = next(c for c in CASES if c["name"].startswith(name))
         with L.Dfa(case["fsm"]) as dfa:
