@@ -72,6 +72,7 @@ struct fsm_b200_dfa {
 	/* device */
 	void *d_blob;            /* table rows followed by is_end bytes (u8 per row) */
 	uint8_t *d_absorb;       /* [ntable] 1 = every byte loops back to the state itself */
+	uint32_t has_absorbing;  /* some real (non-dead) state is absorbing */
 	/* host copies for introspection / stream composition */
 	uint32_t *h_table32;     /* [nstates*256], NO_EDGE for missing */
 	uint8_t *h_is_end;       /* [ntable] (dead row: 0) */

@@ -214,6 +214,7 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa 
 				self = (v == st);
 			}
 			ab[st] = self ? 1 : 0;
+			if (self && st < S) dfa->has_absorbing = 1;
 		}
 		FSMB_CUDA(cudaMalloc(&dfa->d_absorb, dfa->ntable), { fsm_b200_dfa_free(dfa); return -1; });
 		FSMB_CUDA(cudaMemcpy(dfa->d_absorb, ab.data(), dfa->ntable, cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });

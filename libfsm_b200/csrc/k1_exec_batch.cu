@@ -271,6 +271,9 @@ k1_lane_kernel(const K1Args a)
 					break;
 				}
 				pos += 32;
+				/* absorbing state (all 256 edges loop back): the rest of the input cannot change
+				 * the record -- stop reading it */
+				if (a.absorb != nullptr && __ldg(a.absorb + st)) { pos = len; break; }
 #pragma unroll
 				for (int k = 0; k < 8; k++) cur[k] = nxt[k];
 			}
@@ -439,8 +442,17 @@ k1_ragged_kernel(const K1Args a)
 			st = r.x;
 			consumed_here = r.y - lo;
 		}
-		cur += consumed_here;
-		if (died || !more) {
+		/* A state whose 256 edges all loop back to itself keeps the walk where it is whatever
+		 * follows (the accept state of an end-unanchored pattern): the rest of the line cannot
+		 * change the record, so it is neither walked nor read. */
+		bool absorbed = false;
+		if (!died && more && a.absorb != nullptr && __ldg(a.absorb + st)) {
+			absorbed = true;
+			cur = end;
+		} else {
+			cur += consumed_here;
+		}
+		if (died || !more || absorbed) {
 			/* line done */
 			const int32_t ret = (!died && is_end[st]) ? 1 : 0;
 			store_result(a, i, ret, st, (uint64_t) (cur - line_beg));
@@ -551,6 +563,7 @@ k1_kstride_kernel(const K1Args a)
 					break;
 				}
 				pos += 32;
+				if (a.absorb != nullptr && __ldg(a.absorb + st)) { pos = len; break; }   /* absorbing: done */
 #pragma unroll
 				for (int k = 0; k < 8; k++) cur[k] = nxt[k];
 			}
@@ -854,6 +867,7 @@ fill_args(K1Args &a, const fsm_b200_dfa *dfa)
 	a.is_end_off = dfa->is_end_off;
 	a.cls_off = dfa->cls_off;
 	a.pitch = dfa->pitch; a.start = dfa->start; a.dead = dfa->dead;
+	a.absorb = (dfa->has_absorbing && getenv("FSM_B200_NO_ABSORB_SKIP") == nullptr) ? dfa->d_absorb : nullptr;
 	a.kblob = static_cast<const uint8_t *>(dfa->d_kblob);
 	a.kblob_bytes = dfa->kblob_bytes; a.kpitch = dfa->kpitch; a.k1pitch = dfa->k1pitch;
 	a.k1_off = dfa->k1_off; a.kend_off = dfa->kend_off; a.klut_off = dfa->klut_off;
