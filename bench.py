@@ -90,28 +90,46 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_leg(fsm, host_sample: np.ndarray, threads: int):
     """Times the reference's own fsm_exec (oracle/_ref, compiled from the reference sources) on
-    the host cores; falls back to the oracle port when the compiled reference is absent."""
+    the host cores; falls back to the oracle port when the compiled reference is absent.  The
+    thread count is swept (all, 1/2, 1/4 of the host threads) and the BEST result of each mode is
+    reported, so an oversubscribed or quota-limited box does not understate the CPU."""
     import reflib
     n = host_sample.shape[0]
     offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(host_sample.shape[1])
     flat = host_sample.reshape(-1)
+    nbytes = flat.size
+    sweep = sorted({max(1, threads), max(1, threads // 2), max(1, threads // 4)}, reverse=True)
+    best = {"asis": (0.0, 0, None, 0.0), "amortised": (0.0, 0, None, 0.0)}
     if reflib.have_ref():
         R = reflib.Ref()
         h = R.from_flat(fsm)
-        t0 = time.perf_counter(); asis = R.exec_batch(h, flat, offsets, mode=0, nthreads=threads); t1 = time.perf_counter()
-        t2 = time.perf_counter(); amort = R.exec_batch(h, flat, offsets, mode=1, nthreads=threads); t3 = time.perf_counter()
-        R.free(h)
         kind = "reference"
+        run = lambda mode, t: R.exec_batch(h, flat, offsets, mode=mode, nthreads=t)
     else:
         O = reflib.Oracle()
-        t0 = time.perf_counter(); asis = O.exec_batch(fsm, flat, offsets, nthreads=threads, validate_each=True); t1 = time.perf_counter()
-        t2 = time.perf_counter(); amort = O.exec_batch(fsm, flat, offsets, nthreads=threads, validate_each=False); t3 = time.perf_counter()
+        h = None
         kind = "port"
-    nbytes = flat.size
-    return {"kind": kind, "asis_gbs": nbytes / (t1 - t0) / 1e9, "amortised_gbs": nbytes / (t3 - t2) / 1e9,
-            "asis_s": t1 - t0, "amortised_s": t3 - t2, "records": amort, "asis_records": asis}
+        run = lambda mode, t: O.exec_batch(fsm, flat, offsets, nthreads=t, validate_each=(mode == 0))
+    for t in sweep:
+        for name, mode in (("asis", 0), ("amortised", 1)):
+            t0 = time.perf_counter(); rec = run(mode, t); dt = time.perf_counter() - t0
+            if nbytes / dt / 1e9 > best[name][0]:
+                best[name] = (nbytes / dt / 1e9, t, rec, dt)
+    if h is not None:
+        R.free(h)
+    return {"kind": kind, "asis_gbs": best["asis"][0], "asis_threads": best["asis"][1], "asis_s": best["asis"][3],
+            "amortised_gbs": best["amortised"][0], "amortised_threads": best["amortised"][1],
+            "amortised_s": best["amortised"][3], "records": best["amortised"][2], "asis_records": best["asis"][2],
+            "threads_swept": sweep}
 
 
 def run_reference_arm(args):
@@ -122,7 +140,7 @@ def run_reference_arm(args):
         return 0
     from libfsm_b200 import workloads
     fsm = load_cfg2_fsm()
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     sample_n = int(os.environ.get("BENCH_REF_SAMPLE", 512 * threads))
     sample_n = max(1024, min(sample_n, 1 << 16))
     host = workloads.cfg2_host(sample_n, LENGTH, args.dist == "adversarial", seed=42)
@@ -131,7 +149,7 @@ def run_reference_arm(args):
     t_total, last = 0.0, None
     for _ in range(args.steps):
         last = cpu_reference_leg(fsm, host, threads)
-        t_total += last["asis_s"]
+        t_total += last["asis_s"]        # the best thread count of the sweep
     nbytes = sample_n * LENGTH
     value = nbytes * args.steps / t_total / 1e9
     sample = f"{sample_n} x {LENGTH} B inputs of the same distribution per step (seed 42)"
@@ -141,8 +159,9 @@ def run_reference_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "configs[1]: 256-state DFA a[ -~]{7}\\z, 2^20 x 1 KiB ASCII per GPU",
                    "distribution": args.dist, "reference_entry": "fsm_exec per input (as-is, per-call fsm_isdfa validation)"},
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": last["kind"], "sample": sample,
-                         "amortised_value": last["amortised_gbs"]},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": last["asis_threads"], "kind": last["kind"], "sample": sample,
+                         "amortised_value": last["amortised_gbs"], "amortised_cores": last["amortised_threads"],
+                         "threads_swept": last["threads_swept"]},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -358,7 +377,7 @@ def main():
         traffic_src = f"{tj['source']}: dram__bytes_read.sum + dram__bytes_write.sum per launch of {tj['kernel']}"
     line = None
     if rank == 0:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         sample_n = max(1024, min(256 * threads, 1 << 15))
         cpu = cpu_reference_leg(fsm, workloads.cfg2_host(sample_n, LENGTH, adversarial, seed=42), threads)
         line = {
@@ -381,9 +400,9 @@ def main():
                          "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src,
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_step,
                          "traffic": traffic, "traffic_source": traffic_src},
-            "cpu_baseline": {"value": cpu["asis_gbs"], "unit": "GB/s", "cores": threads, "kind": cpu["kind"],
-                             "sample": f"{sample_n} x {LENGTH} B inputs, same distribution; reference fsm_exec per input (as-is)",
-                             "amortised_value": cpu["amortised_gbs"]},
+            "cpu_baseline": {"value": cpu["asis_gbs"], "unit": "GB/s", "cores": cpu["asis_threads"], "kind": cpu["kind"],
+                             "sample": f"{sample_n} x {LENGTH} B inputs, same distribution; reference fsm_exec per input (as-is); best of thread counts {cpu['threads_swept']}",
+                             "amortised_value": cpu["amortised_gbs"], "amortised_cores": cpu["amortised_threads"]},
         }
         print(json.dumps(line))
     dfa.close()
