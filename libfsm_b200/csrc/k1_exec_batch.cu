@@ -778,9 +778,15 @@ launch_kstride(const K1Args &a, int sms, cudaStream_t stream)
 		errno = EIO;
 		return -1;
 	}
-	const int block = 1024;
+	int block = 1024;
+	if (const char *e = getenv("FSM_B200_KSTRIDE_BLOCK")) {      /* tuning knob */
+		const int v = atoi(e);
+		if (v >= 64 && v <= 1024 && (v % 32) == 0) block = v;
+	}
+	int per_sm = 1;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem_bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
 	uint64_t want = (a.n + (uint64_t) block - 1) / (uint64_t) block;
-	uint64_t grid = (uint64_t) sms;
+	uint64_t grid = (uint64_t) sms * (uint64_t) per_sm;
 	if (want < grid) grid = want;
 	if (grid == 0) grid = 1;
 	kern<<<(unsigned) grid, block, smem_bytes, stream>>>(a);
