@@ -233,6 +233,16 @@ struct fsm_b200_det_stats {
 };
 int fsm_b200_determinise_stats(struct fsm_b200_det_stats *st);
 
+/* --- minimisation: the partition refinement of fsm_minimise -----------------------------
+ * (src/libfsm/minimise.c:74-190: trim to start- and end-reachable states, then merge
+ * indistinguishable states; end states with different end-id sets are never merged,
+ * minimise.c:733-).  Input: a DFA as a desc (-1/EINVAL otherwise).  Output: the minimal DFA,
+ * unique up to state numbering (classes are numbered by their smallest member here), as a
+ * library-owned desc; an automaton that can match nothing comes back with 0 states.
+ * Returns 0 on success, -1/errno on error. */
+int fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_owned_desc *out);
+int fsm_b200_minimise_stats(struct fsm_b200_det_stats *st);
+
 /* Count of kernel launches issued by this library on this thread since the last reset
  * (bench.py's "gpu_launches"). */
 uint64_t fsm_b200_launch_count(int reset);

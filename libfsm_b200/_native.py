@@ -23,6 +23,7 @@ ABI_SYMBOLS = (
     "fsm_b200_set_exec_variant", "fsm_b200_get_exec_variant",
     "fsm_b200_exec_stream_host", "fsm_b200_exec_stream_dev", "fsm_b200_exec_stream_map_dev",
     "fsm_b200_determinise", "fsm_b200_desc_free", "fsm_b200_determinise_stats",
+    "fsm_b200_minimise", "fsm_b200_minimise_stats",
     "fsm_b200_launch_count",
 )
 
@@ -77,6 +78,8 @@ def _load() -> C.CDLL:
     lib.fsm_b200_desc_free.argtypes = [P(COwnedDesc)]
     lib.fsm_b200_desc_free.restype = None
     lib.fsm_b200_determinise_stats.argtypes = [P(CDetStats)]
+    lib.fsm_b200_minimise.argtypes = [P(CDesc), C.c_int, P(COwnedDesc)]
+    lib.fsm_b200_minimise_stats.argtypes = [P(CDetStats)]
     lib.fsm_b200_launch_count.argtypes = [C.c_int]
     lib.fsm_b200_launch_count.restype = C.c_uint64
     return lib

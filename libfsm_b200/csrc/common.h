@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include <cuda_runtime.h>
 
 #include "../../include/fsm_b200.h"
@@ -42,6 +43,13 @@ constexpr uint32_t SMEM_TABLE_MAX = 96 * 1024;
 constexpr uint32_t SMEM_CLASS_TABLE_MAX = 200 * 1024;
 /* Above this many byte classes the indirection is not worth it for an L2-resident table. */
 constexpr uint32_t CLASS_GLOBAL_MAX = 192;
+
+/* Arrays behind a library-owned description (struct fsm_b200_owned_desc.owner). */
+struct Owner {
+	std::vector<uint8_t> is_end;
+	std::vector<uint64_t> group_off, group_sym, endid_off;
+	std::vector<uint32_t> group_to, endids;
+};
 
 } // namespace fsmb200
 

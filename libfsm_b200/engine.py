@@ -174,6 +174,27 @@ def determinise(nfa: FlatFsm, device: int = 0, state_limit: int = 0) -> FlatFsm:
         lib.fsm_b200_desc_free(C.byref(od))
 
 
+def minimise(dfa: FlatFsm, device: int = 0) -> FlatFsm:
+    """GPU minimisation (mirrors ``fsm_minimise``, reference include/fsm/fsm.h:502-503): the
+    minimal DFA, unique up to state numbering; 0 states if nothing can match."""
+    od = COwnedDesc()
+    cdesc = dfa.as_c()
+    check(lib.fsm_b200_minimise(C.byref(cdesc), device, C.byref(od)), "minimise")
+    try:
+        if od.desc.nstates == 0:
+            return FlatFsm(0, 0, False, np.zeros(0, np.uint8), np.zeros(1, np.uint64),
+                           np.zeros((0, 4), np.uint64), np.zeros(0, np.uint32), None, None, None, None)
+        return FlatFsm.from_c(od.desc)
+    finally:
+        lib.fsm_b200_desc_free(C.byref(od))
+
+
+def minimise_stats() -> dict:
+    st = CDetStats()
+    lib.fsm_b200_minimise_stats(C.byref(st))
+    return {k: getattr(st, k) for k, _ in CDetStats._fields_}
+
+
 def determinise_stats() -> dict:
     st = CDetStats()
     lib.fsm_b200_determinise_stats(C.byref(st))

@@ -297,6 +297,52 @@ fsm_exec(const struct fsm *fsm,
 	return 1;
 }
 
+/* Build a `struct fsm` from a flat DFA description with the reference's own builder API.
+ * Groups arrive sorted by destination, so every edge_set_add_bulk is a pure append. */
+static struct fsm *
+fsm_from_desc(const struct fsm_alloc *alloc, const struct fsm_b200_desc *d)
+{
+	struct fsm *fsm = fsm_new_statealloc(alloc, d->nstates > 0 ? d->nstates : 1);
+	uint32_t s;
+
+	if (fsm == NULL) {
+		return NULL;
+	}
+	if (d->nstates > 0 && !fsm_addstate_bulk(fsm, d->nstates)) {
+		goto fail;
+	}
+	for (s = 0; s < d->nstates; s++) {
+		uint64_t g, e;
+		const uint64_t g0 = d->group_off[s], g1 = d->group_off[s + 1];
+		if (g1 > g0 && !edge_set_advise_growth(&fsm->states[s].edges, fsm->alloc, (size_t) (g1 - g0))) {
+			goto fail;
+		}
+		for (g = g0; g < g1; g++) {
+			uint64_t sym[4];
+			memcpy(sym, &d->group_symbols[4 * g], sizeof sym);
+			if (!edge_set_add_bulk(&fsm->states[s].edges, fsm->alloc, sym, d->group_to[g])) {
+				goto fail;
+			}
+		}
+		if (d->is_end[s]) {
+			fsm_setend(fsm, s, 1);
+			for (e = d->endid_off[s]; e < d->endid_off[s + 1]; e++) {
+				if (!fsm_endid_set(fsm, s, d->endids[e])) {
+					goto fail;
+				}
+			}
+		}
+	}
+	if (d->hasstart) {
+		fsm_setstart(fsm, d->start);
+	}
+	return fsm;
+
+fail:
+	fsm_free(fsm);
+	return NULL;
+}
+
 /* ------------------------------------------------------------------ fsm_determinise --- */
 
 /*
@@ -319,7 +365,6 @@ fsm_determinise_with_config(struct fsm *nfa, const struct fsm_determinise_config
 	struct fsm_b200_flat flat;
 	struct fsm_b200_owned_desc out;
 	struct fsm *dfa;
-	uint32_t s;
 	int rc;
 
 	assert(nfa != NULL);
@@ -350,46 +395,14 @@ fsm_determinise_with_config(struct fsm *nfa, const struct fsm_determinise_config
 	}
 	fsm_b200_flat_free(&flat);
 
-	dfa = fsm_new_statealloc(nfa->alloc, out.desc.nstates > 0 ? out.desc.nstates : 1);
-	if (dfa == NULL) {
-		goto fail;
-	}
-	if (out.desc.nstates > 0 && !fsm_addstate_bulk(dfa, out.desc.nstates)) {
-		goto fail_dfa;
-	}
-	for (s = 0; s < out.desc.nstates; s++) {
-		uint64_t g, e;
-		const uint64_t g0 = out.desc.group_off[s], g1 = out.desc.group_off[s + 1];
-		if (g1 > g0 && !edge_set_advise_growth(&dfa->states[s].edges, dfa->alloc, (size_t) (g1 - g0))) {
-			goto fail_dfa;
-		}
-		for (g = g0; g < g1; g++) {      /* groups arrive sorted by destination: pure appends */
-			uint64_t sym[4];
-			memcpy(sym, &out.desc.group_symbols[4 * g], sizeof sym);
-			if (!edge_set_add_bulk(&dfa->states[s].edges, dfa->alloc, sym, out.desc.group_to[g])) {
-				goto fail_dfa;
-			}
-		}
-		if (out.desc.is_end[s]) {
-			fsm_setend(dfa, s, 1);
-			for (e = out.desc.endid_off[s]; e < out.desc.endid_off[s + 1]; e++) {
-				if (!fsm_endid_set(dfa, s, out.desc.endids[e])) {
-					goto fail_dfa;
-				}
-			}
-		}
-	}
-	fsm_setstart(dfa, 0);
+	dfa = fsm_from_desc(nfa->alloc, &out.desc);
 	fsm_b200_desc_free(&out);
+	if (dfa == NULL) {
+		return FSM_DETERMINISE_WITH_CONFIG_ERRNO;
+	}
 	fsm_b200_invalidate(nfa);
 	fsm_move(nfa, dfa);
 	return FSM_DETERMINISE_WITH_CONFIG_OK;
-
-fail_dfa:
-	fsm_free(dfa);
-fail:
-	fsm_b200_desc_free(&out);
-	return FSM_DETERMINISE_WITH_CONFIG_ERRNO;
 }
 
 int
@@ -403,6 +416,57 @@ fsm_determinise(struct fsm *nfa)
 	default:
 		return 0;
 	}
+}
+
+/* ------------------------------------------------------------------ fsm_minimise ------ */
+
+/*
+ * fsm_minimise (include/fsm/fsm.h:502-503), replacing src/libfsm/minimise.c's entry point.
+ * Same contract: requires a DFA (the reference asserts, minimise.c:89-90; here 0/EINVAL), in
+ * place, 1 on success.  Trim + partition refinement run in the engine (K3); the minimal DFA is
+ * unique up to numbering, so the result is isomorphic to the reference's.  An fsm that can
+ * match nothing ends up with no states, like the reference after its fsm_trim
+ * (minimise.c:93-101).
+ */
+int
+fsm_minimise(struct fsm *fsm)
+{
+	struct fsm_b200_flat flat;
+	struct fsm_b200_owned_desc out;
+	struct fsm *min;
+
+	assert(fsm != NULL);
+	if (fsm_countcaptures(fsm) > 0 || unsupported(fsm, NULL)) {
+		errno = ENOTSUP;
+		return 0;
+	}
+	if (fsm->statecount == 0) {
+		return 1;
+	}
+	if (fsm_b200_flatten(fsm, &flat) != 0) {
+		return 0;
+	}
+	if (!flat.desc.hasstart) {           /* fsm_trim: nothing is reachable; the reference sweeps every state */
+		fsm_b200_flat_free(&flat);
+		min = fsm_new(fsm->alloc);
+		if (min == NULL) return 0;
+		fsm_b200_invalidate(fsm);
+		fsm_move(fsm, min);
+		return 1;
+	}
+	if (fsm_b200_minimise(&flat.desc, device_index(), &out) != 0) {
+		fsm_b200_flat_free(&flat);
+		return 0;
+	}
+	fsm_b200_flat_free(&flat);
+	min = fsm_from_desc(fsm->alloc, &out.desc);
+	fsm_b200_desc_free(&out);
+	if (min == NULL) {
+		return 0;
+	}
+	fsm_b200_invalidate(fsm);
+	fsm_move(fsm, min);
+	return 1;
 }
 
 int

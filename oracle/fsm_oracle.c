@@ -593,6 +593,201 @@ oracle_desc_free(struct oracle_owned_desc *d)
 	memset(&d->desc, 0, sizeof d->desc);
 }
 
+/* ---------------------------------------------------------------------------------
+ * Minimisation (Moore refinement on the trimmed DFA).
+ * --------------------------------------------------------------------------------- */
+struct sigrow { uint32_t state; const uint32_t *sig; size_t len; };
+
+static size_t g_siglen;
+
+static int
+cmp_sigrow(const void *a, const void *b)
+{
+	const struct sigrow *x = a, *y = b;
+	int c = memcmp(x->sig, y->sig, g_siglen * sizeof(uint32_t));
+	if (c != 0) return c;
+	return (x->state > y->state) - (x->state < y->state);
+}
+
+int
+oracle_minimise(const struct fsm_b200_desc *d, struct oracle_owned_desc *out)
+{
+	const uint32_t n = d->nstates;
+	uint32_t *table = NULL, *newid = NULL, *cls = NULL, *ncls_arr = NULL, *sig = NULL, *rep = NULL;
+	uint8_t *reach = NULL, *co = NULL;
+	struct sigrow *rows = NULL;
+	struct vec64 o_goff = {0}, o_gsym = {0}, o_eoff = {0};
+	struct vec32 o_gto = {0}, o_eid = {0};
+	uint32_t m = 0, ncls = 0, s;
+	unsigned c;
+	int rc = -1, changed;
+
+	memset(out, 0, sizeof *out);
+	if (!oracle_isdfa(d)) { errno = EINVAL; return -1; }
+	table = malloc(sizeof *table * (size_t) n * 256 + 4);
+	reach = calloc((size_t) n + 1, 1); co = calloc((size_t) n + 1, 1);
+	newid = malloc(sizeof *newid * ((size_t) n + 1));
+	if (!table || !reach || !co || !newid) goto oom;
+	oracle_flatten(d, table);
+
+	/* trim: reachable from start ... */
+	reach[d->start] = 1;
+	do {
+		changed = 0;
+		for (s = 0; s < n; s++) {
+			if (!reach[s]) continue;
+			for (c = 0; c < 256; c++) {
+				uint32_t t = table[(size_t) s * 256 + c];
+				if (t != NO_EDGE && !reach[t]) { reach[t] = 1; changed = 1; }
+			}
+		}
+	} while (changed);
+	/* ... and able to reach an end state */
+	for (s = 0; s < n; s++) co[s] = d->is_end[s] ? 1 : 0;
+	do {
+		changed = 0;
+		for (s = 0; s < n; s++) {
+			if (co[s]) continue;
+			for (c = 0; c < 256; c++) {
+				uint32_t t = table[(size_t) s * 256 + c];
+				if (t != NO_EDGE && co[t]) { co[s] = 1; changed = 1; break; }
+			}
+		}
+	} while (changed);
+	for (s = 0; s < n; s++) newid[s] = (reach[s] && co[s]) ? m++ : NO_EDGE;
+	if (m == 0 || newid[d->start] == NO_EDGE) {
+		/* nothing left (minimise.c:98-101): an empty fsm */
+		uint64_t *z = calloc(2, sizeof *z), *z2 = calloc(2, sizeof *z2);
+		if (!z || !z2) { free(z); free(z2); goto oom; }
+		out->desc.nstates = 0; out->desc.hasstart = 0;
+		out->desc.group_off = z; out->desc.endid_off = z2;
+		out->blocks[0] = z; out->blocks[1] = z2;
+		rc = 0;
+		goto done;
+	}
+
+	/* Moore refinement over the kept states; signature = (class, class of every successor) */
+	cls = malloc(sizeof *cls * m); ncls_arr = malloc(sizeof *ncls_arr * m);
+	sig = malloc(sizeof *sig * (size_t) m * 257); rows = malloc(sizeof *rows * m);
+	if (!cls || !ncls_arr || !sig || !rows) goto oom;
+	{
+		/* initial classes: non-end states together; end states by end-id set */
+		uint32_t *orig = malloc(sizeof *orig * m);
+		if (!orig) goto oom;
+		for (s = 0; s < n; s++) if (newid[s] != NO_EDGE) orig[newid[s]] = s;
+		for (uint32_t i = 0; i < m; i++) {
+			uint32_t si = orig[i], k;
+			cls[i] = NO_EDGE;
+			if (!d->is_end[si]) { cls[i] = 0; continue; }
+			for (k = 0; k < i; k++) {
+				uint32_t sk = orig[k];
+				size_t li, lk;
+				if (!d->is_end[sk] || cls[k] == NO_EDGE) continue;
+				li = d->endid_off ? (size_t) (d->endid_off[si + 1] - d->endid_off[si]) : 0;
+				lk = d->endid_off ? (size_t) (d->endid_off[sk + 1] - d->endid_off[sk]) : 0;
+				if (li == lk && (li == 0 || memcmp(d->endids + d->endid_off[si], d->endids + d->endid_off[sk], li * sizeof(uint32_t)) == 0)) {
+					cls[i] = cls[k];
+					break;
+				}
+			}
+			if (cls[i] == NO_EDGE) cls[i] = 1 + i;      /* fresh id, distinct from 0 */
+		}
+		g_siglen = 257;
+		for (;;) {
+			uint32_t cnt = 0, i;
+			for (i = 0; i < m; i++) {
+				uint32_t *row = sig + (size_t) i * 257;
+				row[0] = cls[i];
+				for (c = 0; c < 256; c++) {
+					uint32_t t = table[(size_t) orig[i] * 256 + c];
+					row[1 + c] = (t == NO_EDGE || newid[t] == NO_EDGE) ? NO_EDGE : cls[newid[t]];
+				}
+				rows[i].state = i; rows[i].sig = row; rows[i].len = 257;
+			}
+			qsort(rows, m, sizeof *rows, cmp_sigrow);
+			/* class id = smallest member (rows are sorted by signature then state) */
+			for (i = 0; i < m; i++) {
+				if (i == 0 || memcmp(rows[i].sig, rows[i - 1].sig, 257 * sizeof(uint32_t)) != 0) {
+					cnt++;
+					ncls_arr[rows[i].state] = rows[i].state;
+				} else {
+					ncls_arr[rows[i].state] = ncls_arr[rows[i - 1].state];
+				}
+			}
+			memcpy(cls, ncls_arr, sizeof *cls * m);
+			if (cnt == ncls) break;
+			ncls = cnt;
+		}
+		/* renumber classes densely in order of their smallest member */
+		rep = malloc(sizeof *rep * m);
+		if (!rep) { free(orig); goto oom; }
+		{
+			uint32_t next = 0;
+			for (uint32_t i = 0; i < m; i++) rep[i] = NO_EDGE;
+			for (uint32_t i = 0; i < m; i++) if (cls[i] == i) rep[i] = next++;
+			ncls = next;
+		}
+		/* emit */
+		{
+			uint8_t *is_end = calloc((size_t) ncls + 1, 1);
+			uint32_t i;
+			if (!is_end || !vec64_push(&o_goff, 0) || !vec64_push(&o_eoff, 0)) { free(orig); free(is_end); goto oom; }
+			for (i = 0; i < m; i++) {
+				uint32_t dst_of_sym[256], dsts[256];
+				size_t nd = 0, j;
+				if (cls[i] != i) continue;
+				is_end[rep[i]] = d->is_end[orig[i]];
+				for (c = 0; c < 256; c++) {
+					uint32_t t = table[(size_t) orig[i] * 256 + c];
+					dst_of_sym[c] = (t == NO_EDGE || newid[t] == NO_EDGE) ? NO_EDGE : rep[cls[newid[t]]];
+					if (dst_of_sym[c] != NO_EDGE) dsts[nd++] = dst_of_sym[c];
+				}
+				nd = sort_unique(dsts, nd);
+				for (j = 0; j < nd; j++) {
+					uint64_t sym[4] = {0, 0, 0, 0};
+					for (c = 0; c < 256; c++) if (dst_of_sym[c] == dsts[j]) sym[c >> 6] |= 1ull << (c & 63);
+					if (!vec64_push(&o_gsym, sym[0]) || !vec64_push(&o_gsym, sym[1]) || !vec64_push(&o_gsym, sym[2]) ||
+					    !vec64_push(&o_gsym, sym[3]) || !vec32_push(&o_gto, dsts[j])) { free(orig); free(is_end); goto oom; }
+				}
+				if (!vec64_push(&o_goff, o_gto.n)) { free(orig); free(is_end); goto oom; }
+				if (d->is_end[orig[i]] && d->endid_off) {
+					uint64_t q;
+					for (q = d->endid_off[orig[i]]; q < d->endid_off[orig[i] + 1]; q++) {
+						if (!vec32_push(&o_eid, d->endids[q])) { free(orig); free(is_end); goto oom; }
+					}
+				}
+				if (!vec64_push(&o_eoff, o_eid.n)) { free(orig); free(is_end); goto oom; }
+			}
+			out->desc.nstates = ncls;
+			out->desc.start = rep[cls[newid[d->start]]];
+			out->desc.hasstart = 1;
+			out->desc.is_end = is_end;
+			out->desc.group_off = o_goff.a;
+			out->desc.group_symbols = o_gsym.a ? o_gsym.a : calloc(4, sizeof(uint64_t));
+			out->desc.group_to = o_gto.a ? o_gto.a : calloc(1, sizeof(uint32_t));
+			out->desc.endid_off = o_eoff.a;
+			out->desc.endids = o_eid.a ? o_eid.a : calloc(1, sizeof(uint32_t));
+			out->blocks[0] = is_end;
+			out->blocks[1] = (void *) out->desc.group_off;
+			out->blocks[2] = (void *) out->desc.group_symbols;
+			out->blocks[3] = (void *) out->desc.group_to;
+			out->blocks[4] = (void *) out->desc.endid_off;
+			out->blocks[5] = (void *) out->desc.endids;
+			o_goff.a = NULL; o_gsym.a = NULL; o_gto.a = NULL; o_eoff.a = NULL; o_eid.a = NULL;
+		}
+		free(orig);
+		rc = 0;
+	}
+	goto done;
+oom:
+	errno = ENOMEM;
+	rc = -1;
+done:
+	free(table); free(reach); free(co); free(newid); free(cls); free(ncls_arr); free(sig); free(rows); free(rep);
+	free(o_goff.a); free(o_gsym.a); free(o_gto.a); free(o_eoff.a); free(o_eid.a);
+	return rc;
+}
+
 uint32_t
 oracle_canonicalise(const struct fsm_b200_desc *d, uint32_t *canon_table,
 	uint32_t *canon_of_state)

@@ -54,6 +54,14 @@ int oracle_determinise(const struct fsm_b200_desc *nfa, size_t state_limit,
 	struct oracle_owned_desc *out);
 void oracle_desc_free(struct oracle_owned_desc *d);
 
+/* fsm_minimise (src/libfsm/minimise.c:74-190): trim states that are unreachable from the start
+ * or cannot reach an end state (fsm_trim FSM_TRIM_START_AND_END_REACHABLE, minimise.c:93-96),
+ * then merge states that cannot be distinguished -- by end-ness, by end-id set
+ * (split_ecs_by_end_metadata, minimise.c:733-) or by any label -- with plain Moore partition
+ * refinement.  The minimal DFA is unique up to numbering; states are numbered here by the
+ * smallest original state of each class.  Input must be a DFA.  Returns 0, or -1 errno. */
+int oracle_minimise(const struct fsm_b200_desc *dfa, struct oracle_owned_desc *out);
+
 /* Canonical form of a DFA for isomorphism checks: BFS renumbering from the start state
  * following symbols 0..255 in order (unreachable states dropped).
  * canon_table [ncanon][256] (UINT32_MAX = no edge), canon_of_state[nstates]

@@ -330,7 +330,45 @@ def main_det():
           f"largest DFA {max(c['dfa'].nstates for c in cases)} states")
 
 
+def main_min():
+    """golden_minimise.npz: (reference-determinised DFA, the reference's fsm_minimise of it), in
+    the reference's own pipeline order (determinise then minimise on the same struct fsm, as
+    re(1)/lx(1)/retest do: src/re/main.c:872-881)."""
+    R = reflib.Ref()
+    cases = []
+    det = goldenio.load_det_cases(os.path.join(HERE, "golden_determinise.npz"))
+    for c in det:
+        h = R.from_flat(c["nfa"])
+        R.determinise(h)
+        dfa_in = R.flatten(h)
+        R.minimise(h)
+        cases.append({"name": "min:" + c["name"], "nfa": dfa_in, "dfa": R.flatten(h)})
+        R.free(h)
+    for pat in (r"a[ -~]{7}\z", r"[0-9]+\.[0-9]+", r"^(GET|POST) /[a-z]+ HTTP/1\.[01]$", r"(a|b)*abb(a|b)*", r"x{3,5}y|x{4}z", "(foo|bar)+baz|qux"):
+        h = R.re_comp(pat.replace("\\\\", "\\"))
+        R.determinise(h)
+        dfa_in = R.flatten(h)
+        R.minimise(h)
+        cases.append({"name": "min:re:" + pat, "nfa": dfa_in, "dfa": R.flatten(h)})
+        R.free(h)
+    # unions with end ids: states that differ only in their end-id sets must stay apart
+    hs = []
+    for i, p in enumerate(["abc", "abd", "ab.", "xyz"]):
+        hh = R.compile_dfa(p); R.setendid(hh, 10 + i); hs.append(hh)
+    u = R.union_array(hs)
+    R.determinise(u)
+    dfa_in = R.flatten(u)
+    R.minimise(u)
+    cases.append({"name": "min:endids:union4", "nfa": dfa_in, "dfa": R.flatten(u)})
+    R.free(u)
+    goldenio.save_det_cases(os.path.join(HERE, "golden_minimise.npz"), cases)
+    print(f"wrote golden_minimise.npz: {len(cases)} cases, {os.path.getsize(os.path.join(HERE, 'golden_minimise.npz')) / 1024:.0f} KiB, "
+          f"largest input {max(c['nfa'].nstates for c in cases)} -> {max(c['dfa'].nstates for c in cases)} states")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) < 2 or sys.argv[1] == "min":
+        main_min()
     if len(sys.argv) < 2 or sys.argv[1] == "exec":
         main()
     if len(sys.argv) < 2 or sys.argv[1] == "det":

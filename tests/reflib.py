@@ -69,6 +69,7 @@ class Oracle:
         L.oracle_flatten.restype = None
         L.oracle_epsilon_closure.argtypes = [P(CDesc), P(vp), P(vp)]
         L.oracle_determinise.argtypes = [P(CDesc), C.c_size_t, P(OwnedDesc)]
+        L.oracle_minimise.argtypes = [P(CDesc), P(OwnedDesc)]
         L.oracle_desc_free.argtypes = [P(OwnedDesc)]
         L.oracle_desc_free.restype = None
         L.oracle_canonicalise.argtypes = [P(CDesc), vp, vp]
@@ -127,6 +128,20 @@ class Oracle:
             raise OSError(C.get_errno(), "oracle_determinise")
         try:
             if od.desc.nstates == 0 and not od.desc.group_off:
+                return FlatFsm(0, 0, False, np.zeros(0, np.uint8), np.zeros(1, np.uint64),
+                               np.zeros((0, 4), np.uint64), np.zeros(0, np.uint32), None, None, None, None)
+            return FlatFsm.from_c(od.desc)
+        finally:
+            self.lib.oracle_desc_free(C.byref(od))
+
+    def minimise(self, f: FlatFsm) -> FlatFsm:
+        d = f.as_c()
+        od = OwnedDesc()
+        rc = self.lib.oracle_minimise(C.byref(d), C.byref(od))
+        if rc != 0:
+            raise OSError(C.get_errno(), "oracle_minimise")
+        try:
+            if od.desc.nstates == 0:
                 return FlatFsm(0, 0, False, np.zeros(0, np.uint8), np.zeros(1, np.uint64),
                                np.zeros((0, 4), np.uint64), np.zeros(0, np.uint32), None, None, None, None)
             return FlatFsm.from_c(od.desc)
