@@ -230,7 +230,20 @@ def main():
     if fused:
         from libfsm_b200.peer import GatherRing
         compact = args.gather_records == "compact"
-        ring = GatherRing(n, world, rank, local, nbuf, elem_bytes=4 if compact else 16)
+        try:
+            ring = GatherRing(n, world, rank, local, nbuf, elem_bytes=4 if compact else 16)
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+        except Exception as e:                      # no peer access on this box: NCCL all-gather instead
+            print(f"[bench] rank {rank}: peer mapping failed ({e}); falling back to --gather nccl", file=sys.stderr)
+            ring = None
+            ok = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # every rank must agree on the path
+        if int(ok.item()) == 0:
+            if ring is not None:
+                ring.close()
+            ring, fused, compact = None, False, False
+            args.gather = "nccl"
+    if fused:
         peer_args = [ring.peer_slot_ptrs(b) for b in range(nbuf)]
         sig_args = [ring.signal_args(b) for b in range(nbuf)]
         own_out = [torch.empty((n, 16), dtype=torch.uint8, device=dev) for _ in range(nbuf)] if compact else None
