@@ -164,6 +164,50 @@ k2_adjacency_kernel(NfaDev nfa, const uint64_t *cl_off, const uint32_t *cl_to, c
 	if (!FILL) aend[s] = end;
 }
 
+/* sort every (state, class) destination list once, so that the per-candidate gather below
+ * concatenates SORTED runs (one long hub run + a few short ones in practice) */
+__global__ void
+k2_adjacency_sort_kernel(uint64_t nkeys, const uint64_t *adj_off, uint32_t *adj_to)
+{
+	const uint64_t key = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (key >= nkeys) return;
+	uint32_t *a = adj_to + adj_off[key];
+	const uint32_t n = (uint32_t) (adj_off[key + 1] - adj_off[key]);
+	if (n < 2) return;
+	if (n <= 64) {
+		for (uint32_t i = 1; i < n; i++) {
+			const uint32_t v = a[i];
+			uint32_t j = i;
+			while (j > 0 && a[j - 1] > v) { a[j] = a[j - 1]; j--; }
+			a[j] = v;
+		}
+		return;
+	}
+	for (uint32_t start = n / 2; start-- > 0; ) {
+		uint32_t root = start;
+		for (;;) {
+			uint32_t child = 2 * root + 1;
+			if (child >= n) break;
+			if (child + 1 < n && a[child] < a[child + 1]) child++;
+			if (a[root] >= a[child]) break;
+			const uint32_t t = a[root]; a[root] = a[child]; a[child] = t;
+			root = child;
+		}
+	}
+	for (uint32_t end = n; end-- > 1; ) {
+		const uint32_t t0 = a[0]; a[0] = a[end]; a[end] = t0;
+		uint32_t root = 0;
+		for (;;) {
+			uint32_t child = 2 * root + 1;
+			if (child >= end) break;
+			if (child + 1 < end && a[child] < a[child + 1]) child++;
+			if (a[root] >= a[child]) break;
+			const uint32_t t = a[root]; a[root] = a[child]; a[child] = t;
+			root = child;
+		}
+	}
+}
+
 /* ------------------------------------------------------------------ K2 kernels --------- */
 
 struct Pool {
@@ -203,7 +247,7 @@ k2_expand_fill_kernel(Pool pool, uint32_t fbeg, uint32_t nf, uint32_t K, const u
 		const size_t key = (size_t) pool.data[i] * K + k;
 		for (uint64_t j = adj_off[key]; j < adj_off[key + 1]; j++) a[n++] = adj_to[j];
 	}
-	if (n <= 48) {                      /* insertion sort */
+	if (n <= 512) {                     /* insertion sort: the input is a few sorted runs */
 		for (uint32_t i = 1; i < n; i++) {
 			const uint32_t v = a[i];
 			uint32_t j = i;
@@ -535,6 +579,7 @@ fsm_b200_determinise(const struct fsm_b200_desc *nfa, int device, size_t state_l
 	if (d_adjto.reserve(adj_total + 1, false, st)) return -1;
 	k2_adjacency_kernel<true><<<blocks_for(n, 128), 128, 0, st>>>(dn, have_closure ? d_cloff.p : nullptr, d_clto.p, d_gcls.p, K,
 	    nullptr, d_adjoff.p, d_cursor.p, d_adjto.p, nullptr); count_launch();
+	k2_adjacency_sort_kernel<<<blocks_for(NK), 256, 0, st>>>(NK, d_adjoff.p, d_adjto.p); count_launch();
 
 	/* ---- K2: frontier-batched subset construction ---- */
 	const auto t_exp = std::chrono::steady_clock::now();
