@@ -129,3 +129,17 @@ def test_shim_selftest_c_program():
     p = subprocess.run([SELFTEST], capture_output=True, timeout=300)
     assert p.returncode == 0, (p.stdout.decode(), p.stderr.decode())
     assert b"shim selftest ok" in p.stdout
+
+
+REFTESTS_DIR = os.path.join(ROOT, "build", "shim", "reftests")
+REFTESTS = sorted(os.listdir(REFTESTS_DIR)) if os.path.isdir(REFTESTS_DIR) else []
+
+
+@pytest.mark.skipif(not REFTESTS, reason="reference unit tests not built against the shim")
+@pytest.mark.parametrize("name", REFTESTS)
+def test_reference_own_c_unit_tests_pass_against_the_shim(name):
+    """The reference's own C unit tests (tests/endids/*.c, tests/re_strings/*.c), compiled
+    unmodified from the reference tree and linked to the shim, so their fsm_determinise /
+    fsm_minimise / fsm_exec calls run on the GPU; they assert internally and exit 0."""
+    p = subprocess.run([os.path.join(REFTESTS_DIR, name)], capture_output=True, timeout=300)
+    assert p.returncode == 0, (name, p.stdout.decode()[-2000:], p.stderr.decode()[-2000:])
