@@ -14,6 +14,7 @@ Usage: python tests/golden/make_golden.py
 from __future__ import annotations
 
 import glob
+import json
 import os
 import sys
 
@@ -366,7 +367,54 @@ def main_min():
           f"largest input {max(c['nfa'].nstates for c in cases)} -> {max(c['dfa'].nstates for c in cases)} states")
 
 
+def main_fixtures():
+    """golden_re_fixtures.npz: the reference's regex golden files (tests/<dialect>/inN.re ->
+    outN.fsm, compared by the reference with `fsm -t equal`), as (dialect, re(1) arguments, regex
+    bytes, expected automaton).  Kept only if the reference's own re(1) reproduces outN.fsm here."""
+    import subprocess
+    import tempfile
+    R = reflib.Ref()
+    re_ref = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "re_ref")
+    dirs = [("pcre", "pcre", []), ("pcre-anchor", "pcre", []), ("pcre-repeat", "pcre", []), ("pcre-flags", "pcre", ["-b"]),
+            ("native", "native", []), ("glob", "glob", []), ("like", "like", []), ("literal", "literal", []), ("sql", "sql", [])]
+    out, meta, kept, skipped = {}, [], 0, 0
+    for d, dialect, extra in dirs:
+        for path in sorted(glob.glob(os.path.join(REF_TESTS, d, "in*.re"))):
+            n = os.path.basename(path)[2:-3]
+            outp = os.path.join(REF_TESTS, d, f"out{n}.fsm")
+            if not os.path.exists(outp):
+                continue
+            args = list(extra)
+            modep = os.path.join(REF_TESTS, d, f"mode{n}")
+            if os.path.exists(modep):
+                args = ["-F", open(modep).read().strip()] + args
+            regex = open(path, "rb").read()
+            with tempfile.TemporaryDirectory() as td:
+                rf = os.path.join(td, "in.re"); open(rf, "wb").write(regex)
+                p = subprocess.run([re_ref] + args + ["-r", dialect, "-py", rf], capture_output=True, timeout=60)
+                if p.returncode != 0:
+                    skipped += 1; continue
+                gf = os.path.join(td, "got.fsm"); open(gf, "wb").write(p.stdout)
+                hg, he = R.parse_file(gf), R.parse_file(outp)
+                same = R.equal(hg, he)
+                exp = R.flatten(he)
+                R.free(hg); R.free(he)
+            if not same:
+                skipped += 1; continue
+            pre = f"f{kept}_"
+            goldenio.pack_fsm(pre, exp, out)
+            out[pre + "regex"] = np.frombuffer(regex, dtype=np.uint8)
+            meta.append({"name": f"{d}:in{n}", "dialect": dialect, "args": args})
+            kept += 1
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "golden_re_fixtures.npz"), **out)
+    print(f"wrote golden_re_fixtures.npz: {kept} fixtures ({skipped} skipped), "
+          f"{os.path.getsize(os.path.join(HERE, 'golden_re_fixtures.npz')) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) < 2 or sys.argv[1] == "fixtures":
+        main_fixtures()
     if len(sys.argv) < 2 or sys.argv[1] == "min":
         main_min()
     if len(sys.argv) < 2 or sys.argv[1] == "exec":

@@ -94,3 +94,16 @@ def load_det_cases(path: str) -> list[dict]:
         c["closure_to"] = z[p + "cl_to"] if (p + "cl_to") in z.files else None
         cases.append(c)
     return cases
+
+
+def load_re_fixtures(path: str) -> list[dict]:
+    """The reference's regex golden files: name, dialect, re(1) args, regex bytes, expected automaton."""
+    z = np.load(path)
+    meta = json.loads(bytes(z["meta"]).decode())
+    out = []
+    for i, m in enumerate(meta):
+        c = dict(m)
+        c["regex"] = bytes(z[f"f{i}_regex"])
+        c["fsm"] = unpack_fsm(f"f{i}_", z)
+        out.append(c)
+    return out

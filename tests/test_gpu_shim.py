@@ -143,3 +143,40 @@ def test_reference_own_c_unit_tests_pass_against_the_shim(name):
     fsm_minimise / fsm_exec calls run on the GPU; they assert internally and exit 0."""
     p = subprocess.run([os.path.join(REFTESTS_DIR, name)], capture_output=True, timeout=300)
     assert p.returncode == 0, (name, p.stdout.decode()[-2000:], p.stderr.decode()[-2000:])
+
+
+FIXTURES_NPZ = os.path.join(ROOT, "tests", "golden", "golden_re_fixtures.npz")
+
+
+def _fixtures():
+    import goldenio
+    return goldenio.load_re_fixtures(FIXTURES_NPZ) if os.path.exists(FIXTURES_NPZ) else []
+
+
+@needs_bins
+def test_reference_regex_golden_files_through_re_b200(ref, tmp_path):
+    """The reference's regex golden-file tests (tests/pcre, pcre-anchor, pcre-repeat, pcre-flags,
+    native, glob, like, literal, sql: `re -r D -py inN.re` compared with outN.fsm by language
+    equality, tests/pcre/Makefile:44-78) replayed with the relinked re(1): re_comp is the
+    reference's, fsm_determinise / fsm_minimise run through K2 / K3, the comparator is the
+    reference's fsm_equal."""
+    fixtures = _fixtures()
+    assert len(fixtures) >= 200
+    if not os.environ.get("FSM_B200_ALL_FIXTURES"):
+        fixtures = fixtures[::2]          # every re(1) process pays a CUDA context start-up (~0.4 s)
+    bad = []
+    for k, fx in enumerate(fixtures):
+        rf = tmp_path / "in.re"
+        rf.write_bytes(fx["regex"])
+        p = subprocess.run([RE_B200] + fx["args"] + ["-r", fx["dialect"], "-py", str(rf)], capture_output=True, timeout=120)
+        if p.returncode != 0:
+            bad.append((fx["name"], "exit", p.returncode, p.stderr[-200:]))
+            continue
+        gf = tmp_path / "got.fsm"
+        gf.write_bytes(p.stdout)
+        hg = ref.parse_file(str(gf))
+        he = ref.from_flat(fx["fsm"])
+        if not ref.equal(hg, he):
+            bad.append((fx["name"], "language differs"))
+        ref.free(hg); ref.free(he)
+    assert not bad, bad[:10]
