@@ -123,6 +123,11 @@ struct fsm_b200_dfa_info {
 };
 int fsm_b200_dfa_info(const fsm_b200_dfa *dfa, struct fsm_b200_dfa_info *info);
 
+/* The table layout fsm_b200_dfa_compile WOULD choose for `desc` (entry width, row pitch,
+ * shared-memory residency, byte classes, k-stride), computed on the host without touching
+ * any device; same validation and errno as fsm_b200_dfa_compile.  info->device = UINT32_MAX. */
+int fsm_b200_dfa_plan(const struct fsm_b200_desc *desc, struct fsm_b200_dfa_info *info);
+
 /* Copy the dense table back as uint32 next-state indices, [nstates][256], with
  * UINT32_MAX for "no edge".  For tests of the flattener; not a hot path. */
 int fsm_b200_dfa_table(const fsm_b200_dfa *dfa, uint32_t *out /* [nstates*256] */);

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libfsm_b200.so")
 #: every symbol include/fsm_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = (
     "fsm_b200_abi_version", "fsm_b200_device_count", "fsm_b200_last_error",
-    "fsm_b200_dfa_compile", "fsm_b200_dfa_free", "fsm_b200_dfa_info", "fsm_b200_dfa_table",
+    "fsm_b200_dfa_compile", "fsm_b200_dfa_free", "fsm_b200_dfa_info", "fsm_b200_dfa_plan", "fsm_b200_dfa_table",
     "fsm_b200_exec_batch_host", "fsm_b200_exec_batch_dev", "fsm_b200_exec_batch_dev_gather",
     "fsm_b200_dev_alloc", "fsm_b200_dev_free", "fsm_b200_dev_zero", "fsm_b200_dev_read",
     "fsm_b200_ipc_export", "fsm_b200_ipc_open", "fsm_b200_ipc_close",
@@ -58,6 +58,7 @@ def _load() -> C.CDLL:
     lib.fsm_b200_dfa_free.argtypes = [vp]
     lib.fsm_b200_dfa_free.restype = None
     lib.fsm_b200_dfa_info.argtypes = [vp, P(CDfaInfo)]
+    lib.fsm_b200_dfa_plan.argtypes = [P(CDesc), P(CDfaInfo)]
     lib.fsm_b200_dfa_table.argtypes = [vp, vp]
     lib.fsm_b200_exec_batch_host.argtypes = [vp, vp, vp, sz, vp]
     lib.fsm_b200_exec_batch_dev.argtypes = [vp, vp, vp, u64, u64, sz, vp, vp]

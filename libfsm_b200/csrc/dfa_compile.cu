@@ -46,9 +46,11 @@ desc_is_dfa(const fsm_b200_desc *d)
 
 } // namespace
 
-extern "C" int
-fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
+/* device >= 0: validate, lay out, upload.  device < 0: validate and lay out only (the plan). */
+static int
+compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 {
+	const bool upload = device >= 0;
 	if (desc == nullptr || out == nullptr || desc->reserved != 0) {
 		set_error("dfa_compile: bad argument");
 		errno = EINVAL;
@@ -199,10 +201,12 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa 
 	}
 	if (dfa->nclasses) memcpy(blob.data() + dfa->cls_off, dfa->class_of, 256);
 
-	FSMB_CUDA(cudaSetDevice(device), { fsm_b200_dfa_free(dfa); return -1; });
-	FSMB_CUDA(cudaMalloc(&dfa->d_blob, dfa->blob_bytes), { fsm_b200_dfa_free(dfa); return -1; });
-	FSMB_CUDA(cudaMemcpy(dfa->d_blob, blob.data(), dfa->blob_bytes, cudaMemcpyHostToDevice),
-	    { fsm_b200_dfa_free(dfa); return -1; });
+	if (upload) {
+		FSMB_CUDA(cudaSetDevice(device), { fsm_b200_dfa_free(dfa); return -1; });
+		FSMB_CUDA(cudaMalloc(&dfa->d_blob, dfa->blob_bytes), { fsm_b200_dfa_free(dfa); return -1; });
+		FSMB_CUDA(cudaMemcpy(dfa->d_blob, blob.data(), dfa->blob_bytes, cudaMemcpyHostToDevice),
+		    { fsm_b200_dfa_free(dfa); return -1; });
+	}
 
 	{   /* absorbing states (all 256 edges are self-loops; also the dead row): a stream chunk entered
 	     * in such a state leaves in it, so K1b needs no scan job for it */
@@ -216,8 +220,10 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa 
 			ab[st] = self ? 1 : 0;
 			if (self && st < S) dfa->has_absorbing = 1;
 		}
-		FSMB_CUDA(cudaMalloc(&dfa->d_absorb, dfa->ntable), { fsm_b200_dfa_free(dfa); return -1; });
-		FSMB_CUDA(cudaMemcpy(dfa->d_absorb, ab.data(), dfa->ntable, cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
+		if (upload) {
+			FSMB_CUDA(cudaMalloc(&dfa->d_absorb, dfa->ntable), { fsm_b200_dfa_free(dfa); return -1; });
+			FSMB_CUDA(cudaMemcpy(dfa->d_absorb, ab.data(), dfa->ntable, cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
+		}
 	}
 
 	/* ---- k-stride form: with C byte classes and C^K <= 256, index rows by the class tuple of
@@ -276,8 +282,10 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa 
 				for (int c = 0; c < 256; c++) kb[klut_off + 256u * j + c] = (uint8_t) (kcls[c] * wgt);
 				wgt *= KC;
 			}
-			FSMB_CUDA(cudaMalloc(&dfa->d_kblob, kbytes), { fsm_b200_dfa_free(dfa); return -1; });
-			FSMB_CUDA(cudaMemcpy(dfa->d_kblob, kb.data(), kbytes, cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
+			if (upload) {
+				FSMB_CUDA(cudaMalloc(&dfa->d_kblob, kbytes), { fsm_b200_dfa_free(dfa); return -1; });
+				FSMB_CUDA(cudaMemcpy(dfa->d_kblob, kb.data(), kbytes, cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
+			}
 			dfa->kstride = K; dfa->kclasses = KC; dfa->kpitch = kpitch; dfa->k1pitch = k1pitch;
 			dfa->k1_off = k1_off; dfa->kend_off = kend_off; dfa->klut_off = klut_off; dfa->kblob_bytes = kbytes;
 		}
@@ -286,7 +294,34 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa 
 	return 0;
 }
 
+extern "C" int
+fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
+{
+	if (device < 0) {
+		set_error("dfa_compile: bad device %d", device);
+		errno = EINVAL;
+		return -1;
+	}
+	return compile_impl(desc, device, out);
+}
+
 namespace fsmb200 { void scratch_free(fsm_b200_dfa *dfa); void stream_scratch_free(fsm_b200_dfa *dfa); }
+
+/* The layout a compile WOULD choose, without touching any device: host logic only. */
+extern "C" int
+fsm_b200_dfa_plan(const struct fsm_b200_desc *desc, struct fsm_b200_dfa_info *info)
+{
+	fsm_b200_dfa *dfa = nullptr;
+	if (info == nullptr) {
+		errno = EINVAL;
+		return -1;
+	}
+	if (compile_impl(desc, -1, &dfa) != 0) return -1;
+	const int rc = fsm_b200_dfa_info(dfa, info);
+	info->device = 0xFFFFFFFFu;
+	fsm_b200_dfa_free(dfa);            /* nothing was allocated on a device: frees host copies only */
+	return rc;
+}
 
 extern "C" void
 fsm_b200_dfa_free(fsm_b200_dfa *dfa)

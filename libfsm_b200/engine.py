@@ -35,6 +35,16 @@ def launch_count(reset: bool = False) -> int:
     return int(lib.fsm_b200_launch_count(1 if reset else 0))
 
 
+def plan(fsm: FlatFsm) -> dict:
+    """The table layout a compile would choose for `fsm`, computed on the host (no device needed):
+    entry width, row pitch, shared-memory residency, byte classes, k-stride.  Raises like
+    ``Dfa(...)`` (EINVAL) when `fsm` is not a DFA."""
+    info = CDfaInfo()
+    cdesc = fsm.as_c()
+    check(lib.fsm_b200_dfa_plan(C.byref(cdesc), C.byref(info)), "dfa_plan")
+    return {k: int(getattr(info, k)) for k, _ in CDfaInfo._fields_}
+
+
 def _is_torch_cuda(x) -> bool:
     return hasattr(x, "is_cuda") and bool(x.is_cuda)
 

@@ -1,0 +1,76 @@
+"""CPU: the flattener's host logic -- validation and table-layout decisions -- through
+fsm_b200_dfa_plan (no device needed), on the golden automata recorded from the reference."""
+import errno
+import os
+
+import pytest
+
+import goldenio
+import libfsm_b200 as L
+
+CASES = {c["name"]: c for c in goldenio.load_exec_cases(os.path.join(goldenio.GOLDEN_DIR, "golden_exec.npz"))}
+
+
+def case(prefix):
+    return next(c for n, c in CASES.items() if n.startswith(prefix))
+
+
+def test_config2_dfa_layout():
+    p = L.plan(case("cfg2:uniform")["fsm"])
+    assert p["nstates"] == 256 and p["ntable_states"] == 256 and p["complete"] == 1   # no dead row needed
+    assert p["entry_bytes"] == 1 and p["row_pitch_bytes"] == 260 and p["smem_resident"] == 1
+    assert p["nclasses"] == 0 and p["kstride"] == 4                                     # 3 byte classes -> K = 4
+    assert p["table_bytes"] == 256 * 260
+
+
+def test_incomplete_dfa_gets_a_dead_row():
+    p = L.plan(case("anchored:^abc[0-9]+x$")["fsm"])
+    assert p["complete"] == 0 and p["ntable_states"] == p["nstates"] + 1
+    assert p["entry_bytes"] == 1 and p["smem_resident"] == 1 and p["kstride"] == 0     # small table: one-byte kernel
+
+
+def test_wide_tables_use_byte_class_rows():
+    f = case("union6:")["fsm"]
+    p = L.plan(f)
+    assert f.nstates > 256 and p["entry_bytes"] == 2
+    assert 1 <= p["nclasses"] <= 64 and p["smem_resident"] == 1                        # classed rows fit shared memory
+    assert p["row_pitch_bytes"] >= 2 * p["nclasses"] and (p["row_pitch_bytes"] // 4) % 2 == 1   # odd word pitch
+    assert p["kstride"] == 0
+
+
+def test_kstride_choices():
+    assert L.plan(case("cfg1:digits")["fsm"])["kstride"] == 4
+    assert L.plan(case("endids:union6x5")["fsm"])["kstride"] == 2                        # <= 16 classes, > 32 rows
+    assert L.plan(case("utf8:")["fsm"])["kstride"] == 0                                  # 8 states: stays one-byte
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_plan_agrees_with_validation(oracle, name):
+    c = CASES[name]
+    if c["is_dfa"]:
+        p = L.plan(c["fsm"])
+        assert p["nstates"] == c["fsm"].nstates and p["start"] == c["fsm"].start
+        complete = bool((oracle.flatten(c["fsm"]) != 0xFFFFFFFF).all())
+        assert p["complete"] == int(complete)
+    else:
+        with pytest.raises(L.FsmB200Error) as ei:
+            L.plan(c["fsm"])
+        assert ei.value.errno == errno.EINVAL
+
+
+def test_layout_knobs(monkeypatch):
+    f = case("cfg2:uniform")["fsm"]
+    monkeypatch.setenv("FSM_B200_ROW_PAD", "0")
+    assert L.plan(f)["row_pitch_bytes"] == 256
+    monkeypatch.delenv("FSM_B200_ROW_PAD")
+    monkeypatch.setenv("FSM_B200_FORCE_CLASSED", "1")
+    p = L.plan(f)
+    assert p["nclasses"] == 3 and p["row_pitch_bytes"] == 4 and p["smem_resident"] == 1
+    monkeypatch.delenv("FSM_B200_FORCE_CLASSED")
+    monkeypatch.setenv("FSM_B200_KSTRIDE", "2")
+    assert L.plan(f)["kstride"] == 2
+    monkeypatch.setenv("FSM_B200_KSTRIDE", "0")
+    assert L.plan(f)["kstride"] == 0
+    monkeypatch.delenv("FSM_B200_KSTRIDE")
+    monkeypatch.setenv("FSM_B200_NO_KSTRIDE", "1")
+    assert L.plan(f)["kstride"] == 0
