@@ -167,6 +167,12 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 	dfa->is_end_off = (uint32_t) table_pad;
 	dfa->cls_off = (uint32_t) (table_pad + end_pad);
 	dfa->blob_bytes = table_pad + end_pad + (dfa->nclasses ? 256u : 0u);
+	if (dfa->blob_bytes >= (1ull << 32)) {      /* kernel-side offsets are 32-bit */
+		fsm_b200_dfa_free(dfa);
+		set_error("dfa_compile: transition table of %llu bytes is not supported (>= 4 GiB)", (unsigned long long) dfa->blob_bytes);
+		errno = ENOTSUP;
+		return -1;
+	}
 
 	std::vector<uint8_t> blob;
 	try {
