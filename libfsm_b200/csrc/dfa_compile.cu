@@ -132,19 +132,32 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 		dfa->smem_resident = 1;
 		dfa->pitch = (uint32_t) dense_pitch;
 	} else {
-		/* byte classes: symbols whose columns are identical in every row */
+		/* byte classes: symbols whose columns are identical in every row.  One pass hashes
+		 * every column (O(256 S)); equal hashes are confirmed against the class representative */
 		uint8_t rep[256];
-		for (int c = 0; c < 256; c++) {
-			int found = -1;
-			for (uint32_t k = 0; k < C && found < 0; k++) {
-				bool same = true;
-				for (uint32_t s = 0; s < S && same; s++) {
-					same = t32[(size_t) s * 256 + c] == t32[(size_t) s * 256 + rep[k]];
+		{
+			std::vector<uint64_t> colhash(256, 0x9e3779b97f4a7c15ull);
+			for (uint32_t st = 0; st < S; st++) {
+				const uint32_t *row = t32 + (size_t) st * 256;
+				for (int c = 0; c < 256; c++) {
+					uint64_t h = colhash[c] ^ row[c];
+					h *= 0xff51afd7ed558ccdull;
+					colhash[c] = h ^ (h >> 29);
 				}
-				if (same) found = (int) k;
 			}
-			if (found < 0) { rep[C] = (uint8_t) c; found = (int) C; C++; }
-			dfa->class_of[c] = (uint8_t) found;
+			for (int c = 0; c < 256; c++) {
+				int found = -1;
+				for (uint32_t k = 0; k < C && found < 0; k++) {
+					if (colhash[rep[k]] != colhash[c]) continue;
+					bool same = true;
+					for (uint32_t st = 0; st < S && same; st++) {
+						same = t32[(size_t) st * 256 + c] == t32[(size_t) st * 256 + rep[k]];
+					}
+					if (same) found = (int) k;
+				}
+				if (found < 0) { rep[C] = (uint8_t) c; found = (int) C; C++; }
+				dfa->class_of[c] = (uint8_t) found;
+			}
 		}
 		uint64_t cpitch = ((uint64_t) C * eb + 3u) & ~3ull;
 		if (((cpitch >> 2) & 1u) == 0) cpitch += 4;          /* odd word pitch spreads rows over banks */
