@@ -114,6 +114,8 @@ fsm_b200_flat_free(struct fsm_b200_flat *flat)
 	memset(&flat->desc, 0, sizeof flat->desc);
 }
 
+#ifndef FSM_B200_SHIM_FLATTEN_ONLY
+
 /* ------------------------------------------------------------------ device-table cache */
 
 /* Content fingerprint: everything fsm_exec can observe (start, end bits, epsilon presence,
@@ -486,3 +488,5 @@ fsm_exec_batch(const struct fsm *fsm, const unsigned char *base, const uint64_t 
 	}
 	return fsm_b200_exec_batch_host(dfa, base, offsets, n, out);
 }
+
+#endif /* FSM_B200_SHIM_FLATTEN_ONLY */
