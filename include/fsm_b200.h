@@ -231,10 +231,23 @@ int fsm_b200_determinise(const struct fsm_b200_desc *nfa, int device, size_t sta
 	struct fsm_b200_owned_desc *out);
 void fsm_b200_desc_free(struct fsm_b200_owned_desc *d);
 
+/* Same, with flags.  FSM_B200_DET_REFERENCE_NUMBERING: number the DFA states exactly as the
+ * reference does, i.e. in the order its LIFO worklist (determinise.c:118-185) meets them when
+ * every state lists its successors in the entry order of the pairwise label-group analysis
+ * (determinise.c:898-1054, :1056-1335, :2331-2505) -- the output is then the reference's
+ * `struct fsm` state for state, not merely isomorphic to it.  The per-state successor orders
+ * are computed on the device (libfsm_b200/csrc/refnum.h explains the closed form), the
+ * worklist walk itself is sequential and runs on the host.  fsm_b200_determinise() uses
+ * flags 0 unless the environment says FSM_B200_DET_NUMBERING=reference. */
+#define FSM_B200_DET_REFERENCE_NUMBERING 1u
+int fsm_b200_determinise_ex(const struct fsm_b200_desc *nfa, int device, size_t state_limit,
+	unsigned flags, struct fsm_b200_owned_desc *out);
+
 /* Timing of the last determinise on this thread, milliseconds, for bench.py. */
 struct fsm_b200_det_stats {
 	double ms_total, ms_closure, ms_expand, ms_intern, ms_emit;
 	uint64_t dfa_states, dfa_groups, rounds, kernel_launches;
+	double ms_numbering;     /* reference numbering (0 when not requested) */
 };
 int fsm_b200_determinise_stats(struct fsm_b200_det_stats *st);
 

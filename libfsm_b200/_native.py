@@ -22,7 +22,7 @@ ABI_SYMBOLS = (
     "fsm_b200_ipc_export", "fsm_b200_ipc_open", "fsm_b200_ipc_close",
     "fsm_b200_set_exec_variant", "fsm_b200_get_exec_variant",
     "fsm_b200_exec_stream_host", "fsm_b200_exec_stream_dev", "fsm_b200_exec_stream_map_dev",
-    "fsm_b200_determinise", "fsm_b200_desc_free", "fsm_b200_determinise_stats",
+    "fsm_b200_determinise", "fsm_b200_determinise_ex", "fsm_b200_desc_free", "fsm_b200_determinise_stats",
     "fsm_b200_minimise", "fsm_b200_minimise_stats",
     "fsm_b200_launch_count",
 )
@@ -39,7 +39,7 @@ class CDetStats(C.Structure):
     _fields_ = [("ms_total", C.c_double), ("ms_closure", C.c_double), ("ms_expand", C.c_double),
                 ("ms_intern", C.c_double), ("ms_emit", C.c_double),
                 ("dfa_states", C.c_uint64), ("dfa_groups", C.c_uint64), ("rounds", C.c_uint64),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("ms_numbering", C.c_double)]
 
 
 def _load() -> C.CDLL:
@@ -76,6 +76,7 @@ def _load() -> C.CDLL:
     lib.fsm_b200_exec_stream_dev.argtypes = [vp, vp, u64, P(CResult), vp]
     lib.fsm_b200_exec_stream_map_dev.argtypes = [vp, vp, u64, vp, vp, vp, vp]
     lib.fsm_b200_determinise.argtypes = [P(CDesc), C.c_int, sz, P(COwnedDesc)]
+    lib.fsm_b200_determinise_ex.argtypes = [P(CDesc), C.c_int, sz, C.c_uint, P(COwnedDesc)]
     lib.fsm_b200_desc_free.argtypes = [P(COwnedDesc)]
     lib.fsm_b200_desc_free.restype = None
     lib.fsm_b200_determinise_stats.argtypes = [P(CDetStats)]

@@ -27,9 +27,13 @@
  * The DFA is the reference's up to state numbering (BFS discovery order here; LIFO worklist
  * plus analysis order there): same sets of NFA states, hence same state count, language,
  * end bits and end-id sets (carried as determinise.c:236-266 / endids.c:782-826 do).
+ * With FSM_B200_DET_REFERENCE_NUMBERING the reference's numbering is reproduced as well:
+ *        refnum      per-state successor orders from rank vectors (refnum.h), the LIFO walk on
+ *                    the host, renumbering on the device before the emit.
  * Integer / set workload: no tensor-core shape anywhere.
  */
 #include "k23_common.cuh"
+#include "refnum.h"
 
 namespace {
 
@@ -415,6 +419,52 @@ k2_rehash_kernel(Table tab, Pool pool, uint32_t nsets)
 	}
 }
 
+/* ------------------------------------------------------------------ reference numbering */
+
+/* leaf rank vectors (refnum.h): thread per NFA state over its K sorted destination lists */
+__global__ void
+k2_refnum_leaf_kernel(uint32_t n, uint32_t K, const uint64_t *adj_off, const uint32_t *adj_to, uint16_t *leaf, uint16_t *leaf_m)
+{
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n) return;
+	leaf_m[s] = (uint16_t) rn_leaf_ranks(adj_off + (size_t) s * K, adj_to, K, leaf + (size_t) s * K);
+}
+
+__global__ void
+k2_refnum_kmax_kernel(const uint64_t *pool_off, uint32_t D, uint32_t *kmax)
+{
+	const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t k = d < D ? (uint32_t) (pool_off[d + 1] - pool_off[d]) : 0;
+	for (int o = 16; o > 0; o >>= 1) k = max(k, __shfl_xor_sync(0xFFFFFFFFu, k, o));
+	if ((threadIdx.x & 31) == 0 && k > 0) atomicMax(kmax, k);
+}
+
+/* successor order of every DFA state: thread per state runs the member tournament on a
+ * binary-counter stack held in its slice of `scratch` (depth * K rank slots per thread) */
+__global__ void
+k2_refnum_order_kernel(Pool pool, uint32_t D, uint32_t K, const uint16_t *leaf, const uint16_t *leaf_m,
+	const uint32_t *trans, uint16_t *scratch, uint32_t depth, uint32_t *order, uint16_t *order_m)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	uint16_t *bufs = scratch + (size_t) t * depth * K;
+	for (uint32_t d = t; d < D; d += gridDim.x * blockDim.x) {
+		const uint64_t b = pool.off[d];
+		order_m[d] = (uint16_t) rn_state_order(pool.data + b, (uint32_t) (pool.off[d + 1] - b), leaf, leaf_m, K, bufs,
+		    trans + (size_t) d * K, order + (size_t) d * K);
+	}
+}
+
+/* trans2[perm[s]][k] = perm[trans[s][k]] */
+__global__ void
+k2_refnum_permute_kernel(const uint32_t *trans, uint32_t D, uint32_t K, const uint32_t *perm, uint32_t *trans2)
+{
+	const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (uint64_t) D * K) return;
+	const uint32_t s = (uint32_t) (i / K), k = (uint32_t) (i % K);
+	const uint32_t to = trans[i];
+	trans2[(size_t) perm[s] * K + k] = to == NONE32 ? NONE32 : perm[to];
+}
+
 /* ------------------------------------------------------------------ host: byte classes - */
 
 } // namespace
@@ -435,11 +485,11 @@ fsm_b200_determinise_stats(struct fsm_b200_det_stats *st)
 	return 0;
 }
 
-extern "C" int
-fsm_b200_determinise(const struct fsm_b200_desc *nfa, int device, size_t state_limit,
+static int
+determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit, unsigned flags,
 	struct fsm_b200_owned_desc *out)
 {
-	if (nfa == nullptr || out == nullptr || nfa->reserved != 0) {
+	if (nfa == nullptr || out == nullptr || nfa->reserved != 0 || (flags & ~(unsigned) FSM_B200_DET_REFERENCE_NUMBERING)) {
 		set_error("determinise: bad argument");
 		errno = EINVAL;
 		return -1;
@@ -658,9 +708,59 @@ fsm_b200_determinise(const struct fsm_b200_desc *nfa, int device, size_t state_l
 	tl_stats.ms_expand = ms_since(t_exp);
 	tl_stats.rounds = rounds;
 
+	const uint32_t D = nsets;
+
+	/* ---- optional: the reference's state numbering (refnum.h) ----
+	 * leaf ranks and per-state successor orders on the device, the LIFO worklist walk
+	 * (determinise.c:118-185, sequential by nature) on the host, the renumbering on the
+	 * device again; the emit below then runs on the renumbered table. */
+	const uint32_t *trans_emit = d_trans.p;
+	std::vector<uint32_t> perm, inv;
+	DBuf<uint32_t> d_trans2;
+	if (flags & FSM_B200_DET_REFERENCE_NUMBERING) {
+		const auto t_num = std::chrono::steady_clock::now();
+		DBuf<uint16_t> d_leaf, d_leafm, d_rnscratch, d_orderm;
+		DBuf<uint32_t> d_order, d_kmax, d_perm;
+		if (d_leaf.reserve(NK + 1, false, st) || d_leafm.reserve(n + 1, false, st) || d_kmax.reserve(1, false, st) ||
+		    d_order.reserve((size_t) D * K + 1, false, st) || d_orderm.reserve(D + 1, false, st) ||
+		    d_perm.reserve(D + 1, false, st) || d_trans2.reserve((size_t) D * K + 1, false, st)) return -1;
+		k2_refnum_leaf_kernel<<<blocks_for(n, 128), 128, 0, st>>>(n, K, d_adjoff.p, d_adjto.p, d_leaf.p, d_leafm.p); count_launch();
+		CK(cudaMemsetAsync(d_kmax.p, 0, 4, st));
+		k2_refnum_kmax_kernel<<<blocks_for(D), 256, 0, st>>>(d_pooloff.p, D, d_kmax.p); count_launch();
+		uint32_t kmax = 0;
+		CK(cudaMemcpyAsync(&kmax, d_kmax.p, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		const uint32_t depth = rn_depth_for(std::max(kmax, 1u));
+		const uint32_t nblk = std::min<uint32_t>(blocks_for(D, 128), 148u * 8u);
+		if (d_rnscratch.reserve((size_t) nblk * 128 * depth * K + 1, false, st)) return -1;
+		k2_refnum_order_kernel<<<nblk, 128, 0, st>>>(Pool{ d_pooloff.p, d_pooldata.p }, D, K, d_leaf.p, d_leafm.p, d_trans.p,
+		    d_rnscratch.p, depth, d_order.p, d_orderm.p); count_launch();
+		std::vector<uint32_t> h_order((size_t) D * K);
+		std::vector<uint16_t> h_orderm(D);
+		CK(cudaMemcpyAsync(h_order.data(), d_order.p, (size_t) D * K * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(h_orderm.data(), d_orderm.p, (size_t) D * 2, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		for (uint32_t s = 0; s < D; s++) {
+			if (h_orderm[s] > K) { set_error("determinise: numbering: bad entry count"); errno = EIO; return -1; }
+			for (uint32_t r = 0; r < h_orderm[s]; r++) {
+				if (h_order[(size_t) s * K + r] >= D) { set_error("determinise: numbering: bad successor"); errno = EIO; return -1; }
+			}
+		}
+		rn_lifo_numbering(D, K, h_order.data(), h_orderm.data(), perm);
+		inv.assign(D, NONE32);
+		for (uint32_t s = 0; s < D; s++) {
+			if (perm[s] >= D || inv[perm[s]] != NONE32) { set_error("determinise: numbering: not a permutation"); errno = EIO; return -1; }
+			inv[perm[s]] = s;
+		}
+		CK(cudaMemcpyAsync(d_perm.p, perm.data(), (size_t) D * 4, cudaMemcpyHostToDevice, st));
+		k2_refnum_permute_kernel<<<blocks_for((uint64_t) D * K), 256, 0, st>>>(d_trans.p, D, K, d_perm.p, d_trans2.p); count_launch();
+		CK(cudaStreamSynchronize(st));   /* perm (host memory) is read by the copy above */
+		trans_emit = d_trans2.p;
+		tl_stats.ms_numbering = ms_since(t_num);
+	}
+
 	/* ---- emit: groups on the device; end bits + end ids on the host (O(pool)) ---- */
 	const auto t_emit = std::chrono::steady_clock::now();
-	const uint32_t D = nsets;
 	uint64_t class_mask[256][4];
 	memset(class_mask, 0, sizeof class_mask);
 	for (int c = 0; c < 256; c++) class_mask[class_of[c]][c >> 6] |= 1ull << (c & 63);
@@ -668,14 +768,14 @@ fsm_b200_determinise(const struct fsm_b200_desc *nfa, int device, size_t state_l
 	DBuf<uint32_t> d_ng, d_ogto;
 	if (d_cmask.reserve(1024, false, st) || d_ng.reserve(D + 1, false, st) || d_ogoff.reserve(D + 2, false, st)) return -1;
 	CK(cudaMemcpyAsync(d_cmask.p, class_mask, sizeof class_mask, cudaMemcpyHostToDevice, st));
-	k2_emit_count_kernel<<<blocks_for(D, 128), 128, 0, st>>>(d_trans.p, D, K, d_ng.p); count_launch();
+	k2_emit_count_kernel<<<blocks_for(D, 128), 128, 0, st>>>(trans_emit, D, K, d_ng.p); count_launch();
 	if (scan.run<uint32_t>(d_ng.p, d_ogoff.p, D) != 0) return -1;
 	own->group_off.assign(D + 1, 0);
 	CK(cudaMemcpyAsync(own->group_off.data(), d_ogoff.p, (D + 1) * 8, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	const uint64_t NG = own->group_off[D];
 	if (d_ogto.reserve(NG + 1, false, st) || d_ogsym.reserve(4 * NG + 4, false, st)) return -1;
-	k2_emit_fill_kernel<<<blocks_for(D, 128), 128, 0, st>>>(d_trans.p, D, K, d_cmask.p, d_ogoff.p, d_ogto.p, d_ogsym.p); count_launch();
+	k2_emit_fill_kernel<<<blocks_for(D, 128), 128, 0, st>>>(trans_emit, D, K, d_cmask.p, d_ogoff.p, d_ogto.p, d_ogsym.p); count_launch();
 	own->group_to.resize(NG);
 	own->group_sym.resize(4 * NG);
 	std::vector<uint32_t> h_pooldata(pool_used);
@@ -697,7 +797,8 @@ fsm_b200_determinise(const struct fsm_b200_desc *nfa, int device, size_t state_l
 		/* end bit + end ids: determinise.c:236-266 over the epsilon-folded members */
 		ids.clear();
 		bool end = false;
-		for (uint64_t i = h_pooloff[s]; i < h_pooloff[s + 1]; i++) {
+		const uint32_t src = inv.empty() ? s : inv[s];    /* pool index of output state s */
+		for (uint64_t i = h_pooloff[src]; i < h_pooloff[src + 1]; i++) {
 			const uint32_t m = h_pooldata[i];
 			if (!h_aend[m]) continue;
 			end = true;
@@ -739,4 +840,20 @@ fsm_b200_determinise(const struct fsm_b200_desc *nfa, int device, size_t state_l
 	tl_stats.dfa_groups = own->group_off[D];
 	tl_stats.kernel_launches = fsm_b200_launch_count(0) - launches0;
 	return 0;
+}
+
+extern "C" int
+fsm_b200_determinise_ex(const struct fsm_b200_desc *nfa, int device, size_t state_limit, unsigned flags,
+	struct fsm_b200_owned_desc *out)
+{
+	return determinise_impl(nfa, device, state_limit, flags, out);
+}
+
+extern "C" int
+fsm_b200_determinise(const struct fsm_b200_desc *nfa, int device, size_t state_limit,
+	struct fsm_b200_owned_desc *out)
+{
+	const char *e = getenv("FSM_B200_DET_NUMBERING");
+	const unsigned flags = (e != nullptr && strcmp(e, "reference") == 0) ? FSM_B200_DET_REFERENCE_NUMBERING : 0u;
+	return determinise_impl(nfa, device, state_limit, flags, out);
 }

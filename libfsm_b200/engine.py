@@ -170,11 +170,20 @@ class StateLimitReached(Exception):
     """FSM_DETERMINISE_WITH_CONFIG_STATE_LIMIT_REACHED (reference include/fsm/fsm.h:481-488)."""
 
 
-def determinise(nfa: FlatFsm, device: int = 0, state_limit: int = 0) -> FlatFsm:
-    """GPU subset construction; the reference's DFA up to state renumbering."""
+DET_REFERENCE_NUMBERING = 1
+
+
+def determinise(nfa: FlatFsm, device: int = 0, state_limit: int = 0, numbering: str | None = None) -> FlatFsm:
+    """GPU subset construction.  numbering=None: the library default (BFS order, i.e. the
+    reference's DFA up to state renumbering, unless FSM_B200_DET_NUMBERING=reference);
+    "reference": state for state the DFA fsm_determinise builds; "bfs": BFS order."""
     od = COwnedDesc()
     cdesc = nfa.as_c()
-    rc = lib.fsm_b200_determinise(C.byref(cdesc), device, state_limit, C.byref(od))
+    if numbering is None:
+        rc = lib.fsm_b200_determinise(C.byref(cdesc), device, state_limit, C.byref(od))
+    else:
+        flags = {"reference": DET_REFERENCE_NUMBERING, "bfs": 0}[numbering]
+        rc = lib.fsm_b200_determinise_ex(C.byref(cdesc), device, state_limit, flags, C.byref(od))
     if rc == 1:
         raise StateLimitReached()
     check(rc, "determinise")

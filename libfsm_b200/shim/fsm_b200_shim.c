@@ -356,7 +356,8 @@ fail:
  * reference runs first, determinise.c:48-52) happens in the engine (K2); this function
  * only marshals: struct fsm -> flat NFA -> [GPU] -> flat DFA -> struct fsm -> fsm_move.
  * State NUMBERS are BFS order instead of the reference's LIFO/analysis order (DESIGN.md
- * section 5): an isomorphic DFA.
+ * section 5): an isomorphic DFA -- unless FSM_B200_DET_NUMBERING=reference, in which case the
+ * engine reproduces the reference's numbering too.
  * Not accelerated: capture actions and eager outputs (determinise.c:268-274 remaps them);
  * such FSMs fail with ERRNO/ENOTSUP rather than silently taking another path.
  */

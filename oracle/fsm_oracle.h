@@ -6,7 +6,7 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * this; libfsm_b200.so never links or calls it.
  *
- * Parity is PINNED: tests/test_oracle_vs_reference.py checks every function here against
+ * Parity is PINNED: tests/test_oracle_reference.py checks every function here against
  * the unmodified reference compiled into oracle/_ref/libfsm_ref.so (same DFAs, same
  * inputs, bit-exact records) and against the golden fixtures in tests/golden/ that were
  * generated from the reference by tests/golden/make_golden.py.
