@@ -150,10 +150,18 @@ static struct cache_entry {
 	uint64_t fp;
 	fsm_b200_dfa *dfa;        /* NULL: known not to be a DFA (errno_val says why) */
 	int errno_val;
-	unsigned long stamp;
+	unsigned long stamp;      /* 0: slot unused */
+	unsigned refs;            /* calls executing on `dfa` right now: not evictable */
+	int doomed;               /* invalidated while in use: the last user frees it */
 } cache[CACHE_SLOTS];
 static unsigned long cache_clock;
 static pthread_mutex_t cache_mu = PTHREAD_MUTEX_INITIALIZER;   /* lx(1) calls from threads */
+
+/* A compiled table pinned for the duration of one call. */
+struct dfa_ref {
+	fsm_b200_dfa *dfa;
+	struct cache_entry *entry;    /* NULL: not cached (every slot was in use), freed on release */
+};
 
 static int
 device_index(void)
@@ -162,46 +170,79 @@ device_index(void)
 	return e != NULL ? atoi(e) : 0;
 }
 
-/* Returns the compiled DFA for `fsm` (cached), or NULL with errno set. */
-static fsm_b200_dfa *
-get_dfa(const struct fsm *fsm)
+/* Pins the compiled DFA for `fsm` (cached) into *ref; 0, or -1 with errno set.
+ * Release with put_dfa.  An entry is only ever evicted or freed while nobody holds it. */
+static int
+get_dfa(const struct fsm *fsm, struct dfa_ref *ref)
 {
 	const uint64_t fp = fingerprint(fsm);
-	struct cache_entry *victim = &cache[0];
+	struct cache_entry *victim = NULL;
 	fsm_b200_dfa *dfa = NULL;
 	struct fsm_b200_flat flat;
 	int i, err = 0;
 
+	ref->dfa = NULL; ref->entry = NULL;
 	pthread_mutex_lock(&cache_mu);
 	for (i = 0; i < CACHE_SLOTS; i++) {
-		if (cache[i].fsm == fsm && cache[i].fp == fp && cache[i].stamp != 0) {
-			cache[i].stamp = ++cache_clock;
-			dfa = cache[i].dfa;
-			err = cache[i].errno_val;
+		struct cache_entry *e = &cache[i];
+		if (e->stamp != 0 && !e->doomed && e->fsm == fsm && e->fp == fp) {
+			e->stamp = ++cache_clock;
+			if (e->dfa == NULL) {
+				err = e->errno_val;
+				pthread_mutex_unlock(&cache_mu);
+				errno = err;
+				return -1;
+			}
+			e->refs++;
+			ref->dfa = e->dfa; ref->entry = e;
 			pthread_mutex_unlock(&cache_mu);
-			if (dfa == NULL) errno = err;
-			return dfa;
+			return 0;
 		}
-		if (cache[i].stamp < victim->stamp) victim = &cache[i];
+		if (e->refs == 0 && !e->doomed && (victim == NULL || e->stamp < victim->stamp)) victim = e;
 	}
 	/* miss: validate + build (the engine restates fsm_all(fsm_isdfa) + fsm_getstart) */
 	if (fsm_b200_flatten(fsm, &flat) != 0) {
 		pthread_mutex_unlock(&cache_mu);
-		return NULL;
+		return -1;
 	}
 	if (fsm_b200_dfa_compile(&flat.desc, device_index(), &dfa) != 0) {
 		err = errno;
 		dfa = NULL;
 	}
 	fsm_b200_flat_free(&flat);
-	if (dfa != NULL || err == EINVAL) {      /* remember DFAs and definite non-DFAs */
+	if (victim != NULL && (dfa != NULL || err == EINVAL)) {      /* remember DFAs and definite non-DFAs */
 		if (victim->stamp != 0 && victim->dfa != NULL) fsm_b200_dfa_free(victim->dfa);
+		memset(victim, 0, sizeof *victim);
 		victim->fsm = fsm; victim->fp = fp; victim->dfa = dfa; victim->errno_val = err;
 		victim->stamp = ++cache_clock;
+		if (dfa != NULL) { victim->refs = 1; ref->entry = victim; }
 	}
 	pthread_mutex_unlock(&cache_mu);
-	if (dfa == NULL) errno = err;
-	return dfa;
+	if (dfa == NULL) {
+		errno = err;
+		return -1;
+	}
+	ref->dfa = dfa;
+	return 0;
+}
+
+static void
+put_dfa(struct dfa_ref *ref)
+{
+	const int saved = errno;
+	if (ref->dfa == NULL) return;
+	if (ref->entry == NULL) {
+		fsm_b200_dfa_free(ref->dfa);             /* was never cached */
+	} else {
+		pthread_mutex_lock(&cache_mu);
+		if (--ref->entry->refs == 0 && ref->entry->doomed) {
+			fsm_b200_dfa_free(ref->entry->dfa);
+			memset(ref->entry, 0, sizeof *ref->entry);
+		}
+		pthread_mutex_unlock(&cache_mu);
+	}
+	ref->dfa = NULL; ref->entry = NULL;
+	errno = saved;
 }
 
 void
@@ -210,10 +251,14 @@ fsm_b200_invalidate(const struct fsm *fsm)
 	int i;
 	pthread_mutex_lock(&cache_mu);
 	for (i = 0; i < CACHE_SLOTS; i++) {
-		if (cache[i].fsm == fsm && cache[i].stamp != 0) {
-			if (cache[i].dfa != NULL) fsm_b200_dfa_free(cache[i].dfa);
-			memset(&cache[i], 0, sizeof cache[i]);
+		struct cache_entry *e = &cache[i];
+		if (e->stamp == 0 || e->doomed || e->fsm != fsm) continue;
+		if (e->refs > 0) {
+			e->doomed = 1;                       /* in use on another thread: freed by its put_dfa */
+			continue;
 		}
+		if (e->dfa != NULL) fsm_b200_dfa_free(e->dfa);
+		memset(e, 0, sizeof *e);
 	}
 	pthread_mutex_unlock(&cache_mu);
 }
@@ -236,7 +281,7 @@ fsm_exec(const struct fsm *fsm,
 	int (*fsm_getc)(void *opaque), void *opaque,
 	fsm_state_t *end, struct fsm_capture *captures)
 {
-	fsm_b200_dfa *dfa;
+	struct dfa_ref ref;
 	struct fsm_b200_result r;
 	unsigned char *buf = NULL;
 	size_t len = 0, cap = 0;
@@ -252,8 +297,7 @@ fsm_exec(const struct fsm *fsm,
 		errno = ENOTSUP;
 		return -1;
 	}
-	dfa = get_dfa(fsm);                 /* -1/EINVAL: not a DFA, no start (exec.c:106-114) */
-	if (dfa == NULL) {
+	if (get_dfa(fsm, &ref) != 0) {      /* -1/EINVAL: not a DFA, no start (exec.c:106-114) */
 		return -1;
 	}
 
@@ -270,6 +314,7 @@ fsm_exec(const struct fsm *fsm,
 			unsigned char *nb = realloc(buf, ncap);
 			if (nb == NULL) {
 				free(buf);
+				put_dfa(&ref);
 				errno = ENOMEM;
 				return -1;
 			}
@@ -278,11 +323,13 @@ fsm_exec(const struct fsm *fsm,
 		buf[len++] = (unsigned char) c;
 	}
 
-	if (fsm_b200_exec_stream_host(dfa, buf, len, &r) != 0) {
+	if (fsm_b200_exec_stream_host(ref.dfa, buf, len, &r) != 0) {
 		free(buf);
+		put_dfa(&ref);
 		return -1;                      /* errno from the engine (EIO: no device) */
 	}
 	free(buf);
+	put_dfa(&ref);
 
 	if (r.ret == 0 && r.consumed < len) {
 		/* the reference stopped reading right after the byte with no edge (exec.c:133-138) */
@@ -476,18 +523,20 @@ int
 fsm_exec_batch(const struct fsm *fsm, const unsigned char *base, const uint64_t *offsets,
 	size_t n, struct fsm_b200_result *out)
 {
-	fsm_b200_dfa *dfa;
+	struct dfa_ref ref;
+	int rc;
 
 	assert(fsm != NULL);
 	if (unsupported(fsm, NULL)) {
 		errno = ENOTSUP;
 		return -1;
 	}
-	dfa = get_dfa(fsm);
-	if (dfa == NULL) {
+	if (get_dfa(fsm, &ref) != 0) {
 		return -1;
 	}
-	return fsm_b200_exec_batch_host(dfa, base, offsets, n, out);
+	rc = fsm_b200_exec_batch_host(ref.dfa, base, offsets, n, out);
+	put_dfa(&ref);
+	return rc;
 }
 
 #endif /* FSM_B200_SHIM_FLATTEN_ONLY */

@@ -1,0 +1,161 @@
+"""CPU: the libfsm-side shim's HOST logic, without a GPU.
+
+build/shim_cpu/ holds the UNCHANGED shim source (libfsm_b200/shim/fsm_b200_shim.c) linked with
+the reference's objects and, in place of libfsm_b200.so, oracle/stub_engine.c -- the plain-C
+oracle answering the engine's symbols (test infrastructure; `make -C libfsm_b200/shim STUB=1`).
+Everything the shim does on the host is therefore exercised here by the reference's own CLIs and
+C unit tests: struct fsm -> flat description, the compiled-table cache (fingerprints, LRU,
+pinning under threads), getc draining and cursor restoration, the struct fsm rebuild after
+determinise / minimise, errno conventions.  The same programs run against the CUDA engine in
+tests/test_gpu_shim.py.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import goldenio
+import reflib
+from test_gpu_shim import FIXTURES_NPZ, RE_REF, FSM_REF, to_fsm5
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CPU_DIR = os.path.join(ROOT, "build", "shim_cpu")
+RE_CPU = os.path.join(CPU_DIR, "re_b200")
+FSM_CPU = os.path.join(CPU_DIR, "fsm_b200")
+
+
+def _build():
+    if os.path.exists("/root/reference/src/libfsm/exec.c") and os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "obj")):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "libfsm_b200", "shim"), "STUB=1", "-j8"], check=True,
+                       stdout=subprocess.DEVNULL)
+
+
+_build()
+pytestmark = pytest.mark.skipif(not (os.path.exists(RE_CPU) and os.path.exists(RE_REF)),
+                                reason="build/shim_cpu not built (needs the reference tree at build time)")
+
+
+def run(binary, args, **kw):
+    p = subprocess.run([binary] + args, capture_output=True, timeout=120, **kw)
+    return p.returncode, p.stdout, p.stderr
+
+
+def test_selftest_program():
+    p = subprocess.run([os.path.join(CPU_DIR, "shim_selftest")], capture_output=True, timeout=120)
+    assert p.returncode == 0, (p.stdout.decode(), p.stderr.decode())
+    assert b"shim selftest ok" in p.stdout
+
+
+@pytest.mark.parametrize("threads,rounds,stall_us", [(4, 40, 0), (32, 5, 200)])
+def test_table_cache_is_safe_under_threads(threads, rounds, stall_us):
+    """More threads than cache slots + a stall inside every engine call: before the cache pinned
+    entries (refs), an entry could be evicted and freed while another thread was executing on it
+    (the stub engine detects the use after free and the verdicts differ)."""
+    env = dict(os.environ)
+    if stall_us:
+        env["FSM_B200_STUB_SLOW"] = str(stall_us)
+    p = subprocess.run([os.path.join(CPU_DIR, "shim_threads"), str(threads), str(rounds)], capture_output=True,
+                       timeout=300, env=env)
+    assert p.returncode == 0, (p.stdout.decode(), p.stderr.decode())
+
+
+REFTESTS_DIR = os.path.join(CPU_DIR, "reftests")
+REFTESTS = sorted(os.listdir(REFTESTS_DIR)) if os.path.isdir(REFTESTS_DIR) else []
+
+
+@pytest.mark.parametrize("name", REFTESTS)
+def test_reference_own_c_unit_tests(name):
+    """tests/endids/*.c and tests/re_strings/*.c of the reference, compiled unmodified."""
+    p = subprocess.run([os.path.join(REFTESTS_DIR, name)], capture_output=True, timeout=300)
+    assert p.returncode == 0, (name, p.stdout.decode()[-2000:], p.stderr.decode()[-2000:])
+
+
+def test_config1_files(tmp_path):
+    rng = np.random.default_rng(1)
+    match = rng.integers(ord("0"), ord("9") + 1, size=1 << 20, dtype=np.uint8)
+    match[rng.random(match.size) < 1 / 64] = ord(".")
+    nomatch = rng.integers(ord("a"), ord("z") + 1, size=1 << 20, dtype=np.uint8)
+    fm, fn = tmp_path / "match.txt", tmp_path / "nomatch.txt"
+    fm.write_bytes(match.tobytes()); fn.write_bytes(nomatch.tobytes())
+    for files in ([str(fm)], [str(fn)], [str(fm), str(fn)], [str(fn), str(fm)]):
+        args = ["-r", "pcre", "-x", r"[0-9]+\.[0-9]+"] + files
+        got, want = run(RE_CPU, args), run(RE_REF, args)
+        assert got[0] == want[0] and got[1] == want[1], (files, got, want)
+
+
+@pytest.mark.parametrize("args", [
+    ["-r", "pcre", r"a[ -~]{7}\z", "xxabcdefgh"],
+    ["-r", "pcre", r"a[ -~]{7}\z", "xxabcdefg"],
+    ["-r", "pcre", r"^abc[0-9]+x$", "abc123x", "abc12", "zzz"],
+    ["-r", "native", "ab*c", "abbbc"],
+    ["-r", "glob", "*.txt", "notes.txt"],
+    ["-r", "literal", "hello", "hello"],
+    ["-r", "pcre", "-z", "abc", "def", "xyz"],
+])
+def test_argv_strings_same_exit_status_and_output(args):
+    got, want = run(RE_CPU, args), run(RE_REF, args)
+    assert got[0] == want[0] and got[1] == want[1], (args, got, want)
+
+
+def test_stdin_stream_cursor(tmp_path):
+    """fsm_fgetc path: `re -x PATTERN FILE` reads FILE through fsm_fgetc; a miss must leave the
+    exit status and output the reference's."""
+    f = tmp_path / "in.txt"
+    f.write_bytes(b"abc123\nzzz\n")
+    for pat in (r"abc[0-9]+", r"^zzz", r"nomatch"):
+        args = ["-r", "pcre", "-x", pat, str(f)]
+        got, want = run(RE_CPU, args), run(RE_REF, args)
+        assert got[0] == want[0] and got[1] == want[1], (pat, got, want)
+
+
+def test_fsm_cli_determinise_and_minimise(tmp_path):
+    """`fsm -pd` / `fsm -pm` of the relinked fsm(1) against the reference's, compared the way
+    the reference's own tests do (tests/determinise/Makefile:11-20: fsm -t equal) + state counts."""
+    cases = goldenio.load_det_cases(os.path.join(goldenio.GOLDEN_DIR, "golden_determinise.npz"))
+    ran = 0
+    for c in cases:
+        txt = to_fsm5(c["nfa"])
+        if txt is None or c["dfa"].nstates > 400:
+            continue
+        inp = tmp_path / "in.fsm"
+        inp.write_text(txt)
+        for flag in ("-pd", "-pm"):
+            outs = {}
+            for tag, binary in (("cpu", FSM_CPU), ("ref", FSM_REF)):
+                p = subprocess.run([binary, flag], stdin=open(inp), capture_output=True, timeout=120)
+                assert p.returncode == 0, (c["name"], flag, tag, p.stderr)
+                outs[tag] = tmp_path / f"out_{tag}.fsm"
+                outs[tag].write_bytes(p.stdout)
+            eq = subprocess.run([FSM_REF, "-t", "equal", str(outs["cpu"]), str(outs["ref"])], capture_output=True, timeout=120)
+            assert eq.returncode == 0, (c["name"], flag, eq.stdout, eq.stderr)
+            cnt = [subprocess.run([FSM_REF, "-q", "count"], stdin=open(outs[t]), capture_output=True).stdout for t in ("cpu", "ref")]
+            assert cnt[0] == cnt[1], (c["name"], flag)
+        ran += 1
+    assert ran >= 10
+
+
+def test_reference_regex_golden_files(tmp_path):
+    """All of the reference's regex golden-file fixtures (tests/pcre*, native, glob, like, literal,
+    sql: `re -r D -py inN.re` vs outN.fsm by fsm_equal) through the relinked re(1)."""
+    if not os.path.exists(FIXTURES_NPZ) or not reflib.have_ref():
+        pytest.skip("fixtures or compiled reference missing")
+    ref = reflib.Ref()
+    fixtures = goldenio.load_re_fixtures(FIXTURES_NPZ)
+    assert len(fixtures) >= 200
+    bad = []
+    for fx in fixtures:
+        rf = tmp_path / "in.re"
+        rf.write_bytes(fx["regex"])
+        p = subprocess.run([RE_CPU] + fx["args"] + ["-r", fx["dialect"], "-py", str(rf)], capture_output=True, timeout=120)
+        if p.returncode != 0:
+            bad.append((fx["name"], "exit", p.returncode, p.stderr[-200:]))
+            continue
+        gf = tmp_path / "got.fsm"
+        gf.write_bytes(p.stdout)
+        hg = ref.parse_file(str(gf))
+        he = ref.from_flat(fx["fsm"])
+        if not ref.equal(hg, he):
+            bad.append((fx["name"], "language differs"))
+        ref.free(hg); ref.free(he)
+    assert not bad, bad[:10]
