@@ -122,17 +122,36 @@ hand_over(struct oracle_owned_desc *od, struct fsm_b200_owned_desc *out)
 	return 0;
 }
 
+/* oracle/refnum_host.cpp: the product's refnum.h functions on the CPU */
+int refnum_host_determinise_desc(const struct fsm_b200_desc *nfa, uint32_t state_limit, struct oracle_owned_desc *out);
+
 int
-fsm_b200_determinise(const struct fsm_b200_desc *nfa, int device, size_t state_limit, struct fsm_b200_owned_desc *out)
+fsm_b200_determinise_ex(const struct fsm_b200_desc *nfa, int device, size_t state_limit, unsigned flags,
+	struct fsm_b200_owned_desc *out)
 {
 	struct oracle_owned_desc od;
 	int rc;
 	(void) device;
 	COUNT(n_det);
 	memset(out, 0, sizeof *out);
-	rc = oracle_determinise(nfa, state_limit, &od);
+	if (flags & FSM_B200_DET_REFERENCE_NUMBERING) {
+		/* same verdicts as the engine: the input count is checked first (determinise.c:65-68),
+		 * then at most limit+1 states may exist (determinise.c:166-169) */
+		if (state_limit != 0 && nfa->nstates > state_limit) return 1;
+		rc = refnum_host_determinise_desc(nfa, (uint32_t) state_limit, &od);
+	} else {
+		rc = oracle_determinise(nfa, state_limit, &od);
+	}
 	if (rc != 0) return rc;
 	return hand_over(&od, out);
+}
+
+int
+fsm_b200_determinise(const struct fsm_b200_desc *nfa, int device, size_t state_limit, struct fsm_b200_owned_desc *out)
+{
+	const char *e = getenv("FSM_B200_DET_NUMBERING");
+	return fsm_b200_determinise_ex(nfa, device, state_limit,
+	    (e != NULL && strcmp(e, "reference") == 0) ? FSM_B200_DET_REFERENCE_NUMBERING : 0u, out);
 }
 
 int

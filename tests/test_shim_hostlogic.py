@@ -159,3 +159,28 @@ def test_reference_regex_golden_files(tmp_path):
             bad.append((fx["name"], "language differs"))
         ref.free(hg); ref.free(he)
     assert not bad, bad[:10]
+
+
+def test_fsm_cli_text_is_the_reference_text_with_reference_numbering(tmp_path):
+    """FSM_B200_DET_NUMBERING=reference: the engine returns the DFA in the reference's own state
+    numbering (here: the product's refnum.h functions run on the CPU, oracle/refnum_host.cpp), the
+    shim rebuilds the struct fsm, and `fsm -pd` prints BYTE FOR BYTE what the reference's fsm(1)
+    prints -- no `fsm -t equal`, no canonicalisation."""
+    cases = goldenio.load_det_cases(os.path.join(goldenio.GOLDEN_DIR, "golden_determinise.npz"))
+    env = dict(os.environ, FSM_B200_DET_NUMBERING="reference")
+    ran = differs_without = 0
+    for c in cases:
+        txt = to_fsm5(c["nfa"])
+        if txt is None or c["dfa"].nstates > 3500:
+            continue
+        inp = tmp_path / "in.fsm"
+        inp.write_text(txt)
+        got = subprocess.run([FSM_CPU, "-pd"], stdin=open(inp), capture_output=True, timeout=120, env=env)
+        bfs = subprocess.run([FSM_CPU, "-pd"], stdin=open(inp), capture_output=True, timeout=120)
+        want = subprocess.run([FSM_REF, "-pd"], stdin=open(inp), capture_output=True, timeout=120)
+        assert got.returncode == 0 and want.returncode == 0, (c["name"], got.stderr)
+        assert got.stdout == want.stdout, c["name"]
+        differs_without += bfs.stdout != want.stdout
+        ran += 1
+    assert ran >= 15
+    assert differs_without > 0      # the flag matters: BFS numbering prints different text somewhere
