@@ -292,7 +292,7 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 				count_launch();
 			}
 			CK(cudaMemcpyAsync(&changed, d_changed.p, 4, cudaMemcpyDeviceToHost, st));
-			CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+			CK(cudaStreamSynchronize(st));
 			if (!changed) break;
 		}
 	}
@@ -302,7 +302,7 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 	uint32_t start_keep = 0;
 	CK(cudaMemcpyAsync(&m64, d_newid.p + n, 8, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(&start_keep, d_keep.p + dfa->start, 4, cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(st));
 	const uint32_t m = (uint32_t) m64;
 	if (m == 0 || !start_keep) {           /* minimise.c:98-101: nothing can match */
 		guard.o = nullptr;
@@ -331,7 +331,7 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 		k3_refine_assign_kernel<<<blocks_for(m), 256, 0, st>>>(m, d_repst.p, d_cmin.p, d_rank.p, d_newcls.p); count_launch();
 		uint64_t cnt = 0;
 		CK(cudaMemcpyAsync(&cnt, d_rank.p + m, 8, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+		CK(cudaStreamSynchronize(st));
 		std::swap(d_cls.p, d_newcls.p);
 		std::swap(d_cls.cap, d_newcls.cap);
 		if (cnt == ncls) break;              /* classes only split: same count == same partition */
@@ -355,7 +355,7 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 	if (scan.run<uint32_t>(d_ng.p, d_ogoff.p, D) != 0) return -1;
 	own->group_off.assign(D + 1, 0);
 	CK(cudaMemcpyAsync(own->group_off.data(), d_ogoff.p, (D + 1) * 8, cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(st));
 	const uint64_t NG = own->group_off[D];
 	if (d_ogto.reserve(NG + 1, false, st) || d_ogsym.reserve(4 * NG + 4, false, st)) return -1;
 	k2_emit_fill_kernel<<<blocks_for(D, 128), 128, 0, st>>>(d_otrans.p, D, K, d_cmask.p, d_ogoff.p, d_ogto.p, d_ogsym.p); count_launch();
@@ -370,9 +370,9 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 	}
 	CK(cudaMemcpyAsync(h_oorig.data(), d_oorig.p, D * 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(&start_new, d_newid.p + dfa->start, 8, cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(st));
 	CK(cudaMemcpyAsync(&start_cls, d_cls.p + start_new, 4, cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(st));
 
 	own->is_end.assign(D, 0);
 	own->endid_off.assign(D + 1, 0);
