@@ -101,3 +101,41 @@ def test_numbering_matches_live_reference_config5_shape(host, words, length):
     table, end = host(nfa)
     assert np.array_equal(table, dfa.dense_table())
     assert np.array_equal(end.astype(bool), np.asarray(dfa.is_end).astype(bool))
+
+
+try:
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    from test_oracle_property import regex as _regex
+except ImportError:                                   # hypothesis is optional
+    _regex = None
+
+if _regex is not None:
+    @pytest.mark.skipif(not reflib.have_ref(), reason="compiled reference not present")
+    @settings(max_examples=80, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+    @given(patterns=st.lists(_regex, min_size=1, max_size=4))
+    def test_numbering_matches_live_reference_regex_unions(host, patterns):
+        """ε-heavy NFAs the way re(1)/rx(1) build them: re_comp, end ids, fsm_union_array
+        (3000 examples of this strategy were run once while pinning; 80 per suite run)."""
+        ref = reflib.Ref()
+        hs = []
+        try:
+            for p in patterns:
+                hs.append(ref.re_comp(p))
+        except ValueError:
+            for h in hs:
+                ref.free(h)
+            return
+        if len(hs) > 1:
+            for i, h in enumerate(hs):
+                ref.setendid(h, i + 1)
+            u = ref.union_array(hs)
+        else:
+            u = hs[0]
+        nfa = ref.flatten(u)
+        ref.determinise(u)
+        dfa = ref.flatten(u)
+        ref.free(u)
+        table, end = host(nfa)
+        assert table.shape[0] == dfa.nstates
+        assert np.array_equal(table, dfa.dense_table()), patterns
+        assert np.array_equal(end.astype(bool), np.asarray(dfa.is_end).astype(bool))
