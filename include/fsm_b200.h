@@ -57,7 +57,7 @@ struct fsm_b200_desc {
 	uint32_t nstates;            /* fsm->statecount */
 	uint32_t start;              /* fsm->start, meaningful iff hasstart */
 	uint32_t hasstart;           /* fsm->hasstart */
-	uint32_t reserved;           /* must be 0 */
+	uint32_t reserved;           /* flags: 0, or FSM_B200_DESC_EAGER (see struct fsm_b200_desc_ext) */
 	const uint8_t  *is_end;      /* [nstates] fsm->states[s].end */
 	const uint64_t *group_off;   /* [nstates+1] */
 	const uint64_t *group_symbols; /* [4*ngroups] */
@@ -66,6 +66,21 @@ struct fsm_b200_desc {
 	const uint32_t *eps_to;      /* [neps] */
 	const uint64_t *endid_off;   /* [nstates+1] or NULL */
 	const uint32_t *endids;      /* [nendids], sorted unique per state */
+};
+
+/* Extended description: a desc whose `reserved` field has FSM_B200_DESC_EAGER set is the first
+ * member of this struct, which adds the CSR of the per-state EAGER OUTPUT id sets
+ * (fsm_eager_output_set / fsm_eager_output_get, include/fsm/fsm.h:273-336,
+ * src/libfsm/eager_output.c): ids a state emits every time it is entered during fsm_exec
+ * (src/libfsm/exec.c:55-83,126-130,140-144), whether or not the input ends up matching.
+ * Unlike end ids they may sit on non-end states.  Sets are sorted and unique per state.
+ * Old callers (reserved == 0) are unaffected: every entry point reads the extra members only
+ * when the flag is set. */
+#define FSM_B200_DESC_EAGER 1u
+struct fsm_b200_desc_ext {
+	struct fsm_b200_desc base;   /* base.reserved & FSM_B200_DESC_EAGER */
+	const uint64_t *eager_off;   /* [nstates+1] */
+	const uint32_t *eager_ids;   /* [neager], sorted unique per state */
 };
 
 /* ------------------------------------------------------------------------------------

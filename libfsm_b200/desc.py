@@ -23,6 +23,15 @@ class CDesc(C.Structure):
     ]
 
 
+DESC_EAGER = 1
+
+
+class CDescExt(C.Structure):
+    """``struct fsm_b200_desc_ext``: a desc with FSM_B200_DESC_EAGER set in ``reserved`` plus the
+    eager-output CSR."""
+    _fields_ = [("base", CDesc), ("eager_off", C.c_void_p), ("eager_ids", C.c_void_p)]
+
+
 class COwnedDesc(C.Structure):
     """``struct fsm_b200_owned_desc``."""
     _fields_ = [("desc", CDesc), ("owner", C.c_void_p)]
@@ -58,6 +67,8 @@ class FlatFsm:
     eps_to: np.ndarray            # u32 [neps]
     endid_off: np.ndarray         # u64 [nstates+1]
     endids: np.ndarray            # u32 [nids]
+    eager_off: np.ndarray | None = None   # u64 [nstates+1]: eager-output ids (None: the fsm has none)
+    eager_ids: np.ndarray | None = None   # u32, sorted unique per state
     _keep: list = field(default_factory=list, repr=False, compare=False)
 
     def __post_init__(self):
@@ -71,6 +82,12 @@ class FlatFsm:
         self.eps_to = np.zeros(0, np.uint32) if self.eps_to is None else _arr(self.eps_to, np.uint32)
         self.endid_off = zeros.copy() if self.endid_off is None else _arr(self.endid_off, np.uint64)
         self.endids = np.zeros(0, np.uint32) if self.endids is None else _arr(self.endids, np.uint32)
+        if self.eager_off is not None:
+            self.eager_off = _arr(self.eager_off, np.uint64)
+            self.eager_ids = _arr(self.eager_ids if self.eager_ids is not None else [], np.uint32)
+            assert self.eager_off.shape == (n + 1,) and int(self.eager_off[-1]) == self.eager_ids.shape[0]
+            if self.eager_ids.size == 0:
+                self.eager_off = self.eager_ids = None
         assert self.is_end.shape == (n,)
         assert self.group_off.shape == (n + 1,) and self.eps_off.shape == (n + 1,) and self.endid_off.shape == (n + 1,)
         assert int(self.group_off[-1]) == self.group_to.shape[0] == self.group_symbols.shape[0]
@@ -83,9 +100,12 @@ class FlatFsm:
                 a = np.zeros(4, dtype=a.dtype)      # never hand NULL for an empty array
                 self._keep.append(a)
             return a.ctypes.data
-        d = CDesc()
+        ext = CDescExt() if self.eager_off is not None else None
+        d = ext.base if ext is not None else CDesc()     # ext.base shares ext's memory and keeps it alive
         d.nstates = int(self.nstates); d.start = int(self.start)
-        d.hasstart = 1 if self.hasstart else 0; d.reserved = 0
+        d.hasstart = 1 if self.hasstart else 0; d.reserved = DESC_EAGER if ext is not None else 0
+        if ext is not None:
+            ext.eager_off = ptr(self.eager_off); ext.eager_ids = ptr(self.eager_ids)
         d.is_end = ptr(self.is_end); d.group_off = ptr(self.group_off)
         d.group_symbols = ptr(self.group_symbols); d.group_to = ptr(self.group_to)
         d.eps_off = ptr(self.eps_off); d.eps_to = ptr(self.eps_to)
@@ -120,6 +140,11 @@ class FlatFsm:
             endid_off=endid_off, endids=take(d.endids, ni, np.uint32))
 
     # -- helpers ------------------------------------------------------------------------
+    def eager_of(self, state: int) -> np.ndarray:
+        if self.eager_off is None:
+            return np.zeros(0, np.uint32)
+        return self.eager_ids[int(self.eager_off[state]):int(self.eager_off[state + 1])]
+
     def endids_of(self, state: int) -> np.ndarray:
         return self.endids[int(self.endid_off[state]):int(self.endid_off[state + 1])]
 
@@ -151,7 +176,7 @@ class FlatFsm:
                        endid_off=z["endid_off"], endids=z["endids"])
 
     @staticmethod
-    def from_edges(nstates, start, ends, edges, eps=(), endids=None) -> "FlatFsm":
+    def from_edges(nstates, start, ends, edges, eps=(), endids=None, eager=None) -> "FlatFsm":
         """Build from explicit (src, symbol|iterable of symbols, dst) edges; groups are
         formed per (src, dst) and kept sorted by dst like the reference's edge_set."""
         groups = [dict() for _ in range(nstates)]
@@ -184,4 +209,21 @@ class FlatFsm:
                        group_symbols=np.array(gsym, dtype=np.uint64).reshape(-1, 4),
                        group_to=np.array(gto, np.uint32), eps_off=np.array(eoff, np.uint64),
                        eps_to=np.array(eto, np.uint32), endid_off=np.array(ioff, np.uint64),
-                       endids=np.array(ids, np.uint32))
+                       endids=np.array(ids, np.uint32), **FlatFsm._eager_csr(nstates, eager))
+
+    @staticmethod
+    def _eager_csr(nstates, eager) -> dict:
+        """{state: ids} -> eager_off / eager_ids keyword arguments (empty when there are none)."""
+        if not eager:
+            return {}
+        off, ids = [0], []
+        for s in range(nstates):
+            ids.extend(sorted(set(int(x) for x in eager.get(s, ()))))
+            off.append(len(ids))
+        return {"eager_off": np.array(off, np.uint64), "eager_ids": np.array(ids, np.uint32)}
+
+    def with_eager(self, eager) -> "FlatFsm":
+        """A copy carrying the eager-output sets {state: ids}."""
+        import dataclasses
+        kw = FlatFsm._eager_csr(self.nstates, eager) or {"eager_off": None, "eager_ids": None}
+        return dataclasses.replace(self, _keep=[], **kw)

@@ -76,6 +76,17 @@ group_scan(const struct fsm_b200_desc *d, uint32_t state, unsigned c)
 	return NO_EDGE;
 }
 
+/* eager-output CSR of a description (both NULL when it has none) */
+static void
+desc_eager(const struct fsm_b200_desc *d, const uint64_t **off, const uint32_t **ids)
+{
+	*off = NULL; *ids = NULL;
+	if (d->reserved & FSM_B200_DESC_EAGER) {
+		const struct fsm_b200_desc_ext *x = (const struct fsm_b200_desc_ext *) d;
+		*off = x->eager_off; *ids = x->eager_ids;
+	}
+}
+
 /* fsm_exec (src/libfsm/exec.c:85-167) without captures / eager outputs (neither is
  * produced by re_comp). */
 int
@@ -110,6 +121,56 @@ oracle_exec(const struct fsm_b200_desc *d, const uint8_t *buf, uint64_t len,
 	out->end = state;
 	out->consumed = offset;
 	out->ret = d->is_end[state] ? 1 : 0;      /* exec.c:153-166 */
+	return out->ret;
+}
+
+static void
+fire(uint32_t id, uint32_t *fired, size_t cap, size_t *n)
+{
+	size_t i, pos = *n < cap ? *n : cap;
+	for (i = 0; i < pos; i++) if (fired[i] == id) return;
+	/* keep the stored prefix sorted: insertion */
+	if (*n < cap) {
+		size_t j = *n;
+		while (j > 0 && fired[j - 1] > id) { fired[j] = fired[j - 1]; j--; }
+		fired[j] = id;
+	}
+	(*n)++;
+}
+
+int
+oracle_exec_eager(const struct fsm_b200_desc *d, const uint8_t *buf, uint64_t len,
+	struct fsm_b200_result *out, uint32_t *fired, size_t cap, size_t *nfired)
+{
+	const uint64_t *xoff; const uint32_t *xids;
+	uint32_t state;
+	uint64_t offset = 0, q;
+
+	*nfired = 0;
+	desc_eager(d, &xoff, &xids);
+	if (!oracle_isdfa(d) || !d->hasstart) {   /* exec.c:106-114 */
+		errno = EINVAL;
+		return -1;
+	}
+	state = d->start;
+	if (xoff != NULL) {                       /* exec.c:126-130: the start state fires too */
+		for (q = xoff[state]; q < xoff[state + 1]; q++) fire(xids[q], fired, cap, nfired);
+	}
+	while (offset < len) {
+		uint32_t next = group_scan(d, state, buf[offset]);
+		if (next == NO_EDGE) {
+			out->ret = 0; out->end = state; out->consumed = offset;
+			return 0;
+		}
+		state = next;
+		if (xoff != NULL) {                   /* exec.c:140-144 */
+			for (q = xoff[state]; q < xoff[state + 1]; q++) fire(xids[q], fired, cap, nfired);
+		}
+		offset++;
+	}
+	out->end = state;
+	out->consumed = offset;
+	out->ret = d->is_end[state] ? 1 : 0;
 	return out->ret;
 }
 
@@ -397,6 +458,9 @@ oracle_determinise(const struct fsm_b200_desc *nfa, size_t state_limit,
 	struct pool pool;
 	struct vec64 o_goff = {0}, o_gsym = {0}, o_eoff = {0};
 	struct vec32 o_gto = {0}, o_eid = {0}, o_end = {0}, tmp = {0};
+	struct vec64 o_xoff = {0};
+	struct vec32 o_xid = {0}, tmp2 = {0};
+	const uint64_t *xoff; const uint32_t *xids;
 	int rc = -1;
 	uint32_t s;
 	size_t c;
@@ -406,6 +470,7 @@ oracle_determinise(const struct fsm_b200_desc *nfa, size_t state_limit,
 	memset(symlist, 0, sizeof symlist);
 	memset(&pool, 0, sizeof pool);
 
+	desc_eager(nfa, &xoff, &xids);
 	if (oracle_epsilon_closure(nfa, &cl_off, &cl_to) != 0) return -1;
 
 	/* determinise.c:65-68 */
@@ -470,7 +535,7 @@ oracle_determinise(const struct fsm_b200_desc *nfa, size_t state_limit,
 		uint32_t st = nfa->start;
 		if (pool_intern(&pool, &st, 1, &isnew) == (uint32_t) -1) goto oom;
 	}
-	if (!vec64_push(&o_goff, 0) || !vec64_push(&o_eoff, 0)) goto oom;
+	if (!vec64_push(&o_goff, 0) || !vec64_push(&o_eoff, 0) || !vec64_push(&o_xoff, 0)) goto oom;
 
 	/* BFS: DFA state id == interned set id (discovery order) */
 	for (uint32_t cur = 0; cur + 1 < pool.off.n; cur++) {
@@ -483,10 +548,20 @@ oracle_determinise(const struct fsm_b200_desc *nfa, size_t state_limit,
 		memset(used, 0, sizeof used);
 		for (c = 0; c < 256; c++) symlist[c].n = 0;
 		tmp.n = 0;
+		tmp2.n = 0;
 
 		for (i = mb; i < me; i++) {
 			uint32_t m = pool.buf.a[i];
 			uint64_t e, k;
+			if (xoff != NULL) {
+				/* eager outputs: every state of the member's closure (epsilons.c:221-253) */
+				for (k = cl_off[m]; k < cl_off[m + 1]; k++) {
+					uint64_t q;
+					for (q = xoff[cl_to[k]]; q < xoff[cl_to[k] + 1]; q++) {
+						if (!vec32_push(&tmp2, xids[q])) goto oom;
+					}
+				}
+			}
 			if (aend[m]) {
 				is_end = 1;
 				/* end ids: union over closure members that are end states
@@ -509,6 +584,9 @@ oracle_determinise(const struct fsm_b200_desc *nfa, size_t state_limit,
 		tmp.n = sort_unique(tmp.a, tmp.n);
 		for (i = 0; i < tmp.n; i++) if (!vec32_push(&o_eid, tmp.a[i])) goto oom;
 		if (!vec64_push(&o_eoff, o_eid.n)) goto oom;
+		tmp2.n = sort_unique(tmp2.a, tmp2.n);
+		for (i = 0; i < tmp2.n; i++) if (!vec32_push(&o_xid, tmp2.a[i])) goto oom;
+		if (!vec64_push(&o_xoff, o_xid.n)) goto oom;
 
 		for (c = 0; c < 256; c++) {
 			int isnew;
@@ -566,6 +644,11 @@ oracle_determinise(const struct fsm_b200_desc *nfa, size_t state_limit,
 		out->blocks[4] = (void *) out->desc.endid_off;
 		out->blocks[5] = (void *) out->desc.endids;
 		o_goff.a = NULL; o_gsym.a = NULL; o_gto.a = NULL; o_eoff.a = NULL; o_eid.a = NULL;
+		if (xoff != NULL && o_xid.n > 0) {
+			out->eager_off = o_xoff.a; out->eager_ids = o_xid.a;
+			out->blocks[6] = o_xoff.a; out->blocks[7] = o_xid.a;
+			o_xoff.a = NULL; o_xid.a = NULL;
+		}
 		rc = 0;
 	}
 	goto done;
@@ -573,6 +656,7 @@ oom:
 	errno = ENOMEM;
 	rc = -1;
 done:
+	free(o_xoff.a); free(o_xid.a); free(tmp2.a);
 	free(cl_off); free(cl_to); free(adj_off); free(adj_sym); free(adj_to);
 	free(aend); free(reach);
 	for (c = 0; c < 256; c++) free(symlist[c].a);
@@ -591,6 +675,7 @@ oracle_desc_free(struct oracle_owned_desc *d)
 		d->blocks[i] = NULL;
 	}
 	memset(&d->desc, 0, sizeof d->desc);
+	d->eager_off = NULL; d->eager_ids = NULL;
 }
 
 /* ---------------------------------------------------------------------------------
@@ -616,13 +701,17 @@ oracle_minimise(const struct fsm_b200_desc *d, struct oracle_owned_desc *out)
 	uint32_t *table = NULL, *newid = NULL, *cls = NULL, *ncls_arr = NULL, *sig = NULL, *rep = NULL;
 	uint8_t *reach = NULL, *co = NULL;
 	struct sigrow *rows = NULL;
-	struct vec64 o_goff = {0}, o_gsym = {0}, o_eoff = {0};
-	struct vec32 o_gto = {0}, o_eid = {0};
+	struct vec64 o_goff = {0}, o_gsym = {0}, o_eoff = {0}, o_xoff = {0};
+	struct vec32 o_gto = {0}, o_eid = {0}, o_xid = {0}, xtmp = {0};
+	const uint64_t *xoff; const uint32_t *xids;
+	uint32_t *dist = NULL;
+	uint8_t *collected = NULL, *broken = NULL;
 	uint32_t m = 0, ncls = 0, s;
 	unsigned c;
 	int rc = -1, changed;
 
 	memset(out, 0, sizeof *out);
+	desc_eager(d, &xoff, &xids);
 	if (!oracle_isdfa(d)) { errno = EINVAL; return -1; }
 	table = malloc(sizeof *table * (size_t) n * 256 + 4);
 	reach = calloc((size_t) n + 1, 1); co = calloc((size_t) n + 1, 1);
@@ -675,23 +764,56 @@ oracle_minimise(const struct fsm_b200_desc *d, struct oracle_owned_desc *out)
 		uint32_t *orig = malloc(sizeof *orig * m);
 		if (!orig) goto oom;
 		for (s = 0; s < n; s++) if (newid[s] != NO_EDGE) orig[newid[s]] = s;
+		if (xoff != NULL) {
+			/* Eager outputs split classes too (same_end_metadata, minimise.c:705-731) -- but the
+			 * reference only LOOKS at a state's eager ids while it walks its initial class (states of
+			 * equal shortest distance to an end state, listed in descending state order) and stops at
+			 * the first state that is neither an end state nor has eager outputs
+			 * (minimise.c:771-782): ids on states behind it are not seen, those states are merged as
+			 * if they had none, and fsm_consolidate later gives the merged state the union. */
+			uint32_t i, round;
+			dist = malloc(sizeof *dist * m); collected = calloc(m, 1); broken = calloc((size_t) m + 1, 1);
+			if (!dist || !collected || !broken) { free(orig); goto oom; }
+			for (i = 0; i < m; i++) dist[i] = d->is_end[orig[i]] ? 0 : NO_EDGE;
+			for (round = 1; ; round++) {             /* level-synchronous backward BFS */
+				int any = 0;
+				for (i = 0; i < m; i++) {
+					if (dist[i] != NO_EDGE) continue;
+					for (c = 0; c < 256; c++) {
+						uint32_t t = table[(size_t) orig[i] * 256 + c];
+						if (t != NO_EDGE && newid[t] != NO_EDGE && dist[newid[t]] == round - 1) { any = 1; dist[i] = NO_EDGE - 1; break; }
+					}
+				}
+				for (i = 0; i < m; i++) if (dist[i] == NO_EDGE - 1) dist[i] = round;
+				if (!any) break;
+			}
+			for (i = m; i-- > 0; ) {
+				const uint32_t si = orig[i];
+				if (dist[i] == NO_EDGE || broken[dist[i]]) continue;
+				if (d->is_end[si] || xoff[si + 1] > xoff[si]) collected[i] = 1;
+				else broken[dist[i]] = 1;
+			}
+		}
+#define EAGER_LEN(i) ((xoff != NULL && collected[i]) ? (size_t) (xoff[orig[i] + 1] - xoff[orig[i]]) : 0)
 		for (uint32_t i = 0; i < m; i++) {
 			uint32_t si = orig[i], k;
 			cls[i] = NO_EDGE;
-			if (!d->is_end[si]) { cls[i] = 0; continue; }
+			if (!d->is_end[si] && EAGER_LEN(i) == 0) { cls[i] = 0; continue; }
 			for (k = 0; k < i; k++) {
 				uint32_t sk = orig[k];
 				size_t li, lk;
-				if (!d->is_end[sk] || cls[k] == NO_EDGE) continue;
-				li = d->endid_off ? (size_t) (d->endid_off[si + 1] - d->endid_off[si]) : 0;
-				lk = d->endid_off ? (size_t) (d->endid_off[sk + 1] - d->endid_off[sk]) : 0;
-				if (li == lk && (li == 0 || memcmp(d->endids + d->endid_off[si], d->endids + d->endid_off[sk], li * sizeof(uint32_t)) == 0)) {
-					cls[i] = cls[k];
-					break;
-				}
+				if (d->is_end[sk] != d->is_end[si] || cls[k] == NO_EDGE || cls[k] == 0) continue;
+				li = (d->is_end[si] && d->endid_off) ? (size_t) (d->endid_off[si + 1] - d->endid_off[si]) : 0;
+				lk = (d->is_end[sk] && d->endid_off) ? (size_t) (d->endid_off[sk + 1] - d->endid_off[sk]) : 0;
+				if (li != lk || (li != 0 && memcmp(d->endids + d->endid_off[si], d->endids + d->endid_off[sk], li * sizeof(uint32_t)) != 0)) continue;
+				if (EAGER_LEN(i) != EAGER_LEN(k)) continue;
+				if (EAGER_LEN(i) != 0 && memcmp(xids + xoff[si], xids + xoff[sk], EAGER_LEN(i) * sizeof(uint32_t)) != 0) continue;
+				cls[i] = cls[k];
+				break;
 			}
 			if (cls[i] == NO_EDGE) cls[i] = 1 + i;      /* fresh id, distinct from 0 */
 		}
+#undef EAGER_LEN
 		g_siglen = 257;
 		for (;;) {
 			uint32_t cnt = 0, i;
@@ -731,7 +853,7 @@ oracle_minimise(const struct fsm_b200_desc *d, struct oracle_owned_desc *out)
 		{
 			uint8_t *is_end = calloc((size_t) ncls + 1, 1);
 			uint32_t i;
-			if (!is_end || !vec64_push(&o_goff, 0) || !vec64_push(&o_eoff, 0)) { free(orig); free(is_end); goto oom; }
+			if (!is_end || !vec64_push(&o_goff, 0) || !vec64_push(&o_eoff, 0) || !vec64_push(&o_xoff, 0)) { free(orig); free(is_end); goto oom; }
 			for (i = 0; i < m; i++) {
 				uint32_t dst_of_sym[256], dsts[256];
 				size_t nd = 0, j;
@@ -757,6 +879,25 @@ oracle_minimise(const struct fsm_b200_desc *d, struct oracle_owned_desc *out)
 					}
 				}
 				if (!vec64_push(&o_eoff, o_eid.n)) { free(orig); free(is_end); goto oom; }
+				if (xoff != NULL) {
+					/* fsm_consolidate (consolidate.c:306-315): the union over every merged state */
+					uint32_t k; uint64_t q; size_t z;
+					xtmp.n = 0;
+					for (k = 0; k < m; k++) {
+						if (cls[k] != i) continue;
+						for (q = xoff[orig[k]]; q < xoff[orig[k] + 1]; q++) {
+							if (!vec32_push(&xtmp, xids[q])) { free(orig); free(is_end); goto oom; }
+						}
+					}
+					xtmp.n = sort_unique(xtmp.a, xtmp.n);
+					for (z = 0; z < xtmp.n; z++) if (!vec32_push(&o_xid, xtmp.a[z])) { free(orig); free(is_end); goto oom; }
+				}
+				if (!vec64_push(&o_xoff, o_xid.n)) { free(orig); free(is_end); goto oom; }
+			}
+			if (xoff != NULL && o_xid.n > 0) {
+				out->eager_off = o_xoff.a; out->eager_ids = o_xid.a;
+				out->blocks[6] = o_xoff.a; out->blocks[7] = o_xid.a;
+				o_xoff.a = NULL; o_xid.a = NULL;
 			}
 			out->desc.nstates = ncls;
 			out->desc.start = rep[cls[newid[d->start]]];
@@ -785,6 +926,7 @@ oom:
 done:
 	free(table); free(reach); free(co); free(newid); free(cls); free(ncls_arr); free(sig); free(rows); free(rep);
 	free(o_goff.a); free(o_gsym.a); free(o_gto.a); free(o_eoff.a); free(o_eid.a);
+	free(o_xoff.a); free(o_xid.a); free(xtmp.a); free(dist); free(collected); free(broken);
 	return rc;
 }
 

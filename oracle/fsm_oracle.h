@@ -28,6 +28,13 @@ int oracle_isdfa(const struct fsm_b200_desc *d);
 int oracle_exec(const struct fsm_b200_desc *d, const uint8_t *buf, uint64_t len,
 	int validate, struct fsm_b200_result *out);
 
+/* fsm_exec with eager outputs (exec.c:55-83,126-130,140-144): the SET of ids fired along the
+ * walk -- those of the start state, then of every state entered -- ascending, whether or not the
+ * input matches.  `d` may be a plain desc (no ids) or a struct fsm_b200_desc_ext.  *nfired may
+ * exceed cap (only cap ids are stored).  Returns oracle_exec's value (validate = 1). */
+int oracle_exec_eager(const struct fsm_b200_desc *d, const uint8_t *buf, uint64_t len,
+	struct fsm_b200_result *out, uint32_t *fired, size_t cap, size_t *nfired);
+
 /* n independent fsm_exec calls, strings partitioned over nthreads pthreads.
  * Returns 0, or -1/EINVAL if not a DFA. validate_each: as oracle_exec's validate. */
 int oracle_exec_batch(const struct fsm_b200_desc *d, const uint8_t *base,
@@ -45,10 +52,17 @@ int oracle_epsilon_closure(const struct fsm_b200_desc *d, uint64_t **off, uint32
 /* Subset construction (determinise.c:23-335 after epsilons.c:121-288), textbook
  * formulation: DFA state 0 = closure(start); states numbered in BFS discovery order over
  * symbols 0..255.  Result arrays are malloc'd; free with oracle_desc_free.
+ * Eager outputs (input given as struct fsm_b200_desc_ext): a DFA state carries the union of the
+ * ids of every state in the epsilon closure of every member (epsilons.c:221-253 then
+ * determinise.c:2614-2636).
  * Returns 0 ok, 1 state limit reached, -1 errno. */
 struct oracle_owned_desc {
 	struct fsm_b200_desc desc;
 	void *blocks[8];
+	/* eager-output sets of the result (NULL when the input carried none): CSR, sorted unique
+	 * per state; owned through blocks[6], blocks[7].  desc.reserved stays 0. */
+	const uint64_t *eager_off;
+	const uint32_t *eager_ids;
 };
 int oracle_determinise(const struct fsm_b200_desc *nfa, size_t state_limit,
 	struct oracle_owned_desc *out);

@@ -109,6 +109,15 @@ refh_from_desc(const struct fsm_b200_desc *d)
 		}
 	}
 	if (d->hasstart) fsm_setstart(fsm, d->start);
+	if (d->reserved & FSM_B200_DESC_EAGER) {
+		const struct fsm_b200_desc_ext *x = (const struct fsm_b200_desc_ext *) d;
+		for (s = 0; s < d->nstates; s++) {
+			uint64_t e;
+			for (e = x->eager_off[s]; e < x->eager_off[s + 1]; e++) {
+				if (!fsm_eager_output_set(fsm, s, x->eager_ids[e])) goto fail;
+			}
+		}
+	}
 	return fsm;
 fail:
 	fsm_free(fsm);
@@ -329,4 +338,84 @@ refh_endids(const void *fsm, unsigned state, unsigned *ids, size_t cap)
 		(void) ok;
 	}
 	return c;
+}
+
+/* ---- eager outputs (include/fsm/fsm.h:273-336, src/libfsm/eager_output.c) ---------------- */
+
+static int
+cmp_u32(const void *a, const void *b)
+{
+	const unsigned x = *(const unsigned *) a, y = *(const unsigned *) b;
+	return x < y ? -1 : x > y;
+}
+
+int
+refh_eager_set(void *fsm, unsigned state, unsigned id)
+{
+	return fsm_eager_output_set(fsm, state, id);
+}
+
+int
+refh_eager_flatten(const void *vfsm, uint64_t **off_out, uint32_t **ids_out)
+{
+	const struct fsm *fsm = vfsm;
+	const size_t n = fsm->statecount;
+	uint64_t *off = calloc(n + 1, sizeof *off);
+	uint32_t *ids;
+	size_t total = 0, s;
+	if (off == NULL) return -1;
+	for (s = 0; s < n; s++) total += fsm_eager_output_count(fsm, (fsm_state_t) s);
+	ids = calloc(total + 1, sizeof *ids);
+	if (ids == NULL) { free(off); return -1; }
+	total = 0;
+	for (s = 0; s < n; s++) {
+		const size_t c = fsm_eager_output_count(fsm, (fsm_state_t) s);
+		size_t i, w;
+		off[s] = total;
+		if (c == 0) continue;
+		fsm_eager_output_get(fsm, (fsm_state_t) s, c, &ids[total]);
+		qsort(&ids[total], c, sizeof *ids, cmp_u32);
+		for (i = 0, w = 0; i < c; i++) if (i == 0 || ids[total + i] != ids[total + w - 1]) ids[total + w++] = ids[total + i];
+		total += w;
+	}
+	off[n] = total;
+	*off_out = off; *ids_out = ids;
+	return 0;
+}
+
+struct fired { unsigned *ids; size_t cap, used; };
+
+static void
+fired_cb(fsm_output_id_t id, void *opaque)
+{
+	struct fired *f = opaque;
+	size_t i;
+	for (i = 0; i < f->used; i++) if (f->ids[i] == id) return;
+	if (f->used < f->cap) f->ids[f->used] = id;
+	f->used++;
+}
+
+/* One fsm_exec with the eager-output callback installed: the SET of ids the reference fires
+ * (exec.c:126-144), ascending, whether or not the input matches.  *nfired may exceed cap. */
+int
+refh_exec_eager(void *vfsm, const uint8_t *buf, uint64_t len, struct fsm_b200_result *out,
+	unsigned *fired, size_t cap, size_t *nfired)
+{
+	struct fsm *fsm = vfsm;
+	struct fired f = { fired, cap, 0 };
+	int r;
+	fsm_eager_output_set_cb(fsm, fired_cb, &f);
+	r = refh_exec(fsm, buf, len, out);
+	fsm_eager_output_set_cb(fsm, NULL, NULL);
+	qsort(fired, f.used < cap ? f.used : cap, sizeof *fired, cmp_u32);
+	*nfired = f.used;
+	return r;
+}
+
+/* fsm_union_repeated_pattern_group (include/fsm/bool.h): how the reference itself attaches
+ * eager outputs to a union of unanchored patterns.  Consumes the inputs. */
+void *
+refh_union_repeated_pattern_group(size_t n, void **fsms, unsigned id_base)
+{
+	return fsm_union_repeated_pattern_group(n, (struct fsm **) fsms, NULL, id_base);
 }

@@ -60,4 +60,13 @@ int refh_exec_batch(const void *fsm, const uint8_t *base, const uint64_t *offset
 /* fsm_endid_count / fsm_endid_get for one state; returns count, fills up to cap ids. */
 size_t refh_endids(const void *fsm, unsigned state, unsigned *ids, size_t cap);
 
+/* Eager outputs (include/fsm/fsm.h:273-336): set one, dump all as a CSR (sorted unique per
+ * state, malloc'd), run fsm_exec with a collecting callback (ids ascending, *nfired may exceed
+ * cap), and the reference's own way of attaching them to a union of patterns. */
+int   refh_eager_set(void *fsm, unsigned state, unsigned id);
+int   refh_eager_flatten(const void *fsm, uint64_t **off, uint32_t **ids);
+int   refh_exec_eager(void *fsm, const uint8_t *buf, uint64_t len, struct fsm_b200_result *out,
+	unsigned *fired, size_t cap, size_t *nfired);
+void *refh_union_repeated_pattern_group(size_t n, void **fsms, unsigned id_base);
+
 #endif

@@ -40,7 +40,17 @@ def have_ref() -> bool:
 
 
 class OwnedDesc(C.Structure):
-    _fields_ = [("desc", CDesc), ("blocks", C.c_void_p * 8)]
+    _fields_ = [("desc", CDesc), ("blocks", C.c_void_p * 8), ("eager_off", C.c_void_p), ("eager_ids", C.c_void_p)]
+
+
+def _take_eager(f: FlatFsm, off_p, ids_p) -> FlatFsm:
+    """Attach the eager-output CSR found at (off_p, ids_p) -- C pointers, may be NULL -- to f."""
+    if off_p and f.nstates > 0:
+        eo = np.ctypeslib.as_array(C.cast(off_p, C.POINTER(C.c_uint64)), shape=(f.nstates + 1,)).copy()
+        if int(eo[-1]) > 0:
+            f.eager_off = eo
+            f.eager_ids = np.ctypeslib.as_array(C.cast(ids_p, C.POINTER(C.c_uint32)), shape=(int(eo[-1]),)).copy()
+    return f
 
 
 def offsets_for(strings) -> tuple[np.ndarray, np.ndarray]:
@@ -70,6 +80,7 @@ class Oracle:
         L.oracle_epsilon_closure.argtypes = [P(CDesc), P(vp), P(vp)]
         L.oracle_determinise.argtypes = [P(CDesc), C.c_size_t, P(OwnedDesc)]
         L.oracle_minimise.argtypes = [P(CDesc), P(OwnedDesc)]
+        L.oracle_exec_eager.argtypes = [P(CDesc), vp, C.c_uint64, P(CResult), vp, C.c_size_t, P(C.c_size_t)]
         L.oracle_desc_free.argtypes = [P(OwnedDesc)]
         L.oracle_desc_free.restype = None
         L.oracle_canonicalise.argtypes = [P(CDesc), vp, vp]
@@ -130,9 +141,20 @@ class Oracle:
             if od.desc.nstates == 0 and not od.desc.group_off:
                 return FlatFsm(0, 0, False, np.zeros(0, np.uint8), np.zeros(1, np.uint64),
                                np.zeros((0, 4), np.uint64), np.zeros(0, np.uint32), None, None, None, None)
-            return FlatFsm.from_c(od.desc)
+            return _take_eager(FlatFsm.from_c(od.desc), od.eager_off, od.eager_ids)
         finally:
             self.lib.oracle_desc_free(C.byref(od))
+
+    def exec_eager(self, f: FlatFsm, data: bytes):
+        """(record, sorted fired eager-output ids) of one fsm_exec (oracle_exec_eager)."""
+        d = f.as_c()
+        buf = np.frombuffer(data, dtype=np.uint8)
+        r = CResult()
+        fired = np.zeros(256, dtype=np.uint32)
+        n = C.c_size_t(0)
+        ret = self.lib.oracle_exec_eager(C.byref(d), _ptr(buf), len(data), C.byref(r), _ptr(fired), fired.size, C.byref(n))
+        assert ret >= 0 and n.value <= fired.size
+        return (r.ret, r.end, r.consumed), [int(x) for x in fired[:n.value]]
 
     def minimise(self, f: FlatFsm) -> FlatFsm:
         d = f.as_c()
@@ -144,7 +166,7 @@ class Oracle:
             if od.desc.nstates == 0:
                 return FlatFsm(0, 0, False, np.zeros(0, np.uint8), np.zeros(1, np.uint64),
                                np.zeros((0, 4), np.uint64), np.zeros(0, np.uint32), None, None, None, None)
-            return FlatFsm.from_c(od.desc)
+            return _take_eager(FlatFsm.from_c(od.desc), od.eager_off, od.eager_ids)
         finally:
             self.lib.oracle_desc_free(C.byref(od))
 
@@ -172,7 +194,8 @@ def canonical_form(oracle: Oracle, f: FlatFsm):
             inv[cos[s]] = s
     ends = np.array([int(f.is_end[inv[c]]) for c in range(n)], dtype=np.uint8)
     ids = [tuple(int(x) for x in f.endids_of(int(inv[c]))) if ends[c] else () for c in range(n)]
-    return tab, ends, ids
+    eager = [tuple(int(x) for x in f.eager_of(int(inv[c]))) for c in range(n)]
+    return tab, ends, ids, eager
 
 
 class RefFlat(C.Structure):
@@ -204,8 +227,33 @@ class Ref:
         L.refh_exec.argtypes = [vp, vp, C.c_uint64, P(CResult)]
         L.refh_exec_batch.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, C.c_int, vp]
         L.refh_endids.argtypes = [vp, C.c_uint, vp, C.c_size_t]; L.refh_endids.restype = C.c_size_t
+        L.refh_eager_set.argtypes = [vp, C.c_uint, C.c_uint]
+        L.refh_eager_flatten.argtypes = [vp, P(vp), P(vp)]
+        L.refh_exec_eager.argtypes = [vp, vp, C.c_uint64, P(CResult), vp, C.c_size_t, P(C.c_size_t)]
+        L.refh_union_repeated_pattern_group.argtypes = [C.c_size_t, P(vp), C.c_uint]
+        L.refh_union_repeated_pattern_group.restype = vp
         self.libc = C.CDLL(None)
         self.libc.free.argtypes = [vp]
+
+    # -- eager outputs ----------------------------------------------------------------
+    def eager_set(self, h, state: int, ident: int) -> None:
+        assert self.lib.refh_eager_set(h, state, ident) == 1
+
+    def exec_eager(self, h, data: bytes):
+        """(record, sorted fired ids) of one reference fsm_exec with the eager callback set."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        r = CResult()
+        fired = np.zeros(256, dtype=np.uint32)
+        n = C.c_size_t(0)
+        self.lib.refh_exec_eager(h, _ptr(buf), len(data), C.byref(r), _ptr(fired), fired.size, C.byref(n))
+        assert n.value <= fired.size
+        return (r.ret, r.end, r.consumed), [int(x) for x in fired[:n.value]]
+
+    def union_repeated_pattern_group(self, handles, id_base: int = 1):
+        arr = (C.c_void_p * len(handles))(*handles)
+        h = self.lib.refh_union_repeated_pattern_group(len(handles), arr, id_base)
+        assert h
+        return h
 
     # -- construction ---------------------------------------------------------------
     def re_comp(self, pattern: str | bytes, dialect: int = RE_PCRE, flags: int = 0):
@@ -264,9 +312,19 @@ class Ref:
         rf = RefFlat()
         assert self.lib.refh_flatten(h, C.byref(rf)) == 0
         try:
-            return FlatFsm.from_c(rf.desc)
+            f = FlatFsm.from_c(rf.desc)
         finally:
             self.lib.refh_flat_free(C.byref(rf))
+        off, ids = C.c_void_p(), C.c_void_p()
+        assert self.lib.refh_eager_flatten(h, C.byref(off), C.byref(ids)) == 0
+        try:
+            eo = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_uint64)), shape=(f.nstates + 1,)).copy()
+            if int(eo[-1]) > 0:
+                f.eager_off = eo
+                f.eager_ids = np.ctypeslib.as_array(C.cast(ids, C.POINTER(C.c_uint32)), shape=(int(eo[-1]),)).copy()
+        finally:
+            self.libc.free(off); self.libc.free(ids)
+        return f
 
     def compile_dfa(self, pattern, dialect: int = RE_PCRE, flags: int = 0, minimise: bool = True,
                     endid: int | None = None):

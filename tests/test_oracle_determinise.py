@@ -21,6 +21,7 @@ def assert_isomorphic(oracle, got, want):
     assert (a[0] == b[0]).all(), "transition structure differs"
     assert (a[1] == b[1]).all(), "end states differ"
     assert a[2] == b[2], "end-id sets differ"
+    assert a[3] == b[3], "eager-output sets differ"
 
 
 def test_fixture_inventory():
