@@ -168,6 +168,27 @@ int fsm_b200_exec_batch_dev(const fsm_b200_dfa *dfa,
 	const uint8_t *d_base, const uint64_t *d_offsets, uint64_t stride, uint64_t len,
 	size_t n, struct fsm_b200_result *d_out, void *stream);
 
+/* --- eager outputs ---------------------------------------------------------------------------
+ * A DFA compiled from a struct fsm_b200_desc_ext carries per-state eager-output id sets.  The
+ * distinct ids of the whole DFA are numbered densely in ascending order ("bits"); one input's
+ * answer is the bitset of ids fired along its walk: those of the start state, then of every
+ * state entered (exec.c:126-130,140-144), whether or not the input matches -- exactly the set of
+ * ids the reference hands to the fsm_eager_output_cb callback (their order and multiplicity are
+ * not reproduced; the reference's own tests only use the set, tests/eager_output/utils.c:10-24).
+ * fsm_b200_dfa_eager_info: *nbits = number of distinct ids (0: none), *id_of_bit = library-owned
+ * array [nbits] valid until fsm_b200_dfa_free.  The mask of input i is masks[i*words ..
+ * (i+1)*words), words = (nbits + 63) / 64, bit b of word b/64 set <=> id_of_bit[b] fired.
+ * The plain entry points above work on such a DFA too and simply do not report the ids.
+ * At most FSM_B200_EAGER_MAX_IDS distinct ids are supported (-1/ENOTSUP at compile time). */
+#define FSM_B200_EAGER_MAX_IDS 256u
+int fsm_b200_dfa_eager_info(const fsm_b200_dfa *dfa, uint32_t *nbits, const uint32_t **id_of_bit);
+int fsm_b200_exec_batch_eager_host(const fsm_b200_dfa *dfa,
+	const uint8_t *base, const uint64_t *offsets, size_t n,
+	struct fsm_b200_result *out, uint64_t *masks);
+int fsm_b200_exec_batch_eager_dev(const fsm_b200_dfa *dfa,
+	const uint8_t *d_base, const uint64_t *d_offsets, uint64_t stride, uint64_t len,
+	size_t n, struct fsm_b200_result *d_out, uint64_t *d_masks, void *stream);
+
 /* --- multi-GPU: scan fused with the result gather over NVLink peer memory -------------------
  * As _dev, but every record is ALSO stored into npeers (<= 7) peer buffers: peer_outs[r]
  * points at the slot of THIS rank's range inside rank r's gathered buffer (device memory
@@ -257,6 +278,16 @@ void fsm_b200_desc_free(struct fsm_b200_owned_desc *d);
 #define FSM_B200_DET_REFERENCE_NUMBERING 1u
 int fsm_b200_determinise_ex(const struct fsm_b200_desc *nfa, int device, size_t state_limit,
 	unsigned flags, struct fsm_b200_owned_desc *out);
+
+/* Eager outputs through determinise / minimise: give the input as a struct fsm_b200_desc_ext.
+ * A DFA state carries the union of the ids of every state in the epsilon closure of every member
+ * (epsilons.c:221-253, determinise.c:2614-2636); minimise keeps states with different id sets
+ * apart the way the reference does (same_end_metadata, minimise.c:705-731, including its
+ * list-order-dependent blind spot, minimise.c:771-782) and gives a merged state the union
+ * (consolidate.c:306-315).  The result's sets are read with this accessor (CSR over the output
+ * states, sorted unique; both NULL when there are none); the embedded desc keeps reserved == 0. */
+int fsm_b200_owned_desc_eager(const struct fsm_b200_owned_desc *d, const uint64_t **eager_off,
+	const uint32_t **eager_ids);
 
 /* Timing of the last determinise on this thread, milliseconds, for bench.py. */
 struct fsm_b200_det_stats {

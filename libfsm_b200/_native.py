@@ -23,6 +23,8 @@ ABI_SYMBOLS = (
     "fsm_b200_set_exec_variant", "fsm_b200_get_exec_variant",
     "fsm_b200_exec_stream_host", "fsm_b200_exec_stream_dev", "fsm_b200_exec_stream_map_dev",
     "fsm_b200_determinise", "fsm_b200_determinise_ex", "fsm_b200_desc_free", "fsm_b200_determinise_stats",
+    "fsm_b200_owned_desc_eager", "fsm_b200_dfa_eager_info",
+    "fsm_b200_exec_batch_eager_host", "fsm_b200_exec_batch_eager_dev",
     "fsm_b200_minimise", "fsm_b200_minimise_stats",
     "fsm_b200_launch_count",
 )
@@ -77,6 +79,11 @@ def _load() -> C.CDLL:
     lib.fsm_b200_exec_stream_map_dev.argtypes = [vp, vp, u64, vp, vp, vp, vp]
     lib.fsm_b200_determinise.argtypes = [P(CDesc), C.c_int, sz, P(COwnedDesc)]
     lib.fsm_b200_determinise_ex.argtypes = [P(CDesc), C.c_int, sz, C.c_uint, P(COwnedDesc)]
+    lib.fsm_b200_owned_desc_eager.argtypes = [P(COwnedDesc), P(C.c_void_p), P(C.c_void_p)]
+    lib.fsm_b200_dfa_eager_info.argtypes = [C.c_void_p, P(C.c_uint32), P(C.c_void_p)]
+    lib.fsm_b200_exec_batch_eager_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.fsm_b200_exec_batch_eager_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p]
     lib.fsm_b200_desc_free.argtypes = [P(COwnedDesc)]
     lib.fsm_b200_desc_free.restype = None
     lib.fsm_b200_determinise_stats.argtypes = [P(CDetStats)]

@@ -49,6 +49,9 @@ struct Owner {
 	std::vector<uint8_t> is_end;
 	std::vector<uint64_t> group_off, group_sym, endid_off;
 	std::vector<uint32_t> group_to, endids;
+	/* eager-output sets of the result (fsm_b200_owned_desc_eager); empty when there are none */
+	std::vector<uint64_t> eager_off;
+	std::vector<uint32_t> eager_ids;
 };
 
 } // namespace fsmb200
@@ -88,6 +91,10 @@ struct fsm_b200_dfa {
 	void *scratch;
 	/* scratch of the stream (K1b) entry points */
 	void *stream_scratch;
+	/* eager outputs (k1_eager.cu): distinct ids ascending, per-row bit masks [ntable][eager_words] */
+	uint32_t eager_nbits, eager_words;
+	uint32_t *h_eager_ids;
+	uint64_t *d_eager_masks;
 };
 
 #endif

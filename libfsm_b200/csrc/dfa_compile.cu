@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.h"
+#include "eager_host.h"
 
 using namespace fsmb200;
 
@@ -51,7 +52,7 @@ static int
 compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 {
 	const bool upload = device >= 0;
-	if (desc == nullptr || out == nullptr || desc->reserved != 0) {
+	if (desc == nullptr || out == nullptr || (desc->reserved & ~FSM_B200_DESC_EAGER) != 0) {
 		set_error("dfa_compile: bad argument");
 		errno = EINVAL;
 		return -1;
@@ -309,7 +310,45 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 			dfa->k1_off = k1_off; dfa->kend_off = kend_off; dfa->klut_off = klut_off; dfa->kblob_bytes = kbytes;
 		}
 	}
+	/* ---- eager outputs (fsm_b200_desc_ext): dense id numbering + one bit mask per table row ---- */
+	{
+		const uint64_t *xoff; const uint32_t *xids;
+		if (eagerhost::eh_get(desc, &xoff, &xids)) {
+			std::vector<uint32_t> idl;
+			std::vector<uint64_t> masks;
+			eagerhost::eh_id_list(S, xoff, xids, idl);
+			if (idl.size() > FSM_B200_EAGER_MAX_IDS) {
+				fsm_b200_dfa_free(dfa);
+				set_error("dfa_compile: %zu distinct eager-output ids (at most %u are supported)", idl.size(), FSM_B200_EAGER_MAX_IDS);
+				errno = ENOTSUP;
+				return -1;
+			}
+			dfa->eager_nbits = (uint32_t) idl.size();
+			dfa->eager_words = (dfa->eager_nbits + 63u) / 64u;
+			dfa->h_eager_ids = static_cast<uint32_t *>(malloc(sizeof(uint32_t) * idl.size()));
+			if (dfa->h_eager_ids == nullptr) { fsm_b200_dfa_free(dfa); errno = ENOMEM; return -1; }
+			memcpy(dfa->h_eager_ids, idl.data(), sizeof(uint32_t) * idl.size());
+			eagerhost::eh_build_masks(S, dfa->ntable, xoff, xids, idl, dfa->eager_words, masks);
+			if (upload) {
+				FSMB_CUDA(cudaMalloc(&dfa->d_eager_masks, masks.size() * sizeof(uint64_t)), { fsm_b200_dfa_free(dfa); return -1; });
+				FSMB_CUDA(cudaMemcpy(dfa->d_eager_masks, masks.data(), masks.size() * sizeof(uint64_t), cudaMemcpyHostToDevice),
+				    { fsm_b200_dfa_free(dfa); return -1; });
+			}
+		}
+	}
 	*out = dfa;
+	return 0;
+}
+
+extern "C" int
+fsm_b200_dfa_eager_info(const fsm_b200_dfa *dfa, uint32_t *nbits, const uint32_t **id_of_bit)
+{
+	if (dfa == nullptr || nbits == nullptr || id_of_bit == nullptr) {
+		errno = EINVAL;
+		return -1;
+	}
+	*nbits = dfa->eager_nbits;
+	*id_of_bit = dfa->h_eager_ids;
 	return 0;
 }
 
@@ -354,6 +393,8 @@ fsm_b200_dfa_free(fsm_b200_dfa *dfa)
 	}
 	if (dfa->d_kblob != nullptr) cudaFree(dfa->d_kblob);
 	if (dfa->d_absorb != nullptr) cudaFree(dfa->d_absorb);
+	if (dfa->d_eager_masks != nullptr) cudaFree(dfa->d_eager_masks);
+	free(dfa->h_eager_ids);
 	free(dfa->h_table32);
 	free(dfa->h_is_end);
 	delete dfa;

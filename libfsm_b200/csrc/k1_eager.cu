@@ -1,0 +1,189 @@
+/*
+ * k1_eager.cu -- batch execution that also reports EAGER OUTPUTS.
+ *
+ * The reference's fsm_exec calls the fsm_eager_output_cb callback for every eager-output id of
+ * the start state and of every state it enters (src/libfsm/exec.c:55-83,126-130,140-144;
+ * include/fsm/fsm.h:273-336), whether or not the input ends up matching.  Here one lane walks
+ * one input -- as in K1's LANE kernel -- and ORs the per-state id mask (W 64-bit words, built
+ * once by fsm_b200_dfa_compile) into a register accumulator: the answer is the SET of fired ids
+ * as a bitset per input, next to the usual 16-byte record.
+ *
+ * Round 1 status: correctness-first.  The table blob and the masks are read from global memory
+ * through the read-only path (they are a few KB to a few MB and stay L1/L2-resident); the
+ * shared-memory staging, k-stride stepping and vectorised input loads of k1_exec_batch.cu are
+ * not applied yet.  One extra dependent load per byte is the price of the feature on any design:
+ * mask[state] can only be fetched once the state is known.
+ */
+#include <cstring>
+
+#include "common.h"
+
+using namespace fsmb200;
+
+namespace {
+
+struct EagerArgs {
+	const uint8_t *blob;          /* table rows | is_end | class LUT */
+	const uint64_t *masks;        /* [ntable][W] */
+	const uint8_t *base;
+	const uint64_t *offsets;      /* nullptr: fixed stride */
+	uint64_t stride, len, n;
+	fsm_b200_result *out;
+	uint64_t *out_masks;          /* [n][W] */
+	uint32_t pitch, entry_bytes, nclasses, is_end_off, cls_off, start, dead;
+};
+
+template <int W>
+__global__ void __launch_bounds__(256)
+k1_eager_kernel(const EagerArgs a)
+{
+	const uint8_t *is_end = a.blob + a.is_end_off;
+	const uint8_t *cls = a.blob + a.cls_off;
+	const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += nthreads) {
+		uint64_t beg, len;
+		if (a.offsets != nullptr) { beg = a.offsets[i]; len = a.offsets[i + 1] - beg; }
+		else { beg = i * a.stride; len = a.len; }
+		const uint8_t *p = a.base + beg;
+		uint32_t st = a.start;
+		uint64_t acc[W];
+#pragma unroll
+		for (int w = 0; w < W; w++) acc[w] = __ldg(a.masks + (size_t) st * W + w);      /* exec.c:126-130 */
+		uint64_t pos = 0;
+		bool died = false;
+		for (; pos < len; pos++) {
+			uint32_t col = __ldg(p + pos);
+			if (a.nclasses != 0) col = __ldg(cls + col);
+			const uint8_t *row = a.blob + (size_t) st * a.pitch;
+			uint32_t nx;
+			if (a.entry_bytes == 1) nx = __ldg(row + col);
+			else if (a.entry_bytes == 2) nx = __ldg(reinterpret_cast<const uint16_t *>(row) + col);
+			else nx = __ldg(reinterpret_cast<const uint32_t *>(row) + col);
+			if (nx == a.dead) { died = true; break; }       /* exec.c:133-138: no edge, stop reading */
+			st = nx;
+#pragma unroll
+			for (int w = 0; w < W; w++) acc[w] |= __ldg(a.masks + (size_t) st * W + w);  /* exec.c:140-144 */
+		}
+		uint4 v;
+		v.x = (uint32_t) ((!died && __ldg(is_end + st)) ? 1 : 0);
+		v.y = st;
+		v.z = (uint32_t) pos;
+		v.w = (uint32_t) (pos >> 32);
+		*reinterpret_cast<uint4 *>(a.out + i) = v;
+#pragma unroll
+		for (int w = 0; w < W; w++) a.out_masks[i * W + w] = acc[w];
+	}
+}
+
+int
+launch_eager(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets, uint64_t stride, uint64_t len,
+	size_t n, fsm_b200_result *d_out, uint64_t *d_masks, cudaStream_t stream)
+{
+	if (n == 0) return 0;
+	EagerArgs a;
+	memset(&a, 0, sizeof a);
+	a.blob = static_cast<const uint8_t *>(dfa->d_blob);
+	a.masks = dfa->d_eager_masks;
+	a.base = d_base; a.offsets = d_offsets; a.stride = stride; a.len = len; a.n = n;
+	a.out = d_out; a.out_masks = d_masks;
+	a.pitch = dfa->pitch; a.entry_bytes = dfa->entry_bytes; a.nclasses = dfa->nclasses;
+	a.is_end_off = dfa->is_end_off; a.cls_off = dfa->cls_off; a.start = dfa->start; a.dead = dfa->dead;
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dfa->device);
+	const uint64_t want = (n + 255) / 256;
+	const unsigned blocks = (unsigned) (want < (uint64_t) sms * 8 ? want : (uint64_t) sms * 8);    /* grid-stride above that */
+	switch (dfa->eager_words) {
+	case 1: k1_eager_kernel<1><<<blocks, 256, 0, stream>>>(a); break;
+	case 2: k1_eager_kernel<2><<<blocks, 256, 0, stream>>>(a); break;
+	case 3: k1_eager_kernel<3><<<blocks, 256, 0, stream>>>(a); break;
+	case 4: k1_eager_kernel<4><<<blocks, 256, 0, stream>>>(a); break;
+	default:
+		set_error("exec_batch_eager: %u mask words not supported", dfa->eager_words);
+		errno = ENOTSUP;
+		return -1;
+	}
+	count_launch();
+	FSMB_CUDA(cudaGetLastError(), return -1);
+	return 0;
+}
+
+} // namespace
+
+extern "C" int
+fsm_b200_exec_batch_eager_dev(const fsm_b200_dfa *dfa,
+	const uint8_t *d_base, const uint64_t *d_offsets, uint64_t stride, uint64_t len,
+	size_t n, struct fsm_b200_result *d_out, uint64_t *d_masks, void *stream)
+{
+	if (dfa == nullptr || (n > 0 && (d_base == nullptr || d_out == nullptr || d_masks == nullptr)) ||
+	    (d_offsets == nullptr && stride < len)) {
+		set_error("exec_batch_eager_dev: bad argument");
+		errno = EINVAL;
+		return -1;
+	}
+	if (dfa->eager_nbits == 0) {
+		set_error("exec_batch_eager_dev: this DFA has no eager outputs (use fsm_b200_exec_batch_dev)");
+		errno = EINVAL;
+		return -1;
+	}
+	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
+	return launch_eager(dfa, d_base, d_offsets, stride, len, n, d_out, d_masks, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int
+fsm_b200_exec_batch_eager_host(const fsm_b200_dfa *dfa,
+	const uint8_t *base, const uint64_t *offsets, size_t n,
+	struct fsm_b200_result *out, uint64_t *masks)
+{
+	if (dfa == nullptr || (n > 0 && (base == nullptr || offsets == nullptr || out == nullptr || masks == nullptr))) {
+		set_error("exec_batch_eager_host: bad argument");
+		errno = EINVAL;
+		return -1;
+	}
+	if (dfa->eager_nbits == 0) {
+		set_error("exec_batch_eager_host: this DFA has no eager outputs (use fsm_b200_exec_batch_host)");
+		errno = EINVAL;
+		return -1;
+	}
+	if (n == 0) return 0;
+	for (size_t i = 0; i < n; i++) {
+		if (offsets[i + 1] < offsets[i]) {
+			set_error("exec_batch_eager_host: offsets not monotone at %zu", i);
+			errno = EINVAL;
+			return -1;
+		}
+	}
+	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
+	const uint64_t lo = offsets[0], nbytes = offsets[n] - lo;
+	const size_t W = dfa->eager_words;
+	uint8_t *d_in = nullptr; uint64_t *d_off = nullptr, *d_masks = nullptr; fsm_b200_result *d_out = nullptr;
+	cudaStream_t st = nullptr;
+	int rc = -1;
+	errno = 0;
+	/* one shot: the automata that carry eager outputs are matched against short inputs (one
+	 * fsm_exec call of a relinked caller); the double-buffered pipeline of api.cu is not needed */
+	do {
+		if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { st = nullptr; break; }
+		if (cudaMalloc(&d_in, nbytes + 16) != cudaSuccess || cudaMalloc(&d_off, (n + 1) * sizeof(uint64_t)) != cudaSuccess ||
+		    cudaMalloc(&d_out, n * sizeof(fsm_b200_result)) != cudaSuccess || cudaMalloc(&d_masks, n * W * sizeof(uint64_t)) != cudaSuccess) {
+			errno = ENOMEM;
+			break;
+		}
+		if (nbytes > 0 && cudaMemcpyAsync(d_in, base + lo, nbytes, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+		if (cudaMemcpyAsync(d_off, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+		if (launch_eager(dfa, d_in - lo, d_off, 0, 0, n, d_out, d_masks, st) != 0) { rc = -2; break; }
+		if (cudaMemcpyAsync(out, d_out, n * sizeof(fsm_b200_result), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+		if (cudaMemcpyAsync(masks, d_masks, n * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+		if (cudaStreamSynchronize(st) != cudaSuccess) break;
+		rc = 0;
+	} while (0);
+	if (rc == -1) {
+		const cudaError_t e = cudaGetLastError();
+		if (errno != ENOMEM) errno = EIO;
+		set_error("exec_batch_eager_host: %s", e != cudaSuccess ? cudaGetErrorString(e) : "CUDA call failed");
+	} else if (rc == -2) {
+		rc = -1;                          /* launch_eager already set the error */
+	}
+	if (st != nullptr) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+	cudaFree(d_in); cudaFree(d_off); cudaFree(d_out); cudaFree(d_masks);
+	return rc;
+}

@@ -34,6 +34,7 @@
  */
 #include "k23_common.cuh"
 #include "refnum.h"
+#include "eager_host.h"
 
 namespace {
 
@@ -489,7 +490,7 @@ static int
 determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit, unsigned flags,
 	struct fsm_b200_owned_desc *out)
 {
-	if (nfa == nullptr || out == nullptr || nfa->reserved != 0 || (flags & ~(unsigned) FSM_B200_DET_REFERENCE_NUMBERING)) {
+	if (nfa == nullptr || out == nullptr || (nfa->reserved & ~FSM_B200_DESC_EAGER) != 0 || (flags & ~(unsigned) FSM_B200_DET_REFERENCE_NUMBERING)) {
 		set_error("determinise: bad argument");
 		errno = EINVAL;
 		return -1;
@@ -792,7 +793,10 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 
 	own->is_end.assign(D, 0);
 	own->endid_off.assign(D + 1, 0);
-	std::vector<uint32_t> ids;
+	std::vector<uint32_t> ids, xacc;
+	const uint64_t *xoff = nullptr; const uint32_t *xids = nullptr;
+	const bool has_eager = eagerhost::eh_get(nfa, &xoff, &xids);
+	if (has_eager) own->eager_off.assign(D + 1, 0);
 	for (uint32_t s = 0; s < D; s++) {
 		/* end bit + end ids: determinise.c:236-266 over the epsilon-folded members */
 		ids.clear();
@@ -817,7 +821,21 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 		}
 		own->endids.insert(own->endids.end(), ids.begin(), ids.end());
 		own->endid_off[s + 1] = own->endids.size();
+		if (has_eager) {
+			/* eager outputs: the ids of every state in the closure of every member
+			 * (epsilons.c:221-253, determinise.c:2614-2636) */
+			xacc.clear();
+			for (uint64_t i = h_pooloff[src]; i < h_pooloff[src + 1]; i++) {
+				const uint32_t m = h_pooldata[i];
+				if (have_closure) eagerhost::eh_union_over(h_clto.begin() + h_cloff[m], h_clto.begin() + h_cloff[m + 1], xoff, xids, xacc);
+				else eagerhost::eh_union_over(&m, &m + 1, xoff, xids, xacc);
+			}
+			eagerhost::eh_sort_unique(xacc);
+			own->eager_ids.insert(own->eager_ids.end(), xacc.begin(), xacc.end());
+			own->eager_off[s + 1] = own->eager_ids.size();
+		}
 	}
+	if (has_eager && own->eager_ids.empty()) own->eager_off.clear();
 	if (own->group_to.empty()) { own->group_to.push_back(0); own->group_sym.resize(4, 0); }
 	if (own->endids.empty()) own->endids.push_back(0);
 	tl_stats.ms_emit = ms_since(t_emit);
@@ -839,6 +857,17 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 	tl_stats.dfa_states = D;
 	tl_stats.dfa_groups = own->group_off[D];
 	tl_stats.kernel_launches = fsm_b200_launch_count(0) - launches0;
+	return 0;
+}
+
+extern "C" int
+fsm_b200_owned_desc_eager(const struct fsm_b200_owned_desc *d, const uint64_t **eager_off, const uint32_t **eager_ids)
+{
+	if (d == nullptr || eager_off == nullptr || eager_ids == nullptr) { errno = EINVAL; return -1; }
+	const Owner *own = static_cast<const Owner *>(d->owner);
+	const bool has = own != nullptr && !own->eager_off.empty();
+	*eager_off = has ? own->eager_off.data() : nullptr;
+	*eager_ids = has ? own->eager_ids.data() : nullptr;
 	return 0;
 }
 

@@ -24,6 +24,7 @@
  * to the reference's on the reference's own pipeline inputs (tests compare canonical forms).
  */
 #include "k23_common.cuh"
+#include "eager_host.h"
 
 namespace {
 
@@ -195,7 +196,7 @@ fsm_b200_minimise_stats(struct fsm_b200_det_stats *st)
 extern "C" int
 fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_owned_desc *out)
 {
-	if (dfa == nullptr || out == nullptr || dfa->reserved != 0) {
+	if (dfa == nullptr || out == nullptr || (dfa->reserved & ~FSM_B200_DESC_EAGER) != 0) {
 		set_error("minimise: bad argument");
 		errno = EINVAL;
 		return -1;
@@ -231,7 +232,12 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 
 	/* initial classes: 0 for non-end states; end states by end-id set (minimise.c:733-) */
 	std::vector<uint32_t> cls0(n, 0);
-	{
+	const uint64_t *xoff = nullptr; const uint32_t *xids = nullptr;
+	const bool has_eager = eagerhost::eh_get(dfa, &xoff, &xids);
+	if (has_eager) {
+		/* eager-output sets separate states too, the way the reference sees them (eager_host.h) */
+		eagerhost::eh_initial_classes(dfa, xoff, xids, cls0);
+	} else {
 		std::map<std::vector<uint32_t>, uint32_t> ids;
 		for (uint32_t s = 0; s < n; s++) {
 			if (!dfa->is_end[s]) continue;
@@ -383,6 +389,28 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 			own->endids.insert(own->endids.end(), dfa->endids + dfa->endid_off[s], dfa->endids + dfa->endid_off[s + 1]);
 		}
 		own->endid_off[c + 1] = own->endids.size();
+	}
+	if (has_eager) {
+		/* a merged state fires the union of its members' ids (fsm_consolidate, consolidate.c:306-315) */
+		/* d_cls: output state of every kept state (what k3_out_trans_kernel writes into the rows) */
+		std::vector<uint32_t> h_cls(m), h_korig(m);
+		CK(cudaMemcpyAsync(h_cls.data(), d_cls.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(h_korig.data(), d_korig.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		std::vector<std::vector<uint32_t>> acc(D);
+		for (uint32_t i = 0; i < m; i++) {
+			const uint32_t c = h_cls[i];
+			if (c >= D) { set_error("minimise: class index out of range"); errno = EIO; return -1; }
+			const uint32_t s = h_korig[i];
+			acc[c].insert(acc[c].end(), xids + xoff[s], xids + xoff[s + 1]);
+		}
+		own->eager_off.assign(D + 1, 0);
+		for (uint32_t c = 0; c < D; c++) {
+			eagerhost::eh_sort_unique(acc[c]);
+			own->eager_ids.insert(own->eager_ids.end(), acc[c].begin(), acc[c].end());
+			own->eager_off[c + 1] = own->eager_ids.size();
+		}
+		if (own->eager_ids.empty()) own->eager_off.clear();
 	}
 	if (own->group_to.empty()) { own->group_to.push_back(0); own->group_sym.resize(4, 0); }
 	if (own->endids.empty()) own->endids.push_back(0);

@@ -86,6 +86,33 @@ class Dfa:
         check(lib.fsm_b200_dfa_table(self._h, out.ctypes.data), "dfa_table")
         return out
 
+    # ---- eager outputs ----------------------------------------------------------------
+    def eager_ids(self) -> np.ndarray:
+        """The distinct eager-output ids of this DFA, ascending: bit b of a mask <=> eager_ids()[b]."""
+        nbits, ids = C.c_uint32(0), C.c_void_p()
+        check(lib.fsm_b200_dfa_eager_info(self._h, C.byref(nbits), C.byref(ids)), "dfa_eager_info")
+        if nbits.value == 0:
+            return np.zeros(0, np.uint32)
+        return np.ctypeslib.as_array(C.cast(ids, C.POINTER(C.c_uint32)), shape=(nbits.value,)).copy()
+
+    def exec_batch_eager(self, base, offsets):
+        """Host buffers in; (records, masks uint64 [n, words]) out: the usual records plus, per
+        input, the bitset of eager-output ids fired along its walk (``fired_ids`` decodes one)."""
+        base = np.ascontiguousarray(base, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = offsets.shape[0] - 1
+        words = (len(self.eager_ids()) + 63) // 64
+        out = np.empty(max(n, 0), dtype=RESULT_DTYPE)
+        masks = np.zeros((max(n, 0), max(words, 1)), dtype=np.uint64)
+        bptr = base.ctypes.data if base.size else np.zeros(16, np.uint8).ctypes.data
+        check(lib.fsm_b200_exec_batch_eager_host(self._h, bptr, offsets.ctypes.data, n, out.ctypes.data, masks.ctypes.data),
+              "exec_batch_eager_host")
+        return out, masks[:, :words]
+
+    def fired_ids(self, mask_row) -> list:
+        ids = self.eager_ids()
+        return [int(ids[b]) for b in range(len(ids)) if (int(mask_row[b >> 6]) >> (b & 63)) & 1]
+
     # ---- batched execution -----------------------------------------------------------
     def exec_batch(self, base, offsets=None, *, stride=None, length=None, n=None, out=None):
         """n independent fsm_exec calls.
@@ -188,7 +215,7 @@ def determinise(nfa: FlatFsm, device: int = 0, state_limit: int = 0, numbering: 
         raise StateLimitReached()
     check(rc, "determinise")
     try:
-        return FlatFsm.from_c(od.desc)
+        return _with_eager(FlatFsm.from_c(od.desc), od)
     finally:
         lib.fsm_b200_desc_free(C.byref(od))
 
@@ -203,9 +230,21 @@ def minimise(dfa: FlatFsm, device: int = 0) -> FlatFsm:
         if od.desc.nstates == 0:
             return FlatFsm(0, 0, False, np.zeros(0, np.uint8), np.zeros(1, np.uint64),
                            np.zeros((0, 4), np.uint64), np.zeros(0, np.uint32), None, None, None, None)
-        return FlatFsm.from_c(od.desc)
+        return _with_eager(FlatFsm.from_c(od.desc), od)
     finally:
         lib.fsm_b200_desc_free(C.byref(od))
+
+
+def _with_eager(f: FlatFsm, od) -> FlatFsm:
+    """Attach the eager-output sets of a library-owned result (fsm_b200_owned_desc_eager)."""
+    off, ids = C.c_void_p(), C.c_void_p()
+    check(lib.fsm_b200_owned_desc_eager(C.byref(od), C.byref(off), C.byref(ids)), "owned_desc_eager")
+    if off and f.nstates > 0:
+        eo = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_uint64)), shape=(f.nstates + 1,)).copy()
+        if int(eo[-1]) > 0:
+            f.eager_off = eo
+            f.eager_ids = np.ctypeslib.as_array(C.cast(ids, C.POINTER(C.c_uint32)), shape=(int(eo[-1]),)).copy()
+    return f
 
 
 def minimise_stats() -> dict:

@@ -15,11 +15,15 @@
  *     reference's per-call fsm_all(fsm, fsm_isdfa) (exec.c:106) costs O(edges) per input;
  *   - the walk runs on the GPU (one long input: K1b chunk maps; a batch: K1).  There is no
  *     CPU walk in here: without a usable device the call fails with -1/EIO.
+ * Eager outputs (exec.c:126-144): the engine returns the SET of ids fired along the walk; the
+ * callback set with fsm_eager_output_set_cb is then called once per fired id, ascending, after
+ * the walk (the reference calls it as it goes, once per state entry; its own tests only use the
+ * set, tests/eager_output/utils.c:10-24).
  * Not accelerated (returns -1/ENOTSUP): FSMs with capture actions when `captures` is
- * non-NULL (exec.c:41-44,157-163) and FSMs with eager outputs (exec.c:126-144) -- neither
- * is produced by re_comp or used by any CLI.
+ * non-NULL (exec.c:41-44,157-163) -- not produced by re_comp, no CLI passes captures.
  */
 #include <assert.h>
+#include <stddef.h>
 #include <errno.h>
 #include <pthread.h>
 #include <stdio.h>
@@ -36,17 +40,29 @@
 #include <adt/edgeset.h>
 
 #include "libfsm/internal.h"
+#include "libfsm/eager_output.h"
 
 #include "fsm_b200_shim.h"
 
 /* ------------------------------------------------------------------ flattening ------- */
 
+static int
+cmp_u32(const void *a, const void *b)
+{
+	const uint32_t x = *(const uint32_t *) a, y = *(const uint32_t *) b;
+	return x < y ? -1 : x > y;
+}
+
+/* struct fsm_b200_flat starts like a struct fsm_b200_desc_ext */
+typedef char flat_is_ext[(offsetof(struct fsm_b200_flat, eager_off) == offsetof(struct fsm_b200_desc_ext, eager_off) &&
+	offsetof(struct fsm_b200_flat, eager_ids) == offsetof(struct fsm_b200_desc_ext, eager_ids)) ? 1 : -1];
+
 int
 fsm_b200_flatten(const struct fsm *fsm, struct fsm_b200_flat *out)
 {
 	const size_t n = fsm->statecount;
-	size_t ngroups = 0, neps = 0, nids = 0, s;
-	uint8_t *is_end; uint64_t *goff, *gsym, *eoff, *ioff; uint32_t *gto, *eto, *ids;
+	size_t ngroups = 0, neps = 0, nids = 0, nxids = 0, s;
+	uint8_t *is_end; uint64_t *goff, *gsym, *eoff, *ioff, *xoff = NULL; uint32_t *gto, *eto, *ids, *xids = NULL;
 	fsm_state_t start;
 
 	memset(out, 0, sizeof *out);
@@ -57,6 +73,7 @@ fsm_b200_flatten(const struct fsm *fsm, struct fsm_b200_flat *out)
 		while (edge_set_group_iter_next(&it, &info)) ngroups++;
 		neps += state_set_count(fsm->states[s].epsilons);
 		if (fsm->states[s].end) nids += fsm_endid_count(fsm, (fsm_state_t) s);
+		if (fsm->states[s].has_eager_outputs) nxids += fsm_eager_output_count(fsm, (fsm_state_t) s);
 	}
 	is_end = calloc(n + 1, 1);
 	goff = calloc(n + 1, sizeof *goff);
@@ -66,12 +83,16 @@ fsm_b200_flatten(const struct fsm *fsm, struct fsm_b200_flat *out)
 	eto = calloc(neps + 1, sizeof *eto);
 	ioff = calloc(n + 1, sizeof *ioff);
 	ids = calloc(nids + 1, sizeof *ids);
-	if (!is_end || !goff || !gsym || !gto || !eoff || !eto || !ioff || !ids) {
-		free(is_end); free(goff); free(gsym); free(gto); free(eoff); free(eto); free(ioff); free(ids);
+	if (nxids > 0) {
+		xoff = calloc(n + 1, sizeof *xoff);
+		xids = calloc(nxids + 1, sizeof *xids);
+	}
+	if (!is_end || !goff || !gsym || !gto || !eoff || !eto || !ioff || !ids || (nxids > 0 && (!xoff || !xids))) {
+		free(is_end); free(goff); free(gsym); free(gto); free(eoff); free(eto); free(ioff); free(ids); free(xoff); free(xids);
 		errno = ENOMEM;
 		return -1;
 	}
-	ngroups = neps = nids = 0;
+	ngroups = neps = nids = nxids = 0;
 	for (s = 0; s < n; s++) {
 		struct edge_group_iter it;
 		struct edge_group_iter_info info;
@@ -92,8 +113,20 @@ fsm_b200_flatten(const struct fsm *fsm, struct fsm_b200_flat *out)
 			const size_t c = fsm_endid_count(fsm, (fsm_state_t) s);
 			if (c > 0 && fsm_endid_get(fsm, (fsm_state_t) s, c, &ids[nids])) nids += c;
 		}
+		if (xoff != NULL) {
+			/* eager outputs: stored in insertion order (eager_output.c:160-216); sets here */
+			size_t c = fsm->states[s].has_eager_outputs ? fsm_eager_output_count(fsm, (fsm_state_t) s) : 0, i, w = 0;
+			xoff[s] = nxids;
+			if (c > 0) {
+				fsm_eager_output_get(fsm, (fsm_state_t) s, c, &xids[nxids]);
+				qsort(&xids[nxids], c, sizeof *xids, cmp_u32);
+				for (i = 0; i < c; i++) if (i == 0 || xids[nxids + i] != xids[nxids + w - 1]) xids[nxids + w++] = xids[nxids + i];
+				nxids += w;
+			}
+		}
 	}
 	goff[n] = ngroups; eoff[n] = neps; ioff[n] = nids;
+	if (xoff != NULL) xoff[n] = nxids;
 	out->desc.nstates = (uint32_t) n;
 	out->desc.hasstart = (uint32_t) fsm_getstart(fsm, &start);
 	out->desc.start = out->desc.hasstart ? start : 0;
@@ -103,6 +136,11 @@ fsm_b200_flatten(const struct fsm *fsm, struct fsm_b200_flat *out)
 	out->desc.endid_off = ioff; out->desc.endids = ids;
 	out->blocks[0] = is_end; out->blocks[1] = goff; out->blocks[2] = gsym; out->blocks[3] = gto;
 	out->blocks[4] = eoff; out->blocks[5] = eto; out->blocks[6] = ioff; out->blocks[7] = ids;
+	if (xoff != NULL) {
+		out->desc.reserved = FSM_B200_DESC_EAGER;
+		out->eager_off = xoff; out->eager_ids = xids;
+		out->blocks[8] = xoff; out->blocks[9] = xids;
+	}
 	return 0;
 }
 
@@ -110,8 +148,9 @@ void
 fsm_b200_flat_free(struct fsm_b200_flat *flat)
 {
 	size_t i;
-	for (i = 0; i < 8; i++) { free(flat->blocks[i]); flat->blocks[i] = NULL; }
+	for (i = 0; i < sizeof flat->blocks / sizeof flat->blocks[0]; i++) { free(flat->blocks[i]); flat->blocks[i] = NULL; }
 	memset(&flat->desc, 0, sizeof flat->desc);
+	flat->eager_off = NULL; flat->eager_ids = NULL;
 }
 
 #ifndef FSM_B200_SHIM_FLATTEN_ONLY
@@ -121,6 +160,15 @@ fsm_b200_flat_free(struct fsm_b200_flat *flat)
 /* Content fingerprint: everything fsm_exec can observe (start, end bits, epsilon presence,
  * edge groups).  O(groups), allocation-free; the reference spends O(edges) per call on
  * validation alone. */
+static int
+fp_eager_cb(fsm_state_t state, fsm_output_id_t id, void *opaque)
+{
+	uint64_t *h = opaque;
+	(void) state;
+	*h += 0x9e3779b97f4a7c15ull * ((uint64_t) id + 1);     /* order-independent: stored order is insertion order */
+	return 1;
+}
+
 static uint64_t
 fingerprint(const struct fsm *fsm)
 {
@@ -133,7 +181,11 @@ fingerprint(const struct fsm *fsm)
 		struct edge_group_iter_info info;
 		MIX(fsm->states[s].end);
 		MIX(state_set_count(fsm->states[s].epsilons));
-		MIX(fsm->states[s].has_eager_outputs);
+		if (fsm->states[s].has_eager_outputs) {
+			uint64_t e = 1;
+			fsm_eager_output_iter_state(fsm, (fsm_state_t) s, fp_eager_cb, &e);
+			MIX(e);
+		}
 		edge_set_group_iter_reset(fsm->states[s].edges, EDGE_GROUP_ITER_ALL, &it);
 		while (edge_set_group_iter_next(&it, &info)) {
 			MIX(info.to); MIX(info.symbols[0]); MIX(info.symbols[1]); MIX(info.symbols[2]); MIX(info.symbols[3]);
@@ -266,12 +318,7 @@ fsm_b200_invalidate(const struct fsm *fsm)
 static int
 unsupported(const struct fsm *fsm, const struct fsm_capture *captures)
 {
-	size_t s;
-	if (captures != NULL && fsm_countcaptures(fsm) > 0) return 1;
-	for (s = 0; s < fsm->statecount; s++) {
-		if (fsm->states[s].has_eager_outputs) return 1;
-	}
-	return 0;
+	return captures != NULL && fsm_countcaptures(fsm) > 0;
 }
 
 /* ------------------------------------------------------------------ fsm_exec ---------- */
@@ -323,10 +370,34 @@ fsm_exec(const struct fsm *fsm,
 		buf[len++] = (unsigned char) c;
 	}
 
-	if (fsm_b200_exec_stream_host(ref.dfa, buf, len, &r) != 0) {
-		free(buf);
-		put_dfa(&ref);
-		return -1;                      /* errno from the engine (EIO: no device) */
+	{
+		uint32_t nbits = 0, b;
+		const uint32_t *id_of_bit = NULL;
+		uint64_t mask[FSM_B200_EAGER_MAX_IDS / 64];
+		const uint64_t off[2] = { 0, len };
+		int rc;
+
+		(void) fsm_b200_dfa_eager_info(ref.dfa, &nbits, &id_of_bit);
+		if (nbits == 0) {
+			rc = fsm_b200_exec_stream_host(ref.dfa, buf, len, &r);
+		} else {
+			/* eager outputs (exec.c:126-144): the walk also reports the set of ids it fired */
+			memset(mask, 0, sizeof mask);
+			rc = fsm_b200_exec_batch_eager_host(ref.dfa, buf != NULL ? buf : (const unsigned char *) "", off, 1, &r, mask);
+		}
+		if (rc != 0) {
+			free(buf);
+			put_dfa(&ref);
+			return -1;                  /* errno from the engine (EIO: no device) */
+		}
+		if (nbits != 0) {
+			fsm_eager_output_cb *cb = NULL;
+			void *cb_opaque = NULL;
+			fsm_eager_output_get_cb(fsm, &cb, &cb_opaque);
+			for (b = 0; cb != NULL && b < nbits; b++) {
+				if ((mask[b >> 6] >> (b & 63)) & 1u) cb(id_of_bit[b], cb_opaque);
+			}
+		}
 	}
 	free(buf);
 	put_dfa(&ref);
@@ -349,7 +420,8 @@ fsm_exec(const struct fsm *fsm,
 /* Build a `struct fsm` from a flat DFA description with the reference's own builder API.
  * Groups arrive sorted by destination, so every edge_set_add_bulk is a pure append. */
 static struct fsm *
-fsm_from_desc(const struct fsm_alloc *alloc, const struct fsm_b200_desc *d)
+fsm_from_desc(const struct fsm_alloc *alloc, const struct fsm_b200_desc *d,
+	const uint64_t *eager_off, const uint32_t *eager_ids)
 {
 	struct fsm *fsm = fsm_new_statealloc(alloc, d->nstates > 0 ? d->nstates : 1);
 	uint32_t s;
@@ -385,6 +457,16 @@ fsm_from_desc(const struct fsm_alloc *alloc, const struct fsm_b200_desc *d)
 	if (d->hasstart) {
 		fsm_setstart(fsm, d->start);
 	}
+	if (eager_off != NULL) {
+		for (s = 0; s < d->nstates; s++) {
+			uint64_t e;
+			for (e = eager_off[s]; e < eager_off[s + 1]; e++) {
+				if (!fsm_eager_output_set(fsm, s, eager_ids[e])) {
+					goto fail;
+				}
+			}
+		}
+	}
 	return fsm;
 
 fail:
@@ -405,8 +487,9 @@ fail:
  * State NUMBERS are BFS order instead of the reference's LIFO/analysis order (DESIGN.md
  * section 5): an isomorphic DFA -- unless FSM_B200_DET_NUMBERING=reference, in which case the
  * engine reproduces the reference's numbering too.
- * Not accelerated: capture actions and eager outputs (determinise.c:268-274 remaps them);
- * such FSMs fail with ERRNO/ENOTSUP rather than silently taking another path.
+ * Eager outputs are carried by the engine (determinise.c:268-274, :2614-2636).
+ * Not accelerated: capture actions (determinise.c:268-270 remaps them); such FSMs fail with
+ * ERRNO/ENOTSUP rather than silently taking another path.
  */
 enum fsm_determinise_with_config_res
 fsm_determinise_with_config(struct fsm *nfa, const struct fsm_determinise_config *config)
@@ -445,10 +528,16 @@ fsm_determinise_with_config(struct fsm *nfa, const struct fsm_determinise_config
 	}
 	fsm_b200_flat_free(&flat);
 
-	dfa = fsm_from_desc(nfa->alloc, &out.desc);
-	fsm_b200_desc_free(&out);
-	if (dfa == NULL) {
-		return FSM_DETERMINISE_WITH_CONFIG_ERRNO;
+	{
+		/* eager outputs carried by the engine (determinise.c:268-274); like the reference, the
+		 * callback registered on the old automaton does not survive the fsm_move */
+		const uint64_t *xoff = NULL; const uint32_t *xids = NULL;
+		(void) fsm_b200_owned_desc_eager(&out, &xoff, &xids);
+		dfa = fsm_from_desc(nfa->alloc, &out.desc, xoff, xids);
+		fsm_b200_desc_free(&out);
+		if (dfa == NULL) {
+			return FSM_DETERMINISE_WITH_CONFIG_ERRNO;
+		}
 	}
 	fsm_b200_invalidate(nfa);
 	fsm_move(nfa, dfa);
@@ -509,10 +598,14 @@ fsm_minimise(struct fsm *fsm)
 		return 0;
 	}
 	fsm_b200_flat_free(&flat);
-	min = fsm_from_desc(fsm->alloc, &out.desc);
-	fsm_b200_desc_free(&out);
-	if (min == NULL) {
-		return 0;
+	{
+		const uint64_t *xoff = NULL; const uint32_t *xids = NULL;
+		(void) fsm_b200_owned_desc_eager(&out, &xoff, &xids);
+		min = fsm_from_desc(fsm->alloc, &out.desc, xoff, xids);
+		fsm_b200_desc_free(&out);
+		if (min == NULL) {
+			return 0;
+		}
 	}
 	fsm_b200_invalidate(fsm);
 	fsm_move(fsm, min);
@@ -539,4 +632,26 @@ fsm_exec_batch(const struct fsm *fsm, const unsigned char *base, const uint64_t 
 	return rc;
 }
 
+int
+fsm_exec_batch_eager(const struct fsm *fsm, const unsigned char *base, const uint64_t *offsets,
+	size_t n, struct fsm_b200_result *out, uint64_t *masks, uint32_t *nbits, const uint32_t **id_of_bit)
+{
+	struct dfa_ref ref;
+	int rc;
+
+	assert(fsm != NULL);
+	assert(nbits != NULL && id_of_bit != NULL);
+	if (get_dfa(fsm, &ref) != 0) {
+		return -1;
+	}
+	rc = fsm_b200_dfa_eager_info(ref.dfa, nbits, id_of_bit);
+	if (rc == 0 && n > 0) {
+		rc = *nbits != 0 ? fsm_b200_exec_batch_eager_host(ref.dfa, base, offsets, n, out, masks)
+		                 : fsm_b200_exec_batch_host(ref.dfa, base, offsets, n, out);
+	}
+	put_dfa(&ref);
+	return rc;
+}
+
 #endif /* FSM_B200_SHIM_FLATTEN_ONLY */
+

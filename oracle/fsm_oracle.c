@@ -694,8 +694,25 @@ cmp_sigrow(const void *a, const void *b)
 	return (x->state > y->state) - (x->state < y->state);
 }
 
+static int minimise_impl(const struct fsm_b200_desc *d, const uint32_t *given_cls0, struct oracle_owned_desc *out);
+
 int
 oracle_minimise(const struct fsm_b200_desc *d, struct oracle_owned_desc *out)
+{
+	return minimise_impl(d, NULL, out);
+}
+
+/* Test hook: the same refinement started from initial classes computed elsewhere (one id per
+ * input state, 0 = plain) -- lets tests check the PRODUCT's host code for the initial partition
+ * (libfsm_b200/csrc/eager_host.h, compiled for the CPU by oracle/eager_host_test.cpp). */
+int
+oracle_minimise_from_classes(const struct fsm_b200_desc *d, const uint32_t *cls0, struct oracle_owned_desc *out)
+{
+	return minimise_impl(d, cls0, out);
+}
+
+static int
+minimise_impl(const struct fsm_b200_desc *d, const uint32_t *given_cls0, struct oracle_owned_desc *out)
 {
 	const uint32_t n = d->nstates;
 	uint32_t *table = NULL, *newid = NULL, *cls = NULL, *ncls_arr = NULL, *sig = NULL, *rep = NULL;
@@ -797,6 +814,7 @@ oracle_minimise(const struct fsm_b200_desc *d, struct oracle_owned_desc *out)
 #define EAGER_LEN(i) ((xoff != NULL && collected[i]) ? (size_t) (xoff[orig[i] + 1] - xoff[orig[i]]) : 0)
 		for (uint32_t i = 0; i < m; i++) {
 			uint32_t si = orig[i], k;
+			if (given_cls0 != NULL) { cls[i] = given_cls0[si]; continue; }
 			cls[i] = NO_EDGE;
 			if (!d->is_end[si] && EAGER_LEN(i) == 0) { cls[i] = 0; continue; }
 			for (k = 0; k < i; k++) {

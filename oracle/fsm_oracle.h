@@ -75,6 +75,9 @@ void oracle_desc_free(struct oracle_owned_desc *d);
  * refinement.  The minimal DFA is unique up to numbering; states are numbered here by the
  * smallest original state of each class.  Input must be a DFA.  Returns 0, or -1 errno. */
 int oracle_minimise(const struct fsm_b200_desc *dfa, struct oracle_owned_desc *out);
+/* Test hook: the same refinement started from a given initial partition (one class id per input
+ * state, 0 = plain non-end state). */
+int oracle_minimise_from_classes(const struct fsm_b200_desc *dfa, const uint32_t *cls0, struct oracle_owned_desc *out);
 
 /* Canonical form of a DFA for isomorphism checks: BFS renumbering from the start state
  * following symbols 0..255 in order (unreachable states dropped).

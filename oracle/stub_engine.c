@@ -29,6 +29,9 @@ struct fsm_b200_dfa {
 	volatile unsigned magic;           /* LIVE until fsm_b200_dfa_free; the struct itself is never
 	                                    * returned to malloc so that a use after free is DETECTED */
 	struct oracle_owned_desc copy;     /* deep copy of the description */
+	struct fsm_b200_desc_ext ext;      /* the copy again, as an ext desc when it has eager outputs */
+	uint32_t nbits;                    /* distinct eager-output ids, ascending */
+	uint32_t *id_of_bit;
 };
 
 static unsigned long n_compile, n_free, n_stream, n_batch, n_det, n_min, n_uaf;   /* atomics */
@@ -50,6 +53,13 @@ dup_block(const void *p, size_t bytes)
 	void *q = malloc(bytes ? bytes : 1);
 	if (q != NULL && bytes) memcpy(q, p, bytes);
 	return q;
+}
+
+static int
+cmp_u32(const void *a, const void *b)
+{
+	const uint32_t x = *(const uint32_t *) a, y = *(const uint32_t *) b;
+	return x < y ? -1 : x > y;
 }
 
 const char *fsm_b200_last_error(void) { return "stub engine (CPU, tests only)"; }
@@ -74,6 +84,21 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *d, int device, fsm_b200_dfa **o
 	dfa->copy.desc.group_to = dfa->copy.blocks[3] = dup_block(d->group_to, G * sizeof(uint32_t));
 	dfa->copy.desc.eps_off = NULL; dfa->copy.desc.eps_to = NULL;    /* a DFA has none */
 	dfa->copy.desc.endid_off = NULL; dfa->copy.desc.endids = NULL;
+	dfa->copy.desc.reserved = 0;
+	dfa->ext.base = dfa->copy.desc;
+	if (d->reserved & FSM_B200_DESC_EAGER) {
+		const struct fsm_b200_desc_ext *x = (const struct fsm_b200_desc_ext *) d;
+		const uint64_t total = x->eager_off[n];
+		uint64_t i; uint32_t w = 0;
+		dfa->ext.eager_off = dfa->copy.blocks[4] = dup_block(x->eager_off, (n + 1) * sizeof(uint64_t));
+		dfa->ext.eager_ids = dfa->copy.blocks[5] = dup_block(x->eager_ids, total * sizeof(uint32_t));
+		dfa->ext.base.reserved = FSM_B200_DESC_EAGER;
+		dfa->id_of_bit = dup_block(x->eager_ids, total * sizeof(uint32_t));
+		qsort(dfa->id_of_bit, total, sizeof(uint32_t), cmp_u32);
+		for (i = 0; i < total; i++) if (i == 0 || dfa->id_of_bit[i] != dfa->id_of_bit[w - 1]) dfa->id_of_bit[w++] = dfa->id_of_bit[i];
+		dfa->nbits = w;
+		if (w > FSM_B200_EAGER_MAX_IDS) { fsm_b200_dfa_free(dfa); errno = ENOTSUP; return -1; }
+	}
 	*out = dfa;
 	return 0;
 }
@@ -87,7 +112,9 @@ fsm_b200_dfa_free(fsm_b200_dfa *dfa)
 	if (dfa->magic != LIVE) { COUNT(n_uaf); return; }                 /* double free */
 	dfa->magic = DEAD;
 	for (i = 0; i < 8; i++) { free(dfa->copy.blocks[i]); dfa->copy.blocks[i] = NULL; }
+	free(dfa->id_of_bit); dfa->id_of_bit = NULL; dfa->nbits = 0;
 	memset(&dfa->copy.desc, 0, sizeof dfa->copy.desc);           /* header kept as a tombstone */
+	memset(&dfa->ext, 0, sizeof dfa->ext);
 }
 
 int
@@ -122,6 +149,47 @@ hand_over(struct oracle_owned_desc *od, struct fsm_b200_owned_desc *out)
 	return 0;
 }
 
+int
+fsm_b200_dfa_eager_info(const fsm_b200_dfa *dfa, uint32_t *nbits, const uint32_t **id_of_bit)
+{
+	*nbits = dfa->nbits;
+	*id_of_bit = dfa->id_of_bit;
+	return 0;
+}
+
+int
+fsm_b200_exec_batch_eager_host(const fsm_b200_dfa *dfa, const uint8_t *base, const uint64_t *offsets, size_t n,
+	struct fsm_b200_result *out, uint64_t *masks)
+{
+	const size_t words = (dfa->nbits + 63u) / 64u;
+	size_t i;
+	COUNT(n_batch);
+	maybe_stall();
+	if (dfa->magic != LIVE) { COUNT(n_uaf); errno = EFAULT; return -1; }
+	for (i = 0; i < n; i++) {
+		uint32_t fired[FSM_B200_EAGER_MAX_IDS];
+		size_t nf = 0, k;
+		oracle_exec_eager(&dfa->ext.base, base + offsets[i], offsets[i + 1] - offsets[i], &out[i], fired,
+		    FSM_B200_EAGER_MAX_IDS, &nf);
+		memset(masks + i * words, 0, words * sizeof *masks);
+		for (k = 0; k < nf; k++) {
+			const uint32_t *p = bsearch(&fired[k], dfa->id_of_bit, dfa->nbits, sizeof(uint32_t), cmp_u32);
+			const size_t b = (size_t) (p - dfa->id_of_bit);
+			masks[i * words + (b >> 6)] |= 1ull << (b & 63);
+		}
+	}
+	return 0;
+}
+
+int
+fsm_b200_owned_desc_eager(const struct fsm_b200_owned_desc *d, const uint64_t **eager_off, const uint32_t **eager_ids)
+{
+	const struct oracle_owned_desc *keep = d->owner;
+	*eager_off = keep != NULL ? keep->eager_off : NULL;
+	*eager_ids = keep != NULL ? keep->eager_ids : NULL;
+	return 0;
+}
+
 /* oracle/refnum_host.cpp: the product's refnum.h functions on the CPU */
 int refnum_host_determinise_desc(const struct fsm_b200_desc *nfa, uint32_t state_limit, struct oracle_owned_desc *out);
 
@@ -134,6 +202,10 @@ fsm_b200_determinise_ex(const struct fsm_b200_desc *nfa, int device, size_t stat
 	(void) device;
 	COUNT(n_det);
 	memset(out, 0, sizeof *out);
+	if ((flags & FSM_B200_DET_REFERENCE_NUMBERING) && (nfa->reserved & FSM_B200_DESC_EAGER)) {
+		errno = ENOTSUP;       /* the CPU harness does not combine the two; the engine does */
+		return -1;
+	}
 	if (flags & FSM_B200_DET_REFERENCE_NUMBERING) {
 		/* same verdicts as the engine: the input count is checked first (determinise.c:65-68),
 		 * then at most limit+1 states may exist (determinise.c:166-169) */

@@ -1,0 +1,81 @@
+"""GPU: eager outputs (include/fsm/fsm.h:273-336) through the engine and
+through the shim.
+
+Status: the semantics are pinned on the CPU -- the oracle against the live reference
+(tests/test_oracle_eager.py), the product's host-side code against the reference
+(tests/test_eager_host.py), and the whole shim with the reference's 22 tests/eager_output programs
+over the CPU stub engine (tests/test_shim_hostlogic.py).  The CUDA side (k1_eager.cu, the carry in
+K2/K3) was written after round 1's GPU budget was spent and has not run on a B200 yet, hence the
+non-strict xfail; an XPASS in the log is the first GPU confirmation.  Sorts last so that a failure
+here cannot disturb the validated tests.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import reflib
+import libfsm_b200 as L
+from test_oracle_determinise import assert_isomorphic
+from test_oracle_eager import diamond, random_nfa
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.timeout(600),
+              pytest.mark.xfail(strict=False, reason="eager-output kernels not yet run on a B200 (CPU-verified only)")]
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFTESTS_DIR = os.path.join(ROOT, "build", "shim", "reftests")
+EAGER_PROGRAMS = sorted(x for x in os.listdir(REFTESTS_DIR) if x.startswith("eager_output")) if os.path.isdir(REFTESTS_DIR) else []
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_exec_fired_sets_match_the_oracle(oracle, seed):
+    rng = np.random.default_rng(8100 + seed)
+    nfa = random_nfa(rng, int(rng.integers(4, 16)))
+    dfa_desc = oracle.determinise(nfa)
+    assert dfa_desc.eager_ids is not None
+    al = np.frombuffer(b"abcdx", dtype=np.uint8)
+    strs = [al[rng.integers(0, al.size, int(rng.integers(0, 40)))].tobytes() for _ in range(500)] + [b""]
+    base, off = reflib.offsets_for(strs)
+    with L.Dfa(dfa_desc) as dfa:
+        assert list(dfa.eager_ids()) == sorted(set(int(x) for x in dfa_desc.eager_ids))
+        rec, masks = dfa.exec_batch_eager(base, off)
+        plain = dfa.exec_batch(base, off)             # the plain entry points work on such a DFA too
+    assert (rec == plain).all()
+    for i, s in enumerate(strs):
+        want_rec, want_ids = oracle.exec_eager(dfa_desc, s)
+        assert (int(rec["ret"][i]), int(rec["consumed"][i])) == (want_rec[0], want_rec[2]), s
+        if want_rec[0] == 1:
+            assert int(rec["end"][i]) == want_rec[1]
+        assert dfa.fired_ids(masks[i]) == want_ids, s
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_determinise_and_minimise_carry_eager_outputs(oracle, seed):
+    rng = np.random.default_rng(8200 + seed)
+    nfa = random_nfa(rng, int(rng.integers(4, 20)))
+    d = L.determinise(nfa)
+    assert_isomorphic(oracle, d, oracle.determinise(nfa))
+    m = L.minimise(d)
+    want = oracle.minimise(d)
+    if want.nstates == 0:
+        assert m.nstates == 0
+    else:
+        assert_isomorphic(oracle, m, want)
+
+
+@pytest.mark.parametrize("eager", [{1: [7]}, {2: [7]}, {1: [7], 2: [8]}])
+def test_minimise_blind_spot_like_the_reference(oracle, eager):
+    f = diamond(eager)
+    assert_isomorphic(oracle, L.minimise(f), oracle.minimise(f))
+
+
+@pytest.mark.skipif(not EAGER_PROGRAMS, reason="reference eager_output tests not built against the shim")
+@pytest.mark.parametrize("name", EAGER_PROGRAMS)
+def test_reference_eager_output_programs_against_the_shim(name):
+    """tests/eager_output/*.c of the reference, unmodified: re_comp x N ->
+    fsm_union_repeated_pattern_group -> fsm_determinise (K2) -> fsm_minimise (K3) -> fsm_exec with
+    the callback (k1_eager.cu)."""
+    p = subprocess.run([os.path.join(REFTESTS_DIR, name)], capture_output=True, timeout=300)
+    assert p.returncode == 0, (name, p.stdout.decode()[-2000:], p.stderr.decode()[-2000:])
