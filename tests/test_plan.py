@@ -74,3 +74,18 @@ def test_layout_knobs(monkeypatch):
     monkeypatch.delenv("FSM_B200_KSTRIDE")
     monkeypatch.setenv("FSM_B200_NO_KSTRIDE", "1")
     assert L.plan(f)["kstride"] == 0
+
+
+def test_plan_accepts_eager_outputs_up_to_the_id_limit():
+    """A desc_ext is validated and laid out like a plain desc; more than FSM_B200_EAGER_MAX_IDS (256)
+    distinct eager-output ids are refused with ENOTSUP at compile time, not at exec time."""
+    import errno
+    from libfsm_b200.desc import FlatFsm
+    n = 300
+    edges = [(s, 97, s + 1) for s in range(n - 1)]
+    ok = FlatFsm.from_edges(n, 0, [n - 1], edges, eager={s: [1000 + s] for s in range(256)})
+    assert L.plan(ok)["nstates"] == n
+    too_many = FlatFsm.from_edges(n, 0, [n - 1], edges, eager={s: [1000 + s] for s in range(257)})
+    with pytest.raises(OSError) as e:
+        L.plan(too_many)
+    assert e.value.errno == errno.ENOTSUP
