@@ -412,7 +412,54 @@ def main_fixtures():
           f"{os.path.getsize(os.path.join(HERE, 'golden_re_fixtures.npz')) / 1024:.0f} KiB")
 
 
+def main_eager():
+    """golden_eager.npz: eager outputs (include/fsm/fsm.h:273-336) through the reference's own
+    pipeline: NFA with eager ids -> fsm_determinise -> fsm_minimise -> fsm_exec with the callback.
+    Random NFAs (the generator of tests/test_oracle_eager.py) and unions built by the reference's
+    fsm_union_repeated_pattern_group, the way tests/eager_output/utils.c:run_test does."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_oracle_eager import diamond, random_nfa
+    R = reflib.Ref()
+    cases = []
+
+    def record(name, h, nfa, inputs):
+        R.determinise(h)
+        dfa = R.flatten(h)
+        R.minimise(h)
+        mn = R.flatten(h)
+        fired, rets = [], []
+        for s in inputs:
+            (ret, _end, _consumed), ids = R.exec_eager(h, s)
+            fired.append(ids); rets.append(int(ret))
+        cases.append({"name": name, "nfa": nfa, "dfa": dfa, "min": mn if mn.nstates else None,
+                      "inputs": inputs, "fired": fired, "rets": rets})
+        R.free(h)
+
+    al = np.frombuffer(b"abcdx", dtype=np.uint8)
+    for seed in range(16):
+        rng = np.random.default_rng(9000 + seed)
+        nfa = random_nfa(rng, int(rng.integers(4, 18)))
+        inputs = [al[rng.integers(0, al.size, int(rng.integers(0, 10)))].tobytes() for _ in range(24)] + [b""]
+        record(f"random:{seed}", R.from_flat(nfa), nfa, inputs)
+    for k, eager in enumerate([{1: [7]}, {2: [7]}, {1: [7], 2: [8]}]):
+        f = diamond(eager)
+        record(f"blindspot:{k}", R.from_flat(f), f, [b"ac", b"bc", b"a", b"b", b"", b"ab"])
+    RE_SAVE_LINKAGE_INFO = 1 << 9
+    for name, pats, inputs in (
+        ("group:abc,b+,xyz", ["abc", "b+", "xyz"], [b"abc", b"zabcz", b"bbb", b"xyzabc", b"", b"q"]),
+        ("group:anchors", ["^ab", "cd$", "e"], [b"ab", b"xab", b"cd", b"cdx", b"abecd", b"e"]),
+        ("group:overlap", ["a+b", "ab+", "b", "[ab]{3}"], [b"ab", b"aab", b"abb", b"bbb", b"aaa", b"ba"]),
+    ):
+        hs = [R.re_comp(p, flags=RE_SAVE_LINKAGE_INFO) for p in pats]
+        u = R.union_repeated_pattern_group(hs, 1)
+        record(name, u, R.flatten(u), inputs)
+    goldenio.save_eager_cases(os.path.join(HERE, "golden_eager.npz"), cases)
+    print(f"wrote golden_eager.npz: {len(cases)} cases, {os.path.getsize(os.path.join(HERE, 'golden_eager.npz')) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) < 2 or sys.argv[1] == "eager":
+        main_eager()
     if len(sys.argv) < 2 or sys.argv[1] == "fixtures":
         main_fixtures()
     if len(sys.argv) < 2 or sys.argv[1] == "min":

@@ -20,11 +20,17 @@ def pack_fsm(prefix: str, f: FlatFsm, out: dict) -> None:
     out[prefix + "hdr"] = np.array([f.nstates, f.start, int(f.hasstart)], dtype=np.int64)
     for k in FSM_KEYS:
         out[prefix + k] = getattr(f, k)
+    if f.eager_off is not None:                    # eager-output sets (only golden_eager.npz has them)
+        out[prefix + "eager_off"] = f.eager_off
+        out[prefix + "eager_ids"] = f.eager_ids
 
 
 def unpack_fsm(prefix: str, z) -> FlatFsm:
     n, start, has = (int(x) for x in z[prefix + "hdr"])
-    return FlatFsm(nstates=n, start=start, hasstart=bool(has), **{k: z[prefix + k] for k in FSM_KEYS})
+    extra = {}
+    if (prefix + "eager_off") in z.files:
+        extra = {"eager_off": z[prefix + "eager_off"], "eager_ids": z[prefix + "eager_ids"]}
+    return FlatFsm(nstates=n, start=start, hasstart=bool(has), **{k: z[prefix + k] for k in FSM_KEYS}, **extra)
 
 
 def save_exec_cases(path: str, cases: list[dict]) -> None:
@@ -107,3 +113,33 @@ def load_re_fixtures(path: str) -> list[dict]:
         c["fsm"] = unpack_fsm(f"f{i}_", z)
         out.append(c)
     return out
+
+
+def save_eager_cases(path: str, cases: list[dict]) -> None:
+    """case: name, nfa, dfa (the reference's fsm_determinise of nfa), min (its fsm_minimise of dfa, or
+    None when nothing is left), inputs (list of bytes), fired (list of sorted id lists: what the
+    reference's fsm_exec handed to the eager-output callback on `min`, or on `dfa` when min is None),
+    rets (fsm_exec's return per input)."""
+    out, meta = {}, []
+    for i, c in enumerate(cases):
+        p = f"e{i}_"
+        pack_fsm(p + "nfa_", c["nfa"], out)
+        pack_fsm(p + "dfa_", c["dfa"], out)
+        if c["min"] is not None:
+            pack_fsm(p + "min_", c["min"], out)
+        meta.append({"name": c["name"], "has_min": c["min"] is not None,
+                     "inputs": [s.hex() for s in c["inputs"]], "fired": c["fired"], "rets": c["rets"]})
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(path, **out)
+
+
+def load_eager_cases(path: str) -> list[dict]:
+    z = np.load(path)
+    meta = json.loads(bytes(z["meta"]).decode())
+    cases = []
+    for i, m in enumerate(meta):
+        p = f"e{i}_"
+        cases.append({"name": m["name"], "nfa": unpack_fsm(p + "nfa_", z), "dfa": unpack_fsm(p + "dfa_", z),
+                      "min": unpack_fsm(p + "min_", z) if m["has_min"] else None,
+                      "inputs": [bytes.fromhex(h) for h in m["inputs"]], "fired": m["fired"], "rets": m["rets"]})
+    return cases
