@@ -95,9 +95,26 @@ class Dfa:
             return np.zeros(0, np.uint32)
         return np.ctypeslib.as_array(C.cast(ids, C.POINTER(C.c_uint32)), shape=(nbits.value,)).copy()
 
-    def exec_batch_eager(self, base, offsets):
-        """Host buffers in; (records, masks uint64 [n, words]) out: the usual records plus, per
-        input, the bitset of eager-output ids fired along its walk (``fired_ids`` decodes one)."""
+    def exec_batch_eager(self, base, offsets=None, *, stride=None, length=None, n=None):
+        """(records, masks uint64 [n, words]): the usual records plus, per input, the bitset of
+        eager-output ids fired along its walk (``fired_ids`` decodes one).  Host: numpy ``base`` /
+        ``offsets``.  Device: torch.uint8 CUDA ``base`` with torch int64 CUDA ``offsets`` or a fixed
+        ``stride``/``length``/``n``; returns torch tensors ([n, 16] uint8 and [n, words] int64)."""
+        if _is_torch_cuda(base):
+            import torch
+            words = (len(self.eager_ids()) + 63) // 64
+            if offsets is not None:
+                n = int(offsets.numel()) - 1
+                off_ptr, stride, length = offsets.data_ptr(), 0, 0
+            else:
+                off_ptr = None
+                length = stride if length is None else length
+                n = int(base.numel()) // int(stride) if n is None else n
+            out = torch.empty((max(n, 0), 16), dtype=torch.uint8, device=base.device)
+            masks = torch.zeros((max(n, 0), max(words, 1)), dtype=torch.int64, device=base.device)
+            check(lib.fsm_b200_exec_batch_eager_dev(self._h, base.data_ptr(), off_ptr, int(stride), int(length), n,
+                                                    out.data_ptr(), masks.data_ptr(), _stream_ptr()), "exec_batch_eager_dev")
+            return out, masks
         base = np.ascontiguousarray(base, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = offsets.shape[0] - 1

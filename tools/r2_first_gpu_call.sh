@@ -12,6 +12,7 @@ echo "refnum pytest exit $?" >> $O/refnum_pytest.log
 # 1b. eager outputs (k1_eager.cu, carry in K2/K3, the reference's tests/eager_output programs)
 timeout 900 python -m pytest tests/test_gpu_zzz_eager.py -q -m gpu --runxfail > $O/eager_pytest.log 2>&1
 echo "eager pytest exit $?" >> $O/eager_pytest.log
+timeout 300 python tools/bench_eager.py > $O/bench_eager.json 2> $O/bench_eager.err
 # 2. config 5 with both numberings: time split (ms_numbering) + identity with the compiled reference
 NUMBERING=bfs timeout 300 python tools/bench_determinise.py > $O/det_bfs.json 2> $O/det_bfs.err
 NUMBERING=reference timeout 300 python tools/bench_determinise.py > $O/det_reference.json 2> $O/det_reference.err
