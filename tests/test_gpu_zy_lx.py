@@ -1,0 +1,27 @@
+"""GPU: lx(1) relinked, unchanged, against the shim and the CUDA engine: its worker threads call
+fsm_determinise / fsm_minimise concurrently (src/lx/main.c:338-475), i.e. K2 / K3 from a pthread
+pool through the shim.  Behavioural check: the C lexer it generates from tests/data/sample.lx must
+tokenise a sample text exactly like the lexer the reference's own lx generates (oracle/_ref/lx_ref).
+
+The same check passes over the CPU stub engine (tests/test_shim_hostlogic.py); the relinked binary
+was first built after round 1's last GPU session, hence the non-strict xfail until seen to pass."""
+import os
+
+import pytest
+
+from lxcheck import SAMPLE_SPEC, SAMPLE_TEXT, token_stream
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
+              pytest.mark.xfail(strict=False, reason="relinked lx(1) not yet run against the CUDA engine")]
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LX_B200 = os.path.join(ROOT, "build", "shim", "lx_b200")
+LX_REF = os.path.join(ROOT, "oracle", "_ref", "lx_ref")
+
+
+@pytest.mark.skipif(not (os.path.exists(LX_B200) and os.path.exists(LX_REF)), reason="relinked lx(1) not built")
+@pytest.mark.parametrize("concurrency", [1, 8])
+def test_lx_generates_an_equivalent_lexer(tmp_path, concurrency):
+    got = token_stream(LX_B200, SAMPLE_SPEC, SAMPLE_TEXT, tmp_path / "b200", concurrency)
+    want = token_stream(LX_REF, SAMPLE_SPEC, SAMPLE_TEXT, tmp_path / "ref", concurrency)
+    assert got == want and want.count(b"\n") == 37

@@ -184,3 +184,37 @@ def test_fsm_cli_text_is_the_reference_text_with_reference_numbering(tmp_path):
         ran += 1
     assert ran >= 15
     assert differs_without > 0      # the flag matters: BFS numbering prints different text somewhere
+
+
+LX_CPU = os.path.join(CPU_DIR, "lx_b200")
+LX_REF = os.path.join(ROOT, "oracle", "_ref", "lx_ref")
+
+
+@pytest.mark.skipif(not (os.path.exists(LX_CPU) and os.path.exists(LX_REF) and os.path.isdir("/root/reference/src")),
+                    reason="relinked lx(1) / reference tree not available")
+def test_lx_relinked_generates_equivalent_lexers(tmp_path):
+    """lx(1) relinked, unchanged, against the shim: its worker threads run fsm_determinise /
+    fsm_minimise concurrently (src/lx/main.c:338-475).  State numbers in the generated code differ
+    (minimal DFAs are unique up to numbering), so the check is behavioural: the C lexer it generates
+    from the reference's own .lx specifications must tokenise like the one the reference's lx
+    generates -- same tokens, same spellings, same positions."""
+    from lxcheck import SPECS, token_stream
+    for spec, text in SPECS:
+        path = os.path.join("/root/reference", spec)
+        if not os.path.exists(path):
+            continue
+        got = token_stream(LX_CPU, path, text, tmp_path / "cpu")
+        want = token_stream(LX_REF, path, text, tmp_path / "ref")
+        assert got == want, spec
+        assert want.count(b"\n") >= 3
+
+
+@pytest.mark.skipif(not (os.path.exists(LX_CPU) and os.path.exists(LX_REF)), reason="relinked lx(1) not built")
+@pytest.mark.parametrize("concurrency", [1, 8])
+def test_lx_relinked_on_the_repository_sample_spec(tmp_path, concurrency):
+    """Same check on tests/data/sample.lx (written for this repository, so it also runs where the
+    reference tree is absent), with and without lx's thread pool."""
+    from lxcheck import SAMPLE_SPEC, SAMPLE_TEXT, token_stream
+    got = token_stream(LX_CPU, SAMPLE_SPEC, SAMPLE_TEXT, tmp_path / "cpu", concurrency)
+    want = token_stream(LX_REF, SAMPLE_SPEC, SAMPLE_TEXT, tmp_path / "ref", concurrency)
+    assert got == want and want.count(b"\n") == 37
