@@ -683,13 +683,13 @@ oracle_desc_free(struct oracle_owned_desc *d)
  * --------------------------------------------------------------------------------- */
 struct sigrow { uint32_t state; const uint32_t *sig; size_t len; };
 
-static size_t g_siglen;
+enum { SIGLEN = 257 };      /* class of the state + class of each of its 256 successors */
 
 static int
 cmp_sigrow(const void *a, const void *b)
 {
 	const struct sigrow *x = a, *y = b;
-	int c = memcmp(x->sig, y->sig, g_siglen * sizeof(uint32_t));
+	int c = memcmp(x->sig, y->sig, SIGLEN * sizeof(uint32_t));
 	if (c != 0) return c;
 	return (x->state > y->state) - (x->state < y->state);
 }
@@ -832,7 +832,6 @@ minimise_impl(const struct fsm_b200_desc *d, const uint32_t *given_cls0, struct 
 			if (cls[i] == NO_EDGE) cls[i] = 1 + i;      /* fresh id, distinct from 0 */
 		}
 #undef EAGER_LEN
-		g_siglen = 257;
 		for (;;) {
 			uint32_t cnt = 0, i;
 			for (i = 0; i < m; i++) {

@@ -22,7 +22,12 @@ int main(void) {
 """
 
 
-def token_stream(lx_binary: str, spec_path: str, text: bytes, workdir, concurrency: int = 4, env=None) -> bytes:
+def token_stream(lx_binary: str, spec_path: str, text: bytes, workdir, concurrency: int = 1, env=None) -> bytes:
+    # concurrency stays 1: with -C > 1 the REFERENCE's own lx races on an unsynchronised global table
+    # (src/lx/ast.c:151-182, ast_setendmapping's mapping_count / realloc'd array -- ThreadSanitizer
+    # reports it with the unmodified reference, and lx_ref -C 8 under load occasionally prints
+    # nothing), so its output is not a stable yardstick.  The shim's own thread safety is covered by
+    # shim_threads (TSAN-clean) and tests/test_gpu_threads.py.
     os.makedirs(workdir, exist_ok=True)
     for lang, name in (("h", "lexer.h"), ("c", "lexer.c")):
         p = subprocess.run([lx_binary, "-C", str(concurrency), "-l", lang, "-b", "dyn", "-g", "fgetc"], stdin=open(spec_path),
