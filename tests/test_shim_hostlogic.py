@@ -217,3 +217,33 @@ def test_lx_relinked_on_the_repository_sample_spec(tmp_path):
     got = token_stream(LX_CPU, SAMPLE_SPEC, SAMPLE_TEXT, tmp_path / "cpu")
     want = token_stream(LX_REF, SAMPLE_SPEC, SAMPLE_TEXT, tmp_path / "ref")
     assert got == want and want.count(b"\n") == 37
+
+
+def test_shim_is_thread_sanitizer_clean(tmp_path):
+    """The shim + stub engine + thread stress rebuilt with -fsanitize=thread (reference objects as
+    they are): no data race may be reported in fsm_b200_shim.c.  Skips where libtsan is missing."""
+    ref_root = "/root/reference"
+    obj_dir = os.path.join(ROOT, "oracle", "_ref", "obj")
+    if not (os.path.isdir(os.path.join(ref_root, "src")) and os.path.isdir(obj_dir)):
+        pytest.skip("needs the reference tree and its compiled objects")
+    objs = []
+    for d, _, files in os.walk(obj_dir):
+        for f in sorted(files):
+            if f.endswith(".o") and not (d.endswith("libfsm") and f in ("exec.o", "determinise.o", "minimise.o")):
+                objs.append(os.path.join(d, f))
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I" + ref_root + "/include", "-I" + ref_root + "/src", "-I" + ref_root + "/src/libfsm"]
+    so = str(tmp_path / "libfsm_shim.so")
+    p = subprocess.run(["gcc", "-std=gnu99", "-O1", "-g", "-fsanitize=thread", "-fPIC", "-w", "-shared", "-pthread", "-o", so,
+                        os.path.join(ROOT, "libfsm_b200", "shim", "fsm_b200_shim.c"), os.path.join(ROOT, "oracle", "stub_engine.c"),
+                        os.path.join(ROOT, "oracle", "fsm_oracle.c")] + inc + objs +
+                       ["-L" + os.path.join(ROOT, "oracle", "_ref"), "-lrefnum_host", "-Wl,-rpath," + os.path.join(ROOT, "oracle", "_ref"),
+                        "-Wl,-Bsymbolic"], capture_output=True, timeout=300)
+    if p.returncode != 0:
+        pytest.skip("ThreadSanitizer build not available here: " + p.stderr.decode()[-200:])
+    exe = str(tmp_path / "shim_threads")
+    subprocess.run(["gcc", "-std=c99", "-O1", "-g", "-fsanitize=thread", "-pthread", "-w", "-D_XOPEN_SOURCE=600"] + inc +
+                   ["-I" + os.path.join(ROOT, "libfsm_b200", "shim"), "-o", exe, os.path.join(ROOT, "libfsm_b200", "shim", "shim_threads.c"),
+                    "-L" + str(tmp_path), "-lfsm_shim", "-Wl,-rpath," + str(tmp_path)], check=True, timeout=300)
+    r = subprocess.run([exe, "24", "3"], capture_output=True, timeout=600, env=dict(os.environ, FSM_B200_STUB_SLOW="100"))
+    assert r.returncode == 0, (r.stdout.decode()[-500:], r.stderr.decode()[-2000:])
+    assert b"ThreadSanitizer" not in r.stderr, r.stderr.decode()[:3000]
