@@ -1,4 +1,4 @@
-"""GPU: lx(1) relinked, unchanged, against the shim and the CUDA engine (fsm_determinise / fsm_minimise
+"""GPU: lx(1) and rx(1) relinked.  lx(1) relinked, unchanged, against the shim and the CUDA engine (fsm_determinise / fsm_minimise
 of every zone through K2 / K3; run with -C 1 because the reference's own lx races with more threads,
 see tests/lxcheck.py).  Behavioural check: the C lexer it generates from tests/data/sample.lx must
 tokenise a sample text exactly like the lexer the reference's own lx generates (oracle/_ref/lx_ref).
@@ -24,3 +24,17 @@ def test_lx_generates_an_equivalent_lexer(tmp_path):
     got = token_stream(LX_B200, SAMPLE_SPEC, SAMPLE_TEXT, tmp_path / "b200")
     want = token_stream(LX_REF, SAMPLE_SPEC, SAMPLE_TEXT, tmp_path / "ref")
     assert got == want and want.count(b"\n") == 37
+
+
+RX_B200 = os.path.join(ROOT, "build", "shim", "rx_b200")
+RX_REF = os.path.join(ROOT, "oracle", "_ref", "rx_ref")
+
+
+@pytest.mark.skipif(not (os.path.exists(RX_B200) and os.path.exists(RX_REF)), reason="relinked rx(1) not built")
+def test_rx_generates_an_equivalent_matcher(tmp_path):
+    """rx(1) relinked, unchanged: per-pattern determinise + minimise, fsm_union_array, determinise of
+    the union (BASELINE config 3's construction) through K2 / K3; the generated C matcher must give
+    the verdicts of the one the reference's rx generates."""
+    from rxcheck import STRINGS, verdicts
+    got, want = verdicts(RX_B200, tmp_path / "b200"), verdicts(RX_REF, tmp_path / "ref")
+    assert got == want and want.count(b"\n") == len(STRINGS)

@@ -247,3 +247,18 @@ def test_shim_is_thread_sanitizer_clean(tmp_path):
     r = subprocess.run([exe, "24", "3"], capture_output=True, timeout=600, env=dict(os.environ, FSM_B200_STUB_SLOW="100"))
     assert r.returncode == 0, (r.stdout.decode()[-500:], r.stderr.decode()[-2000:])
     assert b"ThreadSanitizer" not in r.stderr, r.stderr.decode()[:3000]
+
+
+RX_CPU = os.path.join(CPU_DIR, "rx_b200")
+RX_REF = os.path.join(ROOT, "oracle", "_ref", "rx_ref")
+
+
+@pytest.mark.skipif(not (os.path.exists(RX_CPU) and os.path.exists(RX_REF)), reason="relinked rx(1) not built")
+def test_rx_relinked_generates_an_equivalent_matcher(tmp_path):
+    """rx(1) relinked, unchanged (src/rx/main.c: per-pattern determinise + minimise + end id,
+    fsm_union_array, determinise of the union -- BASELINE config 3's construction): the C matcher
+    it generates must return the same (match, pattern id) for every test string as the one the
+    reference's rx generates."""
+    from rxcheck import STRINGS, verdicts
+    got, want = verdicts(RX_CPU, tmp_path / "cpu"), verdicts(RX_REF, tmp_path / "ref")
+    assert got == want and want.count(b"\n") == len(STRINGS) and b"1 5" in want

@@ -9,6 +9,9 @@ mkdir -p $O
 # 1. the reference-numbering kernels (non-strict xfail in the suite): run them for real
 timeout 900 python -m pytest tests/test_gpu_zz_refnum.py -q -m gpu --runxfail -x > $O/refnum_pytest.log 2>&1
 echo "refnum pytest exit $?" >> $O/refnum_pytest.log
+# 1a. lx(1) / rx(1) relinked against the CUDA engine
+timeout 600 python -m pytest tests/test_gpu_zy_relinked_clis.py -q -m gpu --runxfail > $O/clis_pytest.log 2>&1
+echo "relinked CLIs pytest exit $?" >> $O/clis_pytest.log
 # 1b. eager outputs (k1_eager.cu, carry in K2/K3, the reference's tests/eager_output programs)
 timeout 900 python -m pytest tests/test_gpu_zzz_eager.py -q -m gpu --runxfail > $O/eager_pytest.log 2>&1
 echo "eager pytest exit $?" >> $O/eager_pytest.log
@@ -24,5 +27,5 @@ timeout 300 build/shim/shim_threads 24 3 > $O/shim_threads.log 2>&1
 echo "shim_threads exit $?" >> $O/shim_threads.log
 # 5. the bench line
 timeout 600 python bench.py > $O/bench.json 2> $O/bench.err
-tail -3 $O/refnum_pytest.log $O/eager_pytest.log $O/gpu_pytest.log $O/shim_threads.log
+tail -3 $O/clis_pytest.log $O/refnum_pytest.log $O/eager_pytest.log $O/gpu_pytest.log $O/shim_threads.log
 cat $O/det_reference.json $O/bench.json
