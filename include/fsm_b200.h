@@ -39,7 +39,9 @@
 extern "C" {
 #endif
 
-#define FSM_B200_ABI_VERSION 1
+/* 2: struct fsm_b200_det_stats grew (ms_numbering); struct fsm_b200_desc_ext and the eager-output,
+ *    determinise_ex and dfa_plan entry points were added.  Everything of version 1 is unchanged. */
+#define FSM_B200_ABI_VERSION 2
 
 /* ------------------------------------------------------------------------------------
  * Flat description of a `struct fsm` (reference src/libfsm/internal.h:52-85).
