@@ -19,7 +19,7 @@ timeout 300 python tools/bench_eager.py > $O/bench_eager.json 2> $O/bench_eager.
 # 2. config 5 with both numberings: time split (ms_numbering) + identity with the compiled reference
 NUMBERING=bfs timeout 300 python tools/bench_determinise.py > $O/det_bfs.json 2> $O/det_bfs.err
 NUMBERING=reference timeout 300 python tools/bench_determinise.py > $O/det_reference.json 2> $O/det_reference.err
-# 3. the whole GPU suite (the shim's cache now pins entries; K2/K3 check launch errors)
+# 3. the whole GPU suite (the shim now pins cached tables while a call runs on them)
 timeout 1200 python -m pytest tests -q -m gpu -x > $O/gpu_pytest.log 2>&1
 echo "gpu pytest exit $?" >> $O/gpu_pytest.log
 # 4. thread stress of the shim against the CUDA engine (more threads than cache slots)
