@@ -108,3 +108,13 @@ def test_reference_eager_output_programs_against_the_shim(name):
     the callback (k1_eager.cu)."""
     p = subprocess.run([os.path.join(REFTESTS_DIR, name)], capture_output=True, timeout=300)
     assert p.returncode == 0, (name, p.stdout.decode()[-2000:], p.stderr.decode()[-2000:])
+
+
+def test_eager_selftest_program_against_the_shim():
+    """libfsm_b200/shim/shim_eager_selftest.c linked to the shim and the CUDA engine: fsm_exec with
+    the callback and fsm_exec_batch_eager agree and give the expected id sets."""
+    exe = os.path.join(ROOT, "build", "shim", "shim_eager_selftest")
+    if not os.path.exists(exe):
+        pytest.skip("shim_eager_selftest not built")
+    p = subprocess.run([exe], capture_output=True, timeout=300)
+    assert p.returncode == 0, (p.stdout.decode(), p.stderr.decode())

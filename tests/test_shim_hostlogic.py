@@ -262,3 +262,12 @@ def test_rx_relinked_generates_an_equivalent_matcher(tmp_path):
     from rxcheck import STRINGS, verdicts
     got, want = verdicts(RX_CPU, tmp_path / "cpu"), verdicts(RX_REF, tmp_path / "ref")
     assert got == want and want.count(b"\n") == len(STRINGS) and b"1 5" in want
+
+
+def test_eager_selftest_program():
+    """libfsm_b200/shim/shim_eager_selftest.c: fsm_union_repeated_pattern_group -> determinise ->
+    minimise through the shim, then fsm_exec + fsm_eager_output_cb and the additive
+    fsm_exec_batch_eager must report the same, expected, id sets."""
+    p = subprocess.run([os.path.join(CPU_DIR, "shim_eager_selftest")], capture_output=True, timeout=120)
+    assert p.returncode == 0, (p.stdout.decode(), p.stderr.decode())
+    assert b"shim eager selftest ok" in p.stdout
