@@ -1,6 +1,6 @@
 /*
  * shim_selftest.c -- exercises the libfsm-facing boundary the way a libfsm user would:
- * re_comp -> fsm_determinise (K2 through the shim) -> fsm_minimise (reference, CPU) ->
+ * re_comp -> fsm_determinise (K2 through the shim) -> fsm_minimise (K3 through the shim) ->
  * fsm_exec per input and fsm_exec_batch for all inputs (K1 / K1b through the shim), then
  * checks that both agree and that fsm_endid_get on `*end` returns the pattern's id.
  * Built by libfsm_b200/shim/Makefile against the reference headers; run by
