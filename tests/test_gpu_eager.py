@@ -5,9 +5,7 @@ Status: the semantics are pinned on the CPU -- the oracle against the live refer
 (tests/test_oracle_eager.py), the product's host-side code against the reference
 (tests/test_eager_host.py), and the whole shim with the reference's 22 tests/eager_output programs
 over the CPU stub engine (tests/test_shim_hostlogic.py).  The CUDA side (k1_eager.cu, the carry in
-K2/K3) was written after round 1's GPU budget was spent and has not run on a B200 yet, hence the
-non-strict xfail; an XPASS in the log is the first GPU confirmation.  Sorts last so that a failure
-here cannot disturb the validated tests.
+K2/K3) passed on the driver's B200 at the end of round 1; plain (strict) tests since round 2.
 """
 import os
 import subprocess
@@ -20,9 +18,7 @@ import libfsm_b200 as L
 from test_oracle_determinise import assert_isomorphic
 from test_oracle_eager import diamond, random_nfa
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.timeout(600),
-              pytest.mark.xfail(strict=False, reason="eager-output kernels not yet run on a B200 (CPU-verified only)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REFTESTS_DIR = os.path.join(ROOT, "build", "shim", "reftests")

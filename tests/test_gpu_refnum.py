@@ -3,12 +3,9 @@ STATE FOR STATE (no canonicalisation): same numbering, same per-state groups in 
 same end bits and end-id sets, against the DFAs the reference recorded in
 tests/golden/golden_determinise.npz.
 
-Status: the numbering functions (libfsm_b200/csrc/refnum.h) are verified bit-exactly on the CPU
-(tests/test_refnum_host.py: goldens + live reference on random NFAs); the four kernels that call
-them on the device were written after this round's GPU budget was spent and have not run on a
-B200 yet, hence the non-strict xfail: an XPASS in the log is the first GPU confirmation.  This
-file sorts last so that nothing else runs after it in the same CUDA context.  The default
-numbering (BFS, tests/test_gpu_determinise.py) is unaffected.
+The numbering functions (libfsm_b200/csrc/refnum.h) are also verified bit-exactly on the CPU
+(tests/test_refnum_host.py: goldens + live reference on random NFAs).  Passed on the driver's B200
+at the end of round 1; plain (strict) tests since round 2.
 """
 import os
 
@@ -19,9 +16,7 @@ import goldenio
 import libfsm_b200 as L
 from libfsm_b200 import workloads
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.timeout(600),
-              pytest.mark.xfail(strict=False, reason="reference-numbering kernels not yet run on a B200 (CPU-verified only)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 CASES = goldenio.load_det_cases(os.path.join(goldenio.GOLDEN_DIR, "golden_determinise.npz"))
 CASES = [c for c in CASES if c["nfa"].hasstart]

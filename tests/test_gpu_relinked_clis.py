@@ -3,16 +3,15 @@ of every zone through K2 / K3; run with -C 1 because the reference's own lx race
 see tests/lxcheck.py).  Behavioural check: the C lexer it generates from tests/data/sample.lx must
 tokenise a sample text exactly like the lexer the reference's own lx generates (oracle/_ref/lx_ref).
 
-The same check passes over the CPU stub engine (tests/test_shim_hostlogic.py); the relinked binary
-was first built after round 1's last GPU session, hence the non-strict xfail until seen to pass."""
+The same check passes over the CPU stub engine (tests/test_shim_hostlogic.py).  Passed on the driver's
+B200 at the end of round 1; a plain (strict) test since round 2."""
 import os
 
 import pytest
 
 from lxcheck import SAMPLE_SPEC, SAMPLE_TEXT, token_stream
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
-              pytest.mark.xfail(strict=False, reason="relinked lx(1) not yet run against the CUDA engine")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LX_B200 = os.path.join(ROOT, "build", "shim", "lx_b200")

@@ -132,8 +132,7 @@ def test_shim_selftest_c_program():
 
 
 REFTESTS_DIR = os.path.join(ROOT, "build", "shim", "reftests")
-# tests/eager_output/*.c run from tests/test_gpu_zzz_eager.py (eager outputs were added after the last
-# GPU session of round 1: non-strict xfail there until they have been seen to pass on a B200)
+# tests/eager_output/*.c run from tests/test_gpu_eager.py
 REFTESTS = sorted(x for x in os.listdir(REFTESTS_DIR) if not x.startswith("eager_output")) if os.path.isdir(REFTESTS_DIR) else []
 
 
