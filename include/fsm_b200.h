@@ -41,7 +41,9 @@ extern "C" {
 
 /* 2: struct fsm_b200_det_stats grew (ms_numbering); struct fsm_b200_desc_ext and the eager-output,
  *    determinise_ex and dfa_plan entry points were added.  Everything of version 1 is unchanged. */
-#define FSM_B200_ABI_VERSION 2
+/* 3: struct fsm_b200_dfa_info grew (kclasses, krange*); fsm_exec_batch_eager of the shim copies the
+ *    id list into caller storage.  Everything else of version 2 is unchanged. */
+#define FSM_B200_ABI_VERSION 3
 
 /* ------------------------------------------------------------------------------------
  * Flat description of a `struct fsm` (reference src/libfsm/internal.h:52-85).
@@ -137,6 +139,11 @@ struct fsm_b200_dfa_info {
 	uint64_t table_bytes;
 	uint32_t nclasses;       /* 0: rows indexed by byte; else by byte class (compressed rows) */
 	uint32_t kstride;        /* 0, or K in {2,4}: a K-bytes-per-lookup table is also resident */
+	uint32_t kclasses;       /* columns per byte of that table (byte classes, or 4 cell codes when krange != 0) */
+	uint32_t krange;         /* 0: the k-stride kernel classifies bytes through shared-memory LUTs; 1 / 2: with
+	                          * integer arithmetic in registers -- the byte class is a function of
+	                          * [b in R0] + 2 [b in R1] for the two byte ranges below (1: both below 0x80) */
+	uint8_t  krange_lo[2], krange_hi[2];   /* R0, R1 (lo > hi: unused) */
 };
 int fsm_b200_dfa_info(const fsm_b200_dfa *dfa, struct fsm_b200_dfa_info *info);
 

@@ -34,7 +34,8 @@ class CDfaInfo(C.Structure):
     _fields_ = [("nstates", C.c_uint32), ("ntable_states", C.c_uint32), ("start", C.c_uint32),
                 ("entry_bytes", C.c_uint32), ("row_pitch_bytes", C.c_uint32), ("complete", C.c_uint32),
                 ("smem_resident", C.c_uint32), ("device", C.c_uint32), ("table_bytes", C.c_uint64),
-                ("nclasses", C.c_uint32), ("kstride", C.c_uint32)]
+                ("nclasses", C.c_uint32), ("kstride", C.c_uint32), ("kclasses", C.c_uint32), ("krange", C.c_uint32),
+                ("krange_lo", C.c_uint8 * 2), ("krange_hi", C.c_uint8 * 2)]
 
 
 class CDetStats(C.Structure):

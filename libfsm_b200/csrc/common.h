@@ -80,6 +80,11 @@ struct fsm_b200_dfa {
 	uint32_t kpitch, k1pitch;            /* row pitches (bytes) of stepK / step1 */
 	uint32_t k1_off, kend_off, klut_off; /* blob offsets */
 	uint32_t kblob_bytes;
+	/* ALU byte classification for the k-stride kernel (0: class LUTs; 1: two ranges below 0x80;
+	 * 2: some range at or above 0x80): see find_cell_ranges in dfa_compile.cu */
+	uint32_t krange;
+	uint32_t kr_add_lo[2], kr_add_hi[2], kr_hxor[2];
+	uint8_t kr_lo[2], kr_hi[2];
 	/* device */
 	void *d_blob;            /* table rows followed by is_end bytes (u8 per row) */
 	uint8_t *d_absorb;       /* [ntable] 1 = every byte loops back to the state itself */

@@ -45,6 +45,55 @@ desc_is_dfa(const fsm_b200_desc *d)
 	return true;
 }
 
+/* Two byte ranges whose 2-bit cell code ([b in R0] + 2 [b in R1]) determines the byte class.
+ * Ranges start and end at class-run boundaries and stay inside one half of the byte space
+ * (the kernel compares 7-bit values and selects the half with bit 7).  Returns 0 (none),
+ * 1 (both ranges below 0x80) or 2 (some range at or above 0x80); an unused second range comes
+ * back empty (lo > hi). */
+uint32_t
+find_cell_ranges(const uint8_t (&cls)[256], uint8_t (&rlo)[2], uint8_t (&rhi)[2])
+{
+	std::vector<int> starts, ends;          /* run boundaries, split at 0x80 */
+	for (int c = 0; c < 256; c++) {
+		if (c == 0 || c == 0x80 || cls[c] != cls[c - 1]) starts.push_back(c);
+		if (c == 255 || c == 0x7F || cls[c] != cls[c + 1]) ends.push_back(c);
+	}
+	struct Rg { int lo, hi; };
+	std::vector<Rg> cand;
+	cand.push_back({ 1, 0 });                /* the empty range: one range may be enough */
+	for (int lo : starts) {
+		for (int hi : ends) {
+			if (hi < lo || (lo < 0x80) != (hi < 0x80)) continue;
+			cand.push_back({ lo, hi });
+		}
+	}
+	auto ok = [&](const Rg &a, const Rg &b) {
+		int cls_of_cell[4] = { -1, -1, -1, -1 };
+		for (int c = 0; c < 256; c++) {
+			const int cell = ((c >= a.lo && c <= a.hi) ? 1 : 0) | ((c >= b.lo && c <= b.hi) ? 2 : 0);
+			if (cls_of_cell[cell] < 0) cls_of_cell[cell] = cls[c];
+			else if (cls_of_cell[cell] != cls[c]) return false;
+		}
+		return true;
+	};
+	/* prefer one range over two, and ranges below 0x80 (one shared half-select in the kernel) */
+	for (int pass = 0; pass < 4; pass++) {
+		const bool single = pass < 2, want_low = (pass & 1) == 0;
+		for (size_t i = 1; i < cand.size(); i++) {
+			for (size_t j = 0; j < (single ? 1 : cand.size()); j++) {
+				if (j == i || (!single && j == 0)) continue;
+				const bool low = cand[i].hi < 0x80 && (j == 0 || cand[j].hi < 0x80);
+				if (want_low != low) continue;
+				if (!ok(cand[i], cand[j])) continue;
+				rlo[0] = (uint8_t) cand[i].lo; rhi[0] = (uint8_t) cand[i].hi;
+				rlo[1] = (uint8_t) cand[j].lo; rhi[1] = (uint8_t) cand[j].hi;
+				return low ? 1u : 2u;
+			}
+		}
+	}
+	return 0;
+}
+
 } // namespace
 
 /* device >= 0: validate, lay out, upload.  device < 0: validate and lay out only (the plan). */
@@ -253,6 +302,7 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 	 * 1 + conflicts to (K + 1 + conflicts) / K. */
 	if (dfa->ntable <= 256 && getenv("FSM_B200_NO_KSTRIDE") == nullptr) {
 		uint8_t kcls[256], rep[256];
+		bool rep_ok[256];
 		uint32_t KC = 0;
 		for (int c = 0; c < 256; c++) {
 			int found = -1;
@@ -264,16 +314,46 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 			if (found < 0) { rep[KC] = (uint8_t) c; found = (int) KC; KC++; }
 			kcls[c] = (uint8_t) found;
 		}
+		for (int c = 0; c < 256; c++) rep_ok[c] = (uint32_t) c < KC;
+		/* ALU classification (k1_kstride_kernel, RNG != 0): when two byte ranges R0, R1 exist such
+		 * that the byte class is a function of the 2-bit cell code [b in R0] + 2 [b in R1], the
+		 * kernel derives the code of 4 bytes at once with integer SIMD-in-register arithmetic
+		 * instead of 4 shared-memory LUT reads; the tables are then indexed by cell codes (4 per
+		 * byte, some possibly unused) instead of by byte classes. */
+		uint32_t krange = 0;
+		uint8_t rlo[2] = { 1, 1 }, rhi[2] = { 0, 0 };          /* lo > hi: empty range */
+		if (KC <= 4 && KC >= 2 && getenv("FSM_B200_NO_KRANGE") == nullptr) {
+			krange = find_cell_ranges(kcls, rlo, rhi);
+			if (krange != 0) {
+				uint8_t cell[256];
+				bool have[4] = { false, false, false, false };
+				for (int c = 0; c < 256; c++) {
+					cell[c] = (uint8_t) (((c >= rlo[0] && c <= rhi[0]) ? 1 : 0) | ((c >= rlo[1] && c <= rhi[1]) ? 2 : 0));
+				}
+				for (int c = 255; c >= 0; c--) { rep[cell[c]] = (uint8_t) c; have[cell[c]] = true; }
+				for (int k = 0; k < 4; k++) rep_ok[k] = have[k];
+				memcpy(kcls, cell, 256);
+				KC = 4;
+			}
+		}
 		uint32_t K = 0;
 		/* K = 4 always pays.  K = 2 trades one table read for two LUT reads per 2 bytes: a win
 		 * only where the table reads conflict (many live states); small DFAs (the 8-state
-		 * UTF-8 validator: 2.20 vs 1.96 TB/s as a stream) stay on the one-byte kernel. */
-		if (KC * KC * KC * KC <= 256) K = 4; else if (KC * KC <= 256 && dfa->ntable > 32) K = 2;
-		if (const char *e = getenv("FSM_B200_KSTRIDE")) { const int v = atoi(e); if ((v == 2 && KC * KC <= 256) || v == 0) K = (uint32_t) v; }
+		 * UTF-8 validator: 2.20 vs 1.96 TB/s as a stream) stay on the one-byte kernel.
+		 * (KC <= 4 <=> KC^4 <= 256, KC <= 16 <=> KC^2 <= 256: no 32-bit overflow for KC = 256.) */
+		if (KC <= 4) K = 4; else if (KC <= 16 && dfa->ntable > 32) K = 2;
+		if (const char *e = getenv("FSM_B200_KSTRIDE")) { const int v = atoi(e); if ((v == 2 && KC <= 16) || v == 0) K = (uint32_t) v; }
+		if (K != 4) krange = 0;
 		if (K != 0) {
 			const uint32_t T = dfa->ntable;
 			uint32_t W = 1;
 			for (uint32_t j = 0; j < K; j++) W *= KC;
+			if (W > 256) {          /* cannot happen: K was chosen so that KC^K <= 256 */
+				fsm_b200_dfa_free(dfa);
+				set_error("dfa_compile: internal error: k-stride tuple space %u", W);
+				errno = EINVAL;
+				return -1;
+			}
 			auto odd_pitch = [](uint32_t nbytes) { uint32_t p = (nbytes + 3u) & ~3u; if (((p >> 2) & 1u) == 0) p += 4; return p; };
 			const uint32_t kpitch = odd_pitch(W), k1pitch = odd_pitch(KC);
 			/* blob: [K class LUTs of 256 B][stepK rows][step1 rows][is_end]; the LUTs and stepK sit
@@ -284,7 +364,7 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 			const uint32_t kbytes = (kend_off + T + 15u) & ~15u;
 			std::vector<uint8_t> kb(kbytes, 0);
 			auto step1 = [&](uint32_t st, uint32_t cls) -> uint32_t {
-				if (st >= S) return dfa->dead;
+				if (st >= S || !rep_ok[cls]) return dfa->dead == NO_EDGE ? st : dfa->dead;   /* unused cell code: never looked up */
 				const uint32_t v = t32[(size_t) st * 256 + rep[cls]];
 				return v == NO_EDGE ? dfa->dead : v;
 			};
@@ -308,6 +388,17 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 			}
 			dfa->kstride = K; dfa->kclasses = KC; dfa->kpitch = kpitch; dfa->k1pitch = k1pitch;
 			dfa->k1_off = k1_off; dfa->kend_off = kend_off; dfa->klut_off = klut_off; dfa->kblob_bytes = kbytes;
+			dfa->krange = krange;
+			for (int k = 0; k < 2; k++) {
+				/* per byte lane, on l = b & 0x7F: bit 7 of l + add_lo is [l >= lo7], of l + add_hi is
+				 * [l > hi7]; hxor selects the half the range lives in (all ones: bytes < 0x80) */
+				const bool empty = rlo[k] > rhi[k];
+				const uint32_t lo7 = rlo[k] & 0x7Fu, hi7 = rhi[k] & 0x7Fu;
+				dfa->kr_add_lo[k] = empty ? 0u : 0x01010101u * (0x80u - lo7);
+				dfa->kr_add_hi[k] = empty ? 0u : 0x01010101u * (0x7Fu - hi7);
+				dfa->kr_hxor[k] = (!empty && rlo[k] >= 0x80u) ? 0u : 0xFFFFFFFFu;
+				dfa->kr_lo[k] = rlo[k]; dfa->kr_hi[k] = rhi[k];
+			}
 		}
 	}
 	/* ---- eager outputs (fsm_b200_desc_ext): dense id numbering + one bit mask per table row ---- */
@@ -418,6 +509,9 @@ fsm_b200_dfa_info(const fsm_b200_dfa *dfa, struct fsm_b200_dfa_info *info)
 	info->table_bytes = dfa->table_bytes;
 	info->nclasses = dfa->nclasses;
 	info->kstride = dfa->kstride;
+	info->krange = dfa->krange;
+	for (int k = 0; k < 2; k++) { info->krange_lo[k] = dfa->kr_lo[k]; info->krange_hi[k] = dfa->kr_hi[k]; }
+	info->kclasses = dfa->kclasses;
 	return 0;
 }
 

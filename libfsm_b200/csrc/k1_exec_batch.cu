@@ -488,8 +488,18 @@ k1_ragged_kernel(const K1Args a)
  *   st  = stepK[st * pitch + idx]                  one dependent read per K bytes
  * Heads, tails and the re-walk of a sector that died use the single-byte class table.
  * 8-bit entries, everything in shared memory (a few KB to a few tens of KB).
+ *
+ * RNG != 0 (K = 4): the tuple index of a 4-byte word is computed in registers, no LUT reads.
+ * The byte class is a function of the 2-bit cell code [b in R0] + 2 [b in R1] of two byte
+ * ranges (dfa_compile.cu: find_cell_ranges).  Per word, all four bytes at once:
+ *   l     = w & 0x7F7F7F7F                              7-bit values: the adds cannot carry across bytes
+ *   in_k  = (l + add_lo_k) & ~(l + add_hi_k) & half_k   bit 7 of every byte: lo_k <= b <= hi_k
+ *   idx   = (dp4a(in_0, {1,4,16,64}) + dp4a(in_1, {2,8,32,128})) >> 7
+ * half_k keeps the bytes of the half of the byte space R_k lives in (bit 7 clear, or set); with
+ * RNG == 1 both ranges lie below 0x80 and share it.  One shared-memory wavefront per 4 bytes
+ * instead of five.
  */
-template <int K, bool HAS_DEAD>
+template <int K, bool HAS_DEAD, int RNG>
 __global__ void __launch_bounds__(1024, 1)
 k1_kstride_kernel(const K1Args a)
 {
@@ -543,6 +553,16 @@ k1_kstride_kernel(const K1Args a)
 #pragma unroll
 				for (int k = 0; k < 8; k++) {
 					const uint32_t w = cur[k];
+					if (RNG != 0) {
+						const uint32_t l = w & 0x7F7F7F7Fu;
+						const uint32_t half0 = (w ^ a.kr_hxor[0]) & 0x80808080u;
+						const uint32_t half1 = RNG == 1 ? half0 : ((w ^ a.kr_hxor[1]) & 0x80808080u);
+						const uint32_t in0 = (l + a.kr_add_lo[0]) & ~(l + a.kr_add_hi[0]) & half0;
+						const uint32_t in1 = (l + a.kr_add_lo[1]) & ~(l + a.kr_add_hi[1]) & half1;
+						const uint32_t idx = __dp4a(in1, 0x80200802u, __dp4a(in0, 0x40100401u, 0u));
+						st = tk[st * kp + (idx >> 7)];
+						continue;
+					}
 					const uint32_t c0 = L0[__byte_perm(w, 0u, 0x4440u)], c1 = L1[__byte_perm(w, 0u, 0x4441u)];
 					if (K == 4) {
 						const uint32_t c2 = L2[__byte_perm(w, 0u, 0x4442u)], c3 = L3[__byte_perm(w, 0u, 0x4443u)];
@@ -767,11 +787,11 @@ launch_lane(const K1Args &a, int sms, size_t smem_bytes, int block, cudaStream_t
 	return 0;
 }
 
-template <int K, bool HAS_DEAD>
+template <int K, bool HAS_DEAD, int RNG>
 int
 launch_kstride(const K1Args &a, int sms, cudaStream_t stream)
 {
-	auto kern = k1_kstride_kernel<K, HAS_DEAD>;
+	auto kern = k1_kstride_kernel<K, HAS_DEAD, RNG>;
 	const size_t smem_bytes = (a.kblob_bytes + 127u) & ~127u;
 	if (!set_smem(kern, smem_bytes)) {
 		set_error("k1_kstride: cannot opt in to %zu bytes of shared memory", smem_bytes);
@@ -851,6 +871,20 @@ launch_tile(K1Args a, int sms, int smem_optin, cudaStream_t stream)
 
 int g_variant = 0;
 
+int
+dispatch_kstride(const fsm_b200_dfa *dfa, const K1Args &a, int sms, cudaStream_t stream)
+{
+	const bool dead = !dfa->complete;
+	uint32_t rng = dfa->kstride == 4 ? dfa->krange : 0u;
+	if (getenv("FSM_B200_KSTRIDE_LUT") != nullptr) rng = 0;        /* tuning knob: class LUTs even when ranges exist */
+	if (dfa->kstride == 4) {
+		if (rng == 1) return dead ? launch_kstride<4, true, 1>(a, sms, stream) : launch_kstride<4, false, 1>(a, sms, stream);
+		if (rng == 2) return dead ? launch_kstride<4, true, 2>(a, sms, stream) : launch_kstride<4, false, 2>(a, sms, stream);
+		return dead ? launch_kstride<4, true, 0>(a, sms, stream) : launch_kstride<4, false, 0>(a, sms, stream);
+	}
+	return dead ? launch_kstride<2, true, 0>(a, sms, stream) : launch_kstride<2, false, 0>(a, sms, stream);
+}
+
 } // namespace
 
 namespace fsmb200 {
@@ -877,6 +911,7 @@ fill_args(K1Args &a, const fsm_b200_dfa *dfa)
 	a.kblob = static_cast<const uint8_t *>(dfa->d_kblob);
 	a.kblob_bytes = dfa->kblob_bytes; a.kpitch = dfa->kpitch; a.k1pitch = dfa->k1pitch;
 	a.k1_off = dfa->k1_off; a.kend_off = dfa->kend_off; a.klut_off = dfa->klut_off;
+	for (int k = 0; k < 2; k++) { a.kr_add_lo[k] = dfa->kr_add_lo[k]; a.kr_add_hi[k] = dfa->kr_add_hi[k]; a.kr_hxor[k] = dfa->kr_hxor[k]; }
 }
 
 template <typename E, bool SMEM, bool HAS_DEAD, bool CLS>
@@ -963,9 +998,7 @@ k1_launch_jobs(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d
 	a.base = d_base; a.offsets = d_begs; a.ends = d_ends; a.entry = d_entry; a.n = n; a.n_dev = d_n; a.out = d_out;
 	a.prefer_lane = 1;
 	if (dfa->kstride != 0 && getenv("FSM_B200_STREAM_NO_KSTRIDE") == nullptr) {
-		const bool dead = !dfa->complete;
-		if (dfa->kstride == 4) return dead ? launch_kstride<4, true>(a, sms, stream) : launch_kstride<4, false>(a, sms, stream);
-		return dead ? launch_kstride<2, true>(a, sms, stream) : launch_kstride<2, false>(a, sms, stream);
+		return dispatch_kstride(dfa, a, sms, stream);
 	}
 	return dispatch_lane(dfa, a, sms, stream);
 }
@@ -1026,8 +1059,7 @@ k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offs
 			errno = ENOTSUP;
 			return -1;
 		}
-		if (dfa->kstride == 4) return dead ? launch_kstride<4, true>(a, sms, stream) : launch_kstride<4, false>(a, sms, stream);
-		return dead ? launch_kstride<2, true>(a, sms, stream) : launch_kstride<2, false>(a, sms, stream);
+		return dispatch_kstride(dfa, a, sms, stream);
 	}
 
 	if (!tile_ok) {

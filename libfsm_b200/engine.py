@@ -42,7 +42,15 @@ def plan(fsm: FlatFsm) -> dict:
     info = CDfaInfo()
     cdesc = fsm.as_c()
     check(lib.fsm_b200_dfa_plan(C.byref(cdesc), C.byref(info)), "dfa_plan")
-    return {k: int(getattr(info, k)) for k, _ in CDfaInfo._fields_}
+    return _info_dict(info)
+
+
+def _info_dict(info) -> dict:
+    out = {}
+    for k, _ in CDfaInfo._fields_:
+        v = getattr(info, k)
+        out[k] = int(v) if isinstance(v, int) else [int(x) for x in v]
+    return out
 
 
 def _is_torch_cuda(x) -> bool:
@@ -65,7 +73,7 @@ class Dfa:
         check(lib.fsm_b200_dfa_compile(C.byref(cdesc), device, C.byref(self._h)), "dfa_compile")
         info = CDfaInfo()
         check(lib.fsm_b200_dfa_info(self._h, C.byref(info)), "dfa_info")
-        self.info = {k: int(getattr(info, k)) for k, _ in CDfaInfo._fields_}
+        self.info = _info_dict(info)
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:

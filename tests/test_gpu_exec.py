@@ -3,6 +3,7 @@ recorded from the reference, against the oracle on seeded inputs, and -- at BASE
 through size-independent properties of the domain."""
 import errno
 import os
+import zlib
 
 import numpy as np
 import pytest
@@ -270,3 +271,57 @@ def test_full_size_config2_properties(torch_cuda, oracle, adversarial):
         want = oracle.exec_batch(fsm, sample.reshape(-1), offsets, nthreads=16)
         got = L.results_from_torch(results["tile64"][idx])
         assert_records_equal(got, want, "full-size sample")
+
+
+RANGE_SPECS = {
+    "two-low": ((0x30, 0x39), (0x2E, 0x2E)),
+    "nested-low": ((0x20, 0x7E), (0x61, 0x61)),
+    "low+high": ((0x30, 0x39), (0xC2, 0xDF)),
+    "two-high": ((0x80, 0xBF), (0xE0, 0xEF)),
+    "single": ((0x41, 0x5A), None),
+    "straddle": ((0x70, 0x8F), None),
+    "edges": ((0x00, 0x00), (0xFF, 0xFF)),
+    "top-of-halves": ((0x7F, 0x7F), (0x80, 0x80)),
+}
+
+
+@pytest.mark.parametrize("missing", [0.0, 0.15])
+@pytest.mark.parametrize("spec", sorted(RANGE_SPECS))
+def test_alu_classified_kstride_matches_oracle(torch_cuda, oracle, monkeypatch, spec, missing):
+    """k1_kstride_kernel with RNG != 0 (byte classes derived in registers from two byte ranges,
+    dfa_compile.cu: find_cell_ranges) against the oracle on inputs that use ALL 256 byte values, with
+    bytes concentrated around the range boundaries; the same inputs through the class-LUT form of the
+    kernel (FSM_B200_KSTRIDE_LUT) and the one-byte LANE kernel must agree."""
+    import synth
+    torch = torch_cuda
+    r0, r1 = RANGE_SPECS[spec]
+    fsm = synth.dfa_from_classes(synth.classes_from_ranges(r0, r1), 61, seed=zlib.crc32(spec.encode()) & 0xFFFF, missing=missing)
+    n, length = 4099, 256
+    rng = np.random.default_rng(7)
+    host = rng.integers(0, 256, size=(n, length), dtype=np.uint8)
+    edge_bytes = []
+    for r in (r0, r1):
+        if r is not None:
+            edge_bytes += [max(r[0] - 1, 0), r[0], r[1], min(r[1] + 1, 255), r[0] ^ 0x80, r[1] ^ 0x80]
+    pick = rng.random((n, length)) < 0.6
+    host[pick] = np.array(edge_bytes, dtype=np.uint8)[rng.integers(0, len(edge_bytes), size=int(pick.sum()))]
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(length)
+    want = oracle.exec_batch(fsm, host.reshape(-1), offsets, nthreads=8)
+    with L.Dfa(fsm) as dfa:
+        assert dfa.info["kstride"] == 4 and dfa.info["krange"] in (1, 2), dfa.info
+        dev = torch.from_numpy(host).cuda()
+        L.set_exec_variant("kstride")
+        out = dfa.exec_batch(dev, stride=length, length=length, n=n)
+        torch.cuda.synchronize()
+        assert_records_equal(L.results_from_torch(out), want, f"{spec} ALU-classified")
+        monkeypatch.setenv("FSM_B200_KSTRIDE_LUT", "1")
+        out = dfa.exec_batch(dev, stride=length, length=length, n=n)
+        torch.cuda.synchronize()
+        assert_records_equal(L.results_from_torch(out), want, f"{spec} class LUTs")
+        monkeypatch.delenv("FSM_B200_KSTRIDE_LUT")
+        L.set_exec_variant("lane")
+        out = dfa.exec_batch(dev, stride=length, length=length, n=n)
+        torch.cuda.synchronize()
+        assert_records_equal(L.results_from_torch(out), want, f"{spec} lane")
+        if missing:
+            assert (want["consumed"] < length).any()

@@ -89,3 +89,66 @@ def test_plan_accepts_eager_outputs_up_to_the_id_limit():
     with pytest.raises(OSError) as e:
         L.plan(too_many)
     assert e.value.errno == errno.ENOTSUP
+
+
+def test_kstride_choice_does_not_overflow_with_256_byte_classes():
+    """KC^4 was evaluated in 32 bits, so 256 distinct byte columns (256^4 == 2^32 -> 0)
+    chose K = 4 with an empty tuple table.  18 states: A: c -> 2 + c / 16, B: c -> 2 + c % 16."""
+    from libfsm_b200.desc import FlatFsm
+    edges = [(0, c, 2 + c // 16) for c in range(256)] + [(1, c, 2 + c % 16) for c in range(256)]
+    edges += [(s, list(range(256)), s % 2) for s in range(2, 18)]
+    p = L.plan(FlatFsm.from_edges(18, 0, [17], edges))
+    assert p["kstride"] == 0 and p["krange"] == 0
+
+
+def _cells_refine_classes(p, fsm):
+    """The plan's two ranges: every byte's column of the dense table is determined by its cell code."""
+    import numpy as np
+    t = fsm.dense_table()
+    b = np.arange(256)
+    cell = np.zeros(256, dtype=np.int64)
+    for k in range(2):
+        lo, hi = p["krange_lo"][k], p["krange_hi"][k]
+        assert lo > hi or (lo < 0x80) == (hi < 0x80)         # a range stays inside one half of the byte space
+        cell |= ((b >= lo) & (b <= hi)).astype(np.int64) << k
+    for c in range(4):
+        cols = t[:, cell == c]
+        if cols.shape[1]:
+            assert (cols == cols[:, :1]).all(), f"cell {c} mixes byte classes"
+    return cell
+
+
+def test_alu_classification_ranges():
+    """find_cell_ranges: config 2 (printable / 'a' / rest) and config 1 (digit / '.' / rest) are each
+    two ranges below 0x80; classes that need a range in the upper half give krange 2; classes that no
+    two ranges separate keep the LUT kernel (krange 0)."""
+    import synth
+    f = case("cfg2:uniform")["fsm"]
+    p = L.plan(f)
+    assert p["kstride"] == 4 and p["krange"] == 1 and p["kclasses"] == 4
+    cell = _cells_refine_classes(p, f)
+    assert cell[0x61] not in (cell[0x20], cell[0x7E], cell[0x00]) and cell[0x7F] == cell[0x00] == cell[0xFF]
+    f = case("cfg1:digits")["fsm"]
+    p = L.plan(f)
+    assert p["krange"] == 1
+    _cells_refine_classes(p, f)
+    # upper-half range
+    f = synth.dfa_from_classes(synth.classes_from_ranges((0x30, 0x39), (0xC2, 0xDF)), 40, seed=1)
+    p = L.plan(f)
+    assert p["kstride"] == 4 and p["krange"] == 2
+    _cells_refine_classes(p, f)
+    # a single range is enough for two classes; the second comes back empty
+    f = synth.dfa_from_classes(synth.classes_from_ranges((0x41, 0x5A)), 40, seed=2)
+    p = L.plan(f)
+    assert p["krange"] == 1 and (p["krange_lo"][1] > p["krange_hi"][1])
+    _cells_refine_classes(p, f)
+    # [a-zA-Z] vs digits vs rest: 3 classes in 6 runs -> no two ranges
+    c = synth.classes_from_ranges((0x41, 0x5A), (0x30, 0x39))
+    c[0x61:0x7B] = c[0x41]
+    p = L.plan(synth.dfa_from_classes(c, 40, seed=3))
+    assert p["kstride"] == 4 and p["krange"] == 0 and p["kclasses"] == 3
+    # a range that straddles 0x80 ([0x70, 0x8F]) is two ranges for the engine: one per half
+    f = synth.dfa_from_classes(synth.classes_from_ranges((0x70, 0x8F)), 40, seed=4)
+    p = L.plan(f)
+    assert p["kstride"] == 4 and p["krange"] == 2
+    _cells_refine_classes(p, f)
