@@ -144,6 +144,10 @@ struct fsm_b200_dfa_info {
 	                          * integer arithmetic in registers -- the byte class is a function of
 	                          * [b in R0] + 2 [b in R1] for the two byte ranges below (1: both below 0x80) */
 	uint8_t  krange_lo[2], krange_hi[2];   /* R0, R1 (lo > hi: unused) */
+	uint32_t lines_smem;     /* 1: ragged batches and eager-output batches run the shared-memory lines kernel */
+	uint32_t lines_blob_bytes;/* its blob: 512-byte LUT + class rows (+1 NOP column) + end bytes */
+	uint32_t lines_cols;     /* columns per row there (byte classes + 1) */
+	uint32_t eager_ids;      /* distinct eager-output ids (0: none) */
 };
 int fsm_b200_dfa_info(const fsm_b200_dfa *dfa, struct fsm_b200_dfa_info *info);
 

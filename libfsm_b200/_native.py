@@ -35,7 +35,9 @@ class CDfaInfo(C.Structure):
                 ("entry_bytes", C.c_uint32), ("row_pitch_bytes", C.c_uint32), ("complete", C.c_uint32),
                 ("smem_resident", C.c_uint32), ("device", C.c_uint32), ("table_bytes", C.c_uint64),
                 ("nclasses", C.c_uint32), ("kstride", C.c_uint32), ("kclasses", C.c_uint32), ("krange", C.c_uint32),
-                ("krange_lo", C.c_uint8 * 2), ("krange_hi", C.c_uint8 * 2)]
+                ("krange_lo", C.c_uint8 * 2), ("krange_hi", C.c_uint8 * 2),
+                ("lines_smem", C.c_uint32), ("lines_blob_bytes", C.c_uint32), ("lines_cols", C.c_uint32),
+                ("eager_ids", C.c_uint32)]
 
 
 class CDetStats(C.Structure):

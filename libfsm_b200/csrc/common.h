@@ -43,6 +43,8 @@ constexpr uint32_t SMEM_TABLE_MAX = 96 * 1024;
 constexpr uint32_t SMEM_CLASS_TABLE_MAX = 200 * 1024;
 /* Above this many byte classes the indirection is not worth it for an L2-resident table. */
 constexpr uint32_t CLASS_GLOBAL_MAX = 192;
+/* Largest lines-kernel blob (LUT + class rows + end bytes) staged into shared memory. */
+constexpr uint32_t SMEM_LINES_MAX = 224 * 1024;
 
 /* Arrays behind a library-owned description (struct fsm_b200_owned_desc.owner). */
 struct Owner {
@@ -100,6 +102,17 @@ struct fsm_b200_dfa {
 	uint32_t eager_nbits, eager_words;
 	uint32_t *h_eager_ids;
 	uint64_t *d_eager_masks;
+	/* lines kernel (k1_lines.cu; ragged batches and eager outputs on shared-memory-resident tables):
+	 * rows indexed by byte class plus one NOP column (every state loops to itself: how bytes outside
+	 * a line are walked), states renumbered so that those with eager outputs come last, just before
+	 * the dead row: "something to report in this sector" is one max() per byte.
+	 * blob: [512-byte LUT: byte -> class, 256..511 -> NOP][rows][is_end by new number] */
+	void *d_lblob;
+	uint32_t lblob_bytes, l_pitch, l_entry_bytes, l_end_off, l_first_event, l_dead, l_start, l_ncols;
+	uint32_t *d_lperm_inv;   /* [ntable] new number -> caller's state number (dead row -> ntable - 1) */
+	uint8_t *d_labsorb;      /* [ntable] by new number, or nullptr when no real state is absorbing */
+	uint64_t l_start_mask[4];/* eager ids of the start state (exec.c:126-130) */
+	uint32_t l_planned;      /* the lines blob exists (fits shared memory) */
 };
 
 #endif

@@ -94,6 +94,38 @@ find_cell_ranges(const uint8_t (&cls)[256], uint8_t (&rlo)[2], uint8_t (&rhi)[2]
 	return 0;
 }
 
+/* Byte classes: symbols whose columns are identical in every row.  One pass hashes every column
+ * (O(256 S)); equal hashes are confirmed against the class representative.  cls[c] = class of byte
+ * c (numbered by first occurrence), rep[k] = smallest byte of class k.  Returns the class count. */
+uint32_t
+byte_classes(const uint32_t *t32, uint32_t S, uint8_t (&cls)[256], uint8_t (&rep)[256])
+{
+	uint32_t C = 0;
+	std::vector<uint64_t> colhash(256, 0x9e3779b97f4a7c15ull);
+	for (uint32_t st = 0; st < S; st++) {
+		const uint32_t *row = t32 + (size_t) st * 256;
+		for (int c = 0; c < 256; c++) {
+			uint64_t h = colhash[c] ^ row[c];
+			h *= 0xff51afd7ed558ccdull;
+			colhash[c] = h ^ (h >> 29);
+		}
+	}
+	for (int c = 0; c < 256; c++) {
+		int found = -1;
+		for (uint32_t k = 0; k < C && found < 0; k++) {
+			if (colhash[rep[k]] != colhash[c]) continue;
+			bool same = true;
+			for (uint32_t st = 0; st < S && same; st++) {
+				same = t32[(size_t) st * 256 + c] == t32[(size_t) st * 256 + rep[k]];
+			}
+			if (same) found = (int) k;
+		}
+		if (found < 0) { rep[C] = (uint8_t) c; found = (int) C; C++; }
+		cls[c] = (uint8_t) found;
+	}
+	return C;
+}
+
 } // namespace
 
 /* device >= 0: validate, lay out, upload.  device < 0: validate and lay out only (the plan). */
@@ -182,33 +214,8 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 		dfa->smem_resident = 1;
 		dfa->pitch = (uint32_t) dense_pitch;
 	} else {
-		/* byte classes: symbols whose columns are identical in every row.  One pass hashes
-		 * every column (O(256 S)); equal hashes are confirmed against the class representative */
 		uint8_t rep[256];
-		{
-			std::vector<uint64_t> colhash(256, 0x9e3779b97f4a7c15ull);
-			for (uint32_t st = 0; st < S; st++) {
-				const uint32_t *row = t32 + (size_t) st * 256;
-				for (int c = 0; c < 256; c++) {
-					uint64_t h = colhash[c] ^ row[c];
-					h *= 0xff51afd7ed558ccdull;
-					colhash[c] = h ^ (h >> 29);
-				}
-			}
-			for (int c = 0; c < 256; c++) {
-				int found = -1;
-				for (uint32_t k = 0; k < C && found < 0; k++) {
-					if (colhash[rep[k]] != colhash[c]) continue;
-					bool same = true;
-					for (uint32_t st = 0; st < S && same; st++) {
-						same = t32[(size_t) st * 256 + c] == t32[(size_t) st * 256 + rep[k]];
-					}
-					if (same) found = (int) k;
-				}
-				if (found < 0) { rep[C] = (uint8_t) c; found = (int) C; C++; }
-				dfa->class_of[c] = (uint8_t) found;
-			}
-		}
+		C = byte_classes(t32, S, dfa->class_of, rep);
 		uint64_t cpitch = ((uint64_t) C * eb + 3u) & ~3ull;
 		if (((cpitch >> 2) & 1u) == 0) cpitch += 4;          /* odd word pitch spreads rows over banks */
 		if (cpitch * dfa->ntable + end_pad + 256 <= SMEM_CLASS_TABLE_MAX) {
@@ -303,17 +310,7 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 	if (dfa->ntable <= 256 && getenv("FSM_B200_NO_KSTRIDE") == nullptr) {
 		uint8_t kcls[256], rep[256];
 		bool rep_ok[256];
-		uint32_t KC = 0;
-		for (int c = 0; c < 256; c++) {
-			int found = -1;
-			for (uint32_t k = 0; k < KC && found < 0; k++) {
-				bool same = true;
-				for (uint32_t st = 0; st < S && same; st++) same = t32[(size_t) st * 256 + c] == t32[(size_t) st * 256 + rep[k]];
-				if (same) found = (int) k;
-			}
-			if (found < 0) { rep[KC] = (uint8_t) c; found = (int) KC; KC++; }
-			kcls[c] = (uint8_t) found;
-		}
+		uint32_t KC = byte_classes(t32, S, kcls, rep);
 		for (int c = 0; c < 256; c++) rep_ok[c] = (uint32_t) c < KC;
 		/* ALU classification (k1_kstride_kernel, RNG != 0): when two byte ranges R0, R1 exist such
 		 * that the byte class is a function of the 2-bit cell code [b in R0] + 2 [b in R1], the
@@ -427,6 +424,78 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 			}
 		}
 	}
+	/* ---- lines kernel blob (k1_lines.cu) ---- */
+	if (dfa->ntable <= 32768 && getenv("FSM_B200_NO_LINES") == nullptr) {
+		uint8_t lcls[256], lrep[256];
+		const uint32_t LC = byte_classes(t32, S, lcls, lrep);
+		const uint32_t T = dfa->ntable;
+		const uint32_t leb = T <= 256 ? 1u : 2u;
+		uint32_t lpitch = ((LC + 1) * leb + 3u) & ~3u;
+		if (((lpitch >> 2) & 1u) == 0) lpitch += 4;                /* odd word pitch spreads rows over banks */
+		const uint32_t ltab_off = 512;
+		const uint32_t lend_off = (ltab_off + T * lpitch + 15u) & ~15u;
+		const uint64_t lbytes = ((uint64_t) lend_off + T + 15u) & ~15ull;
+		if ((LC + 1) * leb <= 256 && lbytes <= SMEM_LINES_MAX) {       /* the LUT holds class * entry size in a byte */
+			/* new numbering: plain states, then states with eager outputs, then the dead row */
+			std::vector<uint32_t> perm(T), inv(T);
+			std::vector<uint64_t> hmask;       /* host copy of the row masks, for "has outputs" */
+			const uint64_t *xoff; const uint32_t *xids;
+			const bool has_eager = eagerhost::eh_get(desc, &xoff, &xids);
+			uint32_t nplain = 0;
+			for (uint32_t st = 0; st < S; st++) if (!has_eager || xoff[st + 1] == xoff[st]) { perm[st] = nplain; inv[nplain++] = st; }
+			uint32_t nn = nplain;
+			for (uint32_t st = 0; st < S; st++) if (has_eager && xoff[st + 1] != xoff[st]) { perm[st] = nn; inv[nn++] = st; }
+			if (!complete) { perm[S] = S; inv[S] = S; }
+			std::vector<uint8_t> lb(lbytes, 0);
+			for (int c = 0; c < 256; c++) { lb[c] = (uint8_t) (lcls[c] * leb); lb[256 + c] = (uint8_t) (LC * leb); }
+			for (uint32_t ns = 0; ns < T; ns++) {
+				const uint32_t os = inv[ns];
+				uint8_t *row = lb.data() + ltab_off + (size_t) ns * lpitch;
+				for (uint32_t k = 0; k <= LC; k++) {
+					uint32_t v;
+					if (k == LC) v = ns;                                        /* NOP column */
+					else if (os >= S) v = perm[dfa->dead];                      /* dead row absorbs */
+					else {
+						const uint32_t t = t32[(size_t) os * 256 + lrep[k]];
+						v = perm[t == NO_EDGE ? dfa->dead : t];
+					}
+					if (leb == 1) row[k] = (uint8_t) v; else reinterpret_cast<uint16_t *>(row)[k] = (uint16_t) v;
+				}
+				lb[lend_off + ns] = dfa->h_is_end[os];
+			}
+			dfa->lblob_bytes = (uint32_t) lbytes; dfa->l_pitch = lpitch; dfa->l_entry_bytes = leb;
+			dfa->l_end_off = lend_off; dfa->l_ncols = LC + 1;
+			dfa->l_first_event = (has_eager || !complete) ? nplain : NO_EDGE;
+			dfa->l_dead = complete ? NO_EDGE : S;
+			dfa->l_start = perm[dfa->start];
+			if (has_eager && dfa->eager_words <= 4) {
+				std::vector<uint32_t> idl;
+				eagerhost::eh_id_list(S, xoff, xids, idl);
+				eagerhost::eh_build_masks(S, dfa->ntable, xoff, xids, idl, dfa->eager_words, hmask);
+				for (uint32_t w = 0; w < dfa->eager_words; w++) dfa->l_start_mask[w] = hmask[(size_t) dfa->start * dfa->eager_words + w];
+			}
+			if (upload) {
+				FSMB_CUDA(cudaMalloc(&dfa->d_lblob, lbytes), { fsm_b200_dfa_free(dfa); return -1; });
+				FSMB_CUDA(cudaMemcpy(dfa->d_lblob, lb.data(), lbytes, cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
+				FSMB_CUDA(cudaMalloc(&dfa->d_lperm_inv, T * sizeof(uint32_t)), { fsm_b200_dfa_free(dfa); return -1; });
+				FSMB_CUDA(cudaMemcpy(dfa->d_lperm_inv, inv.data(), T * sizeof(uint32_t), cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
+				if (dfa->has_absorbing) {
+					std::vector<uint8_t> lab(T, 0);
+					for (uint32_t ns = 0; ns < T; ns++) {
+						const uint32_t os = inv[ns];
+						bool self = os < S;
+						for (int c = 0; c < 256 && self; c++) self = t32[(size_t) os * 256 + c] == os;
+						lab[ns] = self ? 1 : 0;
+					}
+					FSMB_CUDA(cudaMalloc(&dfa->d_labsorb, T), { fsm_b200_dfa_free(dfa); return -1; });
+					FSMB_CUDA(cudaMemcpy(dfa->d_labsorb, lab.data(), T, cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
+				}
+			} else {
+				dfa->d_lblob = nullptr;
+			}
+			dfa->l_planned = 1;
+		}
+	}
 	*out = dfa;
 	return 0;
 }
@@ -485,6 +554,9 @@ fsm_b200_dfa_free(fsm_b200_dfa *dfa)
 	if (dfa->d_kblob != nullptr) cudaFree(dfa->d_kblob);
 	if (dfa->d_absorb != nullptr) cudaFree(dfa->d_absorb);
 	if (dfa->d_eager_masks != nullptr) cudaFree(dfa->d_eager_masks);
+	if (dfa->d_lblob != nullptr) cudaFree(dfa->d_lblob);
+	if (dfa->d_lperm_inv != nullptr) cudaFree(dfa->d_lperm_inv);
+	if (dfa->d_labsorb != nullptr) cudaFree(dfa->d_labsorb);
 	free(dfa->h_eager_ids);
 	free(dfa->h_table32);
 	free(dfa->h_is_end);
@@ -512,6 +584,10 @@ fsm_b200_dfa_info(const fsm_b200_dfa *dfa, struct fsm_b200_dfa_info *info)
 	info->krange = dfa->krange;
 	for (int k = 0; k < 2; k++) { info->krange_lo[k] = dfa->kr_lo[k]; info->krange_hi[k] = dfa->kr_hi[k]; }
 	info->kclasses = dfa->kclasses;
+	info->lines_smem = dfa->l_planned;
+	info->lines_blob_bytes = dfa->l_planned ? dfa->lblob_bytes : 0;
+	info->lines_cols = dfa->l_planned ? dfa->l_ncols : 0;
+	info->eager_ids = dfa->eager_nbits;
 	return 0;
 }
 

@@ -17,6 +17,7 @@
 #include <cstring>
 
 #include "common.h"
+#include "k1_exec_batch.h"
 
 using namespace fsmb200;
 
@@ -80,6 +81,9 @@ launch_eager(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_o
 	size_t n, fsm_b200_result *d_out, uint64_t *d_masks, cudaStream_t stream)
 {
 	if (n == 0) return 0;
+	if (k1_lines_eligible(dfa)) {          /* table fits shared memory: the tuned kernel (k1_lines.cu) */
+		return k1_lines_launch(dfa, d_base, d_offsets, stride, len, n, d_out, d_masks, stream);
+	}
 	EagerArgs a;
 	memset(&a, 0, sizeof a);
 	a.blob = static_cast<const uint8_t *>(dfa->d_blob);

@@ -24,52 +24,13 @@
 
 #include "common.h"
 #include "k1_exec_batch.h"
+#include "k1_device.cuh"
 
 using namespace fsmb200;
 
 namespace {
 
 /* ------------------------------------------------------------------ device helpers -- */
-
-__device__ __forceinline__ uint32_t
-smem_u32(const void *p)
-{
-	return (uint32_t) __cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void
-mbar_init(uint32_t bar, uint32_t count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
-}
-
-__device__ __forceinline__ void
-mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void
-mbar_wait(uint32_t bar, uint32_t parity)
-{
-	uint32_t done;
-	do {
-		asm volatile(
-		    "{\n\t.reg .pred p;\n\t"
-		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-		    "selp.u32 %0, 1, 0, p;\n\t}"
-		    : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-	} while (!done);
-}
-
-/* 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP). */
-__device__ __forceinline__ void
-tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-	asm volatile(
-	    "cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-	    :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
 
 /* 2-D TMA tensor tile global -> shared (SASS: UTMALDG). */
 __device__ __forceinline__ void
@@ -79,28 +40,6 @@ tma_tile_g2s(uint32_t dst, const CUtensorMap *map, uint32_t c0, uint32_t c1, uin
 	    "cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes"
 	    " [%0], [%1, {%2, %3}], [%4];"
 	    :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-
-/* Stage the DFA blob (table rows + is_end bytes) into shared memory with TMA bulk
- * copies issued by one thread; everybody waits on the mbarrier. */
-__device__ __forceinline__ void
-stage_blob(uint8_t *smem, const uint8_t *blob, uint32_t blob_bytes, uint64_t *bar)
-{
-	const uint32_t bar_a = smem_u32(bar);
-	if (threadIdx.x == 0) {
-		mbar_init(bar_a, 1);
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		mbar_expect_tx(bar_a, blob_bytes);
-		const uint32_t dst = smem_u32(smem);
-		for (uint32_t off = 0; off < blob_bytes; off += 16384u) {
-			const uint32_t nb = min(16384u, blob_bytes - off);
-			tma_bulk_g2s(dst + off, blob + off, nb, bar_a);
-		}
-	}
-	mbar_wait(bar_a, 0);
 }
 
 /* Table lookups.  Indexing the extern shared array directly lets ptxas emit, per input
@@ -129,15 +68,6 @@ template <typename E> struct TableGmem {
 		st = (T).step(st, __byte_perm((w), 0u, 0x4442u));  \
 		st = (T).step(st, __byte_perm((w), 0u, 0x4443u));  \
 	} while (0)
-
-__device__ __forceinline__ void
-ld256(const uint8_t *p, uint32_t (&w)[8])
-{
-	asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	    : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]),
-	      "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
-	    : "l"(p));
-}
 
 /* One 16-byte record per input; with the fused gather the same record is also stored into
  * every peer GPU's gathered buffer (P2P stores over NVLink, posted: they overlap the scan). */
@@ -871,6 +801,18 @@ launch_tile(K1Args a, int sms, int smem_optin, cudaStream_t stream)
 
 int g_variant = 0;
 
+struct K1SignalArgs { uint32_t *flags[8]; uint32_t n, value; };
+
+/* the completion signal of a rank that had nothing to scan (see signal_done) */
+__global__ void
+k1_signal_only_kernel(const K1SignalArgs a)
+{
+	if (threadIdx.x == 0) {
+		for (uint32_t r = 0; r < a.n; r++) *reinterpret_cast<volatile uint32_t *>(a.flags[r]) = a.value;
+		__threadfence_system();
+	}
+}
+
 int
 dispatch_kstride(const fsm_b200_dfa *dfa, const K1Args &a, int sms, cudaStream_t stream)
 {
@@ -1009,7 +951,18 @@ k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offs
 	fsm_b200_result *const *peer_outs, int npeers, int peer_compact,
 	uint32_t *sig_counter, uint32_t *const *sig_flags, uint32_t sig_value)
 {
-	if (n == 0) return 0;
+	if (n == 0) {
+		/* an empty shard still has to publish its completion flag, or a peer polling it waits forever */
+		if (sig_counter != nullptr && sig_flags != nullptr && npeers >= 0 && npeers <= 7) {
+			K1SignalArgs sa;
+			for (int r = 0; r <= npeers; r++) sa.flags[r] = sig_flags[r];
+			sa.n = (uint32_t) npeers + 1u; sa.value = sig_value;
+			k1_signal_only_kernel<<<1, 32, 0, stream>>>(sa);
+			count_launch();
+			FSMB_CUDA(cudaGetLastError(), return -1);
+		}
+		return 0;
+	}
 	int sms = 0, smem_optin = 0;
 	if (!device_props(dfa->device, &sms, &smem_optin)) {
 		set_error("k1: cannot query device %d", dfa->device);
@@ -1034,6 +987,11 @@ k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offs
 	}
 
 	if (variant == K1_AUTO) variant = g_variant;
+	/* ragged batches on shared-memory-resident tables: the lines kernel (k1_lines.cu) */
+	if (variant == K1_AUTO && d_offsets != nullptr && npeers == 0 && sig_counter == nullptr &&
+	    k1_lines_eligible(dfa) && getenv("FSM_B200_K1_VARIANT") == nullptr) {
+		return k1_lines_launch(dfa, d_base, d_offsets, 0, 0, n, d_out, nullptr, stream);
+	}
 	const bool tile_ok = k1_tile_eligible(dfa, d_base, d_offsets, stride, len, n);
 	if (variant == K1_AUTO) {
 		/* Measured on B200 (profiles/r1_k1_variants.jsonl): LANE >= TILE64 on both config-2

@@ -64,5 +64,10 @@ int k1_launch_jobs(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_
 	const uint64_t *d_ends, const uint32_t *d_entry, size_t n_max, const uint32_t *d_n,
 	fsm_b200_result *d_out, cudaStream_t stream);
 
+/* Ragged / eager batches on shared-memory-resident tables (k1_lines.cu). */
+bool k1_lines_eligible(const fsm_b200_dfa *dfa);
+int k1_lines_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,
+	uint64_t stride, uint64_t len, size_t n, fsm_b200_result *d_out, uint64_t *d_masks, cudaStream_t stream);
+
 } // namespace fsmb200
 #endif

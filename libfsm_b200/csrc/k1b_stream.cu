@@ -444,20 +444,12 @@ stream_scratch_free(fsm_b200_dfa *dfa)
 }
 }
 
-extern "C" int
-fsm_b200_exec_stream_dev(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len,
-	struct fsm_b200_result *out, void *stream)
+/* exec_stream on device memory; the caller holds ss->mu (scratch arena, d_in and stream are shared
+ * by every call on this DFA). */
+static int
+exec_stream_dev_locked(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len,
+	struct fsm_b200_result *out, cudaStream_t st, StreamScratch *ss)
 {
-	if (dfa == nullptr || out == nullptr || (len > 0 && d_buf == nullptr)) {
-		set_error("exec_stream_dev: bad argument");
-		errno = EINVAL;
-		return -1;
-	}
-	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
-	StreamScratch *ss = ss_get(dfa);
-	if (ss == nullptr) { errno = ENOMEM; return -1; }
-	std::lock_guard<std::mutex> g(ss->mu);
-	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	if (len == 0) {
 		out->ret = dfa->h_is_end[dfa->start] ? 1 : 0;
 		out->end = dfa->start;
@@ -479,6 +471,22 @@ fsm_b200_exec_stream_dev(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t
 		out->consumed = len;
 	}
 	return 0;
+}
+
+extern "C" int
+fsm_b200_exec_stream_dev(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len,
+	struct fsm_b200_result *out, void *stream)
+{
+	if (dfa == nullptr || out == nullptr || (len > 0 && d_buf == nullptr)) {
+		set_error("exec_stream_dev: bad argument");
+		errno = EINVAL;
+		return -1;
+	}
+	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
+	StreamScratch *ss = ss_get(dfa);
+	if (ss == nullptr) { errno = ENOMEM; return -1; }
+	std::lock_guard<std::mutex> g(ss->mu);
+	return exec_stream_dev_locked(dfa, d_buf, len, out, static_cast<cudaStream_t>(stream), ss);
 }
 
 extern "C" int
@@ -532,26 +540,23 @@ fsm_b200_exec_stream_host(const fsm_b200_dfa *dfa, const uint8_t *buf, uint64_t 
 	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
 	StreamScratch *ss = ss_get(dfa);
 	if (ss == nullptr) { errno = ENOMEM; return -1; }
-	cudaStream_t st;
-	const uint8_t *d_in;
-	{
-		std::lock_guard<std::mutex> g(ss->mu);
-		if (ss->stream == nullptr) {
-			FSMB_CUDA(cudaStreamCreateWithFlags(&ss->stream, cudaStreamNonBlocking), return -1);
-		}
-		if (ss->in_cap < len + 64) {
-			if (ss->d_in) cudaFree(ss->d_in);
-			ss->d_in = nullptr; ss->in_cap = 0;
-			void *p = nullptr;
-			FSMB_CUDA(cudaMalloc(&p, len + len / 8 + 4096), return -1);
-			ss->d_in = static_cast<uint8_t *>(p);
-			ss->in_cap = len + len / 8 + 4096;
-		}
-		st = ss->stream;
-		d_in = ss->d_in;
-		if (len > 0) {
-			FSMB_CUDA(cudaMemcpyAsync(ss->d_in, buf, len, cudaMemcpyHostToDevice, st), return -1);
-		}
+	/* ss->mu is held across copy + scan + read-back: two threads running fsm_exec on the SAME fsm
+	 * share the cached DFA and with it d_in and the stream (the lock used to be dropped
+	 * between the H2D copy and the scan) */
+	std::lock_guard<std::mutex> g(ss->mu);
+	if (ss->stream == nullptr) {
+		FSMB_CUDA(cudaStreamCreateWithFlags(&ss->stream, cudaStreamNonBlocking), return -1);
 	}
-	return fsm_b200_exec_stream_dev(dfa, d_in, len, out, st);
+	if (ss->in_cap < len + 64) {
+		if (ss->d_in) cudaFree(ss->d_in);
+		ss->d_in = nullptr; ss->in_cap = 0;
+		void *p = nullptr;
+		FSMB_CUDA(cudaMalloc(&p, len + len / 8 + 4096), return -1);
+		ss->d_in = static_cast<uint8_t *>(p);
+		ss->in_cap = len + len / 8 + 4096;
+	}
+	if (len > 0) {
+		FSMB_CUDA(cudaMemcpyAsync(ss->d_in, buf, len, cudaMemcpyHostToDevice, ss->stream), return -1);
+	}
+	return exec_stream_dev_locked(dfa, ss->d_in, len, out, ss->stream, ss);
 }

@@ -223,7 +223,11 @@ device_index(void)
 }
 
 /* Pins the compiled DFA for `fsm` (cached) into *ref; 0, or -1 with errno set.
- * Release with put_dfa.  An entry is only ever evicted or freed while nobody holds it. */
+ * Release with put_dfa.  An entry is only ever evicted or freed while nobody holds it.
+ * The flatten + validate + table build + upload of a miss run OUTSIDE cache_mu (lx(1) compiles
+ * many zones from a thread pool): two threads that miss on the same automaton at the
+ * same time both build it, the second one finds the first one's entry when it comes back and
+ * drops its own copy. */
 static int
 get_dfa(const struct fsm *fsm, struct dfa_ref *ref)
 {
@@ -231,45 +235,55 @@ get_dfa(const struct fsm *fsm, struct dfa_ref *ref)
 	struct cache_entry *victim = NULL;
 	fsm_b200_dfa *dfa = NULL;
 	struct fsm_b200_flat flat;
-	int i, err = 0;
+	int i, err = 0, pass;
 
 	ref->dfa = NULL; ref->entry = NULL;
-	pthread_mutex_lock(&cache_mu);
-	for (i = 0; i < CACHE_SLOTS; i++) {
-		struct cache_entry *e = &cache[i];
-		if (e->stamp != 0 && !e->doomed && e->fsm == fsm && e->fp == fp) {
-			e->stamp = ++cache_clock;
-			if (e->dfa == NULL) {
-				err = e->errno_val;
+	for (pass = 0; pass < 2; pass++) {
+		pthread_mutex_lock(&cache_mu);
+		victim = NULL;
+		for (i = 0; i < CACHE_SLOTS; i++) {
+			struct cache_entry *e = &cache[i];
+			if (e->stamp != 0 && !e->doomed && e->fsm == fsm && e->fp == fp) {
+				e->stamp = ++cache_clock;
+				if (e->dfa == NULL) {
+					err = e->errno_val;
+					pthread_mutex_unlock(&cache_mu);
+					if (dfa != NULL) fsm_b200_dfa_free(dfa);
+					errno = err;
+					return -1;
+				}
+				e->refs++;
+				ref->dfa = e->dfa; ref->entry = e;
 				pthread_mutex_unlock(&cache_mu);
-				errno = err;
-				return -1;
+				if (dfa != NULL) fsm_b200_dfa_free(dfa);      /* somebody else was faster */
+				return 0;
 			}
-			e->refs++;
-			ref->dfa = e->dfa; ref->entry = e;
-			pthread_mutex_unlock(&cache_mu);
-			return 0;
+			if (e->refs == 0 && !e->doomed && (victim == NULL || e->stamp < victim->stamp)) victim = e;
 		}
-		if (e->refs == 0 && !e->doomed && (victim == NULL || e->stamp < victim->stamp)) victim = e;
-	}
-	/* miss: validate + build (the engine restates fsm_all(fsm_isdfa) + fsm_getstart) */
-	if (fsm_b200_flatten(fsm, &flat) != 0) {
+		if (pass == 1) break;                /* still a miss, our build in hand: insert below, lock held */
 		pthread_mutex_unlock(&cache_mu);
-		return -1;
+
+		/* miss: validate + build (the engine restates fsm_all(fsm_isdfa) + fsm_getstart) */
+		if (fsm_b200_flatten(fsm, &flat) != 0) {
+			return -1;
+		}
+		if (fsm_b200_dfa_compile(&flat.desc, device_index(), &dfa) != 0) {
+			err = errno;
+			dfa = NULL;
+		}
+		fsm_b200_flat_free(&flat);
 	}
-	if (fsm_b200_dfa_compile(&flat.desc, device_index(), &dfa) != 0) {
-		err = errno;
-		dfa = NULL;
-	}
-	fsm_b200_flat_free(&flat);
 	if (victim != NULL && (dfa != NULL || err == EINVAL)) {      /* remember DFAs and definite non-DFAs */
-		if (victim->stamp != 0 && victim->dfa != NULL) fsm_b200_dfa_free(victim->dfa);
+		fsm_b200_dfa *old = (victim->stamp != 0) ? victim->dfa : NULL;
 		memset(victim, 0, sizeof *victim);
 		victim->fsm = fsm; victim->fp = fp; victim->dfa = dfa; victim->errno_val = err;
 		victim->stamp = ++cache_clock;
 		if (dfa != NULL) { victim->refs = 1; ref->entry = victim; }
+		pthread_mutex_unlock(&cache_mu);
+		if (old != NULL) fsm_b200_dfa_free(old);                 /* device frees outside the lock too */
+	} else {
+		pthread_mutex_unlock(&cache_mu);
 	}
-	pthread_mutex_unlock(&cache_mu);
 	if (dfa == NULL) {
 		errno = err;
 		return -1;
@@ -331,6 +345,7 @@ fsm_exec(const struct fsm *fsm,
 	struct dfa_ref ref;
 	struct fsm_b200_result r;
 	unsigned char *buf = NULL;
+	const unsigned char *data = NULL;
 	size_t len = 0, cap = 0;
 	const char *sgetc_start = NULL;
 	long file_start = -1;
@@ -349,25 +364,52 @@ fsm_exec(const struct fsm *fsm,
 	}
 
 	if (fsm_getc == fsm_sgetc) {
+		/* the reference's own string cursor (getc.c:16-34): the bytes are already in memory, up to the
+		 * NUL -- take them in place instead of one indirect call per byte, and leave the cursor where
+		 * draining would have left it (on the NUL; fsm_sgetc does not step past it) */
 		sgetc_start = *(const char **) opaque;
+		len = strlen(sgetc_start);
+		data = (const unsigned char *) sgetc_start;
+		*(const char **) opaque = sgetc_start + len;
 	} else if (fsm_getc == fsm_fgetc) {
-		file_start = ftell((FILE *) opaque);
-	}
-
-	/* drain the callback (exec.c:132) */
-	while (c = fsm_getc(opaque), c != EOF) {
-		if (len == cap) {
-			size_t ncap = cap ? cap * 2 : 4096;
-			unsigned char *nb = realloc(buf, ncap);
-			if (nb == NULL) {
-				free(buf);
-				put_dfa(&ref);
-				errno = ENOMEM;
-				return -1;
+		/* the reference's own FILE cursor (getc.c:36-51): block reads instead of fgetc per byte */
+		FILE *f = opaque;
+		file_start = ftell(f);
+		for (;;) {
+			size_t got;
+			if (cap - len < (1u << 20)) {
+				size_t ncap = cap ? cap * 2 : (4u << 20);
+				unsigned char *nb = realloc(buf, ncap);
+				if (nb == NULL) {
+					free(buf);
+					put_dfa(&ref);
+					errno = ENOMEM;
+					return -1;
+				}
+				buf = nb; cap = ncap;
 			}
-			buf = nb; cap = ncap;
+			got = fread(buf + len, 1, cap - len, f);
+			len += got;
+			if (got == 0) break;          /* EOF or error: fsm_fgetc returns EOF for both */
 		}
-		buf[len++] = (unsigned char) c;
+		data = buf;
+	} else {
+		/* any other callback: drain it (exec.c:132) */
+		while (c = fsm_getc(opaque), c != EOF) {
+			if (len == cap) {
+				size_t ncap = cap ? cap * 2 : 4096;
+				unsigned char *nb = realloc(buf, ncap);
+				if (nb == NULL) {
+					free(buf);
+					put_dfa(&ref);
+					errno = ENOMEM;
+					return -1;
+				}
+				buf = nb; cap = ncap;
+			}
+			buf[len++] = (unsigned char) c;
+		}
+		data = buf;
 	}
 
 	{
@@ -379,11 +421,11 @@ fsm_exec(const struct fsm *fsm,
 
 		(void) fsm_b200_dfa_eager_info(ref.dfa, &nbits, &id_of_bit);
 		if (nbits == 0) {
-			rc = fsm_b200_exec_stream_host(ref.dfa, buf, len, &r);
+			rc = fsm_b200_exec_stream_host(ref.dfa, data, len, &r);
 		} else {
 			/* eager outputs (exec.c:126-144): the walk also reports the set of ids it fired */
 			memset(mask, 0, sizeof mask);
-			rc = fsm_b200_exec_batch_eager_host(ref.dfa, buf != NULL ? buf : (const unsigned char *) "", off, 1, &r, mask);
+			rc = fsm_b200_exec_batch_eager_host(ref.dfa, data != NULL ? data : (const unsigned char *) "", off, 1, &r, mask);
 		}
 		if (rc != 0) {
 			free(buf);
@@ -634,9 +676,10 @@ fsm_exec_batch(const struct fsm *fsm, const unsigned char *base, const uint64_t 
 
 int
 fsm_exec_batch_eager(const struct fsm *fsm, const unsigned char *base, const uint64_t *offsets,
-	size_t n, struct fsm_b200_result *out, uint64_t *masks, uint32_t *nbits, const uint32_t **id_of_bit)
+	size_t n, struct fsm_b200_result *out, uint64_t *masks, uint32_t *nbits, uint32_t *id_of_bit)
 {
 	struct dfa_ref ref;
+	const uint32_t *ids = NULL;
 	int rc;
 
 	assert(fsm != NULL);
@@ -644,7 +687,10 @@ fsm_exec_batch_eager(const struct fsm *fsm, const unsigned char *base, const uin
 	if (get_dfa(fsm, &ref) != 0) {
 		return -1;
 	}
-	rc = fsm_b200_dfa_eager_info(ref.dfa, nbits, id_of_bit);
+	rc = fsm_b200_dfa_eager_info(ref.dfa, nbits, &ids);
+	if (rc == 0 && *nbits > 0) {
+		memcpy(id_of_bit, ids, *nbits * sizeof *id_of_bit);      /* a copy: the cached table may be evicted after put_dfa */
+	}
 	if (rc == 0 && n > 0) {
 		rc = *nbits != 0 ? fsm_b200_exec_batch_eager_host(ref.dfa, base, offsets, n, out, masks)
 		                 : fsm_b200_exec_batch_host(ref.dfa, base, offsets, n, out);

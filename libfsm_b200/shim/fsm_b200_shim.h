@@ -39,9 +39,11 @@ int fsm_exec_batch(const struct fsm *fsm, const unsigned char *base, const uint6
  * plus per input the bitset of eager-output ids fired along its walk: masks[i*words + b/64] bit
  * b%64 <=> id_of_bit[b] fired, words = (*nbits + 63) / 64 (the caller sizes masks for
  * FSM_B200_EAGER_MAX_IDS / 64 words per input, or calls once with n == 0 to learn *nbits).
- * *id_of_bit stays valid until the fsm is changed or freed. */
+ * id_of_bit is CALLER storage for FSM_B200_EAGER_MAX_IDS entries; the first *nbits are filled with
+ * the distinct eager-output ids of the automaton, ascending (a copy: nothing the library owns is
+ * handed out, so the table cache may evict the compiled automaton at any time). */
 int fsm_exec_batch_eager(const struct fsm *fsm, const unsigned char *base, const uint64_t *offsets,
-	size_t n, struct fsm_b200_result *out, uint64_t *masks, uint32_t *nbits, const uint32_t **id_of_bit);
+	size_t n, struct fsm_b200_result *out, uint64_t *masks, uint32_t *nbits, uint32_t *id_of_bit);
 
 /* Drop the cached device table of `fsm` (call from fsm_free and from mutators; the shim
  * also revalidates a cheap fingerprint on every call, so this is an optimisation). */

@@ -55,7 +55,7 @@ main(void)
 	unsigned char base[256];
 	uint64_t offsets[NC + 1], masks[NC * (FSM_B200_EAGER_MAX_IDS / 64)];
 	struct fsm_b200_result rec[NC];
-	const uint32_t *id_of_bit = NULL;
+	uint32_t id_of_bit[FSM_B200_EAGER_MAX_IDS];
 	uint32_t nbits = 0;
 	size_t i, off = 0, words;
 	int fails = 0;
@@ -77,7 +77,7 @@ main(void)
 	}
 	offsets[NC] = off;
 	memset(masks, 0, sizeof masks);
-	if (fsm_exec_batch_eager(u, base, offsets, NC, rec, masks, &nbits, &id_of_bit) != 0) {
+	if (fsm_exec_batch_eager(u, base, offsets, NC, rec, masks, &nbits, id_of_bit) != 0) {
 		fprintf(stderr, "FAIL: fsm_exec_batch_eager (errno %d)\n", errno);
 		return 1;
 	}

@@ -26,6 +26,7 @@
 #include <adt/edgeset.h>
 
 #include "libfsm/internal.h"
+#include "libfsm/eager_output.h"
 
 #include "ref_harness.h"
 
@@ -418,4 +419,117 @@ void *
 refh_union_repeated_pattern_group(size_t n, void **fsms, unsigned id_base)
 {
 	return fsm_union_repeated_pattern_group(n, (struct fsm **) fsms, NULL, id_base);
+}
+
+/* n fsm_exec calls with the eager-output callback, over nthreads pthreads; the callback slot lives
+ * in the fsm (eager_output.c:27-63), so every thread works on its own fsm_clone.  masks[i*words..]
+ * gets bit b set when id_of_bit[b] (ascending) fired on line i.
+ * mode 0 "as-is": the reference's fsm_exec per line.  mode 1 "amortised": validation hoisted; per
+ * byte the reference's own edge_set_transition, per state entered fsm_eager_output_iter_state. */
+struct ejob {
+	struct fsm *fsm; const uint8_t *base; const uint64_t *offsets;
+	size_t lo, hi; int mode; struct fsm_b200_result *out;
+	uint64_t *masks; size_t words; const uint32_t *id_of_bit; size_t nbits;
+	uint64_t *cur;
+};
+
+static void
+ejob_cb(fsm_output_id_t id, void *opaque)
+{
+	struct ejob *j = opaque;
+	size_t lo = 0, hi = j->nbits;
+	while (lo < hi) {
+		const size_t mid = (lo + hi) / 2;
+		if (j->id_of_bit[mid] < id) lo = mid + 1; else hi = mid;
+	}
+	if (lo < j->nbits && j->id_of_bit[lo] == id) j->cur[lo >> 6] |= (uint64_t) 1 << (lo & 63);
+}
+
+static int
+ejob_iter_cb(fsm_state_t state, fsm_output_id_t id, void *opaque)
+{
+	(void) state;
+	ejob_cb(id, opaque);
+	return 1;
+}
+
+static void *
+eworker(void *opaque)
+{
+	struct ejob *j = opaque;
+	size_t i;
+	if (j->mode == 0) fsm_eager_output_set_cb(j->fsm, ejob_cb, j);
+	for (i = j->lo; i < j->hi; i++) {
+		const uint8_t *buf = j->base + j->offsets[i];
+		const uint64_t len = j->offsets[i + 1] - j->offsets[i];
+		j->cur = j->masks + i * j->words;
+		memset(j->cur, 0, j->words * sizeof *j->cur);
+		if (j->mode == 0) {
+			refh_exec(j->fsm, buf, len, &j->out[i]);
+			if (j->out[i].ret != 1) {
+				/* fsm_exec does not report where a failed walk stopped; the record's `end` does */
+				fsm_state_t state = j->fsm->start, next;
+				uint64_t off = 0;
+				while (off < len && edge_set_transition(j->fsm->states[state].edges, buf[off], &next)) { state = next; off++; }
+				j->out[i].end = state;
+			}
+		} else {
+			fsm_state_t state = j->fsm->start;
+			uint64_t off = 0;
+			int dead = 0;
+			if (j->fsm->states[state].has_eager_outputs) fsm_eager_output_iter_state(j->fsm, state, ejob_iter_cb, j);
+			while (off < len) {
+				fsm_state_t next;
+				if (!edge_set_transition(j->fsm->states[state].edges, buf[off], &next)) { dead = 1; break; }
+				state = next;
+				if (j->fsm->states[state].has_eager_outputs) fsm_eager_output_iter_state(j->fsm, state, ejob_iter_cb, j);
+				off++;
+			}
+			j->out[i].ret = (!dead && fsm_isend(j->fsm, state)) ? 1 : 0;
+			j->out[i].end = state;
+			j->out[i].consumed = off;
+		}
+	}
+	if (j->mode == 0) fsm_eager_output_set_cb(j->fsm, NULL, NULL);
+	return NULL;
+}
+
+int
+refh_exec_eager_batch(void *vfsm, const uint8_t *base, const uint64_t *offsets, size_t n,
+	int mode, int nthreads, struct fsm_b200_result *out, uint64_t *masks, size_t words,
+	const uint32_t *id_of_bit, size_t nbits)
+{
+	struct fsm *fsm = vfsm;
+	pthread_t tids[256];
+	struct ejob jobs[256];
+	int t, made = 0, rc = 0;
+	fsm_state_t st;
+
+	if (!fsm_all(fsm, fsm_isdfa) || !fsm_getstart(fsm, &st)) { errno = EINVAL; return -1; }
+	if (nthreads < 1) nthreads = 1;
+	if (nthreads > 256) nthreads = 256;
+	for (t = 0; t < nthreads; t++) {
+		jobs[t].fsm = t == 0 ? fsm : fsm_clone(fsm);
+		if (jobs[t].fsm == NULL) { rc = -1; break; }
+		made = t + 1;
+		jobs[t].base = base; jobs[t].offsets = offsets;
+		jobs[t].lo = n * (size_t) t / (size_t) nthreads;
+		jobs[t].hi = n * (size_t) (t + 1) / (size_t) nthreads;
+		jobs[t].mode = mode; jobs[t].out = out;
+		jobs[t].masks = masks; jobs[t].words = words; jobs[t].id_of_bit = id_of_bit; jobs[t].nbits = nbits;
+	}
+	if (rc == 0) {
+		if (nthreads == 1) {
+			eworker(&jobs[0]);
+		} else {
+			int started = 0;
+			for (t = 0; t < nthreads; t++) {
+				if (pthread_create(&tids[t], NULL, eworker, &jobs[t]) != 0) { rc = -1; errno = EAGAIN; break; }
+				started = t + 1;
+			}
+			for (t = 0; t < started; t++) pthread_join(tids[t], NULL);
+		}
+	}
+	for (t = 1; t < made; t++) fsm_free(jobs[t].fsm);
+	return rc;
 }

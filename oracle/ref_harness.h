@@ -68,5 +68,12 @@ int   refh_eager_flatten(const void *fsm, uint64_t **off, uint32_t **ids);
 int   refh_exec_eager(void *fsm, const uint8_t *buf, uint64_t len, struct fsm_b200_result *out,
 	unsigned *fired, size_t cap, size_t *nfired);
 void *refh_union_repeated_pattern_group(size_t n, void **fsms, unsigned id_base);
+/* n fsm_exec calls with the callback installed, nthreads pthreads (each on its own fsm_clone: the
+ * callback slot lives in the fsm).  masks[i * words ..): bit b <=> id_of_bit[b] (ascending) fired on
+ * line i.  mode 0: the reference's fsm_exec as-is; mode 1: validation hoisted, the reference's own
+ * edge_set_transition + fsm_eager_output_iter_state per byte.  out[i].end is filled for ret == 0 too. */
+int   refh_exec_eager_batch(void *fsm, const uint8_t *base, const uint64_t *offsets, size_t n,
+	int mode, int nthreads, struct fsm_b200_result *out, uint64_t *masks, size_t words,
+	const uint32_t *id_of_bit, size_t nbits);
 
 #endif

@@ -457,7 +457,53 @@ def main_eager():
     print(f"wrote golden_eager.npz: {len(cases)} cases, {os.path.getsize(os.path.join(HERE, 'golden_eager.npz')) / 1024:.0f} KiB")
 
 
+def main_cfg3():
+    """golden_cfg3.npz: BASELINE config 3's two automata as the REFERENCE builds them, plus a sample of
+    lines with the reference's own answers.
+      eager    libfsm_b200.workloads.cfg3_patterns(): 128 patterns, unanchored but for 2 `^` and 10 `$`
+               ones: re_comp(RE_SAVE_LINKAGE_INFO) -> fsm_union_repeated_pattern_group(id_base 1) ->
+               fsm_determinise -> fsm_minimise (tests/eager_output/utils.c:67-131); per line the
+               reference's fsm_exec record and the set of eager-output ids its callback received
+      anchored cfg3_anchored_patterns(): rx(1)'s recipe (src/rx/main.c:487-566,1353,1371: per pattern
+               det + min + setendid(i), fsm_union_array, fsm_determinise, no final minimise)"""
+    from libfsm_b200 import workloads
+    R = reflib.Ref()
+    out = {}
+    RE_SAVE_LINKAGE_INFO = 1 << 9
+    pats, inst = workloads.cfg3_patterns()
+    hs = [R.re_comp(p, reflib.RE_PCRE, RE_SAVE_LINKAGE_INFO) for p in pats]
+    u = R.union_repeated_pattern_group(hs, 1)
+    R.determinise(u)
+    ndet = R.countstates(u)
+    R.minimise(u)
+    f = R.flatten(u)
+    goldenio.pack_fsm("eager_", f, out)
+    base, off = workloads.cfg3_lines_host(2000, inst, seed=11)
+    ids = np.unique(f.eager_ids)
+    rec, masks = R.exec_eager_batch(u, base, off, ids, mode=0, nthreads=8)
+    out.update(eager_base=base, eager_offsets=off, eager_expect=rec.view(np.uint8), eager_masks=masks, eager_idlist=ids)
+    R.free(u)
+    apats, ainst = workloads.cfg3_anchored_patterns()
+    h = R.union_dfa(apats, state_limit=500000)
+    fa = R.flatten(h)
+    goldenio.pack_fsm("anch_", fa, out)
+    base, off = workloads.cfg3_lines_host(2000, ainst, seed=12, at_start=True)
+    rec = R.exec_batch(h, base, off, mode=1, nthreads=8)
+    asis = R.exec_batch(h, base, off, mode=0, nthreads=8)
+    assert (asis["ret"] == rec["ret"]).all() and (asis["consumed"] == rec["consumed"]).all()
+    out.update(anch_base=base, anch_offsets=off, anch_expect=rec.view(np.uint8))
+    R.free(h)
+    out["meta"] = np.frombuffer(json.dumps({"eager_det_states": ndet, "eager_min_states": f.nstates,
+                                            "anch_states": fa.nstates}).encode(), dtype=np.uint8)
+    path = os.path.join(HERE, "golden_cfg3.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote golden_cfg3.npz: eager {ndet} -> {f.nstates} states ({ids.size} eager ids), anchored {fa.nstates} states, "
+          f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) < 2 or sys.argv[1] == "cfg3":
+        main_cfg3()
     if len(sys.argv) < 2 or sys.argv[1] == "eager":
         main_eager()
     if len(sys.argv) < 2 or sys.argv[1] == "fixtures":

@@ -143,3 +143,16 @@ def load_eager_cases(path: str) -> list[dict]:
                       "min": unpack_fsm(p + "min_", z) if m["has_min"] else None,
                       "inputs": [bytes.fromhex(h) for h in m["inputs"]], "fired": m["fired"], "rets": m["rets"]})
     return cases
+
+
+def load_cfg3(path: str | None = None) -> dict:
+    """golden_cfg3.npz (make_golden.py main_cfg3): {"eager": {fsm, base, offsets, expect, masks, idlist},
+    "anchored": {fsm, base, offsets, expect}, "meta": {...}}."""
+    z = np.load(path or os.path.join(GOLDEN_DIR, "golden_cfg3.npz"))
+    return {
+        "eager": {"fsm": unpack_fsm("eager_", z), "base": z["eager_base"], "offsets": z["eager_offsets"],
+                  "expect": z["eager_expect"].view(RESULT_DTYPE), "masks": z["eager_masks"], "idlist": z["eager_idlist"]},
+        "anchored": {"fsm": unpack_fsm("anch_", z), "base": z["anch_base"], "offsets": z["anch_offsets"],
+                     "expect": z["anch_expect"].view(RESULT_DTYPE)},
+        "meta": json.loads(bytes(z["meta"]).decode()),
+    }

@@ -232,6 +232,7 @@ class Ref:
         L.refh_exec_eager.argtypes = [vp, vp, C.c_uint64, P(CResult), vp, C.c_size_t, P(C.c_size_t)]
         L.refh_union_repeated_pattern_group.argtypes = [C.c_size_t, P(vp), C.c_uint]
         L.refh_union_repeated_pattern_group.restype = vp
+        L.refh_exec_eager_batch.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, C.c_int, vp, vp, C.c_size_t, vp, C.c_size_t]
         self.libc = C.CDLL(None)
         self.libc.free.argtypes = [vp]
 
@@ -248,6 +249,21 @@ class Ref:
         self.lib.refh_exec_eager(h, _ptr(buf), len(data), C.byref(r), _ptr(fired), fired.size, C.byref(n))
         assert n.value <= fired.size
         return (r.ret, r.end, r.consumed), [int(x) for x in fired[:n.value]]
+
+    def exec_eager_batch(self, h, base: np.ndarray, offsets: np.ndarray, id_of_bit: np.ndarray, mode: int = 1,
+                         nthreads: int = 1):
+        """(records, masks uint64 [n, words]) of n reference fsm_exec calls with the eager callback;
+        bit b of a mask <=> id_of_bit[b] fired.  mode 0: fsm_exec as-is, mode 1: validation hoisted."""
+        n = offsets.shape[0] - 1
+        ids = np.ascontiguousarray(id_of_bit, dtype=np.uint32)
+        words = max(1, (ids.size + 63) // 64)
+        out = np.zeros(n, dtype=RESULT_DTYPE)
+        masks = np.zeros((n, words), dtype=np.uint64)
+        rc = self.lib.refh_exec_eager_batch(h, _ptr(base), offsets.ctypes.data, n, mode, nthreads, _ptr(out), _ptr(masks),
+                                            words, _ptr(ids), ids.size)
+        if rc != 0:
+            raise OSError(C.get_errno(), "refh_exec_eager_batch")
+        return out, masks
 
     def union_repeated_pattern_group(self, handles, id_base: int = 1):
         arr = (C.c_void_p * len(handles))(*handles)

@@ -59,3 +59,63 @@ def test_union_dfa_over_ragged_lines(ref, oracle, npat):
     for i in np.nonzero(want["ret"] == 1)[0][:500]:
         assert list(fsm.endids_of(int(got["end"][i]))) == ref.endids(h, int(want["end"][i]))
     ref.free(h)
+
+
+# ---- the two config-3 automata of tests/golden/golden_cfg3.npz (built by the reference) ---------
+
+@pytest.fixture(scope="module")
+def cfg3():
+    import goldenio
+    return goldenio.load_cfg3()
+
+
+def test_cfg3_eager_golden_lines(cfg3):
+    """128 mostly unanchored patterns, fsm_union_repeated_pattern_group + det + min: records and fired
+    eager-output id sets of the golden sample, through the host entry point and through the device
+    entry point (lines kernel), bit-exact vs what the reference's fsm_exec + callback produced."""
+    import torch
+    c = cfg3["eager"]
+    with L.Dfa(c["fsm"]) as dfa:
+        assert dfa.info["lines_smem"] == 1 and dfa.info["eager_ids"] == c["idlist"].size
+        assert (dfa.eager_ids() == c["idlist"]).all()
+        rec, masks = dfa.exec_batch_eager(c["base"], c["offsets"])
+        assert (rec == c["expect"]).all()
+        assert (masks == c["masks"]).all()
+        drec, dmasks = dfa.exec_batch_eager(torch.from_numpy(c["base"]).cuda(), torch.from_numpy(c["offsets"].astype(np.int64)).cuda())
+        torch.cuda.synchronize()
+        assert (L.results_from_torch(drec) == c["expect"]).all()
+        assert (dmasks.cpu().numpy().view(np.uint64) == c["masks"]).all()
+        # the plain entry points on the same automaton: same records, no ids
+        assert (dfa.exec_batch(c["base"], c["offsets"]) == c["expect"]).all()
+    assert (c["masks"] != 0).any(axis=1).mean() > 0.3 and (c["expect"]["ret"] == 1).any()
+
+
+def test_cfg3_anchored_golden_lines(cfg3):
+    c = cfg3["anchored"]
+    with L.Dfa(c["fsm"]) as dfa:
+        assert dfa.info["lines_smem"] == 1
+        assert (dfa.exec_batch(c["base"], c["offsets"]) == c["expect"]).all()
+    assert 0.2 < (c["expect"]["ret"] == 1).mean() < 0.8
+
+
+@pytest.mark.parametrize("lo,hi", [(0, 40), (64, 256), (1, 1000)])
+def test_cfg3_eager_vs_reference_large_sample(ref, cfg3, lo, hi):
+    """300 k seeded lines (incl. empty lines and lines much longer than a sector) through the lines
+    kernel vs the compiled reference (refh_exec_eager_batch: its own edge_set_transition walk and
+    fsm_eager_output_iter_state per state entered), records + id bitsets bit-exact; and the absorbing
+    exit / NOP-column machinery at every alignment (the lines are packed back to back)."""
+    import torch
+    from libfsm_b200 import workloads
+    c = cfg3["eager"]
+    _, inst = workloads.cfg3_patterns()
+    base, off = workloads.cfg3_lines_host(300000 if hi <= 256 else 60000, inst, seed=lo * 7 + hi, lo=lo, hi=hi)
+    h = ref.from_flat(c["fsm"])
+    want, wmasks = ref.exec_eager_batch(h, base, off, c["idlist"], mode=1, nthreads=16)
+    ref.free(h)
+    with L.Dfa(c["fsm"]) as dfa:
+        drec, dmasks = dfa.exec_batch_eager(torch.from_numpy(base).cuda(), torch.from_numpy(off.astype(np.int64)).cuda())
+        torch.cuda.synchronize()
+        got, gmasks = L.results_from_torch(drec), dmasks.cpu().numpy().view(np.uint64)
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, (bad[:5], got[bad[:5]], want[bad[:5]])
+    assert (gmasks == wmasks).all()

@@ -56,3 +56,25 @@ def test_first_group_wins_on_ambiguous_symbol(oracle):
     f = FlatFsm.from_edges(3, 0, [1], [(0, ord("a"), 2), (0, ord("a"), 1)])
     assert not oracle.isdfa(f)
     assert oracle.flatten(f)[0, ord("a")] == 1      # groups sorted by destination: 1 before 2
+
+
+def test_oracle_matches_reference_on_config3_automata(oracle):
+    """golden_cfg3.npz: the two BASELINE config-3 automata as the reference builds them (128-pattern
+    fsm_union_repeated_pattern_group + det + min with eager outputs; rx-style anchored union with end
+    ids) and the reference's answers on 2000 log lines each: records, and for the eager automaton the
+    set of ids its callback received."""
+    import numpy as np
+    import goldenio
+    g = goldenio.load_cfg3()
+    e = g["eager"]
+    assert g["meta"]["eager_min_states"] == e["fsm"].nstates and e["idlist"].size == 118
+    got = oracle.exec_batch(e["fsm"], e["base"], e["offsets"], nthreads=4)
+    assert (got == e["expect"]).all()
+    ids = e["idlist"]
+    for i in range(0, len(e["offsets"]) - 1, 7):
+        s = e["base"][int(e["offsets"][i]):int(e["offsets"][i + 1])].tobytes()
+        _, fired = oracle.exec_eager(e["fsm"], s)
+        want = [int(ids[b]) for b in range(ids.size) if (int(e["masks"][i][b >> 6]) >> (b & 63)) & 1]
+        assert fired == want, i
+    a = g["anchored"]
+    assert (oracle.exec_batch(a["fsm"], a["base"], a["offsets"], nthreads=4) == a["expect"]).all()
