@@ -87,6 +87,8 @@ struct fsm_b200_dfa {
 	uint32_t krange;
 	uint32_t kr_add_lo[2], kr_add_hi[2], kr_hxor[2];
 	uint8_t kr_lo[2], kr_hi[2];
+	void *d_rblob;           /* k-range kernel: [256 B cell LUT][stepK transposed 256 x 256][step1 rows][is_end] */
+	uint32_t rblob_bytes, r_k1_off, r_kend_off;
 	/* device */
 	void *d_blob;            /* table rows followed by is_end bytes (u8 per row) */
 	uint8_t *d_absorb;       /* [ntable] 1 = every byte loops back to the state itself */
@@ -98,6 +100,8 @@ struct fsm_b200_dfa {
 	void *scratch;
 	/* scratch of the stream (K1b) entry points */
 	void *stream_scratch;
+	/* scratch of fsm_b200_exec_batch_eager_host */
+	void *eager_scratch;
 	/* eager outputs (k1_eager.cu): distinct ids ascending, per-row bit masks [ntable][eager_words] */
 	uint32_t eager_nbits, eager_words;
 	uint32_t *h_eager_ids;
@@ -111,6 +115,7 @@ struct fsm_b200_dfa {
 	uint32_t lblob_bytes, l_pitch, l_entry_bytes, l_end_off, l_first_event, l_dead, l_start, l_ncols;
 	uint32_t *d_lperm_inv;   /* [ntable] new number -> caller's state number (dead row -> ntable - 1) */
 	uint8_t *d_labsorb;      /* [ntable] by new number, or nullptr when no real state is absorbing */
+	uint64_t *d_lev_masks;   /* [ntable - l_first_event][eager_words]: id masks of the states with outputs, by new number */
 	uint64_t l_start_mask[4];/* eager ids of the start state (exec.c:126-130) */
 	uint32_t l_planned;      /* the lines blob exists (fits shared memory) */
 };

@@ -386,6 +386,25 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 			dfa->kstride = K; dfa->kclasses = KC; dfa->kpitch = kpitch; dfa->k1pitch = k1pitch;
 			dfa->k1_off = k1_off; dfa->kend_off = kend_off; dfa->klut_off = klut_off; dfa->kblob_bytes = kbytes;
 			dfa->krange = krange;
+			if (krange != 0) {
+				/* the k-range kernel's own blob: stepK stored [tuple][state] so that the lookup address is
+				 * 2 * (128 * tuple) + state -- one LEA from the dp4a result */
+				const uint32_t r_k1_off = 256u + 256u * 256u;
+				const uint32_t r_kend_off = (r_k1_off + T * k1pitch + 15u) & ~15u;
+				const uint32_t rbytes = (r_kend_off + T + 15u) & ~15u;
+				std::vector<uint8_t> rb(rbytes, 0);
+				memcpy(rb.data(), kb.data() + klut_off, 256);                       /* L0: byte -> cell code */
+				for (uint32_t st = 0; st < T; st++) {
+					for (uint32_t idx = 0; idx < W; idx++) rb[256u + idx * 256u + st] = kb[ktab_off + st * kpitch + idx];
+					memcpy(rb.data() + r_k1_off + st * k1pitch, kb.data() + k1_off + st * k1pitch, k1pitch);
+					rb[r_kend_off + st] = dfa->h_is_end[st];
+				}
+				if (upload) {
+					FSMB_CUDA(cudaMalloc(&dfa->d_rblob, rbytes), { fsm_b200_dfa_free(dfa); return -1; });
+					FSMB_CUDA(cudaMemcpy(dfa->d_rblob, rb.data(), rbytes, cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
+				}
+				dfa->rblob_bytes = rbytes; dfa->r_k1_off = r_k1_off; dfa->r_kend_off = r_kend_off;
+			}
 			for (int k = 0; k < 2; k++) {
 				/* per byte lane, on l = b & 0x7F: bit 7 of l + add_lo is [l >= lo7], of l + add_hi is
 				 * [l > hi7]; hxor selects the half the range lives in (all ones: bytes < 0x80) */
@@ -479,6 +498,15 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 				FSMB_CUDA(cudaMemcpy(dfa->d_lblob, lb.data(), lbytes, cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
 				FSMB_CUDA(cudaMalloc(&dfa->d_lperm_inv, T * sizeof(uint32_t)), { fsm_b200_dfa_free(dfa); return -1; });
 				FSMB_CUDA(cudaMemcpy(dfa->d_lperm_inv, inv.data(), T * sizeof(uint32_t), cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
+				if (has_eager && dfa->eager_words <= 4 && !hmask.empty()) {
+					const uint32_t W = dfa->eager_words, nev = T - nplain;
+					std::vector<uint64_t> ev((size_t) nev * W + 1, 0);
+					for (uint32_t ns = nplain; ns < T; ns++) {
+						for (uint32_t w = 0; w < W; w++) ev[(size_t) (ns - nplain) * W + w] = hmask[(size_t) inv[ns] * W + w];
+					}
+					FSMB_CUDA(cudaMalloc(&dfa->d_lev_masks, ev.size() * sizeof(uint64_t)), { fsm_b200_dfa_free(dfa); return -1; });
+					FSMB_CUDA(cudaMemcpy(dfa->d_lev_masks, ev.data(), ev.size() * sizeof(uint64_t), cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
+				}
 				if (dfa->has_absorbing) {
 					std::vector<uint8_t> lab(T, 0);
 					for (uint32_t ns = 0; ns < T; ns++) {
@@ -523,7 +551,7 @@ fsm_b200_dfa_compile(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa 
 	return compile_impl(desc, device, out);
 }
 
-namespace fsmb200 { void scratch_free(fsm_b200_dfa *dfa); void stream_scratch_free(fsm_b200_dfa *dfa); }
+namespace fsmb200 { void scratch_free(fsm_b200_dfa *dfa); void stream_scratch_free(fsm_b200_dfa *dfa); void eager_scratch_free(fsm_b200_dfa *dfa); }
 
 /* The layout a compile WOULD choose, without touching any device: host logic only. */
 extern "C" int
@@ -547,16 +575,19 @@ fsm_b200_dfa_free(fsm_b200_dfa *dfa)
 	if (dfa == nullptr) return;
 	fsmb200::scratch_free(dfa);
 	fsmb200::stream_scratch_free(dfa);
+	fsmb200::eager_scratch_free(dfa);
 	if (dfa->d_blob != nullptr) {
 		cudaSetDevice(dfa->device);
 		cudaFree(dfa->d_blob);
 	}
 	if (dfa->d_kblob != nullptr) cudaFree(dfa->d_kblob);
+	if (dfa->d_rblob != nullptr) cudaFree(dfa->d_rblob);
 	if (dfa->d_absorb != nullptr) cudaFree(dfa->d_absorb);
 	if (dfa->d_eager_masks != nullptr) cudaFree(dfa->d_eager_masks);
 	if (dfa->d_lblob != nullptr) cudaFree(dfa->d_lblob);
 	if (dfa->d_lperm_inv != nullptr) cudaFree(dfa->d_lperm_inv);
 	if (dfa->d_labsorb != nullptr) cudaFree(dfa->d_labsorb);
+	if (dfa->d_lev_masks != nullptr) cudaFree(dfa->d_lev_masks);
 	free(dfa->h_eager_ids);
 	free(dfa->h_table32);
 	free(dfa->h_is_end);

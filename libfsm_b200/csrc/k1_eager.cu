@@ -15,6 +15,8 @@
  * mask[state] can only be fetched once the state is known.
  */
 #include <cstring>
+#include <mutex>
+#include <new>
 
 #include "common.h"
 #include "k1_exec_batch.h"
@@ -22,6 +24,33 @@
 using namespace fsmb200;
 
 namespace {
+
+/* per-DFA scratch of the _host entry point */
+struct EagerScratch {
+	std::mutex mu;
+	cudaStream_t stream = nullptr;
+	void *d_in = nullptr, *d_off = nullptr, *d_out = nullptr, *d_masks = nullptr;
+	size_t in_cap = 0, off_cap = 0, out_cap = 0, masks_cap = 0;
+	bool grow(void **p, size_t *cap, size_t want) {
+		if (*cap >= want) return true;
+		if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+		const size_t ncap = want + want / 4 + 4096;
+		if (cudaMalloc(p, ncap) != cudaSuccess) { cudaGetLastError(); *p = nullptr; return false; }
+		*cap = ncap;
+		return true;
+	}
+};
+
+std::mutex g_eager_scratch_mu;
+
+EagerScratch *
+eager_scratch_get(const fsm_b200_dfa *cdfa)
+{
+	fsm_b200_dfa *dfa = const_cast<fsm_b200_dfa *>(cdfa);
+	std::lock_guard<std::mutex> g(g_eager_scratch_mu);
+	if (dfa->eager_scratch == nullptr) dfa->eager_scratch = new (std::nothrow) EagerScratch();
+	return static_cast<EagerScratch *>(dfa->eager_scratch);
+}
 
 struct EagerArgs {
 	const uint8_t *blob;          /* table rows | is_end | class LUT */
@@ -159,35 +188,46 @@ fsm_b200_exec_batch_eager_host(const fsm_b200_dfa *dfa,
 	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
 	const uint64_t lo = offsets[0], nbytes = offsets[n] - lo;
 	const size_t W = dfa->eager_words;
-	uint8_t *d_in = nullptr; uint64_t *d_off = nullptr, *d_masks = nullptr; fsm_b200_result *d_out = nullptr;
-	cudaStream_t st = nullptr;
-	int rc = -1;
-	errno = 0;
-	/* one shot: the automata that carry eager outputs are matched against short inputs (one
-	 * fsm_exec call of a relinked caller); the double-buffered pipeline of api.cu is not needed */
-	do {
-		if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { st = nullptr; break; }
-		if (cudaMalloc(&d_in, nbytes + 16) != cudaSuccess || cudaMalloc(&d_off, (n + 1) * sizeof(uint64_t)) != cudaSuccess ||
-		    cudaMalloc(&d_out, n * sizeof(fsm_b200_result)) != cudaSuccess || cudaMalloc(&d_masks, n * W * sizeof(uint64_t)) != cudaSuccess) {
-			errno = ENOMEM;
-			break;
-		}
-		if (nbytes > 0 && cudaMemcpyAsync(d_in, base + lo, nbytes, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
-		if (cudaMemcpyAsync(d_off, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st) != cudaSuccess) break;
-		if (launch_eager(dfa, d_in - lo, d_off, 0, 0, n, d_out, d_masks, st) != 0) { rc = -2; break; }
-		if (cudaMemcpyAsync(out, d_out, n * sizeof(fsm_b200_result), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
-		if (cudaMemcpyAsync(masks, d_masks, n * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
-		if (cudaStreamSynchronize(st) != cudaSuccess) break;
-		rc = 0;
-	} while (0);
-	if (rc == -1) {
-		const cudaError_t e = cudaGetLastError();
-		if (errno != ENOMEM) errno = EIO;
-		set_error("exec_batch_eager_host: %s", e != cudaSuccess ? cudaGetErrorString(e) : "CUDA call failed");
-	} else if (rc == -2) {
-		rc = -1;                          /* launch_eager already set the error */
+	/* grow-only buffers and one stream per DFA, under a mutex (the shim's fsm_exec comes here for every
+	 * input of an automaton with eager outputs: no cudaMalloc / cudaFree / stream creation per call) */
+	EagerScratch *sc = eager_scratch_get(dfa);
+	if (sc == nullptr) { errno = ENOMEM; return -1; }
+	std::lock_guard<std::mutex> guard(sc->mu);
+	if (sc->stream == nullptr) {
+		FSMB_CUDA(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking), return -1);
 	}
-	if (st != nullptr) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
-	cudaFree(d_in); cudaFree(d_off); cudaFree(d_out); cudaFree(d_masks);
-	return rc;
+	if (!sc->grow(&sc->d_in, &sc->in_cap, nbytes + 64) || !sc->grow(&sc->d_off, &sc->off_cap, (n + 1) * sizeof(uint64_t)) ||
+	    !sc->grow(&sc->d_out, &sc->out_cap, n * sizeof(fsm_b200_result)) || !sc->grow(&sc->d_masks, &sc->masks_cap, n * W * sizeof(uint64_t))) {
+		set_error("exec_batch_eager_host: out of device memory");
+		errno = ENOMEM;
+		return -1;
+	}
+	cudaStream_t st = sc->stream;
+	/* keep the alignment of the caller's bytes modulo 32 (sector loads) */
+	uint8_t *d_in = static_cast<uint8_t *>(sc->d_in) + (lo & 31u);
+	if (nbytes > 0) FSMB_CUDA(cudaMemcpyAsync(d_in, base + lo, nbytes, cudaMemcpyHostToDevice, st), return -1);
+	FSMB_CUDA(cudaMemcpyAsync(sc->d_off, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st), return -1);
+	if (launch_eager(dfa, d_in - lo, static_cast<const uint64_t *>(sc->d_off), 0, 0, n, static_cast<fsm_b200_result *>(sc->d_out),
+	    static_cast<uint64_t *>(sc->d_masks), st) != 0) {
+		cudaStreamSynchronize(st);
+		return -1;
+	}
+	FSMB_CUDA(cudaMemcpyAsync(out, sc->d_out, n * sizeof(fsm_b200_result), cudaMemcpyDeviceToHost, st), return -1);
+	FSMB_CUDA(cudaMemcpyAsync(masks, sc->d_masks, n * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, st), return -1);
+	FSMB_CUDA(cudaStreamSynchronize(st), return -1);
+	return 0;
+}
+
+namespace fsmb200 {
+void
+eager_scratch_free(fsm_b200_dfa *dfa)
+{
+	EagerScratch *sc = static_cast<EagerScratch *>(dfa->eager_scratch);
+	if (sc == nullptr) return;
+	cudaSetDevice(dfa->device);
+	if (sc->stream) { cudaStreamSynchronize(sc->stream); cudaStreamDestroy(sc->stream); }
+	cudaFree(sc->d_in); cudaFree(sc->d_off); cudaFree(sc->d_out); cudaFree(sc->d_masks);
+	delete sc;
+	dfa->eager_scratch = nullptr;
+}
 }

@@ -418,18 +418,8 @@ k1_ragged_kernel(const K1Args a)
  *   st  = stepK[st * pitch + idx]                  one dependent read per K bytes
  * Heads, tails and the re-walk of a sector that died use the single-byte class table.
  * 8-bit entries, everything in shared memory (a few KB to a few tens of KB).
- *
- * RNG != 0 (K = 4): the tuple index of a 4-byte word is computed in registers, no LUT reads.
- * The byte class is a function of the 2-bit cell code [b in R0] + 2 [b in R1] of two byte
- * ranges (dfa_compile.cu: find_cell_ranges).  Per word, all four bytes at once:
- *   l     = w & 0x7F7F7F7F                              7-bit values: the adds cannot carry across bytes
- *   in_k  = (l + add_lo_k) & ~(l + add_hi_k) & half_k   bit 7 of every byte: lo_k <= b <= hi_k
- *   idx   = (dp4a(in_0, {1,4,16,64}) + dp4a(in_1, {2,8,32,128})) >> 7
- * half_k keeps the bytes of the half of the byte space R_k lives in (bit 7 clear, or set); with
- * RNG == 1 both ranges lie below 0x80 and share it.  One shared-memory wavefront per 4 bytes
- * instead of five.
  */
-template <int K, bool HAS_DEAD, int RNG>
+template <int K, bool HAS_DEAD>
 __global__ void __launch_bounds__(1024, 1)
 k1_kstride_kernel(const K1Args a)
 {
@@ -483,16 +473,6 @@ k1_kstride_kernel(const K1Args a)
 #pragma unroll
 				for (int k = 0; k < 8; k++) {
 					const uint32_t w = cur[k];
-					if (RNG != 0) {
-						const uint32_t l = w & 0x7F7F7F7Fu;
-						const uint32_t half0 = (w ^ a.kr_hxor[0]) & 0x80808080u;
-						const uint32_t half1 = RNG == 1 ? half0 : ((w ^ a.kr_hxor[1]) & 0x80808080u);
-						const uint32_t in0 = (l + a.kr_add_lo[0]) & ~(l + a.kr_add_hi[0]) & half0;
-						const uint32_t in1 = (l + a.kr_add_lo[1]) & ~(l + a.kr_add_hi[1]) & half1;
-						const uint32_t idx = __dp4a(in1, 0x80200802u, __dp4a(in0, 0x40100401u, 0u));
-						st = tk[st * kp + (idx >> 7)];
-						continue;
-					}
 					const uint32_t c0 = L0[__byte_perm(w, 0u, 0x4440u)], c1 = L1[__byte_perm(w, 0u, 0x4441u)];
 					if (K == 4) {
 						const uint32_t c2 = L2[__byte_perm(w, 0u, 0x4442u)], c3 = L3[__byte_perm(w, 0u, 0x4443u)];
@@ -517,6 +497,136 @@ k1_kstride_kernel(const K1Args a)
 #pragma unroll
 				for (int k = 0; k < 8; k++) cur[k] = nxt[k];
 			}
+		}
+		if (!died) {
+			for (; pos < len; pos++) {
+				const uint32_t nx = STEP1(st, (uint32_t) __ldg(p + pos));
+				if (HAS_DEAD && nx == a.dead) { died = true; break; }
+				st = nx;
+			}
+		}
+		const int32_t ret = (!died && is_end[st]) ? 1 : 0;
+		store_result(a, i, ret, st, pos);
+	}
+	signal_done(a);
+#undef STEP1
+}
+
+
+/* ------------------------------------------------------------------ K-RANGE variant ---- */
+
+/*
+ * K-STRIDE with ALU byte classification (K = 4): the tuple index of a 4-byte word is computed in
+ * registers, no LUT reads.  The byte class is a function of the 2-bit cell code
+ * [b in R0] + 2 [b in R1] of two byte ranges (dfa_compile.cu: find_cell_ranges).  Per word, all four
+ * bytes at once:
+ *   l     = w & 0x7F7F7F7F                              7-bit values: the adds cannot carry across bytes
+ *   in_k  = (l + add_lo_k) & ~(l + add_hi_k) & half_k   bit 7 of every byte: lo_k <= b <= hi_k
+ *   i128  = dp4a(in_0, {1,4,16,64}) + dp4a(in_1, {2,8,32,128})        = 128 * tuple index
+ *   st    = stepK_T[2 * i128 + st]                      table stored [tuple][state], 256 states per tuple
+ * half_k keeps the bytes of the half of the byte space R_k lives in (bit 7 clear, or set); with
+ * RNG == 1 both ranges lie below 0x80 and share it.  11 integer instructions + ONE shared-memory
+ * wavefront per 4 bytes (the LUT form: 12 instructions, 5 wavefronts).
+ * Two sector buffers used alternately (no register copies); the cache lines 2 ahead of the one being
+ * walked are requested into L2 (prefetch.global.L2: 128-byte DRAM bursts instead of 32-byte ones, and
+ * the 256-bit loads then hit L2).
+ * blob: [256 B cell LUT][stepK_T 256 x 256][step1 rows][is_end]
+ */
+template <bool HAS_DEAD, int RNG>
+__global__ void __launch_bounds__(1024, 1)
+k1_krange_kernel(const K1Args a)
+{
+	extern __shared__ __align__(1024) uint8_t smem[];
+	__shared__ uint64_t blob_bar;
+	stage_blob(smem, a.kblob, a.kblob_bytes, &blob_bar);
+
+	const uint8_t *L0 = smem;
+	const uint8_t *t1 = smem + a.k1_off;
+	const uint8_t *is_end = smem + a.kend_off;
+	const uint32_t p1 = a.k1pitch;
+	const uint32_t pfd = a.kr_prefetch;
+	const uint32_t kt_half = (smem_u32(smem) + 256u) >> 1;       /* dynamic shared memory is 1024-aligned */
+#define STEP1(st, b) ((uint32_t) t1[(st) * p1 + L0[(b)]])
+
+	const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
+	const uint64_t n_inputs = a.n_dev != nullptr ? (uint64_t) *a.n_dev : a.n;
+	for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_inputs; i += nthreads) {
+		uint64_t beg, len;
+		if (a.offsets != nullptr) {
+			beg = a.offsets[i];
+			len = (a.ends != nullptr ? a.ends[i] : a.offsets[i + 1]) - beg;
+		} else {
+			beg = i * a.stride;
+			len = a.len;
+		}
+		const uint8_t *p = a.base + beg;
+		uint32_t st = a.entry != nullptr ? a.entry[i] : a.start;
+		uint64_t pos = 0;
+		bool died = false;
+
+		uint64_t head = (uint64_t) ((32u - (uint32_t) (reinterpret_cast<uintptr_t>(p) & 31u)) & 31u);
+		if (head > len) head = len;
+		for (; pos < head; pos++) {
+			const uint32_t nx = STEP1(st, (uint32_t) __ldg(p + pos));
+			if (HAS_DEAD && nx == a.dead) { died = true; break; }
+			st = nx;
+		}
+		if (!died) {
+			const uint64_t body_end = pos + ((len - pos) & ~31ull);      /* whole sectors: [pos, body_end) */
+			uint32_t A[8], B[8];
+			bool stop = false;
+			/* walks one sector; stop = died, or absorbed */
+#define KR_WALK(cur)                                                                                     \
+			do {                                                                                         \
+				const uint32_t entry = st;                                                               \
+				_Pragma("unroll")                                                                        \
+				for (int k = 0; k < 8; k++) {                                                            \
+					const uint32_t w = (cur)[k];                                                         \
+					const uint32_t l = w & 0x7F7F7F7Fu;                                                  \
+					const uint32_t half0 = (w ^ a.kr_hxor[0]) & 0x80808080u;                             \
+					const uint32_t half1 = RNG == 1 ? half0 : ((w ^ a.kr_hxor[1]) & 0x80808080u);        \
+					const uint32_t in0 = (l + a.kr_add_lo[0]) & ~(l + a.kr_add_hi[0]) & half0;           \
+					const uint32_t in1 = (l + a.kr_add_lo[1]) & ~(l + a.kr_add_hi[1]) & half1;           \
+					/* 128 * tuple + half the shared-memory address of stepK_T: the lookup address */    \
+					/* is st + 2 * acc, one IADD3, no separate base */                                   \
+					const uint32_t acc = __dp4a(in1, 0x80200802u, __dp4a(in0, 0x40100401u, kt_half));    \
+					asm("ld.shared.u8 %0, [%1];" : "=r"(st) : "r"(st + acc + acc));                      \
+				}                                                                                        \
+				if (HAS_DEAD && st == a.dead) {                                                          \
+					/* a byte of this sector had no edge: re-walk it to find which */                    \
+					st = entry;                                                                          \
+					for (int k = 0; k < 32; k++) {                                                       \
+						const uint32_t nx = STEP1(st, (uint32_t) __ldg(p + pos + k));                    \
+						if (nx == a.dead) { died = true; pos += (uint64_t) k; break; }                   \
+						st = nx;                                                                         \
+					}                                                                                    \
+					stop = true;                                                                         \
+				} else {                                                                                 \
+					pos += 32;                                                                           \
+					if (a.absorb != nullptr && __ldg(a.absorb + st)) { pos = len; stop = true; }         \
+				}                                                                                        \
+			} while (0)
+			/* first sector of a 128-byte line: ask L2 for the line `pfd` bytes ahead */
+#define KR_FETCH(at, buf)                                                                                \
+			do {                                                                                         \
+				if ((at) < body_end) {                                                                   \
+					ld256(p + (at), buf);                                                                \
+					if (pfd != 0 && (reinterpret_cast<uintptr_t>(p + (at)) & 96u) == 0 && (at) + pfd < len) { \
+						asm volatile("prefetch.global.L2 [%0];" :: "l"(p + (at) + pfd));                 \
+					}                                                                                    \
+				}                                                                                        \
+			} while (0)
+			KR_FETCH(pos, A);
+			while (pos < body_end) {
+				KR_FETCH(pos + 32, B);
+				KR_WALK(A);
+				if (stop || pos >= body_end) break;
+				KR_FETCH(pos + 32, A);
+				KR_WALK(B);
+				if (stop) break;
+			}
+#undef KR_WALK
+#undef KR_FETCH
 		}
 		if (!died) {
 			for (; pos < len; pos++) {
@@ -721,7 +831,10 @@ template <int K, bool HAS_DEAD, int RNG>
 int
 launch_kstride(const K1Args &a, int sms, cudaStream_t stream)
 {
-	auto kern = k1_kstride_kernel<K, HAS_DEAD, RNG>;
+	void (*kern)(const K1Args);
+	if (RNG == 1) kern = k1_krange_kernel<HAS_DEAD, 1>;
+	else if (RNG == 2) kern = k1_krange_kernel<HAS_DEAD, 2>;
+	else kern = k1_kstride_kernel<K, HAS_DEAD>;
 	const size_t smem_bytes = (a.kblob_bytes + 127u) & ~127u;
 	if (!set_smem(kern, smem_bytes)) {
 		set_error("k1_kstride: cannot opt in to %zu bytes of shared memory", smem_bytes);
@@ -814,17 +927,25 @@ k1_signal_only_kernel(const K1SignalArgs a)
 }
 
 int
-dispatch_kstride(const fsm_b200_dfa *dfa, const K1Args &a, int sms, cudaStream_t stream)
+dispatch_kstride(const fsm_b200_dfa *dfa, const K1Args &a0, int sms, cudaStream_t stream)
 {
 	const bool dead = !dfa->complete;
-	uint32_t rng = dfa->kstride == 4 ? dfa->krange : 0u;
+	uint32_t rng = (dfa->kstride == 4 && dfa->d_rblob != nullptr) ? dfa->krange : 0u;
 	if (getenv("FSM_B200_KSTRIDE_LUT") != nullptr) rng = 0;        /* tuning knob: class LUTs even when ranges exist */
-	if (dfa->kstride == 4) {
+	if (rng != 0) {
+		K1Args a = a0;
+		a.kblob = static_cast<const uint8_t *>(dfa->d_rblob);
+		a.kblob_bytes = dfa->rblob_bytes; a.k1_off = dfa->r_k1_off; a.kend_off = dfa->r_kend_off;
+		a.kr_prefetch = 256;
+		if (const char *e = getenv("FSM_B200_KRANGE_PREFETCH")) {      /* tuning knob: L2 prefetch distance, 0 = off */
+			const int v = atoi(e);
+			if (v >= 0 && v <= 65536 && (v % 128) == 0) a.kr_prefetch = (uint32_t) v;
+		}
 		if (rng == 1) return dead ? launch_kstride<4, true, 1>(a, sms, stream) : launch_kstride<4, false, 1>(a, sms, stream);
-		if (rng == 2) return dead ? launch_kstride<4, true, 2>(a, sms, stream) : launch_kstride<4, false, 2>(a, sms, stream);
-		return dead ? launch_kstride<4, true, 0>(a, sms, stream) : launch_kstride<4, false, 0>(a, sms, stream);
+		return dead ? launch_kstride<4, true, 2>(a, sms, stream) : launch_kstride<4, false, 2>(a, sms, stream);
 	}
-	return dead ? launch_kstride<2, true, 0>(a, sms, stream) : launch_kstride<2, false, 0>(a, sms, stream);
+	if (dfa->kstride == 4) return dead ? launch_kstride<4, true, 0>(a0, sms, stream) : launch_kstride<4, false, 0>(a0, sms, stream);
+	return dead ? launch_kstride<2, true, 0>(a0, sms, stream) : launch_kstride<2, false, 0>(a0, sms, stream);
 }
 
 } // namespace

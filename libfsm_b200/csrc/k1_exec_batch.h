@@ -44,7 +44,8 @@ struct K1Args {
 	/* k-stride kernels */
 	const uint8_t *kblob;
 	uint32_t kblob_bytes, kpitch, k1pitch, k1_off, kend_off, klut_off;
-	uint32_t kr_add_lo[2], kr_add_hi[2], kr_hxor[2];   /* RNG kernels: the two cell ranges (dfa_compile.cu) */
+	uint32_t kr_add_lo[2], kr_add_hi[2], kr_hxor[2];   /* k-range kernel: the two cell ranges (dfa_compile.cu) */
+	uint32_t kr_prefetch;       /* k-range kernel: L2 prefetch distance in bytes (0: none) */
 	const uint8_t *absorb;      /* [ntable] 1 = all 256 edges loop back (ragged kernel: stop reading the line) */
 	uint32_t prefer_lane;       /* K1b jobs: long inputs, keep the 3-instructions-per-byte LANE kernel */
 	uint32_t tile_stage_off;    /* TILE variants: shared-memory carve-up */

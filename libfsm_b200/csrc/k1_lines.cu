@@ -15,10 +15,18 @@
  *     itself.  Bytes of a sector that lie outside the line are not skipped: their LUT index gets
  *     256 added (PRMT pulls the high byte from a per-word validity word), which maps to NOP -- no
  *     select on the dependent state chain, no byte-wise head / tail path;
- *   - dfa_compile.cu numbers the states with eager outputs last, just before the dead row, so
- *     "this sector entered a state that has something to report (ids, or the input died)" is one
- *     max() per byte; only then is the sector re-walked byte by byte (out of line) to collect the
- *     ids from global memory and to find the exact offset of a missing edge.
+ *   - dfa_compile.cu numbers the states with eager outputs last, just before the dead row.  Per
+ *     byte the kernel keeps max(st) and the sum of max(st, first_event - 1): after the sector,
+ *       no eager outputs (EV_DEAD): the dead row absorbs, so the sum counts the steps spent dead and
+ *         gives the offset of the missing edge; the state it was taken from is 0..3 exact steps away
+ *         from a per-word snapshot of the walk;
+ *       eager outputs (EV_EAGER): sum == max - (first_event - 1) <=> exactly one state with ids was
+ *         entered, once (86 % of the sectors of BASELINE config 3 enter none, 13.8 % one, 0.5 % more):
+ *         its ids are OR-ed in from a small global array; anything else re-walks the sector byte by
+ *         byte, out of line;
+ *   - every lane asks L2 for the cache line LINES_PREFETCH bytes ahead of the sector it reads
+ *     (prefetch.global.L2): the lanes of a warp sweep a contiguous region of the batch, so together
+ *     they prefetch the region the warp reads next, and the 256-bit loads of the walk hit L2.
  *
  * Algorithmic bytes per line: its bytes, read once, + 16 B record (+ 8 W B id bitset).  Bound:
  * the shared-memory lookup rate (two dependent-free + one dependent LDS per byte), see DESIGN.md.
@@ -39,6 +47,8 @@ struct LinesArgs {
 	const uint32_t *perm_inv;     /* new state number -> caller's */
 	const uint8_t *absorb;        /* by new number, or nullptr */
 	const uint64_t *masks;        /* [ntable][W] by the caller's numbering (global memory) */
+	const uint64_t *ev_masks;     /* [ntable - first_event][W] by new number - first_event */
+	uint32_t prefetch;            /* L2 prefetch distance in bytes, 0 = off */
 	uint64_t start_mask[4];
 	const uint8_t *base;
 	const uint64_t *offsets;      /* n + 1 entries, or nullptr: fixed stride */
@@ -95,7 +105,9 @@ lines_rewalk(uint32_t pitch, uint32_t entry, uint32_t mask,
 
 constexpr int LINES_THREADS = 768;
 
-template <typename E, int W, bool EVENTS>
+enum { EV_NONE = 0, EV_DEAD = 1, EV_EAGER = 2 };
+
+template <typename E, int W, int EV>
 __global__ void __launch_bounds__(LINES_THREADS, 1)
 k1_lines_kernel(const LinesArgs a)
 {
@@ -168,11 +180,17 @@ k1_lines_kernel(const LinesArgs a)
 		const bool more = saddr + 32 < end;              /* the line continues in the next sector */
 		if (more) load_sector(saddr + 32, B);
 
+		if (a.prefetch != 0 && (saddr & 96u) == 0 && saddr + a.prefetch + 128 <= hi_ptr) {
+			asm volatile("prefetch.global.L2 [%0];" :: "l"(saddr + a.prefetch));
+		}
+
 		/* walk all 32 bytes; bytes outside [lo, hi) take the NOP column */
 		const uint32_t mask = (hi > lo) ? ((0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (32u - hi))) : 0u;
 		const uint32_t inv = ~mask;
 		const uint32_t entry = st;
-		uint32_t seen = 0;
+		const uint32_t base = a.first_event - 1u;         /* EV_DEAD: first_event is the dead row */
+		uint32_t seen = 0, ssum = 0;
+		uint32_t snap[8];
 #pragma unroll
 		for (int k = 0; k < 8; k++) {
 			/* byte t of vw = 1 when byte 4k + t is outside the line */
@@ -180,18 +198,43 @@ k1_lines_kernel(const LinesArgs a)
 			/* index = byte | outside << 8 */
 #define LINES_STEP(T)                                                                             \
 			st = (uint32_t) *reinterpret_cast<const E *>(tab + st * pitch + lut[byte_and_flag<T>(A[k], vw)]); \
-			if (EVENTS) seen = max(seen, st);
+			if (EV == EV_EAGER) seen = max(seen, st);                                             \
+			if (EV != EV_NONE) ssum += max(st, base);
 			LINES_STEP(0) LINES_STEP(1) LINES_STEP(2) LINES_STEP(3)
 #undef LINES_STEP
+			if (EV == EV_DEAD) snap[k] = st;
 		}
 		bool died = false;
 		uint32_t consumed_here = hi - lo;
-		if (EVENTS && seen >= a.first_event) {
-			const Rewalk<W> r = lines_rewalk<E, W>(pitch, entry, mask, a.first_event, a.dead, a.perm_inv, a.masks, A);
-			st = r.st;
+		if (EV == EV_DEAD && st == a.dead) {
+			/* the dead row absorbs (NOP steps included): ssum - 32 base = steps spent dead */
+			const uint32_t j = 32u - (ssum - 32u * base);          /* sector byte that had no edge */
+			const uint32_t kq = j >> 2;
+			uint32_t from = entry, word = A[0];
 #pragma unroll
-			for (int k = 0; k < W; k++) acc[k] |= r.m[k];
-			if (r.died) { died = true; consumed_here = r.at - lo; }
+			for (int k = 1; k < 8; k++) { if (kq == (uint32_t) k) { from = snap[k - 1]; word = A[k]; } }
+#pragma unroll
+			for (int t = 0; t < 3; t++) {
+				if ((uint32_t) t < (j & 3u) && ((mask >> (4u * kq + (uint32_t) t)) & 1u)) {
+					from = (uint32_t) *reinterpret_cast<const E *>(tab + from * pitch + lut[(word >> (8 * t)) & 0xFFu]);
+				}
+			}
+			st = from;
+			died = true;
+			consumed_here = j - lo;
+		}
+		if (EV == EV_EAGER && seen >= a.first_event) {
+			if (ssum - 32u * base == seen - base && seen != a.dead) {
+				/* exactly one state with ids entered, once */
+#pragma unroll
+				for (int k = 0; k < W; k++) acc[k] |= __ldg(a.ev_masks + (size_t) (seen - a.first_event) * W + k);
+			} else {
+				const Rewalk<W> r = lines_rewalk<E, W>(pitch, entry, mask, a.first_event, a.dead, a.perm_inv, a.masks, A);
+				st = r.st;
+#pragma unroll
+				for (int k = 0; k < W; k++) acc[k] |= r.m[k];
+				if (r.died) { died = true; consumed_here = r.at - lo; }
+			}
 		}
 		/* A state whose 256 edges all loop back to itself keeps the walk where it is whatever
 		 * follows: the rest of the line cannot change the record (nor fire a new id), so it is
@@ -237,11 +280,11 @@ k1_lines_kernel(const LinesArgs a)
 	}
 }
 
-template <typename E, int W, bool EVENTS>
+template <typename E, int W, int EV>
 int
 launch_lines(const LinesArgs &a, int device, cudaStream_t stream)
 {
-	auto kern = k1_lines_kernel<E, W, EVENTS>;
+	auto kern = k1_lines_kernel<E, W, EV>;
 	const size_t smem_bytes = (a.blob_bytes + 127u) & ~(size_t) 127u;
 	if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes) != cudaSuccess) {
 		cudaGetLastError();
@@ -270,14 +313,14 @@ launch_lines(const LinesArgs &a, int device, cudaStream_t stream)
 
 template <typename E>
 int
-dispatch_lines(const LinesArgs &a, uint32_t words, bool events, int device, cudaStream_t stream)
+dispatch_lines(const LinesArgs &a, uint32_t words, bool dead, int device, cudaStream_t stream)
 {
 	switch (words) {
-	case 0: return events ? launch_lines<E, 0, true>(a, device, stream) : launch_lines<E, 0, false>(a, device, stream);
-	case 1: return launch_lines<E, 1, true>(a, device, stream);
-	case 2: return launch_lines<E, 2, true>(a, device, stream);
-	case 3: return launch_lines<E, 3, true>(a, device, stream);
-	case 4: return launch_lines<E, 4, true>(a, device, stream);
+	case 0: return dead ? launch_lines<E, 0, EV_DEAD>(a, device, stream) : launch_lines<E, 0, EV_NONE>(a, device, stream);
+	case 1: return launch_lines<E, 1, EV_EAGER>(a, device, stream);
+	case 2: return launch_lines<E, 2, EV_EAGER>(a, device, stream);
+	case 3: return launch_lines<E, 3, EV_EAGER>(a, device, stream);
+	case 4: return launch_lines<E, 4, EV_EAGER>(a, device, stream);
 	default:
 		set_error("k1_lines: %u mask words not supported", words);
 		errno = ENOTSUP;
@@ -318,9 +361,14 @@ k1_lines_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *
 	/* without a mask buffer only a missing edge is an event: the dead row is the last one */
 	a.first_event = words != 0 ? dfa->l_first_event : dfa->l_dead;
 	for (uint32_t w = 0; w < words && w < 4; w++) a.start_mask[w] = dfa->l_start_mask[w];
-	const bool events = words != 0 || !dfa->complete;
-	if (dfa->l_entry_bytes == 1) return dispatch_lines<uint8_t>(a, words, events, dfa->device, stream);
-	return dispatch_lines<uint16_t>(a, words, events, dfa->device, stream);
+	a.ev_masks = dfa->d_lev_masks;
+	a.prefetch = 8192;
+	if (const char *e = getenv("FSM_B200_LINES_PREFETCH")) {        /* tuning knob: L2 prefetch distance, 0 = off */
+		const int v = atoi(e);
+		if (v >= 0 && v <= (1 << 20) && (v % 128) == 0) a.prefetch = (uint32_t) v;
+	}
+	if (dfa->l_entry_bytes == 1) return dispatch_lines<uint8_t>(a, words, !dfa->complete, dfa->device, stream);
+	return dispatch_lines<uint16_t>(a, words, !dfa->complete, dfa->device, stream);
 }
 
 } // namespace fsmb200

@@ -25,6 +25,10 @@ constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 constexpr uint64_t EMPTY64 = 0xFFFFFFFFFFFFFFFFull;
 
 #define CK(expr) FSMB_CUDA(expr, return -1)
+/* Synchronise AND pick up a failed launch: a launch that could not start (bad configuration, too
+ * much shared memory) leaves a non-sticky error that only cudaGetLastError reports.  The entry points
+ * clear the thread's error state first, so whatever is found here belongs to this call. */
+#define CK_SYNC(st) do { CK(cudaStreamSynchronize(st)); CK(cudaGetLastError()); } while (0)
 
 /* ------------------------------------------------------------------ device buffers ---- */
 

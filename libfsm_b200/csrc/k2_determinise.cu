@@ -535,6 +535,7 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 		}
 	}
 	cudaStream_t st;
+	(void) cudaGetLastError();          /* CK_SYNC reports launch failures of THIS call only */
 	CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
 	/* declared before every DBuf so that it is destroyed after their cudaFreeAsync calls */
 	struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } sguard{ st };
@@ -595,7 +596,7 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 			CK(cudaMemsetAsync(d_changed.p, 0, 4, st));
 			k2_closure_round_kernel<<<R, 128, 0, st>>>(dn, d_rowstate.p, d_rowof.p, W, d_bits.p, d_changed.p); count_launch();
 			CK(cudaMemcpyAsync(&changed, d_changed.p, 4, cudaMemcpyDeviceToHost, st));
-			CK(cudaStreamSynchronize(st));
+			CK_SYNC(st);
 			if (!changed) break;
 		}
 		k2_closure_count_kernel<<<blocks_for(n), 256, 0, st>>>(n, d_rowof.p, d_colof.p, W, d_bits.p, d_cnt.p); count_launch();
@@ -603,13 +604,13 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 		if (scan.run<uint32_t>(d_cnt.p, d_cloff.p, n) != 0) return -1;
 		h_cloff.resize(n + 1);
 		CK(cudaMemcpyAsync(h_cloff.data(), d_cloff.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
+		CK_SYNC(st);
 		const uint64_t total = h_cloff[n];
 		if (d_clto.reserve(total + 1, false, st)) return -1;
 		k2_closure_fill_kernel<<<blocks_for(n), 256, 0, st>>>(n, d_rowof.p, d_colstate.p, W, d_bits.p, d_cloff.p, d_clto.p); count_launch();
 		h_clto.resize(total);
 		CK(cudaMemcpyAsync(h_clto.data(), d_clto.p, total * 4, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
+		CK_SYNC(st);
 		have_closure = true;
 	}
 	tl_stats.ms_closure = ms_since(t_cl);
@@ -626,7 +627,7 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 	if (scan.run<uint32_t>(d_cnt2.p, d_adjoff.p, NK) != 0) return -1;
 	uint64_t adj_total = 0;
 	CK(cudaMemcpyAsync(&adj_total, d_adjoff.p + NK, 8, cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st));
+	CK_SYNC(st);
 	if (d_adjto.reserve(adj_total + 1, false, st)) return -1;
 	k2_adjacency_kernel<true><<<blocks_for(n, 128), 128, 0, st>>>(dn, have_closure ? d_cloff.p : nullptr, d_clto.p, d_gcls.p, K,
 	    nullptr, d_adjoff.p, d_cursor.p, d_adjto.p, nullptr); count_launch();
@@ -668,7 +669,7 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 		if (scan.run<uint32_t>(d_ub.p, d_coff.p, ncand) != 0) return -1;
 		uint64_t scratch_total = 0;
 		CK(cudaMemcpyAsync(&scratch_total, d_coff.p + ncand, 8, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
+		CK_SYNC(st);
 		if (d_scratch.reserve(scratch_total + 1, false, st)) return -1;
 		k2_expand_fill_kernel<<<blocks_for(ncand, 128), 128, 0, st>>>(pool, fbeg, nf, K, d_adjoff.p, d_adjto.p, d_coff.p,
 		    d_scratch.p, d_len.p, d_hash.p); count_launch();
@@ -692,7 +693,7 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 		uint64_t nnew = 0, newdata = 0;
 		CK(cudaMemcpyAsync(&nnew, d_rank.p + ncand, 8, cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(&newdata, d_newoff.p + ncand, 8, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
+		CK_SYNC(st);
 		/* determinise.c:166-169: adding a state fails when the count BEFORE adding exceeds
 		 * the limit, i.e. at most limit+1 states can ever exist */
 		if (state_limit != 0 && (uint64_t) nsets + nnew > (uint64_t) state_limit + 1) return 1;
@@ -705,7 +706,7 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 		nsets += (uint32_t) nnew;
 		pool_used += newdata;
 	}
-	CK(cudaStreamSynchronize(st));
+	CK_SYNC(st);
 	tl_stats.ms_expand = ms_since(t_exp);
 	tl_stats.rounds = rounds;
 
@@ -730,7 +731,7 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 		k2_refnum_kmax_kernel<<<blocks_for(D), 256, 0, st>>>(d_pooloff.p, D, d_kmax.p); count_launch();
 		uint32_t kmax = 0;
 		CK(cudaMemcpyAsync(&kmax, d_kmax.p, 4, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
+		CK_SYNC(st);
 		const uint32_t depth = rn_depth_for(std::max(kmax, 1u));
 		const uint32_t nblk = std::min<uint32_t>(blocks_for(D, 128), 148u * 8u);
 		if (d_rnscratch.reserve((size_t) nblk * 128 * depth * K + 1, false, st)) return -1;
@@ -740,7 +741,7 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 		std::vector<uint16_t> h_orderm(D);
 		CK(cudaMemcpyAsync(h_order.data(), d_order.p, (size_t) D * K * 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(h_orderm.data(), d_orderm.p, (size_t) D * 2, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
+		CK_SYNC(st);
 		for (uint32_t s = 0; s < D; s++) {
 			if (h_orderm[s] > K) { set_error("determinise: numbering: bad entry count"); errno = EIO; return -1; }
 			for (uint32_t r = 0; r < h_orderm[s]; r++) {
@@ -755,7 +756,7 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 		}
 		CK(cudaMemcpyAsync(d_perm.p, perm.data(), (size_t) D * 4, cudaMemcpyHostToDevice, st));
 		k2_refnum_permute_kernel<<<blocks_for((uint64_t) D * K), 256, 0, st>>>(d_trans.p, D, K, d_perm.p, d_trans2.p); count_launch();
-		CK(cudaStreamSynchronize(st));   /* perm (host memory) is read by the copy above */
+		CK_SYNC(st);   /* perm (host memory) is read by the copy above */
 		trans_emit = d_trans2.p;
 		tl_stats.ms_numbering = ms_since(t_num);
 	}
@@ -773,7 +774,7 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 	if (scan.run<uint32_t>(d_ng.p, d_ogoff.p, D) != 0) return -1;
 	own->group_off.assign(D + 1, 0);
 	CK(cudaMemcpyAsync(own->group_off.data(), d_ogoff.p, (D + 1) * 8, cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st));
+	CK_SYNC(st);
 	const uint64_t NG = own->group_off[D];
 	if (d_ogto.reserve(NG + 1, false, st) || d_ogsym.reserve(4 * NG + 4, false, st)) return -1;
 	k2_emit_fill_kernel<<<blocks_for(D, 128), 128, 0, st>>>(trans_emit, D, K, d_cmask.p, d_ogoff.p, d_ogto.p, d_ogsym.p); count_launch();
@@ -789,7 +790,7 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 	CK(cudaMemcpyAsync(h_pooloff.data(), d_pooloff.p, (D + 1) * 8, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(h_pooldata.data(), d_pooldata.p, pool_used * 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(h_aend.data(), d_aend.p, n, cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st));
+	CK_SYNC(st);
 
 	own->is_end.assign(D, 0);
 	own->endid_off.assign(D + 1, 0);

@@ -256,6 +256,7 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 		if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep_all);
 	}
 	cudaStream_t st;
+	(void) cudaGetLastError();          /* CK_SYNC reports launch failures of THIS call only */
 	CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
 	struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } sguard{ st };
 	Scanner scan; scan.st = st;
@@ -298,7 +299,7 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 				count_launch();
 			}
 			CK(cudaMemcpyAsync(&changed, d_changed.p, 4, cudaMemcpyDeviceToHost, st));
-			CK(cudaStreamSynchronize(st));
+			CK_SYNC(st);
 			if (!changed) break;
 		}
 	}
@@ -308,7 +309,7 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 	uint32_t start_keep = 0;
 	CK(cudaMemcpyAsync(&m64, d_newid.p + n, 8, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(&start_keep, d_keep.p + dfa->start, 4, cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st));
+	CK_SYNC(st);
 	const uint32_t m = (uint32_t) m64;
 	if (m == 0 || !start_keep) {           /* minimise.c:98-101: nothing can match */
 		guard.o = nullptr;
@@ -337,7 +338,7 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 		k3_refine_assign_kernel<<<blocks_for(m), 256, 0, st>>>(m, d_repst.p, d_cmin.p, d_rank.p, d_newcls.p); count_launch();
 		uint64_t cnt = 0;
 		CK(cudaMemcpyAsync(&cnt, d_rank.p + m, 8, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
+		CK_SYNC(st);
 		std::swap(d_cls.p, d_newcls.p);
 		std::swap(d_cls.cap, d_newcls.cap);
 		if (cnt == ncls) break;              /* classes only split: same count == same partition */
@@ -361,7 +362,7 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 	if (scan.run<uint32_t>(d_ng.p, d_ogoff.p, D) != 0) return -1;
 	own->group_off.assign(D + 1, 0);
 	CK(cudaMemcpyAsync(own->group_off.data(), d_ogoff.p, (D + 1) * 8, cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st));
+	CK_SYNC(st);
 	const uint64_t NG = own->group_off[D];
 	if (d_ogto.reserve(NG + 1, false, st) || d_ogsym.reserve(4 * NG + 4, false, st)) return -1;
 	k2_emit_fill_kernel<<<blocks_for(D, 128), 128, 0, st>>>(d_otrans.p, D, K, d_cmask.p, d_ogoff.p, d_ogto.p, d_ogsym.p); count_launch();
@@ -376,9 +377,9 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 	}
 	CK(cudaMemcpyAsync(h_oorig.data(), d_oorig.p, D * 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(&start_new, d_newid.p + dfa->start, 8, cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st));
+	CK_SYNC(st);
 	CK(cudaMemcpyAsync(&start_cls, d_cls.p + start_new, 4, cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st));
+	CK_SYNC(st);
 
 	own->is_end.assign(D, 0);
 	own->endid_off.assign(D + 1, 0);
@@ -396,7 +397,7 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 		std::vector<uint32_t> h_cls(m), h_korig(m);
 		CK(cudaMemcpyAsync(h_cls.data(), d_cls.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(h_korig.data(), d_korig.p, (size_t) m * 4, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
+		CK_SYNC(st);
 		std::vector<std::vector<uint32_t>> acc(D);
 		for (uint32_t i = 0; i < m; i++) {
 			const uint32_t c = h_cls[i];

@@ -8,6 +8,10 @@
  * Together the threads own far more automata than the cache has slots (with more threads than
  * slots an entry can be evicted WHILE another thread is still executing on it) and each runs
  * fsm_exec over its own round-robin, checking each verdict against the one computed single-threaded beforehand.
+ * Second phase: every thread runs fsm_exec on the SAME automaton at once, each over its
+ * own 64 KiB input (so the chunked stream path with its per-DFA staging buffer is used): threads
+ * with an even number expect a match, odd ones none -- a thread that saw another thread's bytes or
+ * verdict fails.
  * Exit status 0 = all verdicts identical.
  */
 #include <errno.h>
@@ -51,6 +55,50 @@ worker(void *arg)
 	return NULL;
 }
 
+enum { SHARED_LEN = 64 * 1024 };
+static struct fsm *shared_fsm;
+struct sjob { int id, fails; char *text; };
+
+static void *
+shared_worker(void *arg)
+{
+	struct sjob *j = arg;
+	int r;
+	for (r = 0; r < ROUNDS; r++) {
+		const char *s = j->text;
+		fsm_state_t end = 0;
+		const int ret = fsm_exec(shared_fsm, fsm_sgetc, &s, &end, NULL);
+		if (ret != (j->id % 2 == 0 ? 1 : 0)) j->fails++;
+		if (s != j->text + SHARED_LEN) j->fails++;          /* the cursor ends on the NUL */
+	}
+	return NULL;
+}
+
+static int
+shared_phase(void)
+{
+	static struct sjob sj[MAXTHREADS];
+	pthread_t th[MAXTHREADS];
+	const char *pat = "[0-9]+\\.[0-9]+x";
+	int t, fails = 0;
+	shared_fsm = re_comp(RE_PCRE, fsm_sgetc, &pat, NULL, RE_FLAGS_NONE, NULL);
+	if (shared_fsm == NULL || !fsm_determinise(shared_fsm) || !fsm_minimise(shared_fsm)) return 1;
+	for (t = 0; t < NTHREADS; t++) {
+		int k;
+		sj[t].id = t; sj[t].fails = 0;
+		sj[t].text = malloc(SHARED_LEN + 1);
+		if (sj[t].text == NULL) return 1;
+		for (k = 0; k < SHARED_LEN; k++) sj[t].text[k] = (char) ('0' + (k * 7 + t) % 10);
+		if (t % 2 == 0) { sj[t].text[SHARED_LEN / 2 + 97 * t] = '.'; sj[t].text[SHARED_LEN / 2 + 97 * t + 3] = 'x'; }
+		sj[t].text[SHARED_LEN] = '\0';
+	}
+	for (t = 0; t < NTHREADS; t++) pthread_create(&th[t], NULL, shared_worker, &sj[t]);
+	for (t = 0; t < NTHREADS; t++) { pthread_join(th[t], NULL); fails += sj[t].fails; free(sj[t].text); }
+	fsm_free(shared_fsm);
+	if (fails) fprintf(stderr, "%d verdict(s) differ when %d threads share one automaton\n", fails, NTHREADS);
+	return fails != 0;
+}
+
 int
 main(int argc, char **argv)
 {
@@ -85,6 +133,7 @@ main(int argc, char **argv)
 	for (t = 0; t < NTHREADS; t++) { pthread_join(th[t], NULL); fails += jobs[t].fails; }
 	for (t = 0; t < NTHREADS; t++) for (f = 0; f < NFSM; f++) fsm_free(jobs[t].fsm[f]);
 	if (fails) { fprintf(stderr, "%d verdict(s) differ under concurrency\n", fails); return 1; }
+	if (shared_phase() != 0) return 1;
 	printf("shim threads ok (%d threads x %d automata x %d rounds)\n", NTHREADS, NFSM, ROUNDS);
 	return 0;
 }
