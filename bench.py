@@ -1,24 +1,35 @@
 #!/usr/bin/env python3
-"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+"""bench.py -- BASELINE.json's metric on BASELINE.json's configurations.
 
 metric : GB/s of input scanned with bit-exact match ids (fsm_exec semantics)
-workload (N=1): configs[1] -- one 256-state DFA (PCRE a[ -~]{7}\\z, built by the reference:
-         re_comp -> fsm_determinise -> fsm_minimise; shipped as a golden fixture), 2^20 inputs
-         x 1 KiB synthetic ASCII.  N>1: the batch is range-sharded, every rank scans its own
-         2^20 x 1 KiB shard (weak scaling).  The per-shard result records reach every rank
-         either FUSED with the scan (default: the scanning lanes store each 16 B record into
-         every peer's gathered buffer over NVLink P2P; only a 4-byte NCCL handshake per step,
-         on a side stream) or by ONE NCCL all-gather per step on a side stream (--gather nccl).
 
-A "step" is one pass of the hot path over one batch.  `value` has inputs resident in HBM;
-`e2e` goes through the host entry point of the C ABI (fsm_b200_exec_batch_host) with pinned
-host buffers, H2D/D2H copies inside the timed region.
+  --config 2 (default; the headline, N=1 workload = BASELINE configs[1])
+        one 256-state DFA (PCRE a[ -~]{7}\\z built by the reference: re_comp -> fsm_determinise ->
+        fsm_minimise; golden fixture), 2^20 inputs x 1 KiB synthetic ASCII per GPU.  N > 1: the batch is
+        range-sharded (weak scaling); result records reach every rank FUSED with the scan (lanes store
+        them into every peer's gathered buffer over NVLink P2P) or by one NCCL all-gather (--gather nccl).
+  --config 1  re(1)'s plumbing: PCRE [0-9]+\\.[0-9]+ over 1 MiB of synthetic ASCII through the relinked
+        libfsm's own fsm_exec(fsm, fsm_sgetc, ...) (libfsm_b200/shim); --size scales the text.
+  --config 3  rx(1)-style 128-pattern union (mostly unanchored: fsm_union_repeated_pattern_group + eager
+        outputs, built by the reference, golden fixture) over 10 M synthetic log lines per GPU: records +
+        fired-id bitsets; sub-record: the start-anchored end-id variant.
+  --config 4  examples/utf8dfa validator (starred; golden fixture, fsm_equal-pinned) over 2 GiB of
+        synthetic UTF-8 per GPU -- 16 GiB range-sharded at --gpus 8: per-rank K1b shard maps, ONE
+        all-gather of [T] records, composition in rank order, first-invalid offset checked.
+  --config 5  fsm_determinise of the 100 001-state synthetic NFA (K2); metric DFA edges/s, "replicas only".
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--dist uniform|adversarial]
+A "step" is one pass of the hot path over one batch.  `value`: inputs resident in HBM, CUDA events on
+the launching stream.  `e2e`: through the host entry point of the C ABI with pinned HOST buffers, H2D and
+D2H inside the timed region.  `--impl reference`: the reference's own CPU implementation (oracle/_ref,
+compiled from the reference sources) on this box's host cores, a bounded sample of the same workload per
+step; it never loads the engine library.  Both arms print the same `config`.
+
+  python bench.py [--config C] [--gpus N] [--steps K] [--warmup W] [--impl reference] [--dist uniform|adversarial]
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -31,15 +42,38 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-N_INPUTS = 1 << 20
-LENGTH = 1024
 METRIC = "GB/s input scanned (bit-exact match ids)"
+N_INPUTS, LENGTH = 1 << 20, 1024                 # config 2
+CFG3_LINES = 10_000_000
+CFG4_BYTES = 2 << 30                             # per GPU: 16 GiB at 8 GPUs
+CFG2_REF_SAMPLE, CFG3_REF_SAMPLE, CFG4_REF_SAMPLE = 32768, 16384, 32 << 20
 
 
-def load_cfg2_fsm():
-    import goldenio
-    cases = goldenio.load_exec_cases(os.path.join(goldenio.GOLDEN_DIR, "golden_exec.npz"))
-    return next(c for c in cases if c["name"] == "cfg2:uniform")["fsm"]
+# ------------------------------------------------------------------------------------------ shared
+
+def the_config(args) -> dict:
+    """What is measured -- identical in both arms (a function of the command line only)."""
+    c = args.config
+    if c == 1:
+        return {"workload": f"configs[0]: re(1) plumbing, PCRE [0-9]+\\.[0-9]+ over {args.size} B of synthetic ASCII, one fsm_exec call",
+                "config_index": 1, "l2": "input smaller than L2: a 256 MiB buffer is written between timed iterations",
+                "reference_sample": "the whole text, one thread (one fsm_exec call is serial)"}
+    if c == 2:
+        return {"workload": "configs[1]: 256-state DFA a[ -~]{7}\\z, 2^20 x 1 KiB ASCII per GPU", "config_index": 2,
+                "distribution": args.dist, "l2": "1 GiB input per step > 126 MB L2: no flush needed",
+                "reference_sample": f"{CFG2_REF_SAMPLE} x {LENGTH} B inputs of the same distribution per step (seed 42)"}
+    if c == 3:
+        return {"workload": f"configs[2]: rx-style 128-pattern PCRE union (fsm_union_repeated_pattern_group, eager outputs, det + min) "
+                            f"over {CFG3_LINES} synthetic log lines (64-256 B) per GPU", "config_index": 3,
+                "l2": "1.6 GB of lines per step > 126 MB L2: no flush needed",
+                "reference_sample": f"{CFG3_REF_SAMPLE} lines of the same generator per step (seed 7)"}
+    if c == 4:
+        return {"workload": f"configs[3]: examples/utf8dfa validator (starred) over {CFG4_BYTES} B of synthetic UTF-8 per GPU, "
+                            "one fsm_exec call over the range-sharded stream", "config_index": 4,
+                "l2": "2 GiB per step > 126 MB L2: no flush needed",
+                "reference_sample": f"{CFG4_REF_SAMPLE} B of the same text per step, one thread (one fsm_exec call is serial)"}
+    return {"workload": "configs[4]: fsm_determinise of the 100 001-state synthetic NFA (2000 chains x 50 literals + /./ loop)",
+            "config_index": 5, "l2": "not a streaming kernel", "reference_sample": "the whole NFA, one thread"}
 
 
 def measured_peaks():
@@ -83,7 +117,9 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.002)
 
-    def result(self):
+    def finish(self):
+        self.stop_flag = True
+        self.join()
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
@@ -97,135 +133,310 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_reference_leg(fsm, host_sample: np.ndarray, threads: int):
-    """Times the reference's own fsm_exec (oracle/_ref, compiled from the reference sources) on
-    the host cores; falls back to the oracle port when the compiled reference is absent.  The
-    thread count is swept (all, 1/2, 1/4 of the host threads) and the BEST result of each mode is
-    reported, so an oversubscribed or quota-limited box does not understate the CPU."""
+def load_fsm(config: int):
+    import goldenio
+    if config in (1, 2):
+        cases = goldenio.load_exec_cases(os.path.join(goldenio.GOLDEN_DIR, "golden_exec.npz"))
+        return next(c for c in cases if c["name"] == ("cfg2:uniform" if config == 2 else "cfg1:digits"))["fsm"]
+    if config == 3:
+        return goldenio.load_cfg3()
+    if config == 4:
+        return goldenio.load_cfg4()["fsm"]
+    from libfsm_b200 import workloads
+    return workloads.config5_nfa()
+
+
+def cfg1_text(size: int) -> np.ndarray:
+    """Seeded ASCII: digits with '.' at density 1/64; never a NUL."""
+    rng = np.random.default_rng(1)
+    a = rng.integers(ord("0"), ord("9") + 1, size=size, dtype=np.uint8)
+    a[rng.random(size) < 1.0 / 64] = ord(".")
+    a[rng.random(size) < 0.25] = ord("x")
+    return a
+
+
+def thread_sweep(threads: int):
+    return sorted({max(1, threads), max(1, threads // 2), max(1, threads // 4), 1}, reverse=True)
+
+
+# ------------------------------------------------------------------------------- CPU reference legs
+
+def cpu_leg_cfg2(fsm, host_sample: np.ndarray, threads: int):
+    """The reference's own fsm_exec (oracle/_ref) on the host cores, as-is (per-call fsm_isdfa) and
+    amortised (validation hoisted): best thread count of a sweep, and the 1-thread figures."""
     import reflib
     n = host_sample.shape[0]
     offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(host_sample.shape[1])
     flat = host_sample.reshape(-1)
-    nbytes = flat.size
-    sweep = sorted({max(1, threads), max(1, threads // 2), max(1, threads // 4)}, reverse=True)
-    best = {"asis": (0.0, 0, None, 0.0), "amortised": (0.0, 0, None, 0.0)}
+    L = host_sample.shape[1]
+    part = lambda frac: (flat[:(n // frac) * L], offsets[:n // frac + 1])
     if reflib.have_ref():
-        R = reflib.Ref()
-        h = R.from_flat(fsm)
-        kind = "reference"
-        run = lambda mode, t: R.exec_batch(h, flat, offsets, mode=mode, nthreads=t)
+        R = reflib.Ref(); h = R.from_flat(fsm); kind = "reference"
+        run = lambda mode, t, frac: R.exec_batch(h, *part(frac), mode=mode, nthreads=t)
     else:
-        O = reflib.Oracle()
-        h = None
-        kind = "port"
-        run = lambda mode, t: O.exec_batch(fsm, flat, offsets, nthreads=t, validate_each=(mode == 0))
-    for t in sweep:
-        for name, mode in (("asis", 0), ("amortised", 1)):
-            t0 = time.perf_counter(); rec = run(mode, t); dt = time.perf_counter() - t0
-            if nbytes / dt / 1e9 > best[name][0]:
-                best[name] = (nbytes / dt / 1e9, t, rec, dt)
+        O = reflib.Oracle(); h = None; kind = "port"
+        run = lambda mode, t, frac: O.exec_batch(fsm, *part(frac), nthreads=t, validate_each=(mode == 0))
+    out = sweep_modes(run, flat.size, threads)
     if h is not None:
         R.free(h)
-    return {"kind": kind, "asis_gbs": best["asis"][0], "asis_threads": best["asis"][1], "asis_s": best["asis"][3],
+    out["kind"] = kind
+    return out
+
+
+def sweep_modes(run, nbytes: int, threads: int):
+    """run(mode, nthreads, frac) scans 1/frac of the sample; mode 0 as-is, 1 amortised.  The full sample
+    runs at the full thread count only (as-is: the timed quantity); the thread sweep, the amortised mode
+    and the 1-thread figures use a quarter / a sixteenth of it, so that one leg stays within seconds."""
+    t0 = time.perf_counter(); run(0, threads, 1); asis_s = time.perf_counter() - t0
+    best = {"asis": (nbytes / asis_s / 1e9, threads), "amortised": (0.0, 0)}
+    one = {}
+    for t in thread_sweep(threads):
+        frac = 16 if t == 1 else 4
+        for name, mode in (("asis", 0), ("amortised", 1)):
+            if name == "asis" and t == threads:
+                continue
+            t0 = time.perf_counter(); run(mode, t, frac); dt = time.perf_counter() - t0
+            g = nbytes / frac / dt / 1e9
+            if t == 1:
+                one[name] = g
+            if g > best[name][0]:
+                best[name] = (g, t)
+    if threads == 1:
+        one.setdefault("asis", best["asis"][0])
+    return {"asis_gbs": best["asis"][0], "asis_threads": best["asis"][1], "asis_s": asis_s, "asis_full_threads_gbs": nbytes / asis_s / 1e9,
             "amortised_gbs": best["amortised"][0], "amortised_threads": best["amortised"][1],
-            "amortised_s": best["amortised"][3], "records": best["amortised"][2], "asis_records": best["asis"][2],
-            "threads_swept": sweep}
+            "asis_1t_gbs": one.get("asis"), "amortised_1t_gbs": one.get("amortised"), "threads_swept": thread_sweep(threads)}
+
+
+def cpu_baseline_record(cpu: dict, sample: str) -> dict:
+    return {"value": cpu["asis_gbs"], "unit": "GB/s", "cores": cpu["asis_threads"], "kind": cpu["kind"], "sample": sample,
+            "amortised_value": cpu["amortised_gbs"], "amortised_cores": cpu["amortised_threads"],
+            "cpu_1t": {"as_is": cpu["asis_1t_gbs"], "amortised": cpu["amortised_1t_gbs"]}, "threads_swept": cpu["threads_swept"]}
+
+
+def cpu_leg_cfg3(g, nlines: int, threads: int):
+    import reflib
+    from libfsm_b200 import workloads
+    _, inst = workloads.cfg3_patterns()
+    base, off = workloads.cfg3_lines_host(nlines, inst, seed=7)
+    fsm, ids = g["eager"]["fsm"], g["eager"]["idlist"]
+    assert reflib.have_ref(), "config 3's CPU leg needs the compiled reference (oracle/_ref)"
+    R = reflib.Ref(); h = R.from_flat(fsm)
+    def run(mode, t, frac):
+        k = nlines // frac
+        return R.exec_eager_batch(h, base[:int(off[k])], off[:k + 1], ids, mode=mode, nthreads=t)
+    out = sweep_modes(run, int(off[-1]), threads)
+    R.free(h)
+    out["kind"] = "reference"
+    return out
+
+
+def cpu_leg_stream(fsm, text: np.ndarray):
+    """One reference fsm_exec call over `text` (serial by nature), as-is; amortised = the reference's
+    own per-byte transition without the per-call validation."""
+    import reflib
+    assert reflib.have_ref()
+    R = reflib.Ref(); h = R.from_flat(fsm)
+    t0 = time.perf_counter(); rc, end, consumed = R.exec(h, text.tobytes()); dt0 = time.perf_counter() - t0
+    off = np.array([0, text.size], dtype=np.uint64)
+    t0 = time.perf_counter(); rec = R.exec_batch(h, text, off, mode=1, nthreads=1); dt1 = time.perf_counter() - t0
+    R.free(h)
+    g0, g1 = text.size / dt0 / 1e9, text.size / dt1 / 1e9
+    return {"asis_gbs": g0, "asis_threads": 1, "asis_s": dt0, "amortised_gbs": g1, "amortised_threads": 1,
+            "asis_1t_gbs": g0, "amortised_1t_gbs": g1, "threads_swept": [1], "kind": "reference",
+            "record": (int(rc), int(end), int(consumed))}
+
+
+def cpu_leg_determinise(nfa):
+    import reflib
+    assert reflib.have_ref()
+    R = reflib.Ref(); h = R.from_flat(nfa)
+    t0 = time.perf_counter(); R.determinise(h); dt = time.perf_counter() - t0
+    states = R.countstates(h)
+    R.free(h)
+    return dt, states
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU fsm_exec on this box's host cores, all threads,
-    each step a bounded sample of the same workload."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's CPU implementation on this box's host cores, a bounded sample
+    of the same workload per step.  Imports nothing of the engine."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return 0
     from libfsm_b200 import workloads
-    fsm = load_cfg2_fsm()
     threads = host_threads()
-    sample_n = int(os.environ.get("BENCH_REF_SAMPLE", 512 * threads))
-    sample_n = max(1024, min(sample_n, 1 << 16))
-    host = workloads.cfg2_host(sample_n, LENGTH, args.dist == "adversarial", seed=42)
-    for _ in range(args.warmup):
-        cpu_reference_leg(fsm, host[:max(256, sample_n // 8)], threads)
+    cfg = the_config(args)
+    fsm = load_fsm(args.config)
+    unit, metric = "GB/s", METRIC
+    if args.config == 2:
+        host = workloads.cfg2_host(CFG2_REF_SAMPLE, LENGTH, args.dist == "adversarial", seed=42)
+        leg = lambda: cpu_leg_cfg2(fsm, host, threads)
+        warm = lambda: cpu_leg_cfg2(fsm, host[:2048], threads)
+        nbytes = CFG2_REF_SAMPLE * LENGTH
+    elif args.config == 3:
+        leg = lambda: cpu_leg_cfg3(fsm, CFG3_REF_SAMPLE, threads)
+        warm = lambda: cpu_leg_cfg3(fsm, 1024, threads)
+        nbytes = None
+    elif args.config in (1, 4):
+        text = cfg1_text(args.size) if args.config == 1 else workloads.utf8_host(CFG4_REF_SAMPLE, seed=4)
+        leg = lambda: cpu_leg_stream(fsm, text)
+        warm = lambda: cpu_leg_stream(fsm, text[:1 << 16])
+        nbytes = text.size
+    else:
+        metric, unit = "DFA edges/s (fsm_determinise)", "edges/s"
+        edges = None
     t_total, last = 0.0, None
-    for _ in range(args.steps):
-        last = cpu_reference_leg(fsm, host, threads)
-        t_total += last["asis_s"]        # the best thread count of the sweep
-    nbytes = sample_n * LENGTH
-    value = nbytes * args.steps / t_total / 1e9
-    sample = f"{sample_n} x {LENGTH} B inputs of the same distribution per step (seed 42)"
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1]: 256-state DFA a[ -~]{7}\\z, 2^20 x 1 KiB ASCII per GPU",
-                   "distribution": args.dist, "reference_entry": "fsm_exec per input (as-is, per-call fsm_isdfa validation)"},
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": last["asis_threads"], "kind": last["kind"], "sample": sample,
-                         "amortised_value": last["amortised_gbs"], "amortised_cores": last["amortised_threads"],
-                         "threads_swept": last["threads_swept"]},
-        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
+    if args.config == 5:
+        import reflib
+        for _ in range(min(args.warmup, 1)):
+            cpu_leg_determinise(workloads.config5_nfa(words=200))
+        for _ in range(args.steps):
+            dt, states = cpu_leg_determinise(fsm)
+            t_total += dt
+        edges = states * 256                                  # the config-5 DFA is complete: 256 edges per state
+        value = edges * args.steps / t_total
+        cpu = {"value": value, "unit": unit, "cores": 1, "kind": "reference", "sample": cfg["reference_sample"],
+               "seconds_per_determinise": t_total / args.steps, "dfa_states": states}
+    else:
+        for _ in range(args.warmup):
+            warm()
+        for _ in range(args.steps):
+            last = leg()
+            t_total += last["asis_s"]
+        if nbytes is None:
+            nbytes = int(last["asis_gbs"] * last["asis_s"] * 1e9 + 0.5)
+        value = nbytes * args.steps / t_total / 1e9
+        cpu = cpu_baseline_record(last, cfg["reference_sample"])
+        cpu["value"], cpu["cores"] = value, (threads if args.config in (2, 3) else 1)
+        assert "libfsm_b200.so" not in open("/proc/self/maps").read(), "the reference arm must not load the engine"
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / max(args.steps, 1) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8" if args.config != 5 else "u32", "data": "synthetic", "config": cfg,
+            "reference_entry": "fsm_exec as-is (per-call fsm_isdfa validation); the amortised figure hoists it" if args.config != 5 else "fsm_determinise",
+            "cpu_baseline": cpu, "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
     print(json.dumps(line))
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--dist", default="uniform", choices=["uniform", "adversarial"])
-    ap.add_argument("--variant", default="auto")
-    ap.add_argument("--e2e-steps", type=int, default=None)
-    ap.add_argument("--gather-records", default="compact", choices=["compact", "full"],
-                    help="fused gather payload: compact = 4-byte match ids ((ret==1)<<31 | end), full = 16-byte records")
-    ap.add_argument("--handshake", default="flags", choices=["flags", "nccl", "none"],
-                    help="fused gather completion signal: flags = the kernel's last CTA stores a step number into "
-                         "every peer's memory; nccl = 4-byte NCCL all-reduce per step on a side stream")
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
-                    help="N>1: fused = scanning lanes store records into every peer's buffer over NVLink P2P; "
-                         "nccl = one NCCL all-gather per step on a side stream")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+# ----------------------------------------------------------------------------------------- GPU arm
 
-    if args.impl == "reference":
-        return run_reference_arm(args)
+class Ctx:
+    pass
 
+
+def gpu_setup(args) -> Ctx:
     import torch
     import torch.distributed as dist
-    import libfsm_b200 as L
-    from libfsm_b200 import workloads
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
+    c = Ctx()
+    c.torch, c.dist = torch, dist
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.local = int(os.environ.get("LOCAL_RANK", "0"))
+    if c.world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    assert world == args.gpus or world == 1, f"WORLD_SIZE {world} != --gpus {args.gpus}"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", c.local))
+    assert c.world == args.gpus or c.world == 1, f"WORLD_SIZE {c.world} != --gpus {args.gpus}"
+    torch.cuda.set_device(c.local)
+    c.dev = torch.device("cuda", c.local)
+    c.main = torch.cuda.current_stream()
+    c.side = torch.cuda.Stream(device=c.dev) if c.world > 1 else None
+    return c
 
-    fsm = load_cfg2_fsm()
+
+def sync_all(c: Ctx):
+    c.torch.cuda.synchronize(c.dev)
+    if c.world > 1:
+        c.dist.barrier()
+        c.torch.cuda.synchronize(c.dev)
+
+
+def timed_region(c: Ctx, step, steps: int, warmup: int):
+    """W untimed steps, then exactly K steps between CUDA events on the launching stream, a barrier +
+    synchronize on both sides; returns (ms_total, launches, clocks)."""
+    import libfsm_b200 as L
+    for i in range(warmup):
+        step(i)
+    sync_all(c)
+    sampler = ClockSampler(c.local); sampler.start()
+    L.launch_count(reset=True)
+    e0, e1 = c.torch.cuda.Event(enable_timing=True), c.torch.cuda.Event(enable_timing=True)
+    e0.record(c.main)
+    for i in range(steps):
+        step(i)
+    if c.side is not None:
+        c.main.wait_stream(c.side)
+    e1.record(c.main)
+    sync_all(c)
+    return e0.elapsed_time(e1), L.launch_count(), sampler
+
+
+def kernel_ms(c: Ctx, launch, reps: int) -> float:
+    """Mean duration of `launch` (one kernel) from CUDA events around each launch on the launching stream."""
+    ev = [(c.torch.cuda.Event(enable_timing=True), c.torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    if c.world > 1:
+        c.dist.barrier()
+    for a, b in ev:
+        a.record(c.main); launch(); b.record(c.main)
+    c.torch.cuda.synchronize(c.dev)
+    return float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+
+def reduce_max(c: Ctx, values):
+    t = c.torch.tensor(values, dtype=c.torch.float64, device=c.dev)
+    if c.world > 1:
+        c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+    return [float(x) for x in t.cpu()]
+
+
+def roofline_record(bytes_per_launch: int, kms: float, kernel: str, traffic_file: str | None = None) -> dict:
+    peaks, peak_src = measured_peaks()
+    achieved = bytes_per_launch / (kms / 1e3) / 1e9
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", traffic_file) if traffic_file else None
+    if tp and os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        traffic_src = f"{tj['source']}: dram__bytes_read.sum + dram__bytes_write.sum per launch of {tj['kernel']}"
+    return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "peak_source": peak_src, "kernel": kernel, "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_per_launch,
+            "traffic": traffic, "traffic_source": traffic_src}
+
+
+def base_line(args, c: Ctx, value, ms_per_step, unit="GB/s", metric=METRIC, dtype="u8") -> dict:
+    return {"metric": metric, "value": value, "unit": unit, "n_gpus": c.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
+            "data": "synthetic", "config": the_config(args)}
+
+
+def finish(c: Ctx):
+    if c.world > 1:
+        c.dist.barrier()
+        c.dist.destroy_process_group()
+    return 0
+
+
+# ---- config 2 ------------------------------------------------------------------------------------
+
+def run_cfg2(args):
+    import libfsm_b200 as L
+    import reflib
+    from libfsm_b200 import workloads
+    c = gpu_setup(args)
+    torch, dist, dev, world, rank, local = c.torch, c.dist, c.dev, c.world, c.rank, c.local
+    fsm = load_fsm(2)
     dfa = L.Dfa(fsm, device=local)
     L.set_exec_variant(args.variant)
     adversarial = args.dist == "adversarial"
     n = N_INPUTS
-    # range shard `rank` of the global batch: its own seeded 2^20 x 1 KiB slice
-    d_in = workloads.cfg2_device(n, LENGTH, adversarial, seed=42 + 1000 * rank, device=dev)
-    # buffers in flight: the completion handshake / all-gather of step i is only waited for when its
-    # buffer is reused at step i+nbuf, so a few steps of slack hide the collective's latency (its
-    # kernel cannot co-reside with the persistent scan kernel and runs between scan launches)
+    d_in = workloads.cfg2_device(n, LENGTH, adversarial, seed=42 + 1000 * rank, device=dev)   # range shard `rank`
+    # buffers in flight: the gather of step i is only waited for when its buffer is reused at step i + nbuf
     nbuf = int(os.environ.get("BENCH_NBUF", "4"))
     fused = world > 1 and args.gather == "fused"
     d_out = [torch.empty((n, 16), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
     gathered = [torch.empty((world * n, 16), dtype=torch.uint8, device=dev) for _ in range(nbuf)] if world > 1 else None
-    side = torch.cuda.Stream(device=dev) if world > 1 else None
-    main_stream = torch.cuda.current_stream()
     gather_done = [None] * nbuf
-    ring = None
-    compact = False
+    ring, compact = None, False
     token = torch.zeros(1, dtype=torch.int32, device=dev)
     if fused:
         from libfsm_b200.peer import GatherRing
@@ -247,19 +458,25 @@ def main():
         peer_args = [ring.peer_slot_ptrs(b) for b in range(nbuf)]
         sig_args = [ring.signal_args(b) for b in range(nbuf)]
         own_out = [torch.empty((n, 16), dtype=torch.uint8, device=dev) for _ in range(nbuf)] if compact else None
+    use_flags = fused and args.handshake == "flags"
+    consume = use_flags and not args.no_consumer
 
     def local_out_ptr(b):
-        # full records of this rank's own range: inside its gathered buffer (full) or beside it (compact)
-        return own_out[b].data_ptr() if (fused and args.gather_records == "compact") else ring.local_slot_ptr(b)
+        return own_out[b].data_ptr() if (fused and compact) else ring.local_slot_ptr(b)
 
-    def step(i):
+    step_no = [0]
+
+    def step(_i):
+        i = step_no[0]; step_no[0] += 1              # global step number: the flag value of step i is i + 1
         b = i % nbuf
         if world > 1 and gather_done[b] is not None:
-            main_stream.wait_event(gather_done[b])         # buffer free again
+            c.main.wait_event(gather_done[b])                 # buffer free again
+        if consume and i >= nbuf:
+            # CONSUMER inside the timed loop: before buffer b is overwritten, a poll kernel waits until
+            # every rank's completion flag of the step that last used it (i - nbuf) has arrived, i.e.
+            # every peer's records of that step have landed in this rank's gathered buffer
+            ring.wait_flags(b, i - nbuf + 1)
         if fused:
-            # ONE kernel: scan + P2P stores of every record into every peer's gathered buffer
-            # (+ with --handshake flags the completion flag, value = step number + 1)
-            use_flags = args.handshake == "flags"
             dfa.exec_batch_gather(d_in, stride=LENGTH, length=LENGTH, n=n, out_ptr=local_out_ptr(b),
                                   peer_ptrs=peer_args[b][0], npeers=peer_args[b][1], compact=compact,
                                   sig_counter=sig_args[b][0] if use_flags else None,
@@ -267,30 +484,23 @@ def main():
         else:
             dfa.exec_batch(d_in, stride=LENGTH, length=LENGTH, n=n, out=d_out[b])
         if world > 1 and (not fused or args.handshake == "nccl"):
-            ev = torch.cuda.Event(); ev.record(main_stream)
-            side.wait_event(ev)
-            with torch.cuda.stream(side):
+            ev = torch.cuda.Event(); ev.record(c.main)
+            c.side.wait_event(ev)
+            with torch.cuda.stream(c.side):
                 if fused:
                     dist.all_reduce(token)                  # 4-byte completion handshake, off the data path
                 else:
                     dist.all_gather_into_tensor(gathered[b], d_out[b])
-                gather_done[b] = torch.cuda.Event(); gather_done[b].record(side)
-
-    def sync_all():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
+                gather_done[b] = torch.cuda.Event(); gather_done[b].record(c.side)
 
     # ---- parity gate: the results we are about to time are the reference's ---------------
-    step(0); sync_all()
-    import reflib
+    step(0); sync_all(c)
     oracle = reflib.Oracle()
     idx = torch.arange(0, n, 64, device=dev)
     sample_host = d_in[idx].cpu().numpy()
     off = np.arange(sample_host.shape[0] + 1, dtype=np.uint64) * np.uint64(LENGTH)
     want = oracle.exec_batch(fsm, sample_host.reshape(-1), off, nthreads=min(16, os.cpu_count() or 1))
-    if fused and args.handshake == "flags":
+    if use_flags:
         flags = ring.read_flags(0)                         # step 0 was launched with sig_value 1
         assert (flags == 1).all(), f"bench: completion flags {flags} != 1 after step 0"
     if fused and compact:
@@ -310,7 +520,6 @@ def main():
         everything = ring.read(0)                          # this rank's gathered buffer: all ranks' records
         got = everything[rank * n:(rank + 1) * n][::64]
         assert (got == want).all(), "bench: GPU results differ from the oracle"
-        # cross-check the P2P-gathered buffer against an NCCL all-gather of the same records
         mine_t = torch.from_numpy(everything[rank * n:(rank + 1) * n].view(np.uint8).reshape(n, 16).copy()).to(dev)
         dist.all_gather_into_tensor(gathered[0], mine_t)
         torch.cuda.synchronize(dev)
@@ -322,38 +531,33 @@ def main():
             mine = gathered[0][rank * n:(rank + 1) * n]
             assert torch.equal(mine, d_out[0]), "bench: all-gather slot mismatch"
 
-    # ---- device-resident timing ----------------------------------------------------------
-    for i in range(args.warmup):
-        step(i)
-    sync_all()
-    sampler = ClockSampler(local); sampler.start()
-    L.launch_count(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(main_stream)
-    for i in range(args.steps):
-        step(i)
-    if world > 1:
-        main_stream.wait_stream(side)
-    e1.record(main_stream)
-    sync_all()
-    ms_total = e0.elapsed_time(e1)
-    launches = L.launch_count()
+    ms_total, launches, sampler = timed_region(c, step, args.steps, args.warmup)
 
-    # kernel-only duration (CUDA events around each launch, on the launching stream)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    if world > 1:
-        dist.barrier()
-    for a, b in kev:
-        a.record(main_stream)
+    def one_kernel(inp=d_in):
         if fused:
-            dfa.exec_batch_gather(d_in, stride=LENGTH, length=LENGTH, n=n, out_ptr=local_out_ptr(0),
+            dfa.exec_batch_gather(inp, stride=LENGTH, length=LENGTH, n=n, out_ptr=local_out_ptr(0),
                                   peer_ptrs=peer_args[0][0], npeers=peer_args[0][1], compact=compact)
         else:
-            dfa.exec_batch(d_in, stride=LENGTH, length=LENGTH, n=n, out=d_out[0])
-        b.record(main_stream)
-    torch.cuda.synchronize(dev)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    sampler.stop_flag = True; sampler.join()
+            dfa.exec_batch(inp, stride=LENGTH, length=LENGTH, n=n, out=d_out[0])
+    kms = kernel_ms(c, one_kernel, args.steps)
+    clocks = sampler.finish()
+
+    # the other distribution of SURVEY 8d ("report both"): kernel-only, same launch configuration
+    other = None
+    if world == 1:
+        d_other = workloads.cfg2_device(n, LENGTH, not adversarial, seed=42, device=dev)
+        for _ in range(3):
+            one_kernel(d_other)
+        oms = kernel_ms(c, lambda: one_kernel(d_other), max(5, min(args.steps, 20)))
+        hs = d_other[idx].cpu().numpy()
+        w2 = oracle.exec_batch(fsm, hs.reshape(-1), off, nthreads=min(16, os.cpu_count() or 1))
+        torch.cuda.synchronize(dev)
+        assert (L.results_from_torch(d_out[0][idx]) == w2).all(), "bench: GPU results differ from the oracle (other distribution)"
+        peaks, _ = measured_peaks()
+        g = n * LENGTH / (oms / 1e3) / 1e9
+        other = {"distribution": "uniform" if adversarial else "adversarial", "kernel_ms": oms, "value": g, "unit": "GB/s",
+                 "frac_of_hbm_peak": g / peaks["hbm_gbs"], "parity": "1/64 sample bit-exact vs the oracle"}
+        del d_other
 
     # ---- end to end through the host entry point, pinned host buffers --------------------
     h_in = torch.empty((n, LENGTH), dtype=torch.uint8, pin_memory=True)
@@ -361,70 +565,478 @@ def main():
     h_off = torch.arange(0, (n + 1) * LENGTH, LENGTH, dtype=torch.int64).pin_memory()
     h_out = torch.empty((n, 16), dtype=torch.uint8, pin_memory=True)
     e2e_steps = args.e2e_steps if args.e2e_steps is not None else max(3, min(args.steps, 10))
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     for _ in range(2):
         dfa.exec_batch_hostptr(h_in.data_ptr(), h_off.data_ptr(), n, h_out.data_ptr())
     assert (L.results_from_torch(h_out)[::64] == want).all()
-    sync_all()
+    sync_all(c)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         dfa.exec_batch_hostptr(h_in.data_ptr(), h_off.data_ptr(), n, h_out.data_ptr())
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
 
-    # ---- reduce over ranks (max time) ----------------------------------------------------
-    t = torch.tensor([ms_total, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, kernel_ms = (float(x) for x in t.cpu())
+    ms_total, e2e_ms, kms = reduce_max(c, [ms_total, e2e_s * 1e3, kms])
     bytes_step = n * LENGTH
-    value = world * bytes_step * args.steps / (ms_total / 1e3) / 1e9
-    e2e_value = world * bytes_step * e2e_steps / (e2e_ms / 1e3) / 1e9
-    peaks, peak_src = measured_peaks()
-    achieved = bytes_step / (kernel_ms / 1e3) / 1e9
-
-    traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_k1_traffic.json")
-    if os.path.exists(tp) and args.dist == "uniform":
-        tj = json.load(open(tp))
-        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-        traffic_src = f"{tj['source']}: dram__bytes_read.sum + dram__bytes_write.sum per launch of {tj['kernel']}"
-    line = None
     if rank == 0:
         threads = host_threads()
-        sample_n = max(1024, min(256 * threads, 1 << 15))
-        cpu = cpu_reference_leg(fsm, workloads.cfg2_host(sample_n, LENGTH, adversarial, seed=42), threads)
-        line = {
-            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: 256-state DFA a[ -~]{7}\\z, 2^20 x 1 KiB ASCII per GPU",
-                       "distribution": args.dist, "variant": args.variant, "table": dfa.info,
-                       "l2": "1 GiB input per step > 126 MB L2: no flush needed",
-                       "multi_gpu": ("single GPU" if world == 1 else
-                                     f"range-sharded batch; scan fused with the gather: lanes store {'4 B match ids ((ret==1)<<31|end)' if args.gather_records == 'compact' else '16 B records'} into every peer's buffer over NVLink P2P; completion signal: {args.handshake}"
-                                     if fused else "range-sharded batch, one NCCL all-gather of 16 B result records per step on a side stream")},
-            "clocks": sampler.result(),
-            "e2e": {"value": e2e_value, "unit": "GB/s", "steps": e2e_steps,
-                    "h2d_bytes_per_step": int(h_in.numel() + h_off.numel() * 8),
-                    "d2h_bytes_per_step": int(h_out.numel()),
-                    "entry": "fsm_b200_exec_batch_host, pinned host buffers"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src,
-                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_step,
-                         "traffic": traffic, "traffic_source": traffic_src},
-            "cpu_baseline": {"value": cpu["asis_gbs"], "unit": "GB/s", "cores": cpu["asis_threads"], "kind": cpu["kind"],
-                             "sample": f"{sample_n} x {LENGTH} B inputs, same distribution; reference fsm_exec per input (as-is); best of thread counts {cpu['threads_swept']}",
-                             "amortised_value": cpu["amortised_gbs"], "amortised_cores": cpu["amortised_threads"]},
-        }
+        cpu = cpu_leg_cfg2(fsm, workloads.cfg2_host(CFG2_REF_SAMPLE, LENGTH, adversarial, seed=42), threads)
+        line = base_line(args, c, world * bytes_step * args.steps / (ms_total / 1e3) / 1e9, ms_total / args.steps)
+        line["engine"] = {"variant": args.variant, "table": dfa.info,
+                          "multi_gpu": ("single GPU" if world == 1 else
+                                        f"range-sharded batch; scan fused with the gather: lanes store "
+                                        f"{'4 B match ids ((ret==1)<<31|end)' if compact else '16 B records'} into every peer's buffer over NVLink P2P; "
+                                        f"completion signal: {args.handshake}; consumer in the timed loop: {'poll kernel on the flags before a buffer is reused' if consume else 'none'}"
+                                        if fused else "range-sharded batch, one NCCL all-gather of 16 B result records per step on a side stream"),
+                          "e2e_numa": numa}
+        line["clocks"] = clocks
+        line["e2e"] = {"value": world * bytes_step * e2e_steps / (e2e_ms / 1e3) / 1e9, "unit": "GB/s", "steps": e2e_steps,
+                       "h2d_bytes_per_step": int(h_in.numel() + h_off.numel() * 8), "d2h_bytes_per_step": int(h_out.numel()),
+                       "entry": "fsm_b200_exec_batch_host, pinned host buffers"}
+        line["gpu_launches"] = int(launches)
+        line["roofline"] = roofline_record(bytes_step, kms, "k1_krange_kernel (K-STRIDE with ALU byte classification)" if dfa.info["krange"] and args.variant in ("auto", "kstride") else args.variant,
+                                           "r2_k1_traffic.json" if args.dist == "uniform" else None)
+        if other is not None:
+            line["other_distribution"] = other
+        line["cpu_baseline"] = cpu_baseline_record(cpu, the_config(args)["reference_sample"])
         print(json.dumps(line))
     dfa.close()
     if world > 1:
         dist.barrier()
         if ring is not None:
             ring.close()
-        dist.destroy_process_group()
-    return 0
+    return finish(c)
+
+
+def bind_to_gpu_numa(local: int):
+    """e2e at N > 1: keep this rank's host threads (the copy loop of exec_batch_host runs on the calling
+    thread) and the page placement of what it allocates from now on on the NUMA node of its GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        node = None
+        try:
+            node = pynvml.nvmlDeviceGetNumaNodeId(h)
+        except Exception:
+            pass
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinityWithinScope(h, words, pynvml.NVML_AFFINITY_SCOPE_NODE)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        cpus = [x for x in cpus if x in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:                                   # noqa: BLE001
+        return {"error": repr(e)}
+
+
+# ---- config 3 ------------------------------------------------------------------------------------
+
+def run_cfg3(args):
+    import libfsm_b200 as L
+    import reflib
+    from libfsm_b200 import workloads
+    c = gpu_setup(args)
+    torch, dist, dev, world, rank, local = c.torch, c.dist, c.dev, c.world, c.rank, c.local
+    g = load_fsm(3)
+    fsm, ids = g["eager"]["fsm"], g["eager"]["idlist"]
+    _, inst = workloads.cfg3_patterns()
+    nlines = int(os.environ.get("BENCH_CFG3_LINES", CFG3_LINES))
+    base, offsets = workloads.cfg3_lines_device(nlines, inst, seed=7 + 1000 * rank, device=dev)
+    total = int(offsets[-1])
+    dfa = L.Dfa(fsm, device=local)
+    words = (ids.size + 63) // 64
+    rec = torch.empty((nlines, 16), dtype=torch.uint8, device=dev)
+    masks = torch.zeros((nlines, words), dtype=torch.int64, device=dev)
+    gathered = torch.empty((world * nlines, 16), dtype=torch.uint8, device=dev) if world > 1 else None
+    lib, chk = L._native.lib, L._native.check
+    stream_ptr = int(c.main.cuda_stream)
+
+    def launch():
+        chk(lib.fsm_b200_exec_batch_eager_dev(dfa._h, base.data_ptr(), offsets.data_ptr(), 0, 0, nlines, rec.data_ptr(), masks.data_ptr(), stream_ptr),
+            "exec_batch_eager_dev")
+
+    def step(_i):
+        launch()
+        if world > 1:                                # records of every shard to every rank: ONE all-gather per step
+            ev = torch.cuda.Event(); ev.record(c.main)
+            c.side.wait_event(ev)
+            with torch.cuda.stream(c.side):
+                dist.all_gather_into_tensor(gathered, rec)
+
+    # parity gate: >= 200 k lines, records + fired-id sets bit-exact vs the compiled reference
+    step(0); sync_all(c)
+    ns = min(nlines, 200_000)
+    hb = base[:int(offsets[ns])].cpu().numpy(); ho = offsets[:ns + 1].cpu().numpy().astype(np.uint64)
+    assert reflib.have_ref(), "config 3's parity gate needs the compiled reference (oracle/_ref)"
+    R = reflib.Ref(); h = R.from_flat(fsm)
+    want, wmasks = R.exec_eager_batch(h, hb, ho, ids, mode=1, nthreads=min(32, host_threads()))
+    R.free(h)
+    got = L.results_from_torch(rec[:ns])
+    assert (got == want).all(), "bench: config 3 records differ from the reference"
+    assert (masks[:ns].cpu().numpy().view(np.uint64) == wmasks).all(), "bench: config 3 fired-id sets differ from the reference"
+
+    ms_total, launches, sampler = timed_region(c, step, args.steps, args.warmup)
+    kms = kernel_ms(c, launch, args.steps)
+    clocks = sampler.finish()
+
+    # sub-record: the start-anchored end-id variant (rx(1)'s own recipe), plain records
+    sub = None
+    if world == 1:
+        afsm = g["anchored"]["fsm"]
+        _, ainst = workloads.cfg3_anchored_patterns()
+        abase, aoff = workloads.cfg3_lines_device(nlines, ainst, seed=7, device=dev, at_start=True)
+        with L.Dfa(afsm, device=local) as adfa:
+            def alaunch():
+                adfa.exec_batch(abase, aoff, out=rec)
+            for _ in range(3):
+                alaunch()
+            torch.cuda.synchronize(dev)
+            ams = kernel_ms(c, alaunch, max(5, min(args.steps, 20)))
+            arec = L.results_from_torch(rec)
+            walked = int(arec["consumed"].sum())
+            hb2 = abase[:int(aoff[ns])].cpu().numpy(); ho2 = aoff[:ns + 1].cpu().numpy().astype(np.uint64)
+            R = reflib.Ref(); h = R.from_flat(afsm)
+            want2 = R.exec_batch(h, hb2, ho2, mode=1, nthreads=min(32, host_threads()))
+            R.free(h)
+            assert (arec[:ns] == want2).all(), "bench: anchored config 3 records differ from the reference"
+            atotal = int(aoff[-1])
+            peaks, _ = measured_peaks()
+            sub = {"dfa": "128 start-anchored patterns, rx(1)'s recipe, end ids", "dfa_states": afsm.nstates, "table": adfa.info, "kernel_ms": ams,
+                   "GBps_bytes_covered": atotal / ams / 1e6, "GBps_bytes_walked": walked / ams / 1e6,
+                   "bytes_covered": atotal, "bytes_walked": walked, "frac_of_hbm_peak_walked": walked / ams / 1e6 / peaks["hbm_gbs"],
+                   "note": "a line that dies (half of them, within their first bytes) or reaches an absorbing accept state is not read further; "
+                           "bytes_walked = sum of the records' consumed offsets", "parity": f"{ns} lines bit-exact vs the compiled reference"}
+        del abase, aoff
+
+    # e2e: host lines -> fsm_b200_exec_batch_eager_host -> host records + bitsets
+    h_base = torch.empty(total, dtype=torch.uint8, pin_memory=True); h_base.copy_(base)
+    h_off = offsets.cpu().pin_memory()
+    h_rec = torch.empty((nlines, 16), dtype=torch.uint8, pin_memory=True)
+    h_masks = torch.zeros((nlines, words), dtype=torch.int64).pin_memory()
+    e2e_steps = args.e2e_steps if args.e2e_steps is not None else 3
+
+    def e2e_call():
+        chk(lib.fsm_b200_exec_batch_eager_host(dfa._h, h_base.data_ptr(), h_off.data_ptr(), nlines, h_rec.data_ptr(), h_masks.data_ptr()),
+            "exec_batch_eager_host")
+    e2e_call()
+    assert (L.results_from_torch(h_rec)[:ns] == want).all()
+    sync_all(c)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_call()
+    e2e_s = time.perf_counter() - t0
+
+    ms_total, e2e_ms, kms = reduce_max(c, [ms_total, e2e_s * 1e3, kms])
+    if rank == 0:
+        cpu = cpu_leg_cfg3(g, CFG3_REF_SAMPLE, host_threads())
+        line = base_line(args, c, world * total * args.steps / (ms_total / 1e3) / 1e9, ms_total / args.steps)
+        line["engine"] = {"table": dfa.info, "dfa_states": fsm.nstates, "eager_ids": int(ids.size), "end_ids": 10,
+                          "lines": nlines, "bytes": total, "records": "16 B record + 16 B id bitset per line",
+                          "bytes_read": "every byte of every line is walked (the union is unanchored: no line dies, no absorbing state)",
+                          "multi_gpu": "single GPU" if world == 1 else "lines range-sharded, one NCCL all-gather of the 16 B records per step on a side stream"}
+        line["clocks"] = clocks
+        line["e2e"] = {"value": world * total * e2e_steps / (e2e_ms / 1e3) / 1e9, "unit": "GB/s", "steps": e2e_steps,
+                       "h2d_bytes_per_step": int(total + h_off.numel() * 8), "d2h_bytes_per_step": int(h_rec.numel() + h_masks.numel() * 8),
+                       "entry": "fsm_b200_exec_batch_eager_host, pinned host buffers"}
+        line["gpu_launches"] = int(launches)
+        line["roofline"] = roofline_record(total, kms, "k1_lines_kernel<u16, 2 mask words, eager>", "r2_lines_traffic.json")
+        line["roofline"]["note"] = "bound by the shared-memory lookup rate (2 LDS per byte, bank conflicts), not HBM: see DESIGN.md"
+        line["parity"] = f"{ns} lines: records and fired-id bitsets bit-exact vs the compiled reference (refh_exec_eager_batch)"
+        if sub is not None:
+            line["anchored_variant"] = sub
+        line["cpu_baseline"] = cpu_baseline_record(cpu, the_config(args)["reference_sample"])
+        print(json.dumps(line))
+    dfa.close()
+    return finish(c)
+
+
+# ---- config 4 (and config 1: the same path through the shim) --------------------------------------
+
+def utf8_device(c: Ctx, nbytes: int, seed: int):
+    """~nbytes of valid UTF-8 on the device: a seeded 64 MiB host block tiled (concatenating valid UTF-8
+    keeps it valid); the last tile is cut at a code-point boundary."""
+    from libfsm_b200 import workloads
+    torch = c.torch
+    block = workloads.utf8_host(64 << 20, seed=seed)
+    reps = (nbytes + block.size - 1) // block.size
+    out = torch.empty(nbytes, dtype=torch.uint8, device=c.dev)
+    tb = torch.from_numpy(block).to(c.dev)
+    pos = 0
+    for _ in range(reps):
+        m = min(block.size, nbytes - pos)
+        out[pos:pos + m] = tb[:m]
+        pos += m
+    # a cut inside a multi-byte sequence: overwrite the tail with ASCII
+    tail = out[-4:].cpu().numpy()
+    k = 0
+    while k < 4 and (tail[-1 - k] & 0xC0) == 0x80:
+        k += 1
+    if k < 4 and tail[-1 - k] >= 0xC0:
+        out[-1 - k:] = 0x41
+    return out
+
+
+def run_cfg4(args):
+    import libfsm_b200 as L
+    import reflib
+    from libfsm_b200 import sharding, workloads
+    c = gpu_setup(args)
+    torch, dist, dev, world, rank, local = c.torch, c.dist, c.dev, c.world, c.rank, c.local
+    fsm = load_fsm(4)
+    nbytes = int(os.environ.get("BENCH_CFG4_BYTES", CFG4_BYTES))
+    dfa = L.Dfa(fsm, device=local)
+    T = dfa.info["ntable_states"]
+    shard = utf8_device(c, nbytes, seed=4)            # every shard: the same seeded valid text (a shard boundary is a code-point boundary)
+    lens = [nbytes] * world
+
+    def gather_maps(ms, md, mf):
+        """ONE all-gather of the [T] records (state u32, dead offset u64, dead-from state u32)."""
+        if world == 1:
+            return [ms], [md], [mf]
+        pack = np.zeros((T, 2), dtype=np.uint64)
+        pack[:, 0] = ms.astype(np.uint64) | (mf.astype(np.uint64) << np.uint64(32))
+        pack[:, 1] = md
+        t = torch.from_numpy(pack.view(np.int64)).to(dev)
+        allp = torch.empty((world, T, 2), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allp, t)
+        a = allp.cpu().numpy().view(np.uint64)
+        return ([(a[r, :, 0] & np.uint64(0xFFFFFFFF)).astype(np.uint32) for r in range(world)], [a[r, :, 1] for r in range(world)],
+                [(a[r, :, 0] >> np.uint64(32)).astype(np.uint32) for r in range(world)])
+
+    def scan(buf):
+        if world == 1:
+            return dfa.exec_stream(buf)
+        ms, md, mf = dfa.exec_stream_map(buf)
+        S, D, F = gather_maps(ms, md, mf)
+        st, consumed, died = sharding.compose_stream_maps(fsm.start, None if dfa.info["complete"] else T - 1, lens, S, D, F)
+        return (0 if died else int(fsm.is_end[st]), st, consumed)
+
+    # parity gate: valid text -> (1, end, total); one corrupted byte in the LAST rank's shard -> (0, ., global offset)
+    ret, end, consumed = scan(shard)
+    assert ret == 1 and consumed == nbytes * world, (ret, end, consumed)
+    bad_at = nbytes // 2 + 12345
+    if rank == world - 1:
+        keep = shard[bad_at:bad_at + 1].clone()
+        # make the byte at bad_at invalid in context: 0xFF never appears in UTF-8
+        shard[bad_at] = 0xFF
+    ret, end, consumed = scan(shard)
+    assert ret == 0 and consumed == nbytes * (world - 1) + bad_at, (ret, consumed, nbytes * (world - 1) + bad_at)
+    if rank == world - 1:
+        shard[bad_at:bad_at + 1] = keep
+    # and a 4 MiB prefix against the reference's own fsm_exec (rank 0)
+    if rank == 0 and reflib.have_ref():
+        pre = shard[:4 << 20].cpu().numpy()
+        cut = pre.size
+        while cut > 0 and (pre[cut - 1] & 0xC0) == 0x80:
+            cut -= 1
+        cut -= 1 if cut > 0 and pre[cut - 1] >= 0xC0 else 0
+        R = reflib.Ref(); h = R.from_flat(fsm)
+        rc, rend, rcons = R.exec(h, pre[:cut].tobytes())
+        R.free(h)
+        assert (rc, rcons) == dfa.exec_stream(shard[:cut])[0::2], "bench: config 4 differs from the reference on the prefix"
+
+    def step(_i):
+        scan(shard)
+    ms_total, launches, sampler = timed_region(c, step, args.steps, args.warmup)
+    # the body kernel's share: exec_stream is a handful of launches; time the whole device-side call
+    t = []
+    for _ in range(max(3, min(args.steps, 10))):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(c.main); dfa.exec_stream(shard) if world == 1 else dfa.exec_stream_map(shard); b.record(c.main)
+        torch.cuda.synchronize(dev); t.append(a.elapsed_time(b))
+    kms = float(np.mean(t))
+    clocks = sampler.finish()
+
+    # e2e: pinned host text -> fsm_b200_exec_stream_host -> verdict (H2D of the whole shard inside)
+    e2e_bytes = min(nbytes, 1 << 30)
+    h_text = torch.empty(e2e_bytes, dtype=torch.uint8, pin_memory=True); h_text.copy_(shard[:e2e_bytes])
+    r = L.desc.CResult()
+    lib, chk = L._native.lib, L._native.check
+    e2e_steps = args.e2e_steps if args.e2e_steps is not None else 3
+    chk(lib.fsm_b200_exec_stream_host(dfa._h, h_text.data_ptr(), e2e_bytes, ctypes.byref(r)), "exec_stream_host")
+    sync_all(c)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        chk(lib.fsm_b200_exec_stream_host(dfa._h, h_text.data_ptr(), e2e_bytes, ctypes.byref(r)), "exec_stream_host")
+    e2e_s = time.perf_counter() - t0
+
+    ms_total, e2e_ms, kms = reduce_max(c, [ms_total, e2e_s * 1e3, kms])
+    if rank == 0:
+        cpu = cpu_leg_stream(fsm, workloads.utf8_host(CFG4_REF_SAMPLE, seed=4))
+        line = base_line(args, c, world * nbytes * args.steps / (ms_total / 1e3) / 1e9, ms_total / args.steps)
+        line["engine"] = {"table": dfa.info, "dfa": "examples/utf8dfa 0..10FFFF starred, det + min: 8 states (fsm_equal with the PCRE-built validator)",
+                          "bytes_per_gpu": nbytes,
+                          "multi_gpu": "single GPU: fsm_b200_exec_stream_dev" if world == 1 else
+                                       f"{world} byte-range shards; per rank K1b shard map (exit state / first dead offset per entry state), ONE all-gather of [T] records, composed in rank order"}
+        line["clocks"] = clocks
+        line["e2e"] = {"value": world * e2e_bytes * e2e_steps / (e2e_ms / 1e3) / 1e9, "unit": "GB/s", "steps": e2e_steps,
+                       "h2d_bytes_per_step": int(e2e_bytes), "d2h_bytes_per_step": 16, "entry": "fsm_b200_exec_stream_host, pinned host text",
+                       "bytes": e2e_bytes}
+        line["gpu_launches"] = int(launches)
+        line["roofline"] = roofline_record(nbytes, kms, "K1b: prefix + body (K1 lane / k-stride over the chunk jobs) + compose, whole device-side call")
+        line["parity"] = "valid text: (1, end, total); one 0xFF at a known offset of the last shard: (0, ., global offset); 4 MiB prefix vs the reference's fsm_exec"
+        line["cpu_baseline"] = cpu_baseline_record(cpu, the_config(args)["reference_sample"])
+        print(json.dumps(line))
+    dfa.close()
+    return finish(c)
+
+
+def run_cfg1(args):
+    """re(1)'s plumbing: the RELINKED libfsm (reference objects + libfsm_b200/shim replacing exec.c /
+    determinise.c / minimise.c) in this process: re_comp -> fsm_determinise -> fsm_minimise -> fsm_exec(fsm,
+    fsm_sgetc, &text, &end, NULL).  value: the stream kernels on device-resident text; e2e: the fsm_exec call."""
+    import libfsm_b200 as L
+    import reflib
+    c = gpu_setup(args)
+    torch, dev, rank, local = c.torch, c.dev, c.rank, c.local
+    fsm = load_fsm(1)
+    text = cfg1_text(args.size)
+    dfa = L.Dfa(fsm, device=local)
+    d_text = torch.from_numpy(text).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    oracle = reflib.Oracle()
+    want = oracle.exec(fsm, text.tobytes(), validate=False)
+    assert dfa.exec_stream(d_text) == want, "bench: config 1 differs from the oracle"
+
+    def step(_i):
+        flush.fill_(1)                               # input smaller than L2: evict it between iterations
+        dfa.exec_stream(d_text)
+    ms_total, launches, sampler = timed_region(c, step, args.steps, args.warmup)
+    tt = []
+    for _ in range(max(5, min(args.steps, 20))):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(c.main); dfa.exec_stream(d_text); b.record(c.main)
+        torch.cuda.synchronize(dev); tt.append(a.elapsed_time(b))
+    kms = float(np.mean(tt))
+    clocks = sampler.finish()
+
+    # e2e through the relinked libfsm
+    shim_path = os.path.join(ROOT, "build", "shim", "libfsm_shim.so")
+    e2e = None
+    if os.path.exists(shim_path):
+        S = ctypes.CDLL(shim_path, use_errno=True)
+        vp = ctypes.c_void_p
+        S.re_comp.restype = vp
+        S.re_comp.argtypes = [ctypes.c_int, vp, vp, vp, ctypes.c_int, vp]
+        S.fsm_determinise.argtypes = [vp]; S.fsm_minimise.argtypes = [vp]; S.fsm_free.argtypes = [vp]; S.fsm_free.restype = None
+        S.fsm_exec.argtypes = [vp, vp, vp, ctypes.POINTER(ctypes.c_uint), vp]
+        sgetc = ctypes.cast(S.fsm_sgetc, vp)
+        pat = ctypes.c_char_p(b"[0-9]+\\.[0-9]+")
+        cur = ctypes.c_char_p(pat.value)
+        h = S.re_comp(5, sgetc, ctypes.byref(cur), None, 0, None)          # RE_PCRE
+        assert h and S.fsm_determinise(h) == 1 and S.fsm_minimise(h) == 1
+        buf = ctypes.create_string_buffer(text.tobytes() + b"\0")
+        end = ctypes.c_uint(0)
+
+        def call():
+            p = ctypes.c_char_p(ctypes.addressof(buf))
+            rc = S.fsm_exec(h, sgetc, ctypes.byref(p), ctypes.byref(end), None)
+            return rc
+        rc = call()
+        assert rc == want[0], (rc, want)
+        e2e_steps = args.e2e_steps if args.e2e_steps is not None else max(5, min(args.steps, 20))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            call()
+        dt = time.perf_counter() - t0
+        S.fsm_free(h)
+        e2e = {"value": text.size * e2e_steps / dt / 1e9, "unit": "GB/s", "steps": e2e_steps, "h2d_bytes_per_step": int(text.size),
+               "d2h_bytes_per_step": 16, "ms_per_call": dt / e2e_steps * 1e3,
+               "entry": "libfsm's fsm_exec(fsm, fsm_sgetc, ...) of the relinked library (build/shim/libfsm_shim.so): strlen + H2D + K1b + verdict"}
+    if rank == 0:
+        cpu = cpu_leg_stream(fsm, text)
+        line = base_line(args, c, text.size * args.steps / (ms_total / 1e3) / 1e9, ms_total / args.steps)
+        line["engine"] = {"table": dfa.info, "bytes": int(text.size), "note": "one fsm_exec call over one input: launch-latency-bound at 1 MiB; --size scales it"}
+        line["clocks"] = clocks
+        line["e2e"] = e2e if e2e is not None else {"unavailable": "build/shim/libfsm_shim.so not built (needs the reference tree at build time)"}
+        line["gpu_launches"] = int(launches)
+        line["roofline"] = roofline_record(int(text.size), kms, "K1b stream path, whole device-side call (includes the 256 MiB L2 flush? no: timed after it)")
+        line["cpu_baseline"] = cpu_baseline_record(cpu, the_config(args)["reference_sample"])
+        print(json.dumps(line))
+    dfa.close()
+    return finish(c)
+
+
+# ---- config 5 ------------------------------------------------------------------------------------
+
+def run_cfg5(args):
+    import libfsm_b200 as L
+    c = gpu_setup(args)
+    torch, rank, local = c.torch, c.rank, c.local
+    nfa = load_fsm(5)
+    dfa = L.determinise(nfa, device=local)                    # warm: memory pool, module load
+    st = L.determinise_stats()
+    edges = int(dfa.nstates) * 256
+    import reflib
+    oracle = reflib.Oracle()
+    # parity: state count + end-id carry on a sample of states + the walk of the NFA's own words
+    assert dfa.nstates == 96543 or dfa.nstates > 90000, dfa.nstates
+    times, walls = [], []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        d = L.determinise(nfa, device=local)
+        w = time.perf_counter() - t0
+        s = L.determinise_stats()
+        if i >= args.warmup:
+            times.append(s["ms_total"]); walls.append(w * 1e3)
+        assert d.nstates == dfa.nstates
+    sampler = ClockSampler(local); sampler.start(); clocks = sampler.finish()
+    ms, wall = float(np.mean(times)), float(np.mean(walls))
+    ms, wall = reduce_max(c, [ms, wall])
+    if rank == 0:
+        dt, ref_states = cpu_leg_determinise(nfa) if reflib.have_ref() else (None, None)
+        if ref_states is not None:
+            assert ref_states == dfa.nstates, (ref_states, dfa.nstates)
+        line = base_line(args, c, c.world * edges / (ms / 1e3), ms, unit="edges/s", metric="DFA edges/s (fsm_determinise)", dtype="u32")
+        line["scaling"] = "weak"
+        line["engine"] = {"nfa_states": int(nfa.nstates), "dfa_states": int(dfa.nstates), "dfa_edges": edges, "stats": st,
+                          "multi_gpu": "replicas only (the frontier hash table is single-GPU)"}
+        line["clocks"] = clocks
+        line["e2e"] = {"value": c.world * edges / (wall / 1e3), "unit": "edges/s", "h2d_bytes_per_step": int(nfa.group_symbols.nbytes + nfa.group_to.nbytes + nfa.group_off.nbytes),
+                       "d2h_bytes_per_step": int(dfa.group_symbols.nbytes + dfa.group_to.nbytes + dfa.group_off.nbytes),
+                       "entry": "fsm_b200_determinise: host NFA description in, host DFA description out", "ms_per_call": wall}
+        line["gpu_launches"] = int(st["kernel_launches"])
+        peaks, peak_src = measured_peaks()
+        moved = line["e2e"]["d2h_bytes_per_step"] + line["e2e"]["h2d_bytes_per_step"]
+        line["roofline"] = {"bound": "hbm", "achieved": moved / (ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": moved / (ms / 1e3) / 1e9 / peaks["hbm_gbs"], "peak_source": peak_src, "traffic": None,
+                            "note": "not a streaming kernel: ~50 frontier rounds of small launches, latency- and host-sync-bound; the fraction is informational"}
+        line["cpu_baseline"] = {"value": None if dt is None else edges / dt, "unit": "edges/s", "cores": 1, "kind": "reference",
+                                "sample": "the whole NFA", "seconds": dt}
+        print(json.dumps(line))
+    return finish(c)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dist", default="uniform", choices=["uniform", "adversarial"])
+    ap.add_argument("--size", type=int, default=1 << 20, help="config 1: bytes of text")
+    ap.add_argument("--variant", default="auto")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--gather-records", default="compact", choices=["compact", "full"],
+                    help="fused gather payload: compact = 4-byte match ids ((ret==1)<<31 | end), full = 16-byte records")
+    ap.add_argument("--handshake", default="flags", choices=["flags", "nccl", "none"],
+                    help="fused gather completion signal: flags = the kernel's last CTA stores a step number into "
+                         "every peer's memory; nccl = 4-byte NCCL all-reduce per step on a side stream")
+    ap.add_argument("--no-consumer", action="store_true", help="do not wait on the completion flags inside the timed loop")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N>1: fused = scanning lanes store records into every peer's buffer over NVLink P2P; "
+                         "nccl = one NCCL all-gather per step on a side stream")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+    if args.config in (3, 4, 5) and args.steps == 50:
+        args.steps = 10                                   # seconds-long setups: keep the default run within minutes
+    return {1: run_cfg1, 2: run_cfg2, 3: run_cfg3, 4: run_cfg4, 5: run_cfg5}[args.config](args)
 
 
 if __name__ == "__main__":

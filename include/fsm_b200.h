@@ -224,6 +224,11 @@ int fsm_b200_exec_batch_dev_gather(const fsm_b200_dfa *dfa,
 	const uint8_t *d_base, const uint64_t *d_offsets, uint64_t stride, uint64_t len, size_t n,
 	struct fsm_b200_result *d_out, void *const *peer_outs, int npeers, int compact,
 	void *sig_counter, void *const *sig_flags, uint32_t sig_value, void *stream);
+/* The consumer side of that signal: enqueue on `stream` a one-warp kernel that polls d_flags[0..n) (n <= 32
+ * flag words in this rank's memory, one per source rank) until each has reached `value` (step numbers
+ * only grow), so that whatever is enqueued behind it reads complete records.  Bounded (about a second):
+ * on expiry it sets *d_timed_out (optional uint32 in device memory) instead of hanging the device. */
+int fsm_b200_wait_flags_dev(int device, const void *d_flags, uint32_t n, uint32_t value, void *d_timed_out, void *stream);
 int fsm_b200_dev_alloc(int device, size_t bytes, void **out);
 int fsm_b200_dev_free(int device, void *p);
 int fsm_b200_dev_zero(int device, void *p, size_t bytes);

@@ -18,7 +18,7 @@ ABI_SYMBOLS = (
     "fsm_b200_abi_version", "fsm_b200_device_count", "fsm_b200_last_error",
     "fsm_b200_dfa_compile", "fsm_b200_dfa_free", "fsm_b200_dfa_info", "fsm_b200_dfa_plan", "fsm_b200_dfa_table",
     "fsm_b200_exec_batch_host", "fsm_b200_exec_batch_dev", "fsm_b200_exec_batch_dev_gather",
-    "fsm_b200_dev_alloc", "fsm_b200_dev_free", "fsm_b200_dev_zero", "fsm_b200_dev_read",
+    "fsm_b200_wait_flags_dev", "fsm_b200_dev_alloc", "fsm_b200_dev_free", "fsm_b200_dev_zero", "fsm_b200_dev_read",
     "fsm_b200_ipc_export", "fsm_b200_ipc_open", "fsm_b200_ipc_close",
     "fsm_b200_set_exec_variant", "fsm_b200_get_exec_variant",
     "fsm_b200_exec_stream_host", "fsm_b200_exec_stream_dev", "fsm_b200_exec_stream_map_dev",
@@ -68,6 +68,7 @@ def _load() -> C.CDLL:
     lib.fsm_b200_exec_batch_host.argtypes = [vp, vp, vp, sz, vp]
     lib.fsm_b200_exec_batch_dev.argtypes = [vp, vp, vp, u64, u64, sz, vp, vp]
     lib.fsm_b200_exec_batch_dev_gather.argtypes = [vp, vp, vp, u64, u64, sz, vp, P(vp), C.c_int, C.c_int, vp, P(vp), C.c_uint32, vp]
+    lib.fsm_b200_wait_flags_dev.argtypes = [C.c_int, vp, C.c_uint32, C.c_uint32, vp, vp]
     lib.fsm_b200_dev_alloc.argtypes = [C.c_int, sz, P(vp)]
     lib.fsm_b200_dev_free.argtypes = [C.c_int, vp]
     lib.fsm_b200_dev_zero.argtypes = [C.c_int, vp, sz]

@@ -289,6 +289,37 @@ fsm_b200_exec_batch_dev_gather(const fsm_b200_dfa *dfa,
 	    static_cast<uint32_t *>(sig_counter), reinterpret_cast<uint32_t *const *>(sig_flags), sig_value);
 }
 
+/* Consumer side of the completion flags: one warp polls flags[0..n) (system scope) until every one has
+ * reached `value`; bounded (about a second) so that a peer that died cannot hang the device. */
+__global__ void
+wait_flags_kernel(const volatile uint32_t *flags, uint32_t n, uint32_t value, uint32_t *timed_out)
+{
+	const uint32_t r = threadIdx.x;
+	if (r >= n) return;
+	const long long t0 = clock64();
+	while ((int32_t) (flags[r] - value) < 0) {
+		__nanosleep(200);
+		if (clock64() - t0 > 2000000000ll) { if (timed_out != nullptr) atomicExch(timed_out, 1u); break; }
+	}
+	__threadfence_system();
+}
+
+extern "C" int
+fsm_b200_wait_flags_dev(int device, const void *d_flags, uint32_t n, uint32_t value, void *d_timed_out, void *stream)
+{
+	if (d_flags == nullptr || n == 0 || n > 32) {
+		set_error("wait_flags_dev: bad argument");
+		errno = EINVAL;
+		return -1;
+	}
+	FSMB_CUDA(cudaSetDevice(device), return -1);
+	wait_flags_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const volatile uint32_t *>(d_flags), n, value,
+	    static_cast<uint32_t *>(d_timed_out));
+	count_launch();
+	FSMB_CUDA(cudaGetLastError(), return -1);
+	return 0;
+}
+
 extern "C" int
 fsm_b200_dev_alloc(int device, size_t bytes, void **out)
 {

@@ -67,24 +67,32 @@ find_cell_ranges(const uint8_t (&cls)[256], uint8_t (&rlo)[2], uint8_t (&rhi)[2]
 			cand.push_back({ lo, hi });
 		}
 	}
-	auto ok = [&](const Rg &a, const Rg &b) {
+	int nclasses = 0;
+	for (int c = 0; c < 256; c++) if (cls[c] + 1 > nclasses) nclasses = cls[c] + 1;
+	/* cells refine classes; *cells = how many of the 4 cell codes occur */
+	auto ok = [&](const Rg &a, const Rg &b, int *cells) {
 		int cls_of_cell[4] = { -1, -1, -1, -1 };
+		*cells = 0;
 		for (int c = 0; c < 256; c++) {
 			const int cell = ((c >= a.lo && c <= a.hi) ? 1 : 0) | ((c >= b.lo && c <= b.hi) ? 2 : 0);
-			if (cls_of_cell[cell] < 0) cls_of_cell[cell] = cls[c];
+			if (cls_of_cell[cell] < 0) { cls_of_cell[cell] = cls[c]; (*cells)++; }
 			else if (cls_of_cell[cell] != cls[c]) return false;
 		}
 		return true;
 	};
-	/* prefer one range over two, and ranges below 0x80 (one shared half-select in the kernel) */
-	for (int pass = 0; pass < 4; pass++) {
-		const bool single = pass < 2, want_low = (pass & 1) == 0;
+	/* prefer one cell per class (inputs of one class then share their tuple index, hence their table
+	 * word: a broadcast instead of a bank conflict), then one range over two, then ranges below 0x80
+	 * (one shared half-select in the kernel) */
+	for (int pass = 0; pass < 8; pass++) {
+		const bool bijective = pass < 4, single = (pass & 3) < 2, want_low = (pass & 1) == 0;
 		for (size_t i = 1; i < cand.size(); i++) {
 			for (size_t j = 0; j < (single ? 1 : cand.size()); j++) {
 				if (j == i || (!single && j == 0)) continue;
 				const bool low = cand[i].hi < 0x80 && (j == 0 || cand[j].hi < 0x80);
 				if (want_low != low) continue;
-				if (!ok(cand[i], cand[j])) continue;
+				int cells = 0;
+				if (!ok(cand[i], cand[j], &cells)) continue;
+				if (bijective && cells != nclasses) continue;
 				rlo[0] = (uint8_t) cand[i].lo; rhi[0] = (uint8_t) cand[i].hi;
 				rlo[1] = (uint8_t) cand[j].lo; rhi[1] = (uint8_t) cand[j].hi;
 				return low ? 1u : 2u;

@@ -527,9 +527,9 @@ k1_kstride_kernel(const K1Args a)
  * half_k keeps the bytes of the half of the byte space R_k lives in (bit 7 clear, or set); with
  * RNG == 1 both ranges lie below 0x80 and share it.  11 integer instructions + ONE shared-memory
  * wavefront per 4 bytes (the LUT form: 12 instructions, 5 wavefronts).
- * Two sector buffers used alternately (no register copies); the cache lines 2 ahead of the one being
- * walked are requested into L2 (prefetch.global.L2: 128-byte DRAM bursts instead of 32-byte ones, and
- * the 256-bit loads then hit L2).
+ * Three sector buffers in rotation (no register copies): loads run two sectors ahead of the walk.
+ * Optionally (kr_prefetch != 0, off by default: it measured slower) the cache line that many bytes
+ * ahead is requested into L2 as well.
  * blob: [256 B cell LUT][stepK_T 256 x 256][step1 rows][is_end]
  */
 template <bool HAS_DEAD, int RNG>
@@ -573,7 +573,7 @@ k1_krange_kernel(const K1Args a)
 		}
 		if (!died) {
 			const uint64_t body_end = pos + ((len - pos) & ~31ull);      /* whole sectors: [pos, body_end) */
-			uint32_t A[8], B[8];
+			uint32_t A[8], B[8], C[8];
 			bool stop = false;
 			/* walks one sector; stop = died, or absorbed */
 #define KR_WALK(cur)                                                                                     \
@@ -616,13 +616,20 @@ k1_krange_kernel(const K1Args a)
 					}                                                                                    \
 				}                                                                                        \
 			} while (0)
+			/* three sector buffers in rotation: the loads run two sectors (64 B per lane, 9.7 MB per
+			 * GPU) ahead of the walk -- with one sector ahead the bytes in flight, not DRAM or the issue
+			 * rate, capped the kernel at 5.3 TB/s */
 			KR_FETCH(pos, A);
+			KR_FETCH(pos + 32, B);
 			while (pos < body_end) {
-				KR_FETCH(pos + 32, B);
+				KR_FETCH(pos + 64, C);
 				KR_WALK(A);
 				if (stop || pos >= body_end) break;
-				KR_FETCH(pos + 32, A);
+				KR_FETCH(pos + 64, A);
 				KR_WALK(B);
+				if (stop || pos >= body_end) break;
+				KR_FETCH(pos + 64, B);
+				KR_WALK(C);
 				if (stop) break;
 			}
 #undef KR_WALK
@@ -936,7 +943,7 @@ dispatch_kstride(const fsm_b200_dfa *dfa, const K1Args &a0, int sms, cudaStream_
 		K1Args a = a0;
 		a.kblob = static_cast<const uint8_t *>(dfa->d_rblob);
 		a.kblob_bytes = dfa->rblob_bytes; a.k1_off = dfa->r_k1_off; a.kend_off = dfa->r_kend_off;
-		a.kr_prefetch = 256;
+		a.kr_prefetch = 0;
 		if (const char *e = getenv("FSM_B200_KRANGE_PREFETCH")) {      /* tuning knob: L2 prefetch distance, 0 = off */
 			const int v = atoi(e);
 			if (v >= 0 && v <= 65536 && (v % 128) == 0) a.kr_prefetch = (uint32_t) v;

@@ -88,6 +88,23 @@ class GatherRing:
         check(lib.fsm_b200_dev_read(self.device, out.ctypes.data, self.local[b] + self.flag_off, 4 * self.world), "dev_read")
         return out
 
+    def wait_flags(self, b: int, value: int) -> None:
+        """Enqueue (current torch stream) the consumer's poll kernel: returns on the device once every
+        rank's completion flag in this rank's buffer b has reached `value`.  A poll that gives up (a
+        peer died) sets the word read by ``timed_out``."""
+        import torch
+        check(lib.fsm_b200_wait_flags_dev(self.device, self.local[b] + self.flag_off, self.world, int(value) & 0xFFFFFFFF,
+                                          self.local[b] + self.counter_off + 64, int(torch.cuda.current_stream().cuda_stream)),
+              "wait_flags_dev")
+
+    def timed_out(self) -> bool:
+        for b in range(self.nbuf):
+            out = np.empty(1, dtype=np.uint32)
+            check(lib.fsm_b200_dev_read(self.device, out.ctypes.data, self.local[b] + self.counter_off + 64, 4), "dev_read")
+            if out[0]:
+                return True
+        return False
+
     def close(self) -> None:
         for p in self._opened:
             lib.fsm_b200_ipc_close(self.device, p)

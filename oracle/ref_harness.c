@@ -533,3 +533,72 @@ refh_exec_eager_batch(void *vfsm, const uint8_t *base, const uint64_t *offsets, 
 	for (t = 1; t < made; t++) fsm_free(jobs[t].fsm);
 	return rc;
 }
+
+/* examples/utf8dfa/main.c restated over the same API calls (its output languages are dot / api / c
+ * only, so the automaton is rebuilt here rather than parsed): one chain of fsm_addedge_literal per
+ * code point from the start state (main.c:64-96), surrogates skipped (:218-224), then
+ * fsm_determinise + fsm_minimise (:229-237).  [lo, hi] = 0..0x10FFFF gives the 9-state DFA that
+ * accepts exactly ONE code point. */
+static int
+utf8_encode(int cp, char c[4])
+{
+	if (cp < 0) return 0;
+	if (cp <= 0x7f) { c[0] = (char) cp; return 1; }
+	if (cp <= 0x7ff) { c[0] = (char) ((cp >> 6) + 192); c[1] = (char) ((cp & 63) + 128); return 2; }
+	if (0xd800 <= cp && cp <= 0xdfff) return 0;
+	if (cp <= 0xffff) { c[0] = (char) ((cp >> 12) + 224); c[1] = (char) (((cp >> 6) & 63) + 128); c[2] = (char) ((cp & 63) + 128); return 3; }
+	if (cp <= 0x10ffff) {
+		c[0] = (char) ((cp >> 18) + 240); c[1] = (char) (((cp >> 12) & 63) + 128);
+		c[2] = (char) (((cp >> 6) & 63) + 128); c[3] = (char) ((cp & 63) + 128);
+		return 4;
+	}
+	return 0;
+}
+
+void *
+refh_utf8dfa(int lo, int hi)
+{
+	struct fsm *fsm = fsm_new(NULL);
+	fsm_state_t start;
+	int cp;
+	if (fsm == NULL) return NULL;
+	if (!fsm_addstate(fsm, &start)) goto fail;
+	fsm_setstart(fsm, start);
+	for (cp = lo; cp <= hi; cp++) {
+		char c[4];
+		fsm_state_t x = start, y;
+		int r, i;
+		if (0xd800 <= cp && cp <= 0xdfff) continue;
+		r = utf8_encode(cp, c);
+		if (r == 0) goto fail;
+		for (i = 0; i < r; i++) {
+			if (!fsm_addstate(fsm, &y)) goto fail;
+			if (!fsm_addedge_literal(fsm, x, y, c[i])) goto fail;
+			x = y;
+		}
+		fsm_setend(fsm, x, 1);
+	}
+	if (!fsm_determinise(fsm)) goto fail;
+	if (!fsm_minimise(fsm)) goto fail;
+	return fsm;
+fail:
+	fsm_free(fsm);
+	return NULL;
+}
+
+/* Kleene star through the reference API: an epsilon edge from every
+ * end state back to the start state, and the start state becomes an end state.  The caller
+ * determinises + minimises. */
+int
+refh_star(void *vfsm)
+{
+	struct fsm *fsm = vfsm;
+	fsm_state_t start, s;
+	if (!fsm_getstart(fsm, &start)) return 0;
+	for (s = 0; s < fsm->statecount; s++) {
+		if (fsm_isend(fsm, s) && !fsm_addedge_epsilon(fsm, s, start)) return 0;
+	}
+	fsm_setend(fsm, start, 1);
+	return 1;
+}
+

@@ -76,4 +76,10 @@ int   refh_exec_eager_batch(void *fsm, const uint8_t *base, const uint64_t *offs
 	int mode, int nthreads, struct fsm_b200_result *out, uint64_t *masks, size_t words,
 	const uint32_t *id_of_bit, size_t nbits);
 
+/* examples/utf8dfa/main.c over the same API calls: the DFA of the code points lo..hi (one code point
+ * per input), determinised + minimised; and the Kleene star (epsilon from every end state to the start
+ * state, start becomes an end state; the caller determinises + minimises): BASELINE config 4's validator. */
+void *refh_utf8dfa(int lo, int hi);
+int   refh_star(void *fsm);
+
 #endif

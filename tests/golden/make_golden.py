@@ -501,7 +501,35 @@ def main_cfg3():
           f"{os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def main_cfg4():
+    """golden_cfg4.npz: BASELINE config 4's validator built the way SURVEY.md 8d says: examples/utf8dfa
+    fed `0..10FFFF` (restated over the same API calls in oracle/ref_harness.c: refh_utf8dfa -- the example
+    can only print dot / api / c) gives the 9-state DFA of ONE code point; epsilon edges from its end
+    states back to the start state + start state accepting (refh_star), fsm_determinise, fsm_minimise give
+    the 8-state stream validator.  fsm_equal with the PCRE-built validator of golden_exec.npz ("utf8:")
+    is recorded in the meta (and asserted here)."""
+    R = reflib.Ref()
+    h = R.utf8dfa(0, 0x10FFFF)
+    one_states = R.countstates(h)
+    R.star(h); R.determinise(h); R.minimise(h)
+    f = R.flatten(h)
+    cases = {c["name"]: c for c in goldenio.load_exec_cases(os.path.join(HERE, "golden_exec.npz"))}
+    pname = next(n for n in cases if n.startswith("utf8:"))
+    p = R.from_flat(cases[pname]["fsm"])
+    eq = R.equal(h, p)
+    assert eq and one_states == 9 and f.nstates == 8
+    out = {}
+    goldenio.pack_fsm("utf8dfa_star_", f, out)
+    out["meta"] = np.frombuffer(json.dumps({"one_codepoint_states": one_states, "validator_states": f.nstates,
+                                            "fsm_equal_with": pname, "fsm_equal": bool(eq)}).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "golden_cfg4.npz"), **out)
+    print(f"wrote golden_cfg4.npz: utf8dfa 0..10FFFF -> {one_states} states, starred + det + min -> {f.nstates} states, fsm_equal({pname}) = {eq}")
+    R.free(h); R.free(p)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg4":          # ~40 s: not part of the default regeneration
+        main_cfg4()
     if len(sys.argv) < 2 or sys.argv[1] == "cfg3":
         main_cfg3()
     if len(sys.argv) < 2 or sys.argv[1] == "eager":

