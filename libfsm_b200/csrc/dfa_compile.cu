@@ -456,7 +456,7 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 		uint8_t lcls[256], lrep[256];
 		const uint32_t LC = byte_classes(t32, S, lcls, lrep);
 		const uint32_t T = dfa->ntable;
-		const uint32_t leb = T <= 256 ? 1u : 2u;
+		const uint32_t leb = 2u;          /* 16-bit entries: the kernel rewrites them into row handles (k1_lines.cu) */
 		uint32_t lpitch = ((LC + 1) * leb + 3u) & ~3u;
 		if (((lpitch >> 2) & 1u) == 0) lpitch += 4;                /* odd word pitch spreads rows over banks */
 		const uint32_t ltab_off = 512;
@@ -491,7 +491,7 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 				lb[lend_off + ns] = dfa->h_is_end[os];
 			}
 			dfa->lblob_bytes = (uint32_t) lbytes; dfa->l_pitch = lpitch; dfa->l_entry_bytes = leb;
-			dfa->l_end_off = lend_off; dfa->l_ncols = LC + 1;
+			dfa->l_end_off = lend_off; dfa->l_ncols = LC + 1; dfa->l_tab_off = ltab_off;
 			dfa->l_first_event = (has_eager || !complete) ? nplain : NO_EDGE;
 			dfa->l_dead = complete ? NO_EDGE : S;
 			dfa->l_start = perm[dfa->start];

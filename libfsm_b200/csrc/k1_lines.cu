@@ -10,26 +10,31 @@
  * sector per loop iteration (256-bit load = one full DRAM sector), three sector buffers: A (being
  * walked), B (next sector of the line), N (first sector of the lane's next line).
  *
- * What keeps the per-byte cost at PRMT + LDS + IMAD + LDS (+ VIMNMX):
- *   - rows are indexed by byte class and have one extra NOP column in which every state loops to
- *     itself.  Bytes of a sector that lie outside the line are not skipped: their LUT index gets
- *     256 added (PRMT pulls the high byte from a per-word validity word), which maps to NOP -- no
- *     select on the dependent state chain, no byte-wise head / tail path;
+ * The walk costs PRMT + LDS.U8 + LEA + LDS.U16 per byte, with no base-address arithmetic:
+ *   - the table rows are indexed by byte class (16-bit entries) and after staging every entry is
+ *     rewritten in shared memory from "next state" to that state's HANDLE = shared-memory address
+ *     of its row / 4, so the dependent step is  st = lds16(4 * st + 2 * class)  -- one LEA;
+ *   - the class LUT sits at a 512-aligned shared-memory address below 32 KiB: its address bits are
+ *     OR-ed into the per-word validity bytes, and the PRMT that extracts byte t of a word builds the
+ *     complete LUT address {byte, address bits | outside-the-line flag, 0, 0};
+ *   - rows have one extra NOP column in which every state loops to itself.  A byte outside the
+ *     line has its value cleared and the flag set: LUT[256] = NOP (one word for all such lanes: no
+ *     bank conflict with the lanes inside their lines).  Words entirely outside the line are
+ *     skipped;
  *   - dfa_compile.cu numbers the states with eager outputs last, just before the dead row.  Per
- *     byte the kernel keeps max(st) and the sum of max(st, first_event - 1): after the sector,
+ *     byte the kernel keeps max(st) and the sum of max(st, first_event - 1) (handles are monotonic
+ *     in the state number): after the sector,
  *       no eager outputs (EV_DEAD): the dead row absorbs, so the sum counts the steps spent dead and
  *         gives the offset of the missing edge; the state it was taken from is 0..3 exact steps away
  *         from a per-word snapshot of the walk;
  *       eager outputs (EV_EAGER): sum == max - (first_event - 1) <=> exactly one state with ids was
  *         entered, once (86 % of the sectors of BASELINE config 3 enter none, 13.8 % one, 0.5 % more):
  *         its ids are OR-ed in from a small global array; anything else re-walks the sector byte by
- *         byte, out of line;
- *   - every lane asks L2 for the cache line LINES_PREFETCH bytes ahead of the sector it reads
- *     (prefetch.global.L2): the lanes of a warp sweep a contiguous region of the batch, so together
- *     they prefetch the region the warp reads next, and the 256-bit loads of the walk hit L2.
+ *         byte, out of line.
  *
  * Algorithmic bytes per line: its bytes, read once, + 16 B record (+ 8 W B id bitset).  Bound:
- * the shared-memory lookup rate (two dependent-free + one dependent LDS per byte), see DESIGN.md.
+ * the shared-memory lookup rate (one conflict-free + one dependent, bank-conflicting LDS per byte),
+ * see DESIGN.md.
  */
 #include <cstring>
 
@@ -42,13 +47,13 @@ using namespace fsmb200;
 namespace {
 
 struct LinesArgs {
-	const uint8_t *blob;          /* [512 B LUT][rows][is_end] */
-	uint32_t blob_bytes, pitch /* bytes */, end_off, first_event, dead, start;
+	const uint8_t *blob;          /* [516 B LUT, padded to 1024][rows][is_end] */
+	uint32_t blob_bytes, pitch /* bytes, multiple of 4 */, tab_off, end_off, ntable, ncols;
+	uint32_t first_event, dead, start;   /* state numbers (new numbering); NO_EDGE when absent */
 	const uint32_t *perm_inv;     /* new state number -> caller's */
 	const uint8_t *absorb;        /* by new number, or nullptr */
 	const uint64_t *masks;        /* [ntable][W] by the caller's numbering (global memory) */
 	const uint64_t *ev_masks;     /* [ntable - first_event][W] by new number - first_event */
-	uint32_t prefetch;            /* L2 prefetch distance in bytes, 0 = off */
 	uint64_t start_mask[4];
 	const uint8_t *base;
 	const uint64_t *offsets;      /* n + 1 entries, or nullptr: fixed stride */
@@ -60,7 +65,7 @@ struct LinesArgs {
 /* the staged blob; file scope so that the out-of-line re-walk addresses it as shared memory too */
 extern __shared__ __align__(1024) uint8_t lines_smem[];
 
-/* {x.byte t, v.byte t, 0, 0}: PRMT with the sign-fill mode for the two upper bytes (v.byte t is 0 or 1) */
+/* {x.byte T, v.byte T, 0, 0}: PRMT with the sign-fill mode for the two upper bytes (v.byte T < 0x80) */
 template <int T>
 __device__ __forceinline__ uint32_t
 byte_and_flag(uint32_t x, uint32_t v)
@@ -70,19 +75,43 @@ byte_and_flag(uint32_t x, uint32_t v)
 	return d;
 }
 
+__device__ __forceinline__ uint32_t
+lds_u8(uint32_t addr)
+{
+	uint32_t v;
+	asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+
+__device__ __forceinline__ uint32_t
+lds_u16(uint32_t addr)
+{
+	uint32_t v;
+	asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+
+/* handle (row address / 4) <-> state number */
+struct Handles {
+	uint32_t tab4;       /* shared address of row 0, / 4 */
+	uint32_t pitch4;     /* row pitch / 4 */
+	uint32_t magic;      /* ceil(2^32 / pitch4): (x * magic) >> 32 == x / pitch4 for x < 2^16 */
+	__device__ __forceinline__ uint32_t of(uint32_t state) const { return tab4 + state * pitch4; }
+	__device__ __forceinline__ uint32_t state(uint32_t h) const { return __umulhi(h - tab4, magic); }
+};
+
 template <int W> struct Rewalk {
-	uint32_t st, at, died;
+	uint32_t st, at, died;        /* st: handle */
 	uint64_t m[W > 0 ? W : 1];
 };
 
 /* Exact walk of one sector: first byte (within `mask`) without an edge and the state it was taken
- * from, ids of every state entered.  Cold path. */
-template <typename E, int W>
+ * from, ids of every state entered.  Cold path; st / dead / first_event are handles. */
+template <int W>
 __device__ __noinline__ Rewalk<W>
-lines_rewalk(uint32_t pitch, uint32_t entry, uint32_t mask,
+lines_rewalk(Handles hd, uint32_t lut_a, uint32_t entry, uint32_t mask,
 	uint32_t first_event, uint32_t dead, const uint32_t *perm_inv, const uint64_t *masks, const uint32_t (&w)[8])
 {
-	const uint8_t *lut = lines_smem;
 	Rewalk<W> r;
 	r.st = entry; r.at = 32; r.died = 0;
 #pragma unroll
@@ -91,11 +120,11 @@ lines_rewalk(uint32_t pitch, uint32_t entry, uint32_t mask,
 	for (uint32_t j = 0; j < 32; j++) {
 		if (!((mask >> j) & 1u)) continue;
 		const uint32_t b = (w[j >> 2] >> (8u * (j & 3u))) & 0xFFu;
-		const uint32_t nx = (uint32_t) *reinterpret_cast<const E *>(lines_smem + 512 + r.st * pitch + lut[b]);
+		const uint32_t nx = lds_u16(4u * r.st + lds_u8(lut_a + b));
 		if (nx == dead) { r.died = 1; r.at = j; break; }
 		r.st = nx;
 		if (W > 0 && nx >= first_event) {
-			const uint32_t old = __ldg(perm_inv + nx);
+			const uint32_t old = __ldg(perm_inv + hd.state(nx));
 #pragma unroll
 			for (int k = 0; k < W; k++) r.m[k] |= __ldg(masks + (size_t) old * W + k);
 		}
@@ -107,16 +136,31 @@ constexpr int LINES_THREADS = 768;
 
 enum { EV_NONE = 0, EV_DEAD = 1, EV_EAGER = 2 };
 
-template <typename E, int W, int EV>
+template <int W, int EV>
 __global__ void __launch_bounds__(LINES_THREADS, 1)
 k1_lines_kernel(const LinesArgs a)
 {
 	__shared__ uint64_t blob_bar;
 	stage_blob(lines_smem, a.blob, a.blob_bytes, &blob_bar);
-	const uint8_t *lut = lines_smem;                  /* byte (+256 when outside the line) -> class * sizeof(E) */
-	const uint8_t *tab = lines_smem + 512;
-	const uint8_t *is_end = lines_smem + a.end_off;
-	const uint32_t pitch = a.pitch;                   /* bytes */
+
+	const uint32_t lut_a = smem_u32(lines_smem);          /* 1024-aligned; must be < 32 KiB for the PRMT trick */
+	Handles hd;
+	hd.tab4 = (lut_a + a.tab_off) >> 2;
+	hd.pitch4 = a.pitch >> 2;
+	hd.magic = 0xFFFFFFFFu / hd.pitch4 + 1u;
+	if (lut_a >= 0x8000u) __trap();                        /* static shared memory grew past 31 KiB: cannot happen in this file */
+	{
+		/* state numbers -> handles, in place (every CTA, once) */
+		uint16_t *ent = reinterpret_cast<uint16_t *>(lines_smem + a.tab_off);
+		const uint32_t nent = a.ntable * (a.pitch >> 1);
+		for (uint32_t e = threadIdx.x; e < nent; e += blockDim.x) ent[e] = (uint16_t) hd.of(ent[e]);
+		__syncthreads();
+	}
+	const uint32_t is_end_a = lut_a + a.end_off;
+	const uint32_t lut_bits = (lut_a >> 8) * 0x01010101u;  /* address byte 1 of the LUT, in every byte */
+	const uint32_t h_first = (EV != EV_NONE) ? hd.of(a.first_event) : 0xFFFFFFFFu;
+	const uint32_t h_dead = a.dead != NO_EDGE ? hd.of(a.dead) : 0xFFFFFFFFu;
+	const uint32_t h_start = hd.of(a.start);
 
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint64_t nwarps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
@@ -167,7 +211,7 @@ k1_lines_kernel(const LinesArgs a)
 			load_sector(nbeg & ~(uintptr_t) 31, N);
 		}
 	}
-	uint32_t st = a.start;
+	uint32_t st = h_start;
 	uintptr_t line_beg = cur;
 	uint64_t acc[W > 0 ? W : 1];
 #pragma unroll
@@ -180,35 +224,47 @@ k1_lines_kernel(const LinesArgs a)
 		const bool more = saddr + 32 < end;              /* the line continues in the next sector */
 		if (more) load_sector(saddr + 32, B);
 
-		if (a.prefetch != 0 && (saddr & 96u) == 0 && saddr + a.prefetch + 128 <= hi_ptr) {
-			asm volatile("prefetch.global.L2 [%0];" :: "l"(saddr + a.prefetch));
-		}
-
-		/* walk all 32 bytes; bytes outside [lo, hi) take the NOP column */
+		/* walk the sector; bytes outside [lo, hi) take the NOP column, words entirely outside are skipped */
 		const uint32_t mask = (hi > lo) ? ((0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (32u - hi))) : 0u;
 		const uint32_t inv = ~mask;
 		const uint32_t entry = st;
-		const uint32_t base = a.first_event - 1u;         /* EV_DEAD: first_event is the dead row */
-		uint32_t seen = 0, ssum = 0;
+		const uint32_t base_ev = h_first - 1u;            /* EV_DEAD: first_event is the dead row */
+		uint32_t seen = 0, ssum = 0, nsteps = 0;
 		uint32_t snap[8];
 #pragma unroll
 		for (int k = 0; k < 8; k++) {
-			/* byte t of vw = 1 when byte 4k + t is outside the line */
-			const uint32_t vw = (((inv >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u;
-			/* index = byte | outside << 8 */
-#define LINES_STEP(T)                                                                             \
-			st = (uint32_t) *reinterpret_cast<const E *>(tab + st * pitch + lut[byte_and_flag<T>(A[k], vw)]); \
-			if (EV == EV_EAGER) seen = max(seen, st);                                             \
-			if (EV != EV_NONE) ssum += max(st, base);
-			LINES_STEP(0) LINES_STEP(1) LINES_STEP(2) LINES_STEP(3)
-#undef LINES_STEP
+			const uint32_t nib = (inv >> (4 * k)) & 0xFu;
 			if (EV == EV_DEAD) snap[k] = st;
+			if (nib != 0xFu) {
+				/* byte t of out01 = 1 when byte 4k + t is outside the line; such bytes read LUT[256] */
+				const uint32_t out01 = (nib * 0x00204081u) & 0x01010101u;
+				const uint32_t x = A[k] & ~(out01 * 0xFFu);
+				const uint32_t vw = out01 | lut_bits;
+#define LINES_STEP(T)                                                                             \
+				st = lds_u16(4u * st + lds_u8(byte_and_flag<T>(x, vw)));                          \
+				if (EV == EV_EAGER) seen = max(seen, st);                                         \
+				if (EV != EV_NONE) ssum += max(st, base_ev);
+				LINES_STEP(0) LINES_STEP(1) LINES_STEP(2) LINES_STEP(3)
+#undef LINES_STEP
+				if (EV != EV_NONE) nsteps += 4;
+				if (EV == EV_DEAD) snap[k] = st;
+			}
 		}
 		bool died = false;
 		uint32_t consumed_here = hi - lo;
-		if (EV == EV_DEAD && st == a.dead) {
-			/* the dead row absorbs (NOP steps included): ssum - 32 base = steps spent dead */
-			const uint32_t j = 32u - (ssum - 32u * base);          /* sector byte that had no edge */
+		if (EV == EV_DEAD && st == h_dead) {
+			/* the dead row absorbs (NOP steps included): ssum - nsteps * base = steps spent dead.  Steps
+			 * are taken in walked words only; map the count back to a sector byte index. */
+			uint32_t dead_steps = ssum - nsteps * base_ev;
+			uint32_t j = 32;                                  /* sector byte that had no edge */
+#pragma unroll
+			for (int k = 7; k >= 0; k--) {
+				const uint32_t nib = (inv >> (4 * k)) & 0xFu;
+				if (nib != 0xFu && dead_steps != 0) {
+					if (dead_steps <= 4u) { j = 4u * (uint32_t) k + (4u - dead_steps); dead_steps = 0; }
+					else dead_steps -= 4u;
+				}
+			}
 			const uint32_t kq = j >> 2;
 			uint32_t from = entry, word = A[0];
 #pragma unroll
@@ -216,20 +272,21 @@ k1_lines_kernel(const LinesArgs a)
 #pragma unroll
 			for (int t = 0; t < 3; t++) {
 				if ((uint32_t) t < (j & 3u) && ((mask >> (4u * kq + (uint32_t) t)) & 1u)) {
-					from = (uint32_t) *reinterpret_cast<const E *>(tab + from * pitch + lut[(word >> (8 * t)) & 0xFFu]);
+					from = lds_u16(4u * from + lds_u8(lut_a + ((word >> (8 * t)) & 0xFFu)));
 				}
 			}
 			st = from;
 			died = true;
 			consumed_here = j - lo;
 		}
-		if (EV == EV_EAGER && seen >= a.first_event) {
-			if (ssum - 32u * base == seen - base && seen != a.dead) {
+		if (EV == EV_EAGER && seen >= h_first) {
+			if (ssum - nsteps * base_ev == seen - base_ev && seen != h_dead) {
 				/* exactly one state with ids entered, once */
+				const uint32_t ev = hd.state(seen) - a.first_event;
 #pragma unroll
-				for (int k = 0; k < W; k++) acc[k] |= __ldg(a.ev_masks + (size_t) (seen - a.first_event) * W + k);
+				for (int k = 0; k < W; k++) acc[k] |= __ldg(a.ev_masks + (size_t) ev * W + k);
 			} else {
-				const Rewalk<W> r = lines_rewalk<E, W>(pitch, entry, mask, a.first_event, a.dead, a.perm_inv, a.masks, A);
+				const Rewalk<W> r = lines_rewalk<W>(hd, lut_a, entry, mask, h_first, h_dead, a.perm_inv, a.masks, A);
 				st = r.st;
 #pragma unroll
 				for (int k = 0; k < W; k++) acc[k] |= r.m[k];
@@ -240,7 +297,7 @@ k1_lines_kernel(const LinesArgs a)
 		 * follows: the rest of the line cannot change the record (nor fire a new id), so it is
 		 * neither walked nor read. */
 		bool absorbed = false;
-		if (!died && more && a.absorb != nullptr && __ldg(a.absorb + st)) {
+		if (!died && more && a.absorb != nullptr && __ldg(a.absorb + hd.state(st))) {
 			absorbed = true;
 			cur = end;
 		} else {
@@ -248,9 +305,10 @@ k1_lines_kernel(const LinesArgs a)
 		}
 		if (died || !more || absorbed) {
 			/* line done */
+			const uint32_t sn = hd.state(st);
 			uint4 v;
-			v.x = (!died && is_end[st]) ? 1u : 0u;
-			v.y = __ldg(a.perm_inv + st);
+			v.x = (!died && lds_u8(is_end_a + sn)) ? 1u : 0u;
+			v.y = __ldg(a.perm_inv + sn);
 			const uint64_t consumed = (uint64_t) (cur - line_beg);
 			v.z = (uint32_t) consumed;
 			v.w = (uint32_t) (consumed >> 32);
@@ -263,7 +321,7 @@ k1_lines_kernel(const LinesArgs a)
 			have = have_next;
 			if (have) {
 				cur = nbeg; end = nend; line_beg = cur;
-				st = a.start;
+				st = h_start;
 #pragma unroll
 				for (int k = 0; k < 8; k++) A[k] = N[k];
 				have_next = i + 32 < wend;
@@ -280,11 +338,11 @@ k1_lines_kernel(const LinesArgs a)
 	}
 }
 
-template <typename E, int W, int EV>
+template <int W, int EV>
 int
 launch_lines(const LinesArgs &a, int device, cudaStream_t stream)
 {
-	auto kern = k1_lines_kernel<E, W, EV>;
+	auto kern = k1_lines_kernel<W, EV>;
 	const size_t smem_bytes = (a.blob_bytes + 127u) & ~(size_t) 127u;
 	if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes) != cudaSuccess) {
 		cudaGetLastError();
@@ -311,16 +369,15 @@ launch_lines(const LinesArgs &a, int device, cudaStream_t stream)
 	return 0;
 }
 
-template <typename E>
 int
 dispatch_lines(const LinesArgs &a, uint32_t words, bool dead, int device, cudaStream_t stream)
 {
 	switch (words) {
-	case 0: return dead ? launch_lines<E, 0, EV_DEAD>(a, device, stream) : launch_lines<E, 0, EV_NONE>(a, device, stream);
-	case 1: return launch_lines<E, 1, EV_EAGER>(a, device, stream);
-	case 2: return launch_lines<E, 2, EV_EAGER>(a, device, stream);
-	case 3: return launch_lines<E, 3, EV_EAGER>(a, device, stream);
-	case 4: return launch_lines<E, 4, EV_EAGER>(a, device, stream);
+	case 0: return dead ? launch_lines<0, EV_DEAD>(a, device, stream) : launch_lines<0, EV_NONE>(a, device, stream);
+	case 1: return launch_lines<1, EV_EAGER>(a, device, stream);
+	case 2: return launch_lines<2, EV_EAGER>(a, device, stream);
+	case 3: return launch_lines<3, EV_EAGER>(a, device, stream);
+	case 4: return launch_lines<4, EV_EAGER>(a, device, stream);
 	default:
 		set_error("k1_lines: %u mask words not supported", words);
 		errno = ENOTSUP;
@@ -349,26 +406,23 @@ k1_lines_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *
 	a.blob = static_cast<const uint8_t *>(dfa->d_lblob);
 	a.blob_bytes = dfa->lblob_bytes;
 	a.pitch = dfa->l_pitch;
+	a.tab_off = dfa->l_tab_off;
 	a.end_off = dfa->l_end_off;
+	a.ntable = dfa->ntable;
+	a.ncols = dfa->l_ncols;
 	a.dead = dfa->l_dead;
 	a.start = dfa->l_start;
 	a.perm_inv = dfa->d_lperm_inv;
 	a.absorb = getenv("FSM_B200_NO_ABSORB_SKIP") == nullptr ? dfa->d_labsorb : nullptr;
 	a.masks = dfa->d_eager_masks;
+	a.ev_masks = dfa->d_lev_masks;
 	a.base = d_base; a.offsets = d_offsets; a.stride = stride; a.len = len; a.n = n;
 	a.out = d_out; a.out_masks = d_masks;
 	const uint32_t words = d_masks != nullptr ? dfa->eager_words : 0u;
 	/* without a mask buffer only a missing edge is an event: the dead row is the last one */
 	a.first_event = words != 0 ? dfa->l_first_event : dfa->l_dead;
 	for (uint32_t w = 0; w < words && w < 4; w++) a.start_mask[w] = dfa->l_start_mask[w];
-	a.ev_masks = dfa->d_lev_masks;
-	a.prefetch = 8192;
-	if (const char *e = getenv("FSM_B200_LINES_PREFETCH")) {        /* tuning knob: L2 prefetch distance, 0 = off */
-		const int v = atoi(e);
-		if (v >= 0 && v <= (1 << 20) && (v % 128) == 0) a.prefetch = (uint32_t) v;
-	}
-	if (dfa->l_entry_bytes == 1) return dispatch_lines<uint8_t>(a, words, !dfa->complete, dfa->device, stream);
-	return dispatch_lines<uint16_t>(a, words, !dfa->complete, dfa->device, stream);
+	return dispatch_lines(a, words, !dfa->complete, dfa->device, stream);
 }
 
 } // namespace fsmb200
