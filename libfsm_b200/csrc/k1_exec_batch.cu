@@ -762,6 +762,142 @@ k1_tile_kernel(const K1Args a, const __grid_constant__ CUtensorMap tmap)
 	}
 }
 
+
+/* ------------------------------------------------------------------ K-RANGE x TILE ------ */
+
+/*
+ * The k-range walk (ALU byte classification, one table read per 4 bytes) fed by the TMA tile ring
+ * of k1_tile_kernel instead of per-lane 256-bit loads.  Why: with one lane per input every lane
+ * streams its own 1 KiB row, and that access pattern -- whatever the load width or depth -- tops out
+ * at 5.8 TB/s on B200 (tools/micro/membench.cu: 32 / 64 / 128 B per lane per step, 1-4 steps in
+ * flight: 5.83 TB/s; 4 lanes reading 128 contiguous bytes of a row: 6.6 TB/s; 8 lanes x 256 B: 7.1;
+ * fully coalesced: 7.2).  Here a warp's tile is 32 rows x CH bytes fetched by ONE 2-D TMA request
+ * (CH contiguous bytes per row, hardware swizzle so that the lanes' 16-byte shared-memory reads do
+ * not conflict), completed on an mbarrier; the lanes then walk their own row out of shared memory.
+ * Fixed-stride, 16-byte aligned batches only (as k1_tile_kernel).
+ * Shared memory: [k-range blob, padded to 1024][per warp: NSTAGE stages of 32 x CH bytes][mbarriers]
+ */
+template <bool HAS_DEAD, int RNG, int CH, int NSTAGE>
+__global__ void __launch_bounds__(1024, 1)
+k1_krange_tile_kernel(const K1Args a, const __grid_constant__ CUtensorMap tmap)
+{
+	extern __shared__ __align__(1024) uint8_t smem[];
+	__shared__ uint64_t blob_bar;
+	constexpr uint32_t STAGE_BYTES = 32u * CH;
+	constexpr int NVEC = CH / 16;
+
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint32_t nwarps = blockDim.x >> 5;
+	uint8_t *stage_base = smem + a.tile_stage_off + (size_t) warp * NSTAGE * STAGE_BYTES;
+	uint64_t *bars = reinterpret_cast<uint64_t *>(smem + a.tile_bar_off) + (size_t) warp * NSTAGE;
+
+	if (lane == 0) {
+#pragma unroll
+		for (int s = 0; s < NSTAGE; s++) mbar_init(smem_u32(&bars[s]), 1);
+	}
+	stage_blob(smem, a.kblob, a.kblob_bytes, &blob_bar);   /* fences + syncs the inits too */
+
+	const uint8_t *L0 = smem;
+	const uint8_t *t1 = smem + a.k1_off;
+	const uint8_t *is_end = smem + a.kend_off;
+	const uint32_t p1 = a.k1pitch;
+	const uint32_t kt_half = (smem_u32(smem) + 256u) >> 1;
+#define STEP1(st, b) ((uint32_t) t1[(st) * p1 + L0[(b)]])
+#define KR_WORD(w)                                                                                   \
+	do {                                                                                             \
+		const uint32_t l_ = (w) & 0x7F7F7F7Fu;                                                       \
+		const uint32_t h0_ = ((w) ^ a.kr_hxor[0]) & 0x80808080u;                                     \
+		const uint32_t h1_ = RNG == 1 ? h0_ : (((w) ^ a.kr_hxor[1]) & 0x80808080u);                  \
+		const uint32_t i0_ = (l_ + a.kr_add_lo[0]) & ~(l_ + a.kr_add_hi[0]) & h0_;                   \
+		const uint32_t i1_ = (l_ + a.kr_add_lo[1]) & ~(l_ + a.kr_add_hi[1]) & h1_;                   \
+		const uint32_t acc_ = __dp4a(i1_, 0x80200802u, __dp4a(i0_, 0x40100401u, kt_half));           \
+		asm("ld.shared.u8 %0, [%1];" : "=r"(st) : "r"(st + acc_ + acc_));                            \
+	} while (0)
+
+	const uint32_t ntiles = (uint32_t) ((a.n + 31) >> 5);
+	const uint32_t gw = blockIdx.x * nwarps + warp;
+	const uint32_t GW = gridDim.x * nwarps;
+	const uint32_t nst = (uint32_t) ((a.len + CH - 1) / CH);      /* stages per tile */
+
+	/* swizzle: physical 16B chunk = logical ^ f(row) (CU_TENSOR_MAP_SWIZZLE_{32,64,128}B) */
+	const uint32_t swz = (CH == 128) ? (lane & 7u) : (CH == 64) ? ((lane >> 1) & 3u) : ((lane >> 2) & 1u);
+	const uint32_t row_off = lane * CH;
+	const uint32_t stage_a = smem_u32(stage_base);
+	const uint32_t bars_a = smem_u32(bars);
+
+	struct Cursor { uint32_t tile, sidx, slot, phase; };
+	Cursor cc = { gw, 0u, 0u, 0u }, ic = cc;        /* gw >= ntiles: nothing to do, but stay for the signal */
+	auto advance = [&](Cursor &c) {
+		if (++c.sidx == nst) { c.sidx = 0; c.tile += GW; }
+		if (++c.slot == (uint32_t) NSTAGE) { c.slot = 0; c.phase ^= 1u; }
+	};
+	auto issue = [&]() {
+		if (ic.tile < ntiles) {
+			if (lane == 0) {
+				const uint32_t bar = bars_a + ic.slot * 8u;
+				mbar_expect_tx(bar, STAGE_BYTES);
+				tma_tile_g2s(stage_a + ic.slot * STAGE_BYTES, &tmap, ic.sidx * CH, ic.tile << 5, bar);
+			}
+			advance(ic);
+		}
+	};
+#pragma unroll
+	for (int s = 0; s < NSTAGE; s++) issue();
+
+	uint32_t st = a.start;
+	uint64_t pos = 0;
+	bool died = false;
+	while (cc.tile < ntiles) {
+		const uint64_t row = ((uint64_t) cc.tile << 5) + lane;
+		if (cc.sidx == 0) { st = a.start; pos = 0; died = false; }
+
+		mbar_wait(bars_a + cc.slot * 8u, cc.phase);
+
+		const uint8_t *srow = stage_base + cc.slot * STAGE_BYTES + row_off;
+		const uint64_t remain = a.len - (uint64_t) cc.sidx * CH;  /* bytes of this input left */
+		if (!died && row < a.n) {
+			if (remain >= CH) {
+#pragma unroll
+				for (int v = 0; v < NVEC; v++) {
+					const uint4 x = *reinterpret_cast<const uint4 *>(srow + (((uint32_t) v ^ swz) << 4));
+					const uint32_t entry = st;
+					KR_WORD(x.x); KR_WORD(x.y); KR_WORD(x.z); KR_WORD(x.w);
+					if (HAS_DEAD && st == a.dead) {
+						/* a byte of this 16-byte chunk had no edge: re-walk it to find which */
+						st = entry;
+						for (uint32_t k = 0; k < 16; k++) {
+							const uint32_t b = srow[((((uint32_t) v ^ swz) << 4) | k)];
+							const uint32_t nx = STEP1(st, b);
+							if (nx == a.dead) { died = true; pos += (uint64_t) k; break; }
+							st = nx;
+						}
+						break;
+					}
+					pos += 16;
+				}
+			} else {
+				for (uint32_t k = 0; k < (uint32_t) remain; k++) {
+					const uint32_t b = srow[((((k >> 4) ^ swz) << 4) | (k & 15u))];
+					const uint32_t nx = STEP1(st, b);
+					if (HAS_DEAD && nx == a.dead) { died = true; break; }
+					st = nx;
+					pos++;
+				}
+			}
+		}
+		if (cc.sidx == nst - 1 && row < a.n) {
+			const int32_t ret = (!died && is_end[st]) ? 1 : 0;
+			store_result(a, row, ret, st, pos);
+		}
+		__syncwarp();       /* every lane has finished reading this slot */
+		advance(cc);
+		issue();            /* refill the slot just freed */
+	}
+	signal_done(a);
+#undef KR_WORD
+#undef STEP1
+}
+
 /* ------------------------------------------------------------------ host side -------- */
 
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
@@ -919,6 +1055,63 @@ launch_tile(K1Args a, int sms, int smem_optin, cudaStream_t stream)
 	return 0;
 }
 
+template <bool HAS_DEAD, int RNG, int CH, int NSTAGE>
+int
+launch_krange_tile(K1Args a, int sms, int smem_optin, cudaStream_t stream)
+{
+	auto kern = k1_krange_tile_kernel<HAS_DEAD, RNG, CH, NSTAGE>;
+	encode_tiled_fn enc = get_encode_tiled();
+	if (enc == nullptr) {
+		set_error("k1_krange_tile: cuTensorMapEncodeTiled unavailable");
+		errno = EIO;
+		return -1;
+	}
+	const uint32_t blob_pad = (a.kblob_bytes + 1023u) & ~1023u;
+	const uint32_t per_warp = (uint32_t) NSTAGE * 32u * CH;
+	int nwarps = (int) (((uint32_t) smem_optin - blob_pad - 1024u) / (per_warp + 8u * NSTAGE));
+	if (nwarps > 32) nwarps = 32;
+	if (const char *e = getenv("FSM_B200_KRTILE_WARPS")) {         /* tuning knob */
+		const int v = atoi(e);
+		if (v >= 1 && v < nwarps) nwarps = v;
+	}
+	if (nwarps < 1) {
+		set_error("k1_krange_tile: table too large");
+		errno = ENOTSUP;
+		return -1;
+	}
+	const uint64_t ntiles = (a.n + 31) >> 5;
+	a.tile_stage_off = blob_pad;
+	a.tile_bar_off = blob_pad + (uint32_t) nwarps * per_warp;
+	const size_t smem_bytes = (size_t) a.tile_bar_off + (size_t) nwarps * NSTAGE * 8u;
+	if (!set_smem(kern, smem_bytes)) {
+		set_error("k1_krange_tile: cannot opt in to %zu bytes of shared memory", smem_bytes);
+		errno = EIO;
+		return -1;
+	}
+	CUtensorMap tmap;
+	const cuuint64_t gdim[2] = { (cuuint64_t) a.stride, (cuuint64_t) a.n };
+	const cuuint64_t gstr[1] = { (cuuint64_t) a.stride };
+	const cuuint32_t box[2] = { (cuuint32_t) CH, 32u };
+	const cuuint32_t estr[2] = { 1u, 1u };
+	const CUtensorMapSwizzle sw = (CH == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+	    : (CH == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+	CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(a.base), gdim, gstr,
+	    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+	    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) {
+		set_error("k1_krange_tile: cuTensorMapEncodeTiled failed (%d)", (int) r);
+		errno = EIO;
+		return -1;
+	}
+	uint64_t grid = (ntiles + (uint64_t) nwarps - 1) / (uint64_t) nwarps;
+	if (grid > (uint64_t) sms) grid = (uint64_t) sms;
+	if (grid == 0) grid = 1;
+	kern<<<(unsigned) grid, nwarps * 32, smem_bytes, stream>>>(a, tmap);
+	count_launch();
+	FSMB_CUDA(cudaGetLastError(), return -1);
+	return 0;
+}
+
 int g_variant = 0;
 
 struct K1SignalArgs { uint32_t *flags[8]; uint32_t n, value; };
@@ -934,7 +1127,7 @@ k1_signal_only_kernel(const K1SignalArgs a)
 }
 
 int
-dispatch_kstride(const fsm_b200_dfa *dfa, const K1Args &a0, int sms, cudaStream_t stream)
+dispatch_kstride(const fsm_b200_dfa *dfa, const K1Args &a0, int sms, cudaStream_t stream, bool tile_ok = false)
 {
 	const bool dead = !dfa->complete;
 	uint32_t rng = (dfa->kstride == 4 && dfa->d_rblob != nullptr) ? dfa->krange : 0u;
@@ -947,6 +1140,25 @@ dispatch_kstride(const fsm_b200_dfa *dfa, const K1Args &a0, int sms, cudaStream_
 		if (const char *e = getenv("FSM_B200_KRANGE_PREFETCH")) {      /* tuning knob: L2 prefetch distance, 0 = off */
 			const int v = atoi(e);
 			if (v >= 0 && v <= 65536 && (v % 128) == 0) a.kr_prefetch = (uint32_t) v;
+		}
+		/* fixed-stride, 16-byte aligned batches of inputs at least a tile wide: TMA tile ring (the DRAM
+		 * access pattern of one lane per row caps at 5.8 TB/s, see k1_krange_tile_kernel) */
+		int tile = 128;
+		if (const char *e = getenv("FSM_B200_KRANGE_TILE")) tile = atoi(e);          /* tuning knob: 0 = per-lane loads, 64, 128 */
+		if (tile_ok && a.len >= 256 && a.entry == nullptr && a.n_dev == nullptr && (tile == 128 || tile == 64)) {
+			int smem_optin = 0, sms2 = 0;
+			if (device_props(dfa->device, &sms2, &smem_optin)) {
+				int stages = 2;
+				if (const char *e = getenv("FSM_B200_KRTILE_STAGES")) { const int v = atoi(e); if (v == 2 || v == 3 || v == 4) stages = v; }
+#define KRT(RNGV, CHV, NSV) (dead ? launch_krange_tile<true, RNGV, CHV, NSV>(a, sms, smem_optin, stream) : launch_krange_tile<false, RNGV, CHV, NSV>(a, sms, smem_optin, stream))
+				if (tile == 128) {
+					if (rng == 1) return stages == 2 ? KRT(1, 128, 2) : stages == 3 ? KRT(1, 128, 3) : KRT(1, 128, 4);
+					return stages == 2 ? KRT(2, 128, 2) : stages == 3 ? KRT(2, 128, 3) : KRT(2, 128, 4);
+				}
+				if (rng == 1) return stages == 2 ? KRT(1, 64, 2) : stages == 3 ? KRT(1, 64, 3) : KRT(1, 64, 4);
+				return stages == 2 ? KRT(2, 64, 2) : stages == 3 ? KRT(2, 64, 3) : KRT(2, 64, 4);
+#undef KRT
+			}
 		}
 		if (rng == 1) return dead ? launch_kstride<4, true, 1>(a, sms, stream) : launch_kstride<4, false, 1>(a, sms, stream);
 		return dead ? launch_kstride<4, true, 2>(a, sms, stream) : launch_kstride<4, false, 2>(a, sms, stream);
@@ -966,6 +1178,14 @@ k1_tile_eligible(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t 
 	return dfa->smem_resident && dfa->nclasses == 0 && d_offsets == nullptr && n > 0 && len > 0 &&
 	    (reinterpret_cast<uintptr_t>(d_base) & 15u) == 0 && (stride & 15u) == 0 &&
 	    stride >= len && stride < (1ull << 32) && n < (1ull << 31) && dfa->entry_bytes <= 2;
+}
+
+/* what the TMA tile ring needs of the BATCH (any table): fixed stride, 16-byte aligned */
+static bool
+k1_tile_base_ok(const uint8_t *d_base, const uint64_t *d_offsets, uint64_t stride, uint64_t len, size_t n)
+{
+	return d_offsets == nullptr && n > 0 && len > 0 && (reinterpret_cast<uintptr_t>(d_base) & 15u) == 0 && (stride & 15u) == 0 &&
+	    stride >= len && stride < (1ull << 32) && n < (1ull << 31);
 }
 
 static void
@@ -1145,7 +1365,7 @@ k1_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offs
 			errno = ENOTSUP;
 			return -1;
 		}
-		return dispatch_kstride(dfa, a, sms, stream);
+		return dispatch_kstride(dfa, a, sms, stream, k1_tile_base_ok(d_base, d_offsets, stride, len, n));
 	}
 
 	if (!tile_ok) {

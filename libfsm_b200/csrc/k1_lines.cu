@@ -217,7 +217,12 @@ k1_lines_kernel(const LinesArgs a)
 #pragma unroll
 	for (int k = 0; k < (W > 0 ? W : 1); k++) acc[k] = W > 0 ? a.start_mask[k] : 0;
 
-	while (have) {
+	/* every lane stays in the loop until the whole warp is done: the vote reconverges the warp at the
+	 * top of every iteration (lanes finish and switch lines at different iterations; without it the
+	 * groups that diverged there ran the walk separately from then on -- ncu: every walk instruction
+	 * executed twice per iteration with two thirds of the lanes) */
+	while (__any_sync(0xFFFFFFFFu, have)) {
+		if (!have) continue;
 		const uintptr_t saddr = cur & ~(uintptr_t) 31;
 		const uint32_t lo = (uint32_t) (cur - saddr);
 		const uint32_t hi = (end - saddr) >= 32 ? 32u : (uint32_t) (end - saddr);
