@@ -1070,9 +1070,12 @@ launch_krange_tile(K1Args a, int sms, int smem_optin, cudaStream_t stream)
 	const uint32_t per_warp = (uint32_t) NSTAGE * 32u * CH;
 	int nwarps = (int) (((uint32_t) smem_optin - blob_pad - 1024u) / (per_warp + 8u * NSTAGE));
 	if (nwarps > 32) nwarps = 32;
+	/* measured on B200 (config 2, CH = 128, 2 stages): throughput grows linearly up to 12 warps per SM
+	 * (each warp is bound by its own lookup chain) and is flat to slightly worse beyond (profiles/) */
+	if (nwarps > 12) nwarps = 12;
 	if (const char *e = getenv("FSM_B200_KRTILE_WARPS")) {         /* tuning knob */
 		const int v = atoi(e);
-		if (v >= 1 && v < nwarps) nwarps = v;
+		if (v >= 1 && v <= 32 && (size_t) blob_pad + 1024u + (size_t) v * (per_warp + 8u * NSTAGE) <= (size_t) smem_optin) nwarps = v;
 	}
 	if (nwarps < 1) {
 		set_error("k1_krange_tile: table too large");
