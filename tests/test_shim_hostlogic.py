@@ -271,3 +271,13 @@ def test_eager_selftest_program():
     p = subprocess.run([os.path.join(CPU_DIR, "shim_eager_selftest")], capture_output=True, timeout=120)
     assert p.returncode == 0, (p.stdout.decode(), p.stderr.decode())
     assert b"shim eager selftest ok" in p.stdout
+
+
+def test_patched_retest_impl_gpu_over_the_stub_engine():
+    """integration/retest_impl_gpu.patch applied to a copy of the reference's src/retest (build time):
+    `retest -l gpu` matches every vector of a regexp block with one fsm_exec_batch call and must agree,
+    line for line, with the DFAVM interpreter on the reference's tests/retest/*.tst (115 vectors)."""
+    import retestcheck
+    if not os.path.exists(os.path.join(ROOT, "build", "shim_cpu", "retest_b200")):
+        pytest.skip("patched retest not built (needs the reference tree at build time)")
+    assert retestcheck.check_all(os.path.join(ROOT, "build", "shim_cpu")) >= 100
