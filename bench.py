@@ -178,6 +178,15 @@ def cpu_leg_cfg2(fsm, host_sample: np.ndarray, threads: int):
         run = lambda mode, t, frac: O.exec_batch(fsm, *part(frac), nthreads=t, validate_each=(mode == 0))
     out = sweep_modes(run, flat.size, threads)
     if h is not None:
+        # secondary baseline: the reference's bytecode engine fsm_vm_match_buffer (yes / no only)
+        fb, ob = part(4)
+        t0 = time.perf_counter(); vm = R.vm_match_batch(h, fb, ob, nthreads=threads); dt = time.perf_counter() - t0
+        f1, o1 = part(16)
+        t0 = time.perf_counter(); R.vm_match_batch(h, f1, o1, nthreads=1); dt1 = time.perf_counter() - t0
+        rec = R.exec_batch(h, fb, ob, mode=1, nthreads=threads)
+        assert ((vm == 1) == (rec["ret"] == 1)).all(), "fsm_vm_match_buffer and fsm_exec disagree"
+        out["cpu_vm"] = {"entry": "fsm_vm_match_buffer (DFAVM interpreter, vm.c:218-229; verdict only)", "gbs": fb.size / dt / 1e9,
+                         "threads": threads, "gbs_1t": f1.size / dt1 / 1e9}
         R.free(h)
     out["kind"] = kind
     return out
@@ -211,7 +220,8 @@ def sweep_modes(run, nbytes: int, threads: int):
 def cpu_baseline_record(cpu: dict, sample: str) -> dict:
     return {"value": cpu["asis_gbs"], "unit": "GB/s", "cores": cpu["asis_threads"], "kind": cpu["kind"], "sample": sample,
             "amortised_value": cpu["amortised_gbs"], "amortised_cores": cpu["amortised_threads"],
-            "cpu_1t": {"as_is": cpu["asis_1t_gbs"], "amortised": cpu["amortised_1t_gbs"]}, "threads_swept": cpu["threads_swept"]}
+            "cpu_1t": {"as_is": cpu["asis_1t_gbs"], "amortised": cpu["amortised_1t_gbs"]}, "threads_swept": cpu["threads_swept"],
+            **({"cpu_vm": cpu["cpu_vm"]} if "cpu_vm" in cpu else {})}
 
 
 def cpu_leg_cfg3(g, nlines: int, threads: int):

@@ -315,6 +315,15 @@ struct fsm_b200_det_stats {
 };
 int fsm_b200_determinise_stats(struct fsm_b200_det_stats *st);
 
+/* --- DFAVM bytecode loader (host code, no device needed) -------------------------------------
+ * A DFA saved in the reference's DFAVM format ("DFAVM$" + encoding 0.1 + u32 length + instruction bytes:
+ * fsm_dfavm_save, src/libfsm/vm.c:39-71; vm/v1.c) becomes a library-owned description (free with
+ * fsm_b200_desc_free) that fsm_b200_dfa_compile takes like any other: state i = the i-th FETCH of the
+ * program, the start state where the program begins; a STOP-success becomes an absorbing accepting state, a STOP-fail a
+ * missing edge.  The VM answers yes / no only, so the description carries no end ids.
+ * Returns 0, or -1 with errno EINVAL (not a DFAVM image / malformed) or ENOTSUP (other encoding). */
+int fsm_b200_dfavm_load(const uint8_t *image, size_t nbytes, struct fsm_b200_owned_desc *out);
+
 /* --- minimisation: the partition refinement of fsm_minimise -----------------------------
  * (src/libfsm/minimise.c:74-190: trim to start- and end-reachable states, then merge
  * indistinguishable states; end states with different end-id sets are never merged,

@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "fsm_b200_determinise", "fsm_b200_determinise_ex", "fsm_b200_desc_free", "fsm_b200_determinise_stats",
     "fsm_b200_owned_desc_eager", "fsm_b200_dfa_eager_info",
     "fsm_b200_exec_batch_eager_host", "fsm_b200_exec_batch_eager_dev",
-    "fsm_b200_minimise", "fsm_b200_minimise_stats",
+    "fsm_b200_minimise", "fsm_b200_minimise_stats", "fsm_b200_dfavm_load",
     "fsm_b200_launch_count",
 )
 
@@ -93,6 +93,7 @@ def _load() -> C.CDLL:
     lib.fsm_b200_determinise_stats.argtypes = [P(CDetStats)]
     lib.fsm_b200_minimise.argtypes = [P(CDesc), C.c_int, P(COwnedDesc)]
     lib.fsm_b200_minimise_stats.argtypes = [P(CDetStats)]
+    lib.fsm_b200_dfavm_load.argtypes = [vp, sz, P(COwnedDesc)]
     lib.fsm_b200_launch_count.argtypes = [C.c_int]
     lib.fsm_b200_launch_count.restype = C.c_uint64
     return lib

@@ -260,6 +260,18 @@ def minimise(dfa: FlatFsm, device: int = 0) -> FlatFsm:
         lib.fsm_b200_desc_free(C.byref(od))
 
 
+def load_dfavm(image: bytes) -> FlatFsm:
+    """A DFA from the reference's DFAVM bytecode image ("DFAVM$", src/libfsm/vm.c:39-71; host code only):
+    state i = the i-th FETCH; yes / no semantics only (no end ids in the image)."""
+    od = COwnedDesc()
+    buf = (C.c_uint8 * len(image)).from_buffer_copy(image)
+    check(lib.fsm_b200_dfavm_load(buf, len(image), C.byref(od)), "dfavm_load")
+    try:
+        return FlatFsm.from_c(od.desc)
+    finally:
+        lib.fsm_b200_desc_free(C.byref(od))
+
+
 def _with_eager(f: FlatFsm, od) -> FlatFsm:
     """Attach the eager-output sets of a library-owned result (fsm_b200_owned_desc_eager)."""
     off, ids = C.c_void_p(), C.c_void_p()

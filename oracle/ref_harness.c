@@ -20,6 +20,8 @@
 #include <fsm/walk.h>
 #include <fsm/parser.h>
 #include <re/re.h>
+#include <fsm/vm.h>
+#include <fsm/options.h>
 
 #include <adt/set.h>
 #include <adt/stateset.h>
@@ -600,5 +602,74 @@ refh_star(void *vfsm)
 	}
 	fsm_setend(fsm, start, 1);
 	return 1;
+}
+
+/* ---- the DFAVM bytecode engine (src/libfsm/vm.c, vm/v1.c): secondary CPU baseline + loader fixture ---- */
+
+enum dfavm_io_result { DFAVM_IO_OK_ = 0 };
+int fsm_dfavm_save(FILE *f, const struct fsm_dfavm *vm);        /* src/libfsm/vm.c:39-49 (internal, not in libfsm.syms) */
+
+/* fsm_vm_compile + fsm_dfavm_save: the "DFAVM$" file image of a DFA (malloc'd). */
+int
+refh_dfavm_bytes(const void *fsm, uint8_t **out, size_t *len)
+{
+	struct fsm_dfavm *vm = fsm_vm_compile(fsm);
+	char *buf = NULL;
+	size_t n = 0;
+	FILE *f;
+	int rc;
+	if (vm == NULL) return -1;
+	f = open_memstream(&buf, &n);
+	if (f == NULL) { fsm_vm_free(vm); return -1; }
+	rc = fsm_dfavm_save(f, vm);
+	fclose(f);
+	fsm_vm_free(vm);
+	if (rc != 0) { free(buf); return -1; }
+	*out = (uint8_t *) buf; *len = n;
+	return 0;
+}
+
+struct vjob { const struct fsm_dfavm *vm; const uint8_t *base; const uint64_t *offsets; size_t lo, hi; uint8_t *out; };
+
+static void *
+vworker(void *opaque)
+{
+	struct vjob *j = opaque;
+	size_t i;
+	for (i = j->lo; i < j->hi; i++) {
+		j->out[i] = (uint8_t) (fsm_vm_match_buffer(j->vm, (const char *) j->base + j->offsets[i],
+		    (size_t) (j->offsets[i + 1] - j->offsets[i])) != 0);
+	}
+	return NULL;
+}
+
+/* n fsm_vm_match_buffer calls (vm.c:218-229 -> vm_match_v1) over nthreads pthreads; out[i] = matched.
+ * The VM is compiled once (the reference's retest does the same, runner.c:430-438). */
+int
+refh_vm_match_batch(const void *fsm, const uint8_t *base, const uint64_t *offsets, size_t n, int nthreads, uint8_t *out)
+{
+	struct fsm_dfavm *vm = fsm_vm_compile(fsm);
+	pthread_t tids[256];
+	struct vjob jobs[256];
+	int t, started = 0, rc = 0;
+	if (vm == NULL) return -1;
+	if (nthreads < 1) nthreads = 1;
+	if (nthreads > 256) nthreads = 256;
+	for (t = 0; t < nthreads; t++) {
+		jobs[t].vm = vm; jobs[t].base = base; jobs[t].offsets = offsets; jobs[t].out = out;
+		jobs[t].lo = n * (size_t) t / (size_t) nthreads;
+		jobs[t].hi = n * (size_t) (t + 1) / (size_t) nthreads;
+	}
+	if (nthreads == 1) {
+		vworker(&jobs[0]);
+	} else {
+		for (t = 0; t < nthreads; t++) {
+			if (pthread_create(&tids[t], NULL, vworker, &jobs[t]) != 0) { rc = -1; errno = EAGAIN; break; }
+			started = t + 1;
+		}
+		for (t = 0; t < started; t++) pthread_join(tids[t], NULL);
+	}
+	fsm_vm_free(vm);
+	return rc;
 }
 

@@ -82,4 +82,9 @@ int   refh_exec_eager_batch(void *fsm, const uint8_t *base, const uint64_t *offs
 void *refh_utf8dfa(int lo, int hi);
 int   refh_star(void *fsm);
 
+/* The reference's bytecode engine: the "DFAVM$" image of a DFA (fsm_vm_compile + fsm_dfavm_save; malloc'd),
+ * and n fsm_vm_match_buffer calls over nthreads pthreads (bool only: vm.c:218-229). */
+int refh_dfavm_bytes(const void *fsm, uint8_t **out, size_t *len);
+int refh_vm_match_batch(const void *fsm, const uint8_t *base, const uint64_t *offsets, size_t n, int nthreads, uint8_t *out);
+
 #endif

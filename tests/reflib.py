@@ -232,6 +232,8 @@ class Ref:
         L.refh_exec_eager.argtypes = [vp, vp, C.c_uint64, P(CResult), vp, C.c_size_t, P(C.c_size_t)]
         L.refh_union_repeated_pattern_group.argtypes = [C.c_size_t, P(vp), C.c_uint]
         L.refh_union_repeated_pattern_group.restype = vp
+        L.refh_dfavm_bytes.argtypes = [vp, P(vp), P(C.c_size_t)]
+        L.refh_vm_match_batch.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, vp]
         L.refh_utf8dfa.argtypes = [C.c_int, C.c_int]; L.refh_utf8dfa.restype = vp
         L.refh_star.argtypes = [vp]
         L.refh_exec_eager_batch.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, C.c_int, vp, vp, C.c_size_t, vp, C.c_size_t]
@@ -272,6 +274,22 @@ class Ref:
         h = self.lib.refh_union_repeated_pattern_group(len(handles), arr, id_base)
         assert h
         return h
+
+    # -- the DFAVM bytecode engine -----------------------------------------------------
+    def dfavm_bytes(self, h) -> bytes:
+        """The "DFAVM$" file image of a DFA: fsm_vm_compile + fsm_dfavm_save."""
+        buf, n = C.c_void_p(), C.c_size_t(0)
+        assert self.lib.refh_dfavm_bytes(h, C.byref(buf), C.byref(n)) == 0
+        try:
+            return C.string_at(buf, n.value)
+        finally:
+            self.libc.free(buf)
+
+    def vm_match_batch(self, h, base: np.ndarray, offsets: np.ndarray, nthreads: int = 1) -> np.ndarray:
+        n = offsets.shape[0] - 1
+        out = np.zeros(n, dtype=np.uint8)
+        assert self.lib.refh_vm_match_batch(h, _ptr(base), offsets.ctypes.data, n, nthreads, _ptr(out)) == 0
+        return out
 
     # -- construction ---------------------------------------------------------------
     def utf8dfa(self, lo: int = 0, hi: int = 0x10FFFF):
