@@ -527,7 +527,41 @@ def main_cfg4():
     R.free(h); R.free(p)
 
 
+canonical_digest = reflib.canonical_digest
+
+
+def main_cfg5eps():
+    """golden_cfg5eps.npz: BASELINE config 5's epsilon-heavy variant: 2000 random 50-letter
+    literals, each compiled by re_comp(RE_LITERAL) and given end id = its index, combined with
+    fsm_union_array (a new start state with an epsilon edge to every sub-automaton; 3998 epsilon edges,
+    201 999 states).  The reference's fsm_determinise needs ~150 s for it on this box; its result is kept as
+    (state count, sha256 of the canonical form) -- the DFA itself would be 90 MB."""
+    R = reflib.Ref()
+    O = reflib.Oracle()
+    rng = np.random.default_rng(12345)
+    words = ["".join(chr(c) for c in rng.integers(97, 123, size=50)) for _ in range(2000)]
+    hs = [R.re_comp(w, reflib.RE_LITERAL, 0) for w in words]
+    for i, h in enumerate(hs):
+        R.setendid(h, i)
+    u = R.union_array(hs)
+    nfa = R.flatten(u)
+    import time
+    t0 = time.time(); R.determinise(u); dt = time.time() - t0
+    dfa = R.flatten(u)
+    out = {}
+    goldenio.pack_fsm("nfa_", nfa, out)
+    out["meta"] = np.frombuffer(json.dumps({"nfa_states": nfa.nstates, "eps_edges": int(nfa.eps_off[-1]), "dfa_states": dfa.nstates,
+                                            "dfa_canonical_sha256": canonical_digest(O, dfa), "reference_determinise_s": dt}).encode(), dtype=np.uint8)
+    path = os.path.join(HERE, "golden_cfg5eps.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote golden_cfg5eps.npz: NFA {nfa.nstates} states / {int(nfa.eps_off[-1])} eps edges -> DFA {dfa.nstates} states in {dt:.1f} s (reference), "
+          f"{os.path.getsize(path) / 1024:.0f} KiB")
+    R.free(u)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg5eps":       # ~3 min: not part of the default regeneration
+        main_cfg5eps()
     if len(sys.argv) > 1 and sys.argv[1] == "cfg4":          # ~40 s: not part of the default regeneration
         main_cfg4()
     if len(sys.argv) < 2 or sys.argv[1] == "cfg3":

@@ -162,3 +162,9 @@ def load_cfg4(path: str | None = None) -> dict:
     """golden_cfg4.npz (make_golden.py main_cfg4): {"fsm": the utf8dfa-star validator, "meta": {...}}."""
     z = np.load(path or os.path.join(GOLDEN_DIR, "golden_cfg4.npz"))
     return {"fsm": unpack_fsm("utf8dfa_star_", z), "meta": json.loads(bytes(z["meta"]).decode())}
+
+
+def load_cfg5eps(path: str | None = None) -> dict:
+    """golden_cfg5eps.npz (make_golden.py main_cfg5eps): {"nfa": FlatFsm, "meta": {dfa_states, dfa_canonical_sha256, ...}}."""
+    z = np.load(path or os.path.join(GOLDEN_DIR, "golden_cfg5eps.npz"))
+    return {"nfa": unpack_fsm("nfa_", z), "meta": json.loads(bytes(z["meta"]).decode())}

@@ -198,6 +198,18 @@ def canonical_form(oracle: Oracle, f: FlatFsm):
     return tab, ends, ids, eager
 
 
+def canonical_digest(oracle, f):
+    """sha256 over the numbering-independent form of a DFA (reflib.canonical_form): table, end bits, end-id sets."""
+    import hashlib
+    tab, ends, ids, _eager = canonical_form(oracle, f)
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(tab, dtype=np.uint32).tobytes())
+    h.update(np.ascontiguousarray(ends, dtype=np.uint8).tobytes())
+    for t in ids:
+        h.update(np.asarray(t, dtype=np.uint32).tobytes() + b"|")
+    return h.hexdigest()
+
+
 class RefFlat(C.Structure):
     _fields_ = [("desc", CDesc), ("blocks", C.c_void_p * 8)]
 

@@ -79,3 +79,18 @@ def test_config5_full_size(oracle):
     assert_isomorphic(oracle, got, want)
     dense_edges = int((oracle.flatten(got) != 0xFFFFFFFF).sum())
     assert dense_edges == got.nstates * 256                         # complete: /./ self-loop at start
+
+
+def test_config5_epsilon_variant_against_the_reference(oracle):
+    """SURVEY.md 8d's epsilon-heavy variant: 2000 re_comp(RE_LITERAL) automata under fsm_union_array
+    (201 999 states, 3998 epsilon edges).  The reference's fsm_determinise took ~150 s for it
+    (tests/golden/make_golden.py main_cfg5eps); the fixture holds its state count and the sha256 of its
+    canonical form, which K2's result has to reproduce."""
+    g = goldenio.load_cfg5eps()
+    nfa, meta = g["nfa"], g["meta"]
+    assert nfa.nstates == meta["nfa_states"]
+    got = L.determinise(nfa)
+    st = L.determinise_stats()
+    print("config5 eps-variant determinise stats:", st, "reference s:", meta["reference_determinise_s"])
+    assert got.nstates == meta["dfa_states"]
+    assert reflib.canonical_digest(oracle, got) == meta["dfa_canonical_sha256"]

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import goldenio
+import reflib
 
 CASES = goldenio.load_exec_cases(os.path.join(goldenio.GOLDEN_DIR, "golden_exec.npz"))
 
@@ -78,3 +79,12 @@ def test_oracle_matches_reference_on_config3_automata(oracle):
         assert fired == want, i
     a = g["anchored"]
     assert (oracle.exec_batch(a["fsm"], a["base"], a["offsets"], nthreads=4) == a["expect"]).all()
+
+
+def test_oracle_determinise_reproduces_the_reference_on_the_epsilon_variant(oracle):
+    """golden_cfg5eps.npz: 2000 re_comp literals under fsm_union_array; the reference's fsm_determinise
+    result is kept as (state count, sha256 of the canonical form)."""
+    g = goldenio.load_cfg5eps()
+    d = oracle.determinise(g["nfa"])
+    assert d.nstates == g["meta"]["dfa_states"]
+    assert reflib.canonical_digest(oracle, d) == g["meta"]["dfa_canonical_sha256"]
