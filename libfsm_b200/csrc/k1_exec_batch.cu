@@ -783,6 +783,7 @@ k1_krange_tile_kernel(const K1Args a, const __grid_constant__ CUtensorMap tmap)
 {
 	extern __shared__ __align__(1024) uint8_t smem[];
 	__shared__ uint64_t blob_bar;
+	__shared__ uint32_t main_done;
 	constexpr uint32_t STAGE_BYTES = 32u * CH;
 	constexpr int NVEC = CH / 16;
 
@@ -795,6 +796,7 @@ k1_krange_tile_kernel(const K1Args a, const __grid_constant__ CUtensorMap tmap)
 #pragma unroll
 		for (int s = 0; s < NSTAGE; s++) mbar_init(smem_u32(&bars[s]), 1);
 	}
+	if (threadIdx.x == 0) main_done = 0u;
 	stage_blob(smem, a.kblob, a.kblob_bytes, &blob_bar);   /* fences + syncs the inits too */
 
 	const uint8_t *L0 = smem;
@@ -815,9 +817,26 @@ k1_krange_tile_kernel(const K1Args a, const __grid_constant__ CUtensorMap tmap)
 	} while (0)
 
 	const uint32_t ntiles = (uint32_t) ((a.n + 31) >> 5);
-	const uint32_t gw = blockIdx.x * nwarps + warp;
-	const uint32_t GW = gridDim.x * nwarps;
 	const uint32_t nst = (uint32_t) ((a.len + CH - 1) / CH);      /* stages per tile */
+
+	/* Tile schedule.  A lane's walk is one dependent chain, so a warp's time per tile is fixed and an SM
+	 * is full at `nmain` warps; static rounds of grid x nmain tiles then leave a ragged last round (config
+	 * 2: 18.45 rounds cost 19).  When the host finds it pays, the CTA carries extra warps that sleep
+	 * through the first `Rm` rounds and the tiles of the last two rounds are dealt to ALL warps at once,
+	 * so every SM stays saturated to the end:
+	 *   round r <  Rm : main warp g takes tile g + r x GWm
+	 *   round r >= Rm : warp with all-warp number ga takes tile Rm x GWm + ga + (r - Rm) x GWa
+	 * (main warps are numbered first among all warps, so leftovers go to warps that are awake anyway). */
+	const uint32_t nmain = a.tile_main_warps ? a.tile_main_warps : nwarps;
+	const uint32_t Rm = a.tile_main_warps ? a.tile_main_rounds : 0xFFFFFFFFu;
+	const bool is_main = warp < nmain;
+	const uint32_t GWm = gridDim.x * nmain, GWa = gridDim.x * nwarps;
+	const uint32_t gwm = blockIdx.x * nmain + warp;
+	const uint32_t gwa = is_main ? gwm : GWm + blockIdx.x * (nwarps - nmain) + (warp - nmain);
+	const uint32_t F0 = a.tile_main_warps ? Rm * GWm : 0u;
+	auto tile_of = [&](uint32_t r) -> uint32_t {
+		return r < Rm ? gwm + r * GWm : F0 + gwa + (r - Rm) * GWa;
+	};
 
 	/* swizzle: physical 16B chunk = logical ^ f(row) (CU_TENSOR_MAP_SWIZZLE_{32,64,128}B) */
 	const uint32_t swz = (CH == 128) ? (lane & 7u) : (CH == 64) ? ((lane >> 1) & 3u) : ((lane >> 2) & 1u);
@@ -825,10 +844,11 @@ k1_krange_tile_kernel(const K1Args a, const __grid_constant__ CUtensorMap tmap)
 	const uint32_t stage_a = smem_u32(stage_base);
 	const uint32_t bars_a = smem_u32(bars);
 
-	struct Cursor { uint32_t tile, sidx, slot, phase; };
-	Cursor cc = { gw, 0u, 0u, 0u }, ic = cc;        /* gw >= ntiles: nothing to do, but stay for the signal */
+	struct Cursor { uint32_t round, tile, sidx, slot, phase; };
+	const uint32_t r0 = (is_main || Rm == 0xFFFFFFFFu) ? 0u : Rm;
+	Cursor cc = { r0, tile_of(r0), 0u, 0u, 0u }, ic = cc;   /* tile >= ntiles: nothing to do, but stay for the signal */
 	auto advance = [&](Cursor &c) {
-		if (++c.sidx == nst) { c.sidx = 0; c.tile += GW; }
+		if (++c.sidx == nst) { c.sidx = 0; c.round++; c.tile = tile_of(c.round); }
 		if (++c.slot == (uint32_t) NSTAGE) { c.slot = 0; c.phase ^= 1u; }
 	};
 	auto issue = [&]() {
@@ -841,6 +861,11 @@ k1_krange_tile_kernel(const K1Args a, const __grid_constant__ CUtensorMap tmap)
 			advance(ic);
 		}
 	};
+	if (!is_main && r0 != 0u) {
+		/* sleep until half of this CTA's main warps have left their main rounds */
+		while (*reinterpret_cast<volatile uint32_t *>(&main_done) * 2u < nmain) __nanosleep(2000);
+	}
+	bool announced = !is_main || Rm == 0xFFFFFFFFu || Rm == 0u;
 #pragma unroll
 	for (int s = 0; s < NSTAGE; s++) issue();
 
@@ -891,8 +916,13 @@ k1_krange_tile_kernel(const K1Args a, const __grid_constant__ CUtensorMap tmap)
 		}
 		__syncwarp();       /* every lane has finished reading this slot */
 		advance(cc);
+		if (!announced && cc.round >= Rm) {
+			announced = true;
+			if (lane == 0) atomicAdd(&main_done, 1u);
+		}
 		issue();            /* refill the slot just freed */
 	}
+	if (!announced && lane == 0) atomicAdd(&main_done, 1u);   /* a main warp that had no tile at all */
 	signal_done(a);
 #undef KR_WORD
 #undef STEP1
@@ -1083,6 +1113,33 @@ launch_krange_tile(K1Args a, int sms, int smem_optin, cudaStream_t stream)
 		return -1;
 	}
 	const uint64_t ntiles = (a.n + 31) >> 5;
+	uint64_t grid = (ntiles + (uint64_t) nwarps - 1) / (uint64_t) nwarps;
+	if (grid > (uint64_t) sms) grid = (uint64_t) sms;
+	if (grid == 0) grid = 1;
+	/* ragged last round: carry sleeping extra warps and deal the last two rounds' tiles to all warps at
+	 * once when that is predicted to be quicker (see the kernel's tile schedule).  Cost model, in units
+	 * of one warp's tile time: an SM runs `nwarps` walks at full speed and is issue-bound beyond that;
+	 * oversubscription costs ~5% more (measured: 16 warps per SM run at 0.95 of 12). */
+	a.tile_main_warps = 0; a.tile_main_rounds = 0;
+	{
+		const char *e = getenv("FSM_B200_KRTILE_TAIL");
+		const bool allow = e == nullptr || atoi(e) != 0;
+		const uint64_t GWm = grid * (uint64_t) nwarps;
+		const uint64_t R = (ntiles + GWm - 1) / GWm;
+		const int max_warps = (int) std::min<uint64_t>(32, ((uint64_t) smem_optin - blob_pad - 1024u) / (per_warp + 8u * NSTAGE));
+		if (allow && grid == (uint64_t) sms && R >= 2 && R < (1u << 20) && max_warps > nwarps) {
+			const uint64_t Fn = ntiles - (R - 2) * GWm;
+			const int need = (int) ((Fn + grid - 1) / grid);             /* warps per CTA for one final round */
+			if (need <= max_warps) {
+				const double cost = (double) (R - 2) + 1.05 * std::max(1.0, (double) Fn / (double) grid / (double) nwarps);
+				if (cost < (double) R - 0.05) {
+					a.tile_main_warps = (uint32_t) nwarps;
+					a.tile_main_rounds = (uint32_t) (R - 2);
+					nwarps = std::max(need, nwarps);
+				}
+			}
+		}
+	}
 	a.tile_stage_off = blob_pad;
 	a.tile_bar_off = blob_pad + (uint32_t) nwarps * per_warp;
 	const size_t smem_bytes = (size_t) a.tile_bar_off + (size_t) nwarps * NSTAGE * 8u;
@@ -1106,9 +1163,6 @@ launch_krange_tile(K1Args a, int sms, int smem_optin, cudaStream_t stream)
 		errno = EIO;
 		return -1;
 	}
-	uint64_t grid = (ntiles + (uint64_t) nwarps - 1) / (uint64_t) nwarps;
-	if (grid > (uint64_t) sms) grid = (uint64_t) sms;
-	if (grid == 0) grid = 1;
 	kern<<<(unsigned) grid, nwarps * 32, smem_bytes, stream>>>(a, tmap);
 	count_launch();
 	FSMB_CUDA(cudaGetLastError(), return -1);

@@ -50,6 +50,8 @@ struct K1Args {
 	uint32_t prefer_lane;       /* K1b jobs: long inputs, keep the 3-instructions-per-byte LANE kernel */
 	uint32_t tile_stage_off;    /* TILE variants: shared-memory carve-up */
 	uint32_t tile_bar_off;
+	uint32_t tile_main_warps;  /* k-range tile kernel: warps per CTA that run the main rounds (0: all) */
+	uint32_t tile_main_rounds; /* ... and how many rounds they run before the all-warp final rounds */
 };
 
 bool k1_tile_eligible(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,

@@ -325,3 +325,27 @@ def test_alu_classified_kstride_matches_oracle(torch_cuda, oracle, monkeypatch, 
         assert_records_equal(L.results_from_torch(out), want, f"{spec} lane")
         if missing:
             assert (want["consumed"] < length).any()
+
+
+@pytest.mark.parametrize("ntiles_extra", [500, 1776 + 778])
+def test_krange_tile_tail_schedule_matches_oracle(torch_cuda, oracle, monkeypatch, ntiles_extra):
+    """k1_krange_tile_kernel's tail schedule (sleeping extra warps, the last two rounds dealt to all
+    warps): batches of just over one / two full rounds of 148 x 12 tiles, where the host picks it, against
+    the oracle and against the same kernel with the schedule switched off."""
+    torch = torch_cuda
+    cases = {c["name"]: c for c in goldenio.load_exec_cases(os.path.join(goldenio.GOLDEN_DIR, "golden_exec.npz"))}
+    fsm = cases["cfg2:uniform"]["fsm"]
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    n, length = (sms * 12 + ntiles_extra) * 32 - 5, 256
+    host = workloads.cfg2_host(n, length, True, seed=11)
+    host[::7, 100] = 0x07                                     # some inputs die mid-way
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(length)
+    want = oracle.exec_batch(fsm, host.reshape(-1), offsets, nthreads=8)
+    with L.Dfa(fsm) as dfa:
+        dev = torch.from_numpy(host).cuda()
+        L.set_exec_variant("auto")
+        for tail in ("1", "0"):
+            monkeypatch.setenv("FSM_B200_KRTILE_TAIL", tail)
+            out = dfa.exec_batch(dev, stride=length, length=length, n=n)
+            torch.cuda.synchronize()
+            assert_records_equal(L.results_from_torch(out), want, f"tail schedule {tail}")
