@@ -604,7 +604,7 @@ def run_cfg2(args):
                        "h2d_bytes_per_step": int(h_in.numel() + h_off.numel() * 8), "d2h_bytes_per_step": int(h_out.numel()),
                        "entry": "fsm_b200_exec_batch_host, pinned host buffers"}
         line["gpu_launches"] = int(launches)
-        line["roofline"] = roofline_record(bytes_step, kms, "k1_krange_kernel (K-STRIDE with ALU byte classification)" if dfa.info["krange"] and args.variant in ("auto", "kstride") else args.variant,
+        line["roofline"] = roofline_record(bytes_step, kms, "k1_krange_tile_kernel (4-byte stride, ALU byte classification, 2-D TMA input tiles)" if dfa.info["krange"] and args.variant in ("auto", "kstride") else args.variant,
                                            "r2_k1_traffic.json" if args.dist == "uniform" else None)
         if other is not None:
             line["other_distribution"] = other

@@ -24,8 +24,10 @@
  * of the whole range: exec_stream uses entry = start; the multi-GPU shard form all-gathers
  * the maps of the ranks' byte ranges and composes them in rank order (sharding.py).
  *
- * Applies to tables with <= 256 rows (8-bit entries, shared-memory resident).  Larger DFAs,
- * and inputs too short to cut, run as a K1 batch of one (a serial walk on one lane).
+ * Applies to every table form up to 65534 states: 8-bit dense rows in shared memory use the prefix
+ * kernel below, everything else (16-/32-bit entries, class-indexed rows, L2-resident tables) the
+ * generic prefix kernel that reads the table through the read-only path; the body is whatever K1 kernel
+ * the table form gets for a batch.  Inputs too short to cut run as a K1 batch of one (one lane).
  */
 #include <cstring>
 #include <mutex>
@@ -55,6 +57,7 @@ struct StreamArgs {
 	const uint8_t *absorb; /* [ntable] */
 	const uint8_t *blob;
 	uint32_t blob_bytes, pitch, dead;
+	uint32_t entry_bytes, cls_off, has_cls;   /* generic prefix kernel: table form (global memory) */
 	/* per (chunk, state) */
 	uint32_t *img, *pdo, *pdf;
 	uint32_t *job_of;      /* [chunk][image state] -> job index; NOJOB / PENDING while unclaimed */
@@ -153,6 +156,50 @@ k1b_prefix_kernel(const StreamArgs a)
 				a.job_end[j] = beg + clen;
 				a.job_entry[j] = st;
 				*slot = j;                      /* read by the compose kernels (later launches) */
+			}
+		}
+	}
+}
+
+/* 1'. prefix for every other table form (16- / 32-bit entries, class-indexed rows, tables too large
+ * for shared memory): the same walk with the table read from global memory through the read-only
+ * path (the rows touched by W steps from consecutive entry states are L1/L2-resident).  T x W lookups
+ * per chunk -- next to a chunk of at least 128 x T bytes that is under 1/8 lookup per input byte. */
+template <typename E>
+__global__ void __launch_bounds__(256)
+k1b_prefix_generic_kernel(const StreamArgs a)
+{
+	const uint64_t total = (uint64_t) a.nchunks * a.T;
+	const uint64_t nthreads = (uint64_t) gridDim.x * blockDim.x;
+	const uint8_t *cls = a.blob + a.cls_off;
+	for (uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+		const uint32_t c = (uint32_t) (idx / a.T), s = (uint32_t) (idx % a.T);
+		const uint64_t beg = (uint64_t) c * a.C;
+		const uint64_t clen = min(a.C, a.len - beg);
+		const uint32_t w = (uint32_t) min((uint64_t) a.W, clen);
+		const uint8_t *p = a.buf + beg;
+		uint32_t st = s, dk = 0, df = s;
+		bool died = false;
+		for (uint32_t k = 0; k < w; k++) {
+			const uint32_t b = __ldg(p + k);
+			const uint32_t col = a.has_cls ? (uint32_t) __ldg(cls + b) : b;
+			const uint32_t nx = (uint32_t) __ldg(reinterpret_cast<const E *>(a.blob + (size_t) st * a.pitch) + col);
+			if (nx == a.dead) { died = true; dk = k; df = st; break; }
+			st = nx;
+		}
+		if (died) {
+			a.img[idx] = DEADMARK; a.pdo[idx] = dk; a.pdf[idx] = df;
+		} else {
+			a.img[idx] = st;
+			uint32_t *slot = &a.job_of[(uint64_t) c * a.T + st];
+			if (a.absorb[st]) {
+				*slot = ABSORBED;
+			} else if (atomicCAS(slot, NOJOB, NOJOB - 1u) == NOJOB) {
+				const uint32_t j = atomicAdd(a.njobs, 1u);
+				a.job_beg[j] = beg + w;
+				a.job_end[j] = beg + clen;
+				a.job_entry[j] = st;
+				*slot = j;
 			}
 		}
 	}
@@ -276,6 +323,15 @@ ss_get(const fsm_b200_dfa *cdfa)
 	return static_cast<StreamScratch *>(dfa->stream_scratch);
 }
 
+constexpr uint32_t K1B_MAX_STATES = 65534u;
+
+/* 8-bit dense rows in shared memory: the round-1 prefix kernel */
+bool
+small_table(const fsm_b200_dfa *dfa)
+{
+	return dfa->smem_resident && dfa->nclasses == 0 && dfa->entry_bytes == 1;
+}
+
 uint32_t
 pick_window(uint32_t T)
 {
@@ -360,15 +416,24 @@ stream_map(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStre
 	FSMB_CUDA(cudaMemsetAsync(a.job_of, 0xFF, cs * sizeof(uint32_t), stream), return -1);
 	FSMB_CUDA(cudaMemsetAsync(a.njobs, 0, sizeof(uint32_t), stream), return -1);
 
-	const size_t smem_bytes = (dfa->blob_bytes + 127u) & ~(size_t) 127u;
-	FSMB_CUDA(cudaFuncSetAttribute(k1b_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes), return -1);
-	{
+	a.entry_bytes = dfa->entry_bytes; a.cls_off = dfa->cls_off; a.has_cls = dfa->nclasses != 0 ? 1u : 0u;
+	if (small_table(dfa)) {
+		const size_t smem_bytes = (dfa->blob_bytes + 127u) & ~(size_t) 127u;
+		FSMB_CUDA(cudaFuncSetAttribute(k1b_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes), return -1);
 		int per_sm = 1;
 		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1b_prefix_kernel, 1024, smem_bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
 		uint64_t want = (cs + 1023) / 1024;
 		const uint64_t cap = (uint64_t) sms * (uint64_t) per_sm;
 		unsigned grid = (unsigned) (want < cap ? want : cap);
 		k1b_prefix_kernel<<<grid, 1024, smem_bytes, stream>>>(a);
+		count_launch();
+	} else {
+		uint64_t want = (cs + 255) / 256;
+		const uint64_t cap = (uint64_t) sms * 8u;
+		const unsigned grid = (unsigned) (want < cap ? want : cap);
+		if (dfa->entry_bytes == 1) k1b_prefix_generic_kernel<uint8_t><<<grid, 256, 0, stream>>>(a);
+		else if (dfa->entry_bytes == 2) k1b_prefix_generic_kernel<uint16_t><<<grid, 256, 0, stream>>>(a);
+		else k1b_prefix_generic_kernel<uint32_t><<<grid, 256, 0, stream>>>(a);
 		count_launch();
 	}
 	/* body: at most one job per (chunk, state); the actual count is read on the device */
@@ -398,8 +463,10 @@ stream_map(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStre
 bool
 parallel_ok(const fsm_b200_dfa *dfa, uint64_t len)
 {
-	if (!(dfa->smem_resident && dfa->nclasses == 0 && dfa->entry_bytes == 1)) return false;
+	/* chunk maps hold 16-bit states (DEAD16 reserved) */
+	if (dfa->nstates > K1B_MAX_STATES) return false;
 	uint64_t min_len = 4096;
+	if (!small_table(dfa)) min_len = 1024ull * dfa->nstates;      /* at least a few chunks of 128 x T bytes */
 	if (const char *e = getenv("FSM_B200_STREAM_MIN")) {
 		const long v = atol(e);
 		if (v >= 0) min_len = (uint64_t) v;
@@ -499,8 +566,8 @@ fsm_b200_exec_stream_map_dev(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint
 		errno = EINVAL;
 		return -1;
 	}
-	if (!(dfa->smem_resident && dfa->nclasses == 0 && dfa->entry_bytes == 1)) {
-		set_error("exec_stream_map_dev: needs a table with <= 256 rows");
+	if (dfa->nstates > K1B_MAX_STATES) {
+		set_error("exec_stream_map_dev: needs a table with at most %u states", K1B_MAX_STATES);
 		errno = ENOTSUP;
 		return -1;
 	}

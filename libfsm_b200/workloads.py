@@ -143,7 +143,7 @@ def cfg3_patterns():
     match, and the subset construction then remembers WHICH patterns have matched -- 2^n states (8
     patterns `ERROR [0-9]{3}`: 18 433 DFA states, 136 after minimise; 64 mixed ones: 2.9 M states in
     447 s) -- for the reference and, the DFA being the same, for K2 alike.  With the trailing literal
-    the 128 patterns give 1625 DFA states, 1509 after minimise.
+    the 128 patterns give 1590 DFA states, 1474 after minimise.
     Returns (patterns, instances): instances[i] is a byte string pattern i matches."""
     pats, inst = [], []
     forms = [(" [0-9]{3} ", " 404 "), ("\\[[0-9]+\\] ", "[17] "), (": [0-9]+ms ", ": 250ms "), ("=[0-9]{2} ", "=42 ")]

@@ -40,6 +40,36 @@ def test_config1_files(tmp_path):
 
 
 @needs_bins
+def test_re_x_large_file_against_the_reference(tmp_path):
+    """`re -x PATTERN FILE` on a 512 MiB file that has to be read to its end (whole-file pattern): the
+    relinked, unchanged re(1) -- fsm_fgetc recognised by the shim and read in fread blocks, K1b over the
+    buffer -- gives the reference's verdict, in less than the reference's time (one fgetc + one group
+    scan per byte).  Timings go to gpurun_out/ for profiles/."""
+    import json
+    import time
+    rng = np.random.default_rng(3)
+    n = 512 << 20
+    data = rng.integers(ord("a"), ord("z") + 1, size=n, dtype=np.uint8)
+    data[rng.random(n, dtype=np.float32) < 0.15] = ord(" ")
+    good, bad = tmp_path / "good.txt", tmp_path / "bad.txt"
+    good.write_bytes(data.tobytes())
+    data[n - 12345] = ord("#")
+    bad.write_bytes(data.tobytes())
+    del data
+    times = {}
+    for name, f, want_rc in (("good", good, 0), ("bad", bad, 1)):
+        args = ["-r", "pcre", "-x", r"^[a-z ]+$", str(f)]
+        t0 = time.perf_counter(); got = run(RE_B200, args); t1 = time.perf_counter(); want = run(RE_REF, args); t2 = time.perf_counter()
+        assert got[0] == want[0] == want_rc and got[1] == want[1], (name, got, want)
+        times[name] = {"re_b200_s": t1 - t0, "re_ref_s": t2 - t1}
+    print("re -x 512 MiB:", times)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "re_x_large_file.json"), "w") as fh:
+        json.dump({"bytes": n, "pattern": "^[a-z ]+$", "times": times}, fh)
+    assert times["good"]["re_b200_s"] < times["good"]["re_ref_s"], times
+
+
+@needs_bins
 @pytest.mark.parametrize("args", [
     ["-r", "pcre", r"a[ -~]{7}\z", "xxabcdefgh"],
     ["-r", "pcre", r"a[ -~]{7}\z", "xxabcdefg"],

@@ -91,7 +91,7 @@ def test_anchored_stream_dies_in_prefix_and_body(oracle, chunk_env):
             assert dfa.exec_stream(buf) == oracle.exec(fsm, data)
 
 
-def test_wide_table_runs_serially_but_exactly(oracle):
+def test_wide_table_short_input_is_exact(oracle):
     fsm = case("union6:")["fsm"]                              # > 256 states: 16-bit entries
     rng = np.random.default_rng(3)
     al = np.frombuffer(b"erowaningfld id=0123456789ABC-xy", dtype=np.uint8)
@@ -99,6 +99,43 @@ def test_wide_table_runs_serially_but_exactly(oracle):
     with L.Dfa(fsm) as dfa:
         assert not dfa.info["smem_resident"] or dfa.info["entry_bytes"] == 2
         assert dfa.exec_stream(data) == oracle.exec(fsm, data.tobytes())
+
+
+def test_wide_class_indexed_table_stream_is_chunked_and_exact(oracle, torch_cuda):
+    """K1b on a table the round-1 prefix kernel could not take (1474 states, class-indexed 16-bit rows):
+    the config-3 union automaton over 8 MiB of concatenated log lines, cut at several lengths, against
+    the oracle's serial walk -- and more than one launch (prefix + body + compose), i.e. not one lane."""
+    c = goldenio.load_cfg3()["eager"]
+    fsm = c["fsm"]
+    _, inst = workloads.cfg3_patterns()
+    base, _ = workloads.cfg3_lines_host(60000, inst, seed=21)
+    data = base[:8 << 20]
+    with L.Dfa(fsm) as dfa:
+        assert dfa.info["entry_bytes"] == 2 and dfa.info["nstates"] > 1024
+        for cut in (data.size, data.size - 3, 3 << 20, (1 << 21) + 1):
+            L.launch_count(reset=True)
+            got = dfa.exec_stream(data[:cut])
+            assert L.launch_count() >= 4, "expected the chunked path"
+            assert got == oracle.exec(fsm, data[:cut].tobytes()), cut
+        assert dfa.exec_stream(torch_cuda.from_numpy(data).cuda()) == oracle.exec(fsm, data.tobytes())
+    a = goldenio.load_cfg3()["anchored"]["fsm"]                  # dies at the first byte that fits no pattern
+    with L.Dfa(a) as dfa:
+        assert dfa.exec_stream(data[:4 << 20]) == oracle.exec(a, data[:4 << 20].tobytes())
+
+
+@pytest.mark.parametrize("missing", [0.0, 0.002, 0.0001])
+def test_wide_random_dfa_stream_every_image_survives(oracle, missing):
+    """Worst case for the speculation, still exact: a random 300-state DFA (16-bit dense rows) whose chains
+    from different entry states do not merge, so every chunk keeps many live images; with a few missing
+    edges the walk dies somewhere in a body job."""
+    import synth
+    fsm = synth.dfa_from_classes(np.arange(256) % 7, 300, seed=5, missing=missing)
+    rng = np.random.default_rng(6)
+    data = rng.integers(0, 256, size=700000, dtype=np.uint8)
+    with L.Dfa(fsm) as dfa:
+        assert dfa.info["entry_bytes"] == 2
+        for cut in (data.size, 400001):
+            assert dfa.exec_stream(data[:cut]) == oracle.exec(fsm, data[:cut].tobytes()), (missing, cut)
 
 
 @pytest.mark.parametrize("name", ["utf8:", "cfg2:uniform", "anchored:^abc[0-9]+x$"])
