@@ -75,6 +75,7 @@ void *refh_union_repeated_pattern_group(size_t n, void **fsms, unsigned id_base)
 int   refh_exec_eager_batch(void *fsm, const uint8_t *base, const uint64_t *offsets, size_t n,
 	int mode, int nthreads, struct fsm_b200_result *out, uint64_t *masks, size_t words,
 	const uint32_t *id_of_bit, size_t nbits);
+double refh_last_walk_seconds(void);
 
 /* examples/utf8dfa/main.c over the same API calls: the DFA of the code points lo..hi (one code point
  * per input), determinised + minimised; and the Kleene star (epsilon from every end state to the start

@@ -281,6 +281,11 @@ class Ref:
             raise OSError(C.get_errno(), "refh_exec_eager_batch")
         return out, masks
 
+    def last_walk_seconds(self) -> float:
+        """Seconds the worker threads of the last exec_eager_batch spent walking (excludes the per-thread fsm_clone)."""
+        self.lib.refh_last_walk_seconds.restype = C.c_double
+        return float(self.lib.refh_last_walk_seconds())
+
     def union_repeated_pattern_group(self, handles, id_base: int = 1):
         arr = (C.c_void_p * len(handles))(*handles)
         h = self.lib.refh_union_repeated_pattern_group(len(handles), arr, id_base)
