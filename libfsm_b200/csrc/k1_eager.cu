@@ -26,12 +26,19 @@ using namespace fsmb200;
 namespace {
 
 /* per-DFA scratch of the _host entry point */
-struct EagerScratch {
-	std::mutex mu;
+struct EagerSlot {
 	cudaStream_t stream = nullptr;
 	void *d_in = nullptr, *d_off = nullptr, *d_out = nullptr, *d_masks = nullptr;
 	size_t in_cap = 0, off_cap = 0, out_cap = 0, masks_cap = 0;
-	bool grow(void **p, size_t *cap, size_t want) {
+	bool busy = false;
+};
+
+/* per-DFA grow-only buffers: two slots so that chunk k+1's host->device copy overlaps chunk k's scan and
+ * device->host copy (PCIe is full duplex; records + id bitsets are a fifth of config 3's traffic) */
+struct EagerScratch {
+	std::mutex mu;
+	EagerSlot slot[2];
+	static bool grow(void **p, size_t *cap, size_t want) {
 		if (*cap >= want) return true;
 		if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
 		const size_t ncap = want + want / 4 + 4096;
@@ -186,36 +193,76 @@ fsm_b200_exec_batch_eager_host(const fsm_b200_dfa *dfa,
 		}
 	}
 	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
-	const uint64_t lo = offsets[0], nbytes = offsets[n] - lo;
 	const size_t W = dfa->eager_words;
-	/* grow-only buffers and one stream per DFA, under a mutex (the shim's fsm_exec comes here for every
+	/* grow-only buffers and streams per DFA, under a mutex (the shim's fsm_exec comes here for every
 	 * input of an automaton with eager outputs: no cudaMalloc / cudaFree / stream creation per call) */
 	EagerScratch *sc = eager_scratch_get(dfa);
 	if (sc == nullptr) { errno = ENOMEM; return -1; }
 	std::lock_guard<std::mutex> guard(sc->mu);
-	if (sc->stream == nullptr) {
-		FSMB_CUDA(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking), return -1);
+
+	size_t chunk_bytes = 64u << 20;
+	if (const char *e = getenv("FSM_B200_HOST_CHUNK_MB")) {
+		long v = atol(e);
+		if (v >= 1 && v <= 4096) chunk_bytes = (size_t) v << 20;
 	}
-	if (!sc->grow(&sc->d_in, &sc->in_cap, nbytes + 64) || !sc->grow(&sc->d_off, &sc->off_cap, (n + 1) * sizeof(uint64_t)) ||
-	    !sc->grow(&sc->d_out, &sc->out_cap, n * sizeof(fsm_b200_result)) || !sc->grow(&sc->d_masks, &sc->masks_cap, n * W * sizeof(uint64_t))) {
-		set_error("exec_batch_eager_host: out of device memory");
-		errno = ENOMEM;
-		return -1;
+	int rc = 0, which = 0;
+	size_t i0 = 0;
+	while (i0 < n && rc == 0) {
+		/* chunk = lines [i0, i1): at least one, at most ~chunk_bytes of bytes and 4 M lines */
+		const uint64_t limit = offsets[i0] + chunk_bytes;
+		size_t lo = i0 + 1, hi = n;
+		while (lo < hi) {
+			const size_t mid = lo + (hi - lo + 1) / 2;
+			if (offsets[mid] <= limit) lo = mid; else hi = mid - 1;
+		}
+		size_t i1 = lo;
+		if (i1 - i0 > (4u << 20)) i1 = i0 + (4u << 20);
+		const size_t cn = i1 - i0;
+		const uint64_t lo_b = offsets[i0];
+		const size_t nbytes = (size_t) (offsets[i1] - lo_b);
+
+		EagerSlot &s = sc->slot[which];
+		which ^= 1;
+		if (s.stream == nullptr) {
+			FSMB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), { rc = -1; break; });
+		}
+		if (s.busy) {
+			FSMB_CUDA(cudaStreamSynchronize(s.stream), { rc = -1; break; });
+			s.busy = false;
+		}
+		if (!EagerScratch::grow(&s.d_in, &s.in_cap, nbytes + 64) || !EagerScratch::grow(&s.d_off, &s.off_cap, (cn + 1) * sizeof(uint64_t)) ||
+		    !EagerScratch::grow(&s.d_out, &s.out_cap, cn * sizeof(fsm_b200_result)) || !EagerScratch::grow(&s.d_masks, &s.masks_cap, cn * W * sizeof(uint64_t))) {
+			set_error("exec_batch_eager_host: out of device memory");
+			errno = ENOMEM;
+			rc = -1;
+			break;
+		}
+		/* keep the alignment of the caller's bytes modulo 32 (sector loads) */
+		uint8_t *d_in = static_cast<uint8_t *>(s.d_in) + (lo_b & 31u);
+		if (nbytes > 0) FSMB_CUDA(cudaMemcpyAsync(d_in, base + lo_b, nbytes, cudaMemcpyHostToDevice, s.stream), { rc = -1; break; });
+		FSMB_CUDA(cudaMemcpyAsync(s.d_off, offsets + i0, (cn + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream), { rc = -1; break; });
+		if (launch_eager(dfa, d_in - lo_b, static_cast<const uint64_t *>(s.d_off), 0, 0, cn, static_cast<fsm_b200_result *>(s.d_out),
+		    static_cast<uint64_t *>(s.d_masks), s.stream) != 0) {
+			rc = -1;
+			break;
+		}
+		FSMB_CUDA(cudaMemcpyAsync(out + i0, s.d_out, cn * sizeof(fsm_b200_result), cudaMemcpyDeviceToHost, s.stream), { rc = -1; break; });
+		FSMB_CUDA(cudaMemcpyAsync(masks + i0 * W, s.d_masks, cn * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream), { rc = -1; break; });
+		s.busy = true;
+		i0 = i1;
 	}
-	cudaStream_t st = sc->stream;
-	/* keep the alignment of the caller's bytes modulo 32 (sector loads) */
-	uint8_t *d_in = static_cast<uint8_t *>(sc->d_in) + (lo & 31u);
-	if (nbytes > 0) FSMB_CUDA(cudaMemcpyAsync(d_in, base + lo, nbytes, cudaMemcpyHostToDevice, st), return -1);
-	FSMB_CUDA(cudaMemcpyAsync(sc->d_off, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st), return -1);
-	if (launch_eager(dfa, d_in - lo, static_cast<const uint64_t *>(sc->d_off), 0, 0, n, static_cast<fsm_b200_result *>(sc->d_out),
-	    static_cast<uint64_t *>(sc->d_masks), st) != 0) {
-		cudaStreamSynchronize(st);
-		return -1;
+	for (EagerSlot &s : sc->slot) {
+		if (s.stream != nullptr && (s.busy || rc != 0)) {
+			cudaError_t e = cudaStreamSynchronize(s.stream);
+			s.busy = false;
+			if (e != cudaSuccess && rc == 0) {
+				set_error("exec_batch_eager_host: %s", cudaGetErrorString(e));
+				errno = EIO;
+				rc = -1;
+			}
+		}
 	}
-	FSMB_CUDA(cudaMemcpyAsync(out, sc->d_out, n * sizeof(fsm_b200_result), cudaMemcpyDeviceToHost, st), return -1);
-	FSMB_CUDA(cudaMemcpyAsync(masks, sc->d_masks, n * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, st), return -1);
-	FSMB_CUDA(cudaStreamSynchronize(st), return -1);
-	return 0;
+	return rc;
 }
 
 namespace fsmb200 {
@@ -225,8 +272,10 @@ eager_scratch_free(fsm_b200_dfa *dfa)
 	EagerScratch *sc = static_cast<EagerScratch *>(dfa->eager_scratch);
 	if (sc == nullptr) return;
 	cudaSetDevice(dfa->device);
-	if (sc->stream) { cudaStreamSynchronize(sc->stream); cudaStreamDestroy(sc->stream); }
-	cudaFree(sc->d_in); cudaFree(sc->d_off); cudaFree(sc->d_out); cudaFree(sc->d_masks);
+	for (EagerSlot &s : sc->slot) {
+		if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+		cudaFree(s.d_in); cudaFree(s.d_off); cudaFree(s.d_out); cudaFree(s.d_masks);
+	}
 	delete sc;
 	dfa->eager_scratch = nullptr;
 }

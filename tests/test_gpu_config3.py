@@ -119,3 +119,25 @@ def test_cfg3_eager_vs_reference_large_sample(ref, cfg3, lo, hi):
     bad = np.nonzero(got != want)[0]
     assert bad.size == 0, (bad[:5], got[bad[:5]], want[bad[:5]])
     assert (gmasks == wmasks).all()
+
+
+def test_cfg3_eager_host_path_pipelines_chunks(ref, cfg3, monkeypatch):
+    """fsm_b200_exec_batch_eager_host cuts a batch into chunks that alternate between two slots (copy-in of
+    one overlaps scan + copy-out of the other): with 1 MiB chunks a 100 k-line batch takes dozens of them,
+    at every alignment; records and id bitsets must equal the reference's, line for line."""
+    from libfsm_b200 import workloads
+    c = cfg3["eager"]
+    _, inst = workloads.cfg3_patterns()
+    base, off = workloads.cfg3_lines_host(100000, inst, seed=99, lo=0, hi=300)
+    h = ref.from_flat(c["fsm"])
+    want, wmasks = ref.exec_eager_batch(h, base, off, c["idlist"], mode=1, nthreads=16)
+    ref.free(h)
+    monkeypatch.setenv("FSM_B200_HOST_CHUNK_MB", "1")
+    with L.Dfa(c["fsm"]) as dfa:
+        L.launch_count(reset=True)
+        rec, masks = dfa.exec_batch_eager(base, off)
+        assert L.launch_count() >= 10
+        assert (rec == want).all() and (masks == wmasks).all()
+        # a sub-range that does not start at offset 0
+        rec2, masks2 = dfa.exec_batch_eager(base, off[5000:60001])
+        assert (rec2 == want[5000:60000]).all() and (masks2 == wmasks[5000:60000]).all()
