@@ -161,7 +161,7 @@ def thread_sweep(threads: int):
 
 # ------------------------------------------------------------------------------- CPU reference legs
 
-def cpu_leg_cfg2(fsm, host_sample: np.ndarray, threads: int):
+def cpu_leg_cfg2(fsm, host_sample: np.ndarray, threads: int, full_at: int | None = None):
     """The reference's own fsm_exec (oracle/_ref) on the host cores, as-is (per-call fsm_isdfa) and
     amortised (validation hoisted): best thread count of a sweep, and the 1-thread figures."""
     import reflib
@@ -176,7 +176,7 @@ def cpu_leg_cfg2(fsm, host_sample: np.ndarray, threads: int):
     else:
         O = reflib.Oracle(); h = None; kind = "port"
         run = lambda mode, t, frac: O.exec_batch(fsm, *part(frac), nthreads=t, validate_each=(mode == 0))
-    out = sweep_modes(run, flat.size, threads)
+    out = sweep_modes(run, flat.size, threads, full_at)
     if h is not None:
         # secondary baseline: the reference's bytecode engine fsm_vm_match_buffer (yes / no only)
         fb, ob = part(4)
@@ -192,20 +192,21 @@ def cpu_leg_cfg2(fsm, host_sample: np.ndarray, threads: int):
     return out
 
 
-def sweep_modes(run, nbytes: int, threads: int):
+def sweep_modes(run, nbytes: int, threads: int, full_at: int | None = None):
     """run(mode, nthreads, frac) scans 1/frac of the sample; mode 0 as-is, 1 amortised.  The full sample
     runs at the full thread count only (as-is: the timed quantity); the thread sweep, the amortised mode
     and the 1-thread figures use a quarter / a sixteenth of it, so that one leg stays within seconds."""
     def timed(mode, t, frac):
         t0 = time.perf_counter(); r = run(mode, t, frac); dt = time.perf_counter() - t0
         return r if isinstance(r, float) else dt          # a leg may report its own timed region
-    asis_s = timed(0, threads, 1)
-    best = {"asis": (nbytes / asis_s / 1e9, threads), "amortised": (0.0, 0)}
+    full = full_at or threads                             # thread count of the full-sample (timed) run
+    asis_s = timed(0, full, 1)
+    best = {"asis": (nbytes / asis_s / 1e9, full), "amortised": (0.0, 0)}
     one = {}
     for t in thread_sweep(threads):
         frac = 16 if t == 1 else 4
         for name, mode in (("asis", 0), ("amortised", 1)):
-            if name == "asis" and t == threads:
+            if name == "asis" and t == full:
                 continue
             dt = timed(mode, t, frac)
             g = nbytes / frac / dt / 1e9
@@ -227,7 +228,7 @@ def cpu_baseline_record(cpu: dict, sample: str) -> dict:
             **({"cpu_vm": cpu["cpu_vm"]} if "cpu_vm" in cpu else {})}
 
 
-def cpu_leg_cfg3(g, nlines: int, threads: int):
+def cpu_leg_cfg3(g, nlines: int, threads: int, full_at: int | None = None):
     import reflib
     from libfsm_b200 import workloads
     _, inst = workloads.cfg3_patterns()
@@ -239,7 +240,7 @@ def cpu_leg_cfg3(g, nlines: int, threads: int):
         k = nlines // frac
         R.exec_eager_batch(h, base[:int(off[k])], off[:k + 1], ids, mode=mode, nthreads=t)
         return R.last_walk_seconds()                      # thread start to join: not the harness's per-thread fsm_clone
-    out = sweep_modes(run, int(off[-1]), threads)
+    out = sweep_modes(run, int(off[-1]), threads, full_at)
     R.free(h)
     out["kind"] = "reference"
     return out
@@ -283,16 +284,16 @@ def run_reference_arm(args):
     unit, metric = "GB/s", METRIC
     if args.config == 2:
         host = workloads.cfg2_host(CFG2_REF_SAMPLE, LENGTH, args.dist == "adversarial", seed=42)
-        leg = lambda: cpu_leg_cfg2(fsm, host, threads)
+        leg = lambda full_at=None: cpu_leg_cfg2(fsm, host, threads, full_at)
         warm = lambda: cpu_leg_cfg2(fsm, host[:2048], threads)
         nbytes = CFG2_REF_SAMPLE * LENGTH
     elif args.config == 3:
-        leg = lambda: cpu_leg_cfg3(fsm, CFG3_REF_SAMPLE, threads)
+        leg = lambda full_at=None: cpu_leg_cfg3(fsm, CFG3_REF_SAMPLE, threads, full_at)
         warm = lambda: cpu_leg_cfg3(fsm, 1024, threads)
         nbytes = None
     elif args.config in (1, 4):
         text = cfg1_text(args.size) if args.config == 1 else workloads.utf8_host(CFG4_REF_SAMPLE, seed=4)
-        leg = lambda: cpu_leg_stream(fsm, text)
+        leg = lambda full_at=None: cpu_leg_stream(fsm, text)
         warm = lambda: cpu_leg_stream(fsm, text[:1 << 16])
         nbytes = text.size
     else:
@@ -313,14 +314,17 @@ def run_reference_arm(args):
     else:
         for _ in range(args.warmup):
             warm()
+        # the timed steps run fsm_exec as-is at the thread count that a calibration sweep found fastest
+        # (on this workload the per-call validation scales worse than the walk: 64 threads beat 128)
+        best_threads = leg()["asis_threads"]
         for _ in range(args.steps):
-            last = leg()
+            last = leg(best_threads)
             t_total += last["asis_s"]
         if nbytes is None:
             nbytes = int(last["asis_gbs"] * last["asis_s"] * 1e9 + 0.5)
         value = nbytes * args.steps / t_total / 1e9
         cpu = cpu_baseline_record(last, cfg["reference_sample"])
-        cpu["value"], cpu["cores"] = value, (threads if args.config in (2, 3) else 1)
+        cpu["value"], cpu["cores"] = value, (best_threads if args.config in (2, 3) else 1)
         assert "libfsm_b200.so" not in open("/proc/self/maps").read(), "the reference arm must not load the engine"
     line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / max(args.steps, 1) * 1e3,
