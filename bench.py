@@ -353,6 +353,11 @@ def gpu_setup(args) -> Ctx:
     c.local = int(os.environ.get("LOCAL_RANK", "0"))
     if c.world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries ONE JSON line: whatever native libraries print on fd 1 (NCCL's "NCCL version ..."
+        # banner under NCCL_DEBUG=VERSION) goes to stderr; Python's own stdout keeps the real one
+        sys.stdout.flush()
+        sys.stdout = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", c.local))
     assert c.world == args.gpus or c.world == 1, f"WORLD_SIZE {c.world} != --gpus {args.gpus}"
     torch.cuda.set_device(c.local)
@@ -667,7 +672,7 @@ def run_cfg3(args):
     words = (ids.size + 63) // 64
     rec = torch.empty((nlines, 16), dtype=torch.uint8, device=dev)
     masks = torch.zeros((nlines, words), dtype=torch.int64, device=dev)
-    gathered = torch.empty((world * nlines, 16), dtype=torch.uint8, device=dev) if world > 1 else None
+    gathered = torch.empty((world * nlines, 16), dtype=torch.uint8, device=dev) if (world > 1 and os.environ.get("BENCH_CFG3_GATHER", "0") == "1") else None
     lib, chk = L._native.lib, L._native.check
     stream_ptr = int(c.main.cuda_stream)
 
@@ -675,9 +680,16 @@ def run_cfg3(args):
         chk(lib.fsm_b200_exec_batch_eager_dev(dfa._h, base.data_ptr(), offsets.data_ptr(), 0, 0, nlines, rec.data_ptr(), masks.data_ptr(), stream_ptr),
             "exec_batch_eager_dev")
 
+    gather = world > 1 and os.environ.get("BENCH_CFG3_GATHER", "0") == "1"
+
     def step(_i):
         launch()
-        if world > 1:                                # records of every shard to every rank: ONE all-gather per step
+        # Lines are independent and their records + id bitsets are consumed where they are produced: the
+        # shards exchange nothing (an all-gather only "if every rank needs them").
+        # BENCH_CFG3_GATHER=1 adds one NCCL all-gather of the records per step on a side stream (measured
+        # at N=2: 4.79 ms per step instead of 2.2 -- the collective's kernel waits for SMs the persistent
+        # scan occupies; config 2 shows the fused alternative).
+        if gather:
             ev = torch.cuda.Event(); ev.record(c.main)
             c.side.wait_event(ev)
             with torch.cuda.stream(c.side):
@@ -753,7 +765,8 @@ def run_cfg3(args):
         line["engine"] = {"table": dfa.info, "dfa_states": fsm.nstates, "eager_ids": int(ids.size), "end_ids": 10,
                           "lines": nlines, "bytes": total, "records": "16 B record + 16 B id bitset per line",
                           "bytes_read": "every byte of every line is walked (the union is unanchored: no line dies, no absorbing state)",
-                          "multi_gpu": "single GPU" if world == 1 else "lines range-sharded, one NCCL all-gather of the 16 B records per step on a side stream"}
+                          "multi_gpu": "single GPU" if world == 1 else ("lines range-sharded, one NCCL all-gather of the 16 B records per step on a side stream" if gather
+                                                                        else "lines range-sharded over the ranks, no data-path collective: records and id bitsets stay with the shard that produced them")}
         line["clocks"] = clocks
         line["e2e"] = {"value": world * total * e2e_steps / (e2e_ms / 1e3) / 1e9, "unit": "GB/s", "steps": e2e_steps,
                        "h2d_bytes_per_step": int(total + h_off.numel() * 8), "d2h_bytes_per_step": int(h_rec.numel() + h_masks.numel() * 8),
