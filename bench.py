@@ -333,7 +333,7 @@ def run_reference_arm(args):
             "reference_entry": "fsm_exec as-is (per-call fsm_isdfa validation); the amortised figure hoists it" if args.config != 5 else "fsm_determinise",
             "cpu_baseline": cpu, "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     return 0
 
 
@@ -622,7 +622,7 @@ def run_cfg2(args):
         if other is not None:
             line["other_distribution"] = other
         line["cpu_baseline"] = cpu_baseline_record(cpu, the_config(args)["reference_sample"])
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     dfa.close()
     if world > 1:
         dist.barrier()
@@ -778,7 +778,7 @@ def run_cfg3(args):
         if sub is not None:
             line["anchored_variant"] = sub
         line["cpu_baseline"] = cpu_baseline_record(cpu, the_config(args)["reference_sample"])
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     dfa.close()
     return finish(c)
 
@@ -909,7 +909,7 @@ def run_cfg4(args):
         line["roofline"] = roofline_record(nbytes, kms, "K1b: prefix + body (K1 lane / k-stride over the chunk jobs) + compose, whole device-side call")
         line["parity"] = "valid text: (1, end, total); one 0xFF at a known offset of the last shard: (0, ., global offset); 4 MiB prefix vs the reference's fsm_exec"
         line["cpu_baseline"] = cpu_baseline_record(cpu, the_config(args)["reference_sample"])
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     dfa.close()
     return finish(c)
 
@@ -986,7 +986,7 @@ def run_cfg1(args):
         line["gpu_launches"] = int(launches)
         line["roofline"] = roofline_record(int(text.size), kms, "K1b stream path, whole device-side call (includes the 256 MiB L2 flush? no: timed after it)")
         line["cpu_baseline"] = cpu_baseline_record(cpu, the_config(args)["reference_sample"])
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     dfa.close()
     return finish(c)
 
@@ -1038,7 +1038,7 @@ def run_cfg5(args):
         line["cpu_baseline"] = {"value": None if dt is None else edges / dt, "unit": "edges/s", "cores": 1, "kind": "reference",
                                 "sample": "the whole NFA", "seconds": dt}
         line["eps_variant"] = cfg5_eps_variant(L, local)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     return finish(c)
 
 
