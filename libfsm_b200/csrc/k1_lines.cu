@@ -21,16 +21,18 @@
  *     line has its value cleared and the flag set: LUT[256] = NOP (one word for all such lanes: no
  *     bank conflict with the lanes inside their lines).  Words entirely outside the line are
  *     skipped;
- *   - dfa_compile.cu numbers the states with eager outputs last, just before the dead row.  Per
- *     byte the kernel keeps max(st) and the sum of max(st, first_event - 1) (handles are monotonic
- *     in the state number): after the sector,
- *       no eager outputs (EV_DEAD): the dead row absorbs, so the sum counts the steps spent dead and
- *         gives the offset of the missing edge; the state it was taken from is 0..3 exact steps away
- *         from a per-word snapshot of the walk;
- *       eager outputs (EV_EAGER): sum == max - (first_event - 1) <=> exactly one state with ids was
- *         entered, once (86 % of the sectors of BASELINE config 3 enter none, 13.8 % one, 0.5 % more):
- *         its ids are OR-ed in from a small global array; anything else re-walks the sector byte by
- *         byte, out of line.
+ *   - dfa_compile.cu numbers the states with eager outputs last, just before the dead row, so
+ *     "has ids" is one compare on the handle (handles are monotonic in the state number):
+ *       no eager outputs (EV_DEAD): per byte the kernel adds max(st, dead - 1): the dead row absorbs,
+ *         so after the sector the sum counts the steps spent dead and gives the offset of the missing
+ *         edge; the state it was taken from is 0..3 exact steps away from a per-word snapshot;
+ *       eager outputs (EV_EAGER): the four states entered in a word are kept; if their maximum has ids
+ *         (1.75 % of the words of BASELINE config 3) the ids of that state -- and, rarely, of the other
+ *         three -- are OR-ed in from a small global array.  OR is idempotent, so the NOP steps need no
+ *         care.  (The first version accounted per sector and re-walked sectors with more than one
+ *         event out of line: 0.5 % of the sectors, but 10 % of the warp iterations had such a lane, on
+ *         its own for 32 serial steps -- 17 % of all executed instructions.)  Only a walk that ends in
+ *         the dead row still takes the out-of-line exact walk, for the offset.
  *
  * Algorithmic bytes per line: its bytes, read once, + 16 B record (+ 8 W B id bitset).  Bound:
  * the shared-memory lookup rate (one conflict-free + one dependent, bank-conflicting LDS per byte),
@@ -234,7 +236,7 @@ k1_lines_kernel(const LinesArgs a)
 		const uint32_t inv = ~mask;
 		const uint32_t entry = st;
 		const uint32_t base_ev = h_first - 1u;            /* EV_DEAD: first_event is the dead row */
-		uint32_t seen = 0, ssum = 0, nsteps = 0;
+		uint32_t ssum = 0, nsteps = 0;
 		uint32_t snap[8];
 #pragma unroll
 		for (int k = 0; k < 8; k++) {
@@ -247,11 +249,42 @@ k1_lines_kernel(const LinesArgs a)
 				const uint32_t vw = out01 | lut_bits;
 #define LINES_STEP(T)                                                                             \
 				st = lds_u16(4u * st + lds_u8(byte_and_flag<T>(x, vw)));                          \
-				if (EV == EV_EAGER) seen = max(seen, st);                                         \
-				if (EV != EV_NONE) ssum += max(st, base_ev);
-				LINES_STEP(0) LINES_STEP(1) LINES_STEP(2) LINES_STEP(3)
+				if (EV == EV_DEAD) ssum += max(st, base_ev);
+				if (EV == EV_EAGER) {
+					/* the four states entered in this word; ids fire per word (OR is idempotent, so the
+					 * NOP steps of bytes outside the line -- which re-enter the same state -- are harmless) */
+					const uint32_t s0 = lds_u16(4u * st + lds_u8(byte_and_flag<0>(x, vw)));
+					const uint32_t s1 = lds_u16(4u * s0 + lds_u8(byte_and_flag<1>(x, vw)));
+					const uint32_t s2 = lds_u16(4u * s1 + lds_u8(byte_and_flag<2>(x, vw)));
+					const uint32_t s3 = lds_u16(4u * s2 + lds_u8(byte_and_flag<3>(x, vw)));
+					st = s3;
+					const uint32_t m = max(max(s0, s1), max(s2, s3));
+					if (m >= h_first) {
+						/* handles grow with the state number: [h_first, h_dead) are the states with ids */
+						if (m < h_dead) {
+							const uint32_t ev = hd.state(m) - a.first_event;
+#pragma unroll
+							for (int q = 0; q < W; q++) acc[q] |= __ldg(a.ev_masks + (size_t) ev * W + q);
+						}
+						const bool others = (s0 >= h_first && s0 != m) || (s1 >= h_first && s1 != m) ||
+						    (s2 >= h_first && s2 != m) || (s3 >= h_first && s3 != m);
+						if (others) {
+							const uint32_t sj[4] = { s0, s1, s2, s3 };
+#pragma unroll
+							for (int j = 0; j < 4; j++) {
+								if (sj[j] >= h_first && sj[j] < h_dead && sj[j] != m) {
+									const uint32_t ev = hd.state(sj[j]) - a.first_event;
+#pragma unroll
+									for (int q = 0; q < W; q++) acc[q] |= __ldg(a.ev_masks + (size_t) ev * W + q);
+								}
+							}
+						}
+					}
+				} else {
+					LINES_STEP(0) LINES_STEP(1) LINES_STEP(2) LINES_STEP(3)
+				}
 #undef LINES_STEP
-				if (EV != EV_NONE) nsteps += 4;
+				if (EV == EV_DEAD) nsteps += 4;
 				if (EV == EV_DEAD) snap[k] = st;
 			}
 		}
@@ -284,19 +317,14 @@ k1_lines_kernel(const LinesArgs a)
 			died = true;
 			consumed_here = j - lo;
 		}
-		if (EV == EV_EAGER && seen >= h_first) {
-			if (ssum - nsteps * base_ev == seen - base_ev && seen != h_dead) {
-				/* exactly one state with ids entered, once */
-				const uint32_t ev = hd.state(seen) - a.first_event;
+		if (EV == EV_EAGER && st == h_dead) {
+			/* a byte of this sector had no edge (the dead row absorbs): the exact walk finds which one and
+			 * the state it was taken from; the ids it collects were OR-ed in above already */
+			const Rewalk<W> r = lines_rewalk<W>(hd, lut_a, entry, mask, h_first, h_dead, a.perm_inv, a.masks, A);
+			st = r.st;
 #pragma unroll
-				for (int k = 0; k < W; k++) acc[k] |= __ldg(a.ev_masks + (size_t) ev * W + k);
-			} else {
-				const Rewalk<W> r = lines_rewalk<W>(hd, lut_a, entry, mask, h_first, h_dead, a.perm_inv, a.masks, A);
-				st = r.st;
-#pragma unroll
-				for (int k = 0; k < W; k++) acc[k] |= r.m[k];
-				if (r.died) { died = true; consumed_here = r.at - lo; }
-			}
+			for (int k = 0; k < W; k++) acc[k] |= r.m[k];
+			if (r.died) { died = true; consumed_here = r.at - lo; }
 		}
 		/* A state whose 256 edges all loop back to itself keeps the walk where it is whatever
 		 * follows: the rest of the line cannot change the record (nor fire a new id), so it is
