@@ -114,6 +114,7 @@ struct fsm_b200_dfa {
 	void *d_lblob;
 	uint32_t lblob_bytes, l_pitch, l_entry_bytes, l_tab_off, l_end_off, l_first_event, l_dead, l_start, l_ncols;
 	uint32_t *d_lperm_inv;   /* [ntable] new number -> caller's state number (dead row -> ntable - 1) */
+	uint32_t *d_lperm;       /* [ntable] caller's state number -> new number */
 	uint8_t *d_labsorb;      /* [ntable] by new number, or nullptr when no real state is absorbing */
 	uint64_t *d_lev_masks;   /* [ntable - l_first_event][eager_words]: id masks of the states with outputs, by new number */
 	uint64_t l_start_mask[4];/* eager ids of the start state (exec.c:126-130) */

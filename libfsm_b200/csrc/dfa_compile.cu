@@ -506,6 +506,8 @@ compile_impl(const struct fsm_b200_desc *desc, int device, fsm_b200_dfa **out)
 				FSMB_CUDA(cudaMemcpy(dfa->d_lblob, lb.data(), lbytes, cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
 				FSMB_CUDA(cudaMalloc(&dfa->d_lperm_inv, T * sizeof(uint32_t)), { fsm_b200_dfa_free(dfa); return -1; });
 				FSMB_CUDA(cudaMemcpy(dfa->d_lperm_inv, inv.data(), T * sizeof(uint32_t), cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
+				FSMB_CUDA(cudaMalloc(&dfa->d_lperm, T * sizeof(uint32_t)), { fsm_b200_dfa_free(dfa); return -1; });
+				FSMB_CUDA(cudaMemcpy(dfa->d_lperm, perm.data(), T * sizeof(uint32_t), cudaMemcpyHostToDevice), { fsm_b200_dfa_free(dfa); return -1; });
 				if (has_eager && dfa->eager_words <= 4 && !hmask.empty()) {
 					const uint32_t W = dfa->eager_words, nev = T - nplain;
 					std::vector<uint64_t> ev((size_t) nev * W + 1, 0);
@@ -594,6 +596,7 @@ fsm_b200_dfa_free(fsm_b200_dfa *dfa)
 	if (dfa->d_eager_masks != nullptr) cudaFree(dfa->d_eager_masks);
 	if (dfa->d_lblob != nullptr) cudaFree(dfa->d_lblob);
 	if (dfa->d_lperm_inv != nullptr) cudaFree(dfa->d_lperm_inv);
+	if (dfa->d_lperm != nullptr) cudaFree(dfa->d_lperm);
 	if (dfa->d_labsorb != nullptr) cudaFree(dfa->d_labsorb);
 	if (dfa->d_lev_masks != nullptr) cudaFree(dfa->d_lev_masks);
 	free(dfa->h_eager_ids);

@@ -166,7 +166,27 @@ fsm_b200_exec_batch_eager_dev(const fsm_b200_dfa *dfa,
 		return -1;
 	}
 	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
-	return launch_eager(dfa, d_base, d_offsets, stride, len, n, d_out, d_masks, static_cast<cudaStream_t>(stream));
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if (n == 1) {
+		/* one (possibly long) input: K1b's chunked form when it is long enough, never one lane */
+		uint64_t beg = 0, ilen = len;
+		if (d_offsets != nullptr) {
+			uint64_t h[2];
+			FSMB_CUDA(cudaMemcpyAsync(h, d_offsets, sizeof h, cudaMemcpyDeviceToHost, st), return -1);
+			FSMB_CUDA(cudaStreamSynchronize(st), return -1);
+			beg = h[0]; ilen = h[1] - h[0];
+		}
+		if (k1b_stream_eager_ok(dfa, ilen)) {
+			fsm_b200_result rec;
+			uint64_t hm[4] = { 0, 0, 0, 0 };
+			if (k1b_exec_stream_eager(dfa, d_base + beg, ilen, &rec, hm, st) != 0) return -1;
+			FSMB_CUDA(cudaMemcpyAsync(d_out, &rec, sizeof rec, cudaMemcpyHostToDevice, st), return -1);
+			FSMB_CUDA(cudaMemcpyAsync(d_masks, hm, dfa->eager_words * sizeof(uint64_t), cudaMemcpyHostToDevice, st), return -1);
+			FSMB_CUDA(cudaStreamSynchronize(st), return -1);     /* rec / hm live on this stack frame */
+			return 0;
+		}
+	}
+	return launch_eager(dfa, d_base, d_offsets, stride, len, n, d_out, d_masks, st);
 }
 
 extern "C" int
@@ -204,6 +224,20 @@ fsm_b200_exec_batch_eager_host(const fsm_b200_dfa *dfa,
 	if (const char *e = getenv("FSM_B200_HOST_CHUNK_MB")) {
 		long v = atol(e);
 		if (v >= 1 && v <= 4096) chunk_bytes = (size_t) v << 20;
+	}
+	if (n == 1 && k1b_stream_eager_ok(dfa, offsets[1] - offsets[0])) {
+		/* one long input (the shim's fsm_exec on an automaton with eager outputs): K1b's chunked form */
+		EagerSlot &s = sc->slot[0];
+		const uint64_t lo_b = offsets[0], nbytes = offsets[1] - offsets[0];
+		if (s.stream == nullptr) FSMB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), return -1);
+		if (!EagerScratch::grow(&s.d_in, &s.in_cap, nbytes + 64)) {
+			set_error("exec_batch_eager_host: out of device memory");
+			errno = ENOMEM;
+			return -1;
+		}
+		FSMB_CUDA(cudaMemcpyAsync(s.d_in, base + lo_b, nbytes, cudaMemcpyHostToDevice, s.stream), return -1);
+		for (size_t w = 0; w < W; w++) masks[w] = 0;
+		return k1b_exec_stream_eager(dfa, static_cast<const uint8_t *>(s.d_in), nbytes, out, masks, s.stream);
 	}
 	int rc = 0, which = 0;
 	size_t i0 = 0;

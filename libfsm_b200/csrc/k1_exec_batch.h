@@ -70,7 +70,12 @@ int k1_launch_jobs(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_
 /* Ragged / eager batches on shared-memory-resident tables (k1_lines.cu). */
 bool k1_lines_eligible(const fsm_b200_dfa *dfa);
 int k1_lines_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,
-	uint64_t stride, uint64_t len, size_t n, fsm_b200_result *d_out, uint64_t *d_masks, cudaStream_t stream);
+	uint64_t stride, uint64_t len, size_t n, fsm_b200_result *d_out, uint64_t *d_masks, cudaStream_t stream,
+	const uint32_t *d_entry = nullptr);
+/* k1b_stream.cu: one long input on an automaton with eager outputs (records + the set of fired ids) */
+bool k1b_stream_eager_ok(const fsm_b200_dfa *dfa, uint64_t len);
+int k1b_exec_stream_eager(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len,
+	fsm_b200_result *h_rec, uint64_t *h_masks, cudaStream_t stream);
 
 } // namespace fsmb200
 #endif

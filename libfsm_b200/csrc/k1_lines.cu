@@ -59,6 +59,8 @@ struct LinesArgs {
 	uint64_t start_mask[4];
 	const uint8_t *base;
 	const uint64_t *offsets;      /* n + 1 entries, or nullptr: fixed stride */
+	const uint32_t *entry;        /* per line: the state its walk starts in (caller's numbering), or nullptr: the start state */
+	const uint32_t *perm;         /* caller's state number -> new number (with entry) */
 	uint64_t stride, len, n;
 	fsm_b200_result *out;
 	uint64_t *out_masks;          /* [n][W] */
@@ -213,7 +215,10 @@ k1_lines_kernel(const LinesArgs a)
 			load_sector(nbeg & ~(uintptr_t) 31, N);
 		}
 	}
-	uint32_t st = h_start;
+	auto first_state = [&](uint64_t line) -> uint32_t {
+		return a.entry != nullptr ? hd.of(__ldg(a.perm + __ldg(a.entry + line))) : h_start;
+	};
+	uint32_t st = have ? first_state(i) : h_start;
 	uintptr_t line_beg = cur;
 	uint64_t acc[W > 0 ? W : 1];
 #pragma unroll
@@ -354,7 +359,7 @@ k1_lines_kernel(const LinesArgs a)
 			have = have_next;
 			if (have) {
 				cur = nbeg; end = nend; line_beg = cur;
-				st = h_start;
+				st = first_state(i);
 #pragma unroll
 				for (int k = 0; k < 8; k++) A[k] = N[k];
 				have_next = i + 32 < wend;
@@ -431,7 +436,8 @@ k1_lines_eligible(const fsm_b200_dfa *dfa)
 /* d_masks == nullptr: plain records only (eager ids, if the DFA has any, are not reported). */
 int
 k1_lines_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *d_offsets,
-	uint64_t stride, uint64_t len, size_t n, fsm_b200_result *d_out, uint64_t *d_masks, cudaStream_t stream)
+	uint64_t stride, uint64_t len, size_t n, fsm_b200_result *d_out, uint64_t *d_masks, cudaStream_t stream,
+	const uint32_t *d_entry)
 {
 	if (n == 0) return 0;
 	LinesArgs a;
@@ -450,6 +456,7 @@ k1_lines_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *
 	a.masks = dfa->d_eager_masks;
 	a.ev_masks = dfa->d_lev_masks;
 	a.base = d_base; a.offsets = d_offsets; a.stride = stride; a.len = len; a.n = n;
+	a.entry = d_entry; a.perm = dfa->d_lperm;
 	a.out = d_out; a.out_masks = d_masks;
 	const uint32_t words = d_masks != nullptr ? dfa->eager_words : 0u;
 	/* without a mask buffer only a missing edge is an event: the dead row is the last one */

@@ -309,6 +309,7 @@ struct StreamScratch {
 	std::mutex mu;
 	Arena arena;
 	uint8_t *d_in = nullptr; size_t in_cap = 0;       /* for the _host entry point */
+	uint8_t *d_eager = nullptr; size_t eager_cap = 0; /* eager streams: per-chunk offsets, entry states, records, id masks */
 	cudaStream_t stream = nullptr;
 };
 
@@ -369,7 +370,7 @@ pick_chunk(uint32_t T, uint32_t W, uint64_t len, int sms)
 /* Run steps 1-5 over d_buf[0..len); leaves StreamOut[T] in h_out. */
 int
 stream_map(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStream_t stream,
-	StreamScratch *ss, std::vector<StreamOut> &h_out)
+	StreamScratch *ss, std::vector<StreamOut> &h_out, StreamArgs *keep = nullptr)
 {
 	const uint32_t T = dfa->nstates;
 	int sms = 0;
@@ -454,6 +455,7 @@ stream_map(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStre
 		count_launch();
 	}
 	FSMB_CUDA(cudaGetLastError(), return -1);
+	if (keep != nullptr) *keep = a;      /* the chunk maps stay in the arena until the next call on this DFA */
 	h_out.resize(T);
 	FSMB_CUDA(cudaMemcpyAsync(h_out.data(), d_out, T * sizeof(StreamOut), cudaMemcpyDeviceToHost, stream), return -1);
 	FSMB_CUDA(cudaStreamSynchronize(stream), return -1);
@@ -494,6 +496,54 @@ stream_serial(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaS
 	return 0;
 }
 
+/* ---- one long input on an automaton with eager outputs ----------------------------------------
+ * The chunk maps (above) give the exit state of every chunk for every entry state, but not the ids
+ * fired on the way.  Second pass: follow the maps from the start state to get the TRUE entry state of
+ * every chunk (one thread, nchunks dependent steps), then run the lines kernel over the chunks as
+ * "lines" that start in those states and OR the per-chunk id sets.  The bytes are read twice; no walk
+ * runs on a single lane. */
+__global__ void
+k1b_true_path_kernel(const StreamArgs a, uint32_t start, uint64_t *off, uint32_t *entry)
+{
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	uint32_t st = start;
+	uint32_t c = 0;
+	for (; c < a.nchunks; c++) {
+		off[c] = (uint64_t) c * a.C;
+		entry[c] = st;
+		const uint16_t nx = chunk_next(a, c, st, nullptr, nullptr);
+		if (nx == DEAD16) { c++; break; }       /* chunk c's own walk stops at the missing edge */
+		st = nx;
+	}
+	const uint64_t stop = min(a.len, (uint64_t) c * a.C);
+	for (; c <= a.nchunks; c++) {               /* nothing after the chunk that died: empty lines */
+		off[c] = stop;
+		if (c < a.nchunks) entry[c] = start;
+	}
+}
+
+template <int W>
+__global__ void
+k1b_or_masks_kernel(const uint64_t *masks, uint32_t n, uint64_t *out)
+{
+	__shared__ uint64_t part[W][256];
+	uint64_t acc[W];
+#pragma unroll
+	for (int w = 0; w < W; w++) acc[w] = 0;
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+#pragma unroll
+		for (int w = 0; w < W; w++) acc[w] |= masks[(size_t) i * W + w];
+	}
+#pragma unroll
+	for (int w = 0; w < W; w++) part[w][threadIdx.x] = acc[w];
+	__syncthreads();
+	if (threadIdx.x < W) {
+		uint64_t v = 0;
+		for (uint32_t t = 0; t < blockDim.x; t++) v |= part[threadIdx.x][t];
+		out[threadIdx.x] = v;
+	}
+}
+
 } // namespace
 
 namespace fsmb200 {
@@ -506,8 +556,64 @@ stream_scratch_free(fsm_b200_dfa *dfa)
 	if (ss->stream) { cudaStreamSynchronize(ss->stream); cudaStreamDestroy(ss->stream); }
 	cudaFree(ss->arena.base);
 	cudaFree(ss->d_in);
+	cudaFree(ss->d_eager);
 	delete ss;
 	dfa->stream_scratch = nullptr;
+}
+
+bool
+k1b_stream_eager_ok(const fsm_b200_dfa *dfa, uint64_t len)
+{
+	return dfa->eager_nbits != 0 && dfa->eager_words >= 1 && dfa->eager_words <= 4 && k1_lines_eligible(dfa) &&
+	    dfa->d_lperm != nullptr && parallel_ok(dfa, len) && getenv("FSM_B200_NO_EAGER_STREAM") == nullptr;
+}
+
+int
+k1b_exec_stream_eager(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len,
+	fsm_b200_result *h_rec, uint64_t *h_masks, cudaStream_t stream)
+{
+	StreamScratch *ss = ss_get(dfa);
+	if (ss == nullptr) { errno = ENOMEM; return -1; }
+	std::lock_guard<std::mutex> g(ss->mu);
+	std::vector<StreamOut> m;
+	StreamArgs a;
+	if (stream_map(dfa, d_buf, len, stream, ss, m, &a) != 0) return -1;
+	const StreamOut &r = m[dfa->start];
+	h_rec->end = r.state;
+	if (r.died) { h_rec->ret = 0; h_rec->consumed = r.dead_off; }
+	else { h_rec->ret = dfa->h_is_end[r.state] ? 1 : 0; h_rec->consumed = len; }
+
+	const uint32_t W = dfa->eager_words, nch = a.nchunks;
+	const size_t need = (size_t) (nch + 1) * 8 + (size_t) nch * 4 + 256 + (size_t) nch * sizeof(fsm_b200_result) +
+	    (size_t) nch * W * 8 + 256 + 64;
+	if (ss->eager_cap < need) {
+		if (ss->d_eager) cudaFree(ss->d_eager);
+		ss->d_eager = nullptr; ss->eager_cap = 0;
+		void *p = nullptr;
+		FSMB_CUDA(cudaMalloc(&p, need + need / 4), return -1);
+		ss->d_eager = static_cast<uint8_t *>(p);
+		ss->eager_cap = need + need / 4;
+	}
+	Arena ar; ar.base = ss->d_eager; ar.cap = ss->eager_cap; ar.used = 0;
+	uint64_t *d_off = ar.take<uint64_t>(nch + 1);
+	uint32_t *d_entry = ar.take<uint32_t>(nch);
+	fsm_b200_result *d_rec = ar.take<fsm_b200_result>(nch);
+	uint64_t *d_masks = ar.take<uint64_t>((size_t) nch * W);
+	uint64_t *d_final = ar.take<uint64_t>(8);
+	k1b_true_path_kernel<<<1, 32, 0, stream>>>(a, dfa->start, d_off, d_entry);
+	count_launch();
+	if (k1_lines_launch(dfa, d_buf, d_off, 0, 0, nch, d_rec, d_masks, stream, d_entry) != 0) return -1;
+	switch (W) {
+	case 1: k1b_or_masks_kernel<1><<<1, 256, 0, stream>>>(d_masks, nch, d_final); break;
+	case 2: k1b_or_masks_kernel<2><<<1, 256, 0, stream>>>(d_masks, nch, d_final); break;
+	case 3: k1b_or_masks_kernel<3><<<1, 256, 0, stream>>>(d_masks, nch, d_final); break;
+	default: k1b_or_masks_kernel<4><<<1, 256, 0, stream>>>(d_masks, nch, d_final); break;
+	}
+	count_launch();
+	FSMB_CUDA(cudaGetLastError(), return -1);
+	FSMB_CUDA(cudaMemcpyAsync(h_masks, d_final, W * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream), return -1);
+	FSMB_CUDA(cudaStreamSynchronize(stream), return -1);
+	return 0;
 }
 }
 

@@ -114,3 +114,66 @@ def test_eager_selftest_program_against_the_shim():
         pytest.skip("shim_eager_selftest not built")
     p = subprocess.run([exe], capture_output=True, timeout=300)
     assert p.returncode == 0, (p.stdout.decode(), p.stderr.decode())
+
+
+def test_one_long_input_with_eager_outputs_is_chunked_and_exact(ref):
+    """fsm_exec on ONE long input of an automaton with eager outputs (what the shim calls for it): K1b's
+    chunk maps give every chunk's true entry state, the lines kernel walks the chunks from those states and
+    the per-chunk id sets are OR-ed -- record and id set equal the reference's single serial walk, through
+    the host and the device entry point, and it is not one lane (several launches)."""
+    import torch
+    from libfsm_b200 import workloads
+    c = goldenio.load_cfg3()["eager"]
+    _, inst = workloads.cfg3_patterns()
+    base, _ = workloads.cfg3_lines_host(60000, inst, seed=33)
+    h = ref.from_flat(c["fsm"])
+    with L.Dfa(c["fsm"]) as dfa:
+        for cut in (8 << 20, (3 << 20) + 17, (1 << 21) + 5):
+            data = np.ascontiguousarray(base[:cut])
+            off = np.array([0, cut], dtype=np.uint64)
+            want, wmasks = ref.exec_eager_batch(h, data, off, c["idlist"], mode=1, nthreads=1)
+            L.launch_count(reset=True)
+            rec, masks = dfa.exec_batch_eager(data, off)
+            assert L.launch_count() >= 5, "expected the chunked path"
+            assert (rec == want).all() and (masks == wmasks).all(), cut
+            drec, dmasks = dfa.exec_batch_eager(torch.from_numpy(data).cuda(), torch.from_numpy(off.astype(np.int64)).cuda())
+            torch.cuda.synchronize()
+            assert (L.results_from_torch(drec) == want).all() and (dmasks.cpu().numpy().view(np.uint64) == wmasks).all(), cut
+        # fewer ids fire on a prefix: the OR really is over the chunks walked
+        assert (wmasks != 0).any()
+    ref.free(h)
+
+
+@pytest.mark.parametrize("die_at", [None, 100, 70000, 299999])
+def test_one_long_input_eager_with_a_missing_edge(oracle, die_at):
+    """The same path on a small INCOMPLETE automaton with eager outputs: the walk dies in a prefix window
+    or in a chunk body; ids fired before the missing edge count, nothing after it does."""
+    rng = np.random.default_rng(8100)
+    dfa_desc = None
+    for seed in range(40):
+        nfa = random_nfa(np.random.default_rng(8200 + seed), 12)
+        d = oracle.determinise(nfa)
+        if d.eager_ids is not None and d.nstates >= 4:
+            dfa_desc = d
+            break
+    assert dfa_desc is not None
+    al = np.frombuffer(b"abcd", dtype=np.uint8)
+    # a long input that stays alive: walk the oracle greedily over bytes that have an edge
+    tab = oracle.flatten(dfa_desc)
+    st, out = dfa_desc.start, []
+    for _ in range(300000):
+        ok = [b for b in al if tab[st, b] != 0xFFFFFFFF]
+        if not ok:
+            break
+        b = int(ok[int(rng.integers(len(ok)))]); out.append(b); st = int(tab[st, b])
+    data = np.array(out, dtype=np.uint8)
+    if data.size < 200000:
+        pytest.skip("this automaton cannot be kept alive for long")
+    if die_at is not None and die_at < data.size:
+        data[die_at] = ord("x")                                  # no edge on 'x' anywhere
+    want_rec, want_ids = oracle.exec_eager(dfa_desc, data.tobytes())
+    off = np.array([0, data.size], dtype=np.uint64)
+    with L.Dfa(dfa_desc) as dfa:
+        rec, masks = dfa.exec_batch_eager(data, off)
+        assert (int(rec["ret"][0]), int(rec["consumed"][0])) == (want_rec[0], want_rec[2])
+        assert dfa.fired_ids(masks[0]) == want_ids
