@@ -1,0 +1,352 @@
+/*
+ * k1b_rep.cuh -- K1b for SMALL automata (at most 12 table rows): the whole stream map in one pass.
+ *
+ * Same monoid formulation as k1b_stream.cu (src/libfsm/exec.c:132-151 is one serial chain; a byte
+ * range maps entry states to exit states and maps compose), but fused: ONE kernel walks the chunks and
+ * folds the chunk maps of a warp, one small kernel folds the warp maps.  No job lists, no memsets.
+ *
+ * Why a separate form: the generic body (k1_lane_kernel over the jobs) keeps ONE copy of the table in
+ * shared memory, and the lanes of a warp -- each in its own state, on its own byte -- collide on its
+ * banks: 1.84 wavefronts per lookup on the UTF-8 validator, L1TEX 98.8 % busy (profiles/
+ * r1_k1b_body_utf8_ncu_full.txt).  A table this small can be REPLICATED PER LANE so that lane l only
+ * ever touches bank l: exactly one wavefront per lookup, whatever the states and bytes.
+ *
+ *   address of entry (state, byte) of lane l  =  state << 14 | (byte >> 2) << 8 | l << 2 | (byte & 3)
+ *
+ * Bits 2..6 are the bank and depend on the lane alone.  Bit 7 is left unused on purpose: it puts the
+ * word index of the byte (byte >> 2) on a byte boundary of the address, so that ONE prmt.b32 per input
+ * byte builds the whole byte-dependent part of the address {byte & 3 | lane bits, byte >> 2, 0, 0} from
+ * two per-word registers -- 3.75 instructions per input byte (3 per word + PRMT, LEA, LDS.U8 per byte),
+ * the dependent chain being LEA + LDS.  16 KiB per table row: 9 rows (UTF-8 validator + dead row) =
+ * 144 KiB of the 227 KiB of shared memory, at most 12 rows.
+ *
+ * Per lane (one chunk of C bytes; C = stream length / lanes of the grid, so the grid is ONE full wave):
+ *   prefix  the first 64 bytes from every entry state (chains from wrong states die or merge), out of
+ *           two 256-bit loads held in registers;
+ *   body    the rest of the chunk from each DISTINCT live, non-absorbing image (one for practical
+ *           automata; more only cost time, never exactness); a walk that meets the dead row finds the
+ *           exact offset in the sector it died in and records it;
+ *   fold    the chunk map (4 bits per entry state) goes to shared memory and lanes 0..T-1 fold the 32
+ *           maps of the warp in order.
+ * k1b_rep_final_kernel folds the warp maps (fan-in 32 per level, in shared memory) and resolves a death
+ * on the true path to its stream offset (re-walking at most one 64-byte prefix).
+ */
+#ifndef FSM_B200_K1B_REP_CUH
+#define FSM_B200_K1B_REP_CUH
+
+#include "common.h"
+#include "k1_device.cuh"
+
+namespace fsmb200 {
+
+constexpr uint32_t REP_MAX_ROWS = 12;        /* 12 x 16 KiB of table + 8 KiB of chunk maps */
+constexpr uint32_t REP_W = 64;               /* prefix window */
+constexpr uint32_t REP_ROW_SHIFT = 14;
+constexpr uint32_t REP_MAPS_BYTES = 32u * 32u * 8u;   /* chunk maps of a CTA, in front of the table */
+constexpr uint32_t REP_DIED_BODY = 0xE, REP_DIED_PREFIX = 0xF;
+
+struct StreamOut {          /* per entry state, [T] */
+	uint32_t state;         /* exit state, or dead-from state when died */
+	uint32_t died;
+	uint64_t dead_off;      /* offset within the range of the first byte without an edge */
+};
+
+struct RepArgs {
+	const uint8_t *buf;
+	uint64_t len, C;
+	uint32_t mis;            /* address of buf modulo 32: chunk c > 0 starts at c * C - mis (sector-aligned) */
+	uint32_t nchunks, nwarps;
+	uint32_t T, ntable, dead;   /* dead = ntable - 1 for incomplete automata, else NO_EDGE */
+	uint32_t absorb_mask;    /* bit s: every byte loops state s back to itself */
+	const uint8_t *dense;    /* [ntable][256] next-state bytes (dead row included) */
+	/* warp maps */
+	uint8_t *wmap;           /* [nwarps][16]: exit state per entry state, 0xFF = died */
+	uint32_t *wdc;           /* [nwarps][16]: chunk in which it died */
+	uint8_t *wds;            /* [nwarps][16]: state in which that chunk was entered */
+	/* deaths in a body walk, by (chunk, image state); written only when it happens */
+	uint64_t *body_off;      /* [nchunks][16] stream offset of the byte without an edge */
+	uint8_t *body_from;      /* [nchunks][16] state it was read in */
+	/* final fold */
+	uint32_t *lv_dc[2];      /* [ceil(nwarps/32)][16] ping-pong death records of the upper levels */
+	uint8_t *lv_ds[2];
+	StreamOut *out;          /* [T] */
+};
+
+__device__ __forceinline__ uint32_t
+prmt_sx(uint32_t a, uint32_t b, uint32_t sel)
+{
+	uint32_t d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));   /* selector bit 3 = sign fill */
+	return d;
+}
+
+__device__ __forceinline__ uint64_t
+rep_chunk_beg(const RepArgs &a, uint32_t c)
+{
+	return c == 0 ? 0ull : (uint64_t) c * a.C - a.mis;
+}
+
+__device__ __forceinline__ uint64_t
+rep_chunk_end(const RepArgs &a, uint32_t c)
+{
+	const uint64_t e = (uint64_t) (c + 1) * a.C - a.mis;
+	return e < a.len ? e : a.len;
+}
+
+/* The table starts at a 16 KiB-aligned SHARED address and its entries hold (next state + table address
+ * >> 14): the state register is the row's address bits, and the dependent chain is exactly
+ * LEA (state << 14 + byte part) -> LDS.U8 -- no base add. */
+__device__ __forceinline__ uint32_t
+lds_u8(uint32_t addr)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+
+/* one byte from a global pointer (heads, tails, the sector a walk died in) */
+#define REP_STEP1(st, b) lds_u8(((st) << REP_ROW_SHIFT) + (((uint32_t) (b) >> 2) << 8) + ((uint32_t) (b) & 3u) + lane4)
+
+/* four bytes of a word: per word SHF + LOP (word indices) and one LOP3 (byte selects | lane bits), per
+ * byte PRMT (address bytes {sel | lane, index, 0, 0}: the index bytes are below 0x40, so their sign
+ * fill is the zero we need) + LEA + LDS.U8 */
+#define REP_STEP4(st, w)                                                  \
+	do {                                                                  \
+		const uint32_t h_ = ((w) >> 2) & 0x3F3F3F3Fu;                     \
+		const uint32_t q_ = ((w) & 0x03030303u) | lanebits;               \
+		st = lds_u8(((st) << REP_ROW_SHIFT) + prmt_sx(q_, h_, 0xCC40u));  \
+		st = lds_u8(((st) << REP_ROW_SHIFT) + prmt_sx(q_, h_, 0xCC51u));  \
+		st = lds_u8(((st) << REP_ROW_SHIFT) + prmt_sx(q_, h_, 0xCC62u));  \
+		st = lds_u8(((st) << REP_ROW_SHIFT) + prmt_sx(q_, h_, 0xCC73u));  \
+	} while (0)
+
+template <bool HAS_DEAD>
+__global__ void __launch_bounds__(1024, 1)
+k1b_rep_kernel(const RepArgs a)
+{
+	extern __shared__ __align__(1024) uint8_t dsm[];
+	uint64_t *wm = reinterpret_cast<uint64_t *>(dsm);        /* [32 warps][32 lanes] chunk maps, 8 KiB */
+	const uint32_t rep_base = (smem_u32(dsm) + REP_MAPS_BYTES + 16383u) & ~16383u;   /* shared address of the table */
+	const uint32_t K = rep_base >> REP_ROW_SHIFT;            /* states live in registers as state + K */
+
+	/* replicate the table: word j of row s of lane l at s << 14 | j << 8 | l << 2.  Consecutive threads
+	 * take consecutive lanes: the global read is a broadcast, the shared store conflict-free. */
+	{
+		const uint32_t *d32 = reinterpret_cast<const uint32_t *>(a.dense);
+		const uint32_t total = a.ntable * 64u * 32u;
+		const uint32_t k4 = K * 0x01010101u;
+		for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+			const uint32_t l = i & 31u, j = (i >> 5) & 63u, s = i >> 11;
+			const uint32_t v = __ldg(d32 + s * 64u + j) + k4;       /* bytes stay below 256: at most 12 + K */
+			asm volatile("st.shared.u32 [%0], %1;" :: "r"(rep_base + ((s << REP_ROW_SHIFT) | (j << 8) | (l << 2))), "r"(v) : "memory");
+		}
+	}
+	__syncthreads();
+
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const uint32_t gw = warp * gridDim.x + blockIdx.x;       /* consecutive warp maps sit on different SMs */
+	if (gw >= a.nwarps) return;
+	const uint32_t lane4 = lane << 2;
+	const uint32_t lanebits = lane4 * 0x01010101u;
+	const uint32_t T = a.T;
+	const uint32_t deadK = a.dead + K;           /* NO_EDGE + K never equals a state */
+	const uint32_t c = gw * 32u + lane;
+	const bool have = c < a.nchunks;
+	const uint64_t beg = have ? rep_chunk_beg(a, c) : 0, end = have ? rep_chunk_end(a, c) : 0;
+
+	uint64_t img = 0;            /* 4 bits per entry state: state after the prefix, or REP_DIED_PREFIX */
+	uint64_t exit_of = 0xFEDCBA9876543210ull;   /* 4 bits per image state: where the body walk from it ends */
+	uint32_t live = 0;           /* image states that need a body walk */
+	uint32_t w = 0;
+	if (have) {
+		w = (uint32_t) min((uint64_t) REP_W, end - beg);
+		const uint8_t *p = a.buf + beg;
+		if (w == REP_W && (reinterpret_cast<uintptr_t>(p) & 31u) == 0) {
+			uint32_t A[8], B[8];
+			ld256(p, A);
+			ld256(p + 32, B);
+#pragma unroll 1
+			for (uint32_t s = 0; s < T; s++) {
+				uint32_t st = s + K;
+#pragma unroll
+				for (int k = 0; k < 8; k++) REP_STEP4(st, A[k]);
+#pragma unroll
+				for (int k = 0; k < 8; k++) REP_STEP4(st, B[k]);
+				st = (HAS_DEAD && st == deadK) ? REP_DIED_PREFIX : st - K;
+				img |= (uint64_t) st << (4u * s);
+			}
+		} else {                 /* the first chunk of an unaligned buffer, a short last chunk */
+#pragma unroll 1
+			for (uint32_t s = 0; s < T; s++) {
+				uint32_t st = s + K;
+				for (uint32_t k = 0; k < w; k++) st = REP_STEP1(st, __ldg(p + k));
+				st = (HAS_DEAD && st == deadK) ? REP_DIED_PREFIX : st - K;
+				img |= (uint64_t) st << (4u * s);
+			}
+		}
+		for (uint32_t s = 0; s < T; s++) {
+			const uint32_t v = (uint32_t) (img >> (4u * s)) & 15u;
+			if (v < REP_DIED_BODY && !((a.absorb_mask >> v) & 1u)) live |= 1u << v;
+		}
+		if (beg + w >= end) live = 0;        /* the prefix was the whole chunk */
+	}
+
+	/* body: one walk per distinct live image (the j-th of every lane at the same time) */
+	while (__any_sync(0xFFFFFFFFu, live != 0)) {
+		if (live != 0) {
+			const uint32_t v = (uint32_t) __ffs((int) live) - 1u;
+			live &= live - 1u;
+			uint32_t st = v + K;
+			uint64_t pos = beg + w;
+			bool died = false;
+			uint32_t from = 0;
+			/* head: up to the first sector boundary (only the first chunk of an unaligned buffer) */
+			while (pos < end && (reinterpret_cast<uintptr_t>(a.buf + pos) & 31u) != 0) {
+				const uint32_t nx = REP_STEP1(st, __ldg(a.buf + pos));
+				if (HAS_DEAD && nx == deadK) { died = true; from = st; break; }
+				st = nx; pos++;
+			}
+			if (!died) {
+				const uint8_t *p = a.buf + pos;
+				const uint64_t nsec = (end - pos) >> 5;
+				uint32_t cur[8], nxt[8];
+				if (nsec > 0) ld256(p, cur);
+				for (uint64_t i = 0; i < nsec; i++) {
+					if (i + 1 < nsec) {
+						ld256(p + 32, nxt);
+					} else {
+#pragma unroll
+						for (int k = 0; k < 8; k++) nxt[k] = 0;
+					}
+					const uint32_t entry = st;
+#pragma unroll
+					for (int k = 0; k < 8; k++) REP_STEP4(st, cur[k]);
+					if (HAS_DEAD && st == deadK) {
+						/* a byte of this sector had no edge: re-walk it to find which */
+						st = entry;
+						for (int k = 0; k < 32; k++) {
+							const uint32_t nx = REP_STEP1(st, __ldg(p + k));
+							if (nx == deadK) { died = true; from = st; pos += (uint64_t) k; break; }
+							st = nx;
+						}
+						break;
+					}
+					pos += 32; p += 32;
+#pragma unroll
+					for (int k = 0; k < 8; k++) cur[k] = nxt[k];
+				}
+			}
+			if (!died) {
+				for (; pos < end; pos++) {
+					const uint32_t nx = REP_STEP1(st, __ldg(a.buf + pos));
+					if (HAS_DEAD && nx == deadK) { died = true; from = st; break; }
+					st = nx;
+				}
+			}
+			uint32_t e = st - K;
+			if (died) {
+				a.body_off[(size_t) c * 16u + v] = pos;
+				a.body_from[(size_t) c * 16u + v] = (uint8_t) (from - K);
+				e = REP_DIED_BODY;
+			}
+			exit_of = (exit_of & ~(15ull << (4u * v))) | ((uint64_t) e << (4u * v));
+		}
+	}
+
+	/* the chunk map: entry state -> exit state / died */
+	uint64_t cmap = 0xFEDCBA9876543210ull;       /* a chunk beyond the end: identity */
+	if (have) {
+		cmap = 0;
+		for (uint32_t s = 0; s < T; s++) {
+			const uint32_t v = (uint32_t) (img >> (4u * s)) & 15u;
+			const uint32_t e = v == REP_DIED_PREFIX ? REP_DIED_PREFIX : (uint32_t) (exit_of >> (4u * v)) & 15u;
+			cmap |= (uint64_t) e << (4u * s);
+		}
+	}
+	wm[warp * 32u + lane] = cmap;
+	__syncwarp();
+	if (lane < T) {
+		uint32_t st = lane, dc = 0xFFFFFFFFu, ds = 0;
+		for (uint32_t l = 0; l < 32; l++) {
+			const uint32_t e = (uint32_t) (wm[warp * 32u + l] >> (4u * st)) & 15u;
+			if (e >= REP_DIED_BODY) { dc = gw * 32u + l; ds = st; st = 0xFFu; break; }
+			st = e;
+		}
+		a.wmap[(size_t) gw * 16u + lane] = (uint8_t) st;
+		a.wdc[(size_t) gw * 16u + lane] = dc;
+		a.wds[(size_t) gw * 16u + lane] = (uint8_t) ds;
+	}
+}
+
+#undef REP_STEP4
+#undef REP_STEP1
+
+/* Fold the warp maps in order (fan-in 32 per level, maps in shared memory), then turn a death on the path
+ * of entry state s into (offset, state): the chunk it happened in is re-walked over its prefix; if the walk
+ * survives that, the body walk from the image recorded where it died. */
+__global__ void __launch_bounds__(1024, 1)
+k1b_rep_final_kernel(const RepArgs a)
+{
+	extern __shared__ __align__(16) uint8_t fm[];
+	const uint32_t T = a.T;
+	uint32_t n = a.nwarps;
+	uint8_t *A = fm, *B = fm + (size_t) a.nwarps * 16u;
+	for (uint32_t i = threadIdx.x; i < n * 4u; i += blockDim.x) {
+		reinterpret_cast<uint32_t *>(A)[i] = reinterpret_cast<const uint32_t *>(a.wmap)[i];
+	}
+	__syncthreads();
+	const uint32_t *dcA = a.wdc;
+	const uint8_t *dsA = a.wds;
+	int pp = 0;
+	while (n > 1) {
+		const uint32_t n2 = (n + 31u) / 32u;
+		uint32_t *dcB = a.lv_dc[pp];
+		uint8_t *dsB = a.lv_ds[pp];
+		for (uint32_t idx = threadIdx.x; idx < n2 * T; idx += blockDim.x) {
+			const uint32_t g = idx / T, s = idx % T;
+			const uint32_t hi = min(n, g * 32u + 32u);
+			uint32_t st = s;
+			for (uint32_t i = g * 32u; i < hi; i++) {
+				const uint32_t e = A[i * 16u + st];
+				if (e == 0xFFu) {
+					dcB[g * 16u + s] = dcA[i * 16u + st];
+					dsB[g * 16u + s] = dsA[i * 16u + st];
+					st = 0xFFu;
+					break;
+				}
+				st = e;
+			}
+			B[g * 16u + s] = (uint8_t) st;
+		}
+		__syncthreads();          /* one CTA: the global death records written above are visible after the barrier */
+		uint8_t *t = A; A = B; B = t;
+		dcA = dcB; dsA = dsB;
+		pp ^= 1;
+		n = n2;
+	}
+	const uint32_t s = threadIdx.x;
+	if (s >= T) return;
+	const uint32_t e = A[s];
+	if (e != 0xFFu) {
+		a.out[s].state = e; a.out[s].died = 0; a.out[s].dead_off = 0xFFFFFFFFFFFFFFFFull;
+		return;
+	}
+	const uint32_t c = dcA[s];
+	uint32_t st = dsA[s];
+	const uint64_t beg = rep_chunk_beg(a, c), end = rep_chunk_end(a, c);
+	const uint32_t w = (uint32_t) min((uint64_t) REP_W, end - beg);
+	for (uint32_t k = 0; k < w; k++) {
+		const uint32_t nx = a.dense[st * 256u + a.buf[beg + k]];
+		if (nx == a.dead) {
+			a.out[s].state = st; a.out[s].died = 1; a.out[s].dead_off = beg + k;
+			return;
+		}
+		st = nx;
+	}
+	a.out[s].state = a.body_from[(size_t) c * 16u + st];
+	a.out[s].died = 1;
+	a.out[s].dead_off = a.body_off[(size_t) c * 16u + st];
+}
+
+} // namespace fsmb200
+#endif

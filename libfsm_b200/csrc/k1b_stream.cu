@@ -36,6 +36,7 @@
 
 #include "common.h"
 #include "k1_exec_batch.h"
+#include "k1b_rep.cuh"
 
 using namespace fsmb200;
 
@@ -253,12 +254,6 @@ k1b_compose1_kernel(const StreamArgs a, uint32_t G, uint16_t *gnext, uint32_t *g
 	}
 }
 
-struct StreamOut {          /* per entry state, [T] */
-	uint32_t state;         /* exit state, or dead-from state when died */
-	uint32_t died;
-	uint64_t dead_off;      /* offset within the range of the first byte without an edge */
-};
-
 /* 3. compose, level 2: one thread per entry state folds the group maps in order. */
 __global__ void
 k1b_compose2_kernel(const StreamArgs a, const uint16_t *gnext, const uint32_t *gchunk, const uint32_t *gstate,
@@ -311,6 +306,11 @@ struct StreamScratch {
 	uint8_t *d_in = nullptr; size_t in_cap = 0;       /* for the _host entry point */
 	uint8_t *d_eager = nullptr; size_t eager_cap = 0; /* eager streams: per-chunk offsets, entry states, records, id masks */
 	cudaStream_t stream = nullptr;
+	/* small automata (k1b_rep.cuh): dense [ntable][256] next-state bytes, absorbing states, output arena */
+	uint8_t *d_dense = nullptr;
+	uint32_t absorb_mask = 0;
+	Arena rep_arena;
+	StreamOut *h_pinned = nullptr;                    /* [REP_MAX_ROWS] read-back buffer */
 };
 
 std::mutex g_ss_mu;
@@ -367,11 +367,117 @@ pick_chunk(uint32_t T, uint32_t W, uint64_t len, int sms)
 	return (size_t) c;
 }
 
+/* ---- small automata: the fused form (k1b_rep.cuh) ------------------------------------------------ */
+
+bool
+rep_eligible(const fsm_b200_dfa *dfa)
+{
+	if (dfa->ntable > REP_MAX_ROWS || dfa->nstates == 0 || dfa->h_table32 == nullptr) return false;
+	if (const char *e = getenv("FSM_B200_STREAM_REP")) return atoi(e) != 0;
+	return true;
+}
+
+int
+stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStream_t stream,
+	StreamScratch *ss, std::vector<StreamOut> &h_out)
+{
+	const uint32_t T = dfa->nstates, NT = dfa->ntable;
+	int sms = 0;
+	FSMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dfa->device), return -1);
+	if (ss->d_dense == nullptr) {
+		/* dense next-state bytes from the host copy of the table (missing edge -> dead row, which absorbs) */
+		std::vector<uint8_t> dense((size_t) NT * 256);
+		uint32_t mask = 0;
+		for (uint32_t s = 0; s < NT; s++) {
+			bool self = true;
+			for (uint32_t b = 0; b < 256; b++) {
+				uint32_t v = s < T ? dfa->h_table32[(size_t) s * 256 + b] : dfa->dead;
+				if (v == NO_EDGE) v = dfa->dead;
+				dense[(size_t) s * 256 + b] = (uint8_t) v;
+				self = self && v == s;
+			}
+			if (self) mask |= 1u << s;
+		}
+		void *p = nullptr;
+		FSMB_CUDA(cudaMalloc(&p, dense.size()), return -1);
+		FSMB_CUDA(cudaMemcpy(p, dense.data(), dense.size(), cudaMemcpyHostToDevice), { cudaFree(p); return -1; });
+		FSMB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ss->h_pinned), REP_MAX_ROWS * sizeof(StreamOut)), { cudaFree(p); return -1; });
+		ss->d_dense = static_cast<uint8_t *>(p);
+		ss->absorb_mask = mask;
+	}
+	RepArgs a;
+	memset(&a, 0, sizeof a);
+	a.buf = d_buf; a.len = len;
+	a.mis = (uint32_t) (reinterpret_cast<uintptr_t>(d_buf) & 31u);
+	a.T = T; a.ntable = NT; a.dead = dfa->complete ? NO_EDGE : dfa->dead;
+	a.absorb_mask = ss->absorb_mask; a.dense = ss->d_dense;
+	/* one chunk per lane of ONE full wave; never so short that the T x 64-byte prefix walks dominate */
+	const uint64_t lanes = (uint64_t) sms * 1024u;
+	uint64_t C = ((len + a.mis + lanes - 1) / lanes + 31u) & ~31ull;
+	uint64_t cmin = (uint64_t) T * REP_W;
+	if (cmin < 256) cmin = 256;
+	cmin = (cmin + 31u) & ~31ull;
+	if (C < cmin) C = cmin;
+	if (const char *e = getenv("FSM_B200_STREAM_CHUNK")) {
+		const long v = atol(e);
+		if (v >= 64 && v <= (1l << 30) && ((uint64_t) v & ~31ull) >= C) C = (uint64_t) v & ~31ull;   /* only larger: one wave */
+	}
+	a.C = C;
+	a.nchunks = (uint32_t) ((len + a.mis + C - 1) / C);
+	a.nwarps = (a.nchunks + 31u) / 32u;
+	const uint32_t nlv = (a.nwarps + 31u) / 32u;
+
+	const size_t need = (size_t) a.nwarps * 16 * (1 + 4 + 1) + (size_t) a.nchunks * 16 * (8 + 1) +
+	    (size_t) nlv * 16 * (4 + 1) * 2 + REP_MAX_ROWS * sizeof(StreamOut) + 16 * 256;
+	if (ss->rep_arena.cap < need) {
+		if (ss->rep_arena.base) cudaFree(ss->rep_arena.base);
+		ss->rep_arena.base = nullptr; ss->rep_arena.cap = 0;
+		void *p = nullptr;
+		FSMB_CUDA(cudaMalloc(&p, need + need / 8), return -1);
+		ss->rep_arena.base = static_cast<uint8_t *>(p);
+		ss->rep_arena.cap = need + need / 8;
+	}
+	Arena &ar = ss->rep_arena;
+	ar.used = 0;
+	a.wmap = ar.take<uint8_t>((size_t) a.nwarps * 16);
+	a.wdc = ar.take<uint32_t>((size_t) a.nwarps * 16);
+	a.wds = ar.take<uint8_t>((size_t) a.nwarps * 16);
+	a.body_off = ar.take<uint64_t>((size_t) a.nchunks * 16);
+	a.body_from = ar.take<uint8_t>((size_t) a.nchunks * 16);
+	for (int k = 0; k < 2; k++) {
+		a.lv_dc[k] = ar.take<uint32_t>((size_t) nlv * 16);
+		a.lv_ds[k] = ar.take<uint8_t>((size_t) nlv * 16);
+	}
+	a.out = ar.take<StreamOut>(REP_MAX_ROWS);
+
+	/* [chunk maps 8 KiB][pad to a 16 KiB-aligned shared address][table]; the pad is at most 16 KiB */
+	const size_t smem = REP_MAPS_BYTES + 16384u + ((size_t) NT << REP_ROW_SHIFT);
+	const unsigned grid = (unsigned) (a.nwarps < (uint32_t) sms ? a.nwarps : (uint32_t) sms);
+	if (dfa->complete) {
+		FSMB_CUDA(cudaFuncSetAttribute(k1b_rep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), return -1);
+		k1b_rep_kernel<false><<<grid, 1024, smem, stream>>>(a);
+	} else {
+		FSMB_CUDA(cudaFuncSetAttribute(k1b_rep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), return -1);
+		k1b_rep_kernel<true><<<grid, 1024, smem, stream>>>(a);
+	}
+	count_launch();
+	const size_t smem2 = (size_t) a.nwarps * 16 + (size_t) nlv * 16 + 16;
+	FSMB_CUDA(cudaFuncSetAttribute(k1b_rep_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2), return -1);
+	k1b_rep_final_kernel<<<1, 1024, smem2, stream>>>(a);
+	count_launch();
+	FSMB_CUDA(cudaGetLastError(), return -1);
+	FSMB_CUDA(cudaMemcpyAsync(ss->h_pinned, a.out, T * sizeof(StreamOut), cudaMemcpyDeviceToHost, stream), return -1);
+	FSMB_CUDA(cudaStreamSynchronize(stream), return -1);
+	h_out.assign(ss->h_pinned, ss->h_pinned + T);
+	return 0;
+}
+
 /* Run steps 1-5 over d_buf[0..len); leaves StreamOut[T] in h_out. */
 int
 stream_map(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStream_t stream,
 	StreamScratch *ss, std::vector<StreamOut> &h_out, StreamArgs *keep = nullptr)
 {
+	if (keep == nullptr && rep_eligible(dfa)) return stream_map_rep(dfa, d_buf, len, stream, ss, h_out);
 	const uint32_t T = dfa->nstates;
 	int sms = 0;
 	FSMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dfa->device), return -1);
@@ -557,6 +663,9 @@ stream_scratch_free(fsm_b200_dfa *dfa)
 	cudaFree(ss->arena.base);
 	cudaFree(ss->d_in);
 	cudaFree(ss->d_eager);
+	cudaFree(ss->d_dense);
+	cudaFree(ss->rep_arena.base);
+	if (ss->h_pinned) cudaFreeHost(ss->h_pinned);
 	delete ss;
 	dfa->stream_scratch = nullptr;
 }
@@ -629,7 +738,7 @@ exec_stream_dev_locked(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t l
 		out->consumed = 0;
 		return 0;
 	}
-	if (!parallel_ok(dfa, len)) {
+	if (!parallel_ok(dfa, len) && !rep_eligible(dfa)) {      /* the fused small-automaton form takes any length */
 		return stream_serial(dfa, d_buf, len, st, ss, out);
 	}
 	std::vector<StreamOut> m;
