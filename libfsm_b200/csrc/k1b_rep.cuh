@@ -42,7 +42,8 @@ namespace fsmb200 {
 constexpr uint32_t REP_MAX_ROWS = 12;        /* 12 x 16 KiB of table + 8 KiB of chunk maps */
 constexpr uint32_t REP_W = 64;               /* prefix window */
 constexpr uint32_t REP_ROW_SHIFT = 14;
-constexpr uint32_t REP_MAPS_BYTES = 32u * 32u * 8u;   /* chunk maps of a CTA, in front of the table */
+constexpr uint32_t REP_CMAPS_BYTES = 32u * 32u * 8u;  /* chunk maps of a CTA (4 bits per entry state) */
+constexpr uint32_t REP_MAPS_BYTES = REP_CMAPS_BYTES + 32u * 16u * 6u + 256u;   /* + warp maps with death records + a counter: in front of the table */
 constexpr uint32_t REP_DIED_BODY = 0xE, REP_DIED_PREFIX = 0xF;
 
 struct StreamOut {          /* per entry state, [T] */
@@ -56,18 +57,20 @@ struct RepArgs {
 	uint64_t len, C;
 	uint32_t mis;            /* address of buf modulo 32: chunk c > 0 starts at c * C - mis (sector-aligned) */
 	uint32_t nchunks, nwarps;
+	uint32_t wpc, nmaps;     /* warps per CTA in use; CTAs = maps the final kernel folds */
 	uint32_t T, ntable, dead;   /* dead = ntable - 1 for incomplete automata, else NO_EDGE */
 	uint32_t absorb_mask;    /* bit s: every byte loops state s back to itself */
+	uint32_t pf_dist;        /* tuning: explicit L2 prefetch this many bytes ahead of the walk, once per 256 B (0: none) */
 	const uint8_t *dense;    /* [ntable][256] next-state bytes (dead row included) */
-	/* warp maps */
-	uint8_t *wmap;           /* [nwarps][16]: exit state per entry state, 0xFF = died */
-	uint32_t *wdc;           /* [nwarps][16]: chunk in which it died */
-	uint8_t *wds;            /* [nwarps][16]: state in which that chunk was entered */
+	/* CTA maps (each CTA folds the maps of its warps) */
+	uint8_t *wmap;           /* [nmaps][16]: exit state per entry state, 0xFF = died */
+	uint32_t *wdc;           /* [nmaps][16]: chunk in which it died */
+	uint8_t *wds;            /* [nmaps][16]: state in which that chunk was entered */
 	/* deaths in a body walk, by (chunk, image state); written only when it happens */
 	uint64_t *body_off;      /* [nchunks][16] stream offset of the byte without an edge */
 	uint8_t *body_from;      /* [nchunks][16] state it was read in */
 	/* final fold */
-	uint32_t *lv_dc[2];      /* [ceil(nwarps/32)][16] ping-pong death records of the upper levels */
+	uint32_t *lv_dc[2];      /* [ceil(nmaps/32)][16] ping-pong death records of the upper levels */
 	uint8_t *lv_ds[2];
 	StreamOut *out;          /* [T] */
 };
@@ -120,12 +123,37 @@ lds_u8(uint32_t addr)
 		st = lds_u8(((st) << REP_ROW_SHIFT) + prmt_sx(q_, h_, 0xCC73u));  \
 	} while (0)
 
-template <bool HAS_DEAD>
+/* 256-bit sector load; HINT: ask L2 to fetch 256 B around a miss (the lane reads the next seven sectors of
+ * that run next, so they become L2 hits instead of DRAM round trips) */
+template <int HINT>
+__device__ __forceinline__ void
+rep_ld256(const uint8_t *p, uint32_t (&w)[8])
+{
+	if (HINT) {
+		asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		    : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+	} else {
+		ld256(p, w);
+	}
+}
+
+__device__ __forceinline__ void
+prefetch_l2(const uint8_t *p)
+{
+	asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
+template <bool HAS_DEAD, int HINT>
 __global__ void __launch_bounds__(1024, 1)
 k1b_rep_kernel(const RepArgs a)
 {
 	extern __shared__ __align__(1024) uint8_t dsm[];
 	uint64_t *wm = reinterpret_cast<uint64_t *>(dsm);        /* [32 warps][32 lanes] chunk maps, 8 KiB */
+	uint32_t *s_wdc = reinterpret_cast<uint32_t *>(dsm + REP_CMAPS_BYTES);            /* [32 warps][16] */
+	uint8_t *s_wmap = dsm + REP_CMAPS_BYTES + 32u * 16u * 4u;                         /* [32 warps][16] */
+	uint8_t *s_wds = s_wmap + 32u * 16u;                                              /* [32 warps][16] */
+	uint32_t *s_done = reinterpret_cast<uint32_t *>(s_wds + 32u * 16u);               /* warps of this CTA that have folded */
+	if (threadIdx.x == 0) *s_done = 0;
 	const uint32_t rep_base = (smem_u32(dsm) + REP_MAPS_BYTES + 16383u) & ~16383u;   /* shared address of the table */
 	const uint32_t K = rep_base >> REP_ROW_SHIFT;            /* states live in registers as state + K */
 
@@ -144,8 +172,10 @@ k1b_rep_kernel(const RepArgs a)
 	__syncthreads();
 
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	const uint32_t gw = warp * gridDim.x + blockIdx.x;       /* consecutive warp maps sit on different SMs */
-	if (gw >= a.nwarps) return;
+	/* CTA b owns the consecutive warp maps [b * wpc, b * wpc + wpc): it folds them itself (below) */
+	const uint32_t gw = blockIdx.x * a.wpc + warp;
+	if (warp >= a.wpc || gw >= a.nwarps) return;
+	const uint32_t nactive = min(a.wpc, a.nwarps - blockIdx.x * a.wpc);
 	const uint32_t lane4 = lane << 2;
 	const uint32_t lanebits = lane4 * 0x01010101u;
 	const uint32_t T = a.T;
@@ -207,34 +237,45 @@ k1b_rep_kernel(const RepArgs a)
 				st = nx; pos++;
 			}
 			if (!died) {
+				/* sectors: two buffers that swap roles (no register copies); the load of sector i + 1 is
+				 * issued before sector i is walked */
 				const uint8_t *p = a.buf + pos;
-				const uint64_t nsec = (end - pos) >> 5;
-				uint32_t cur[8], nxt[8];
-				if (nsec > 0) ld256(p, cur);
-				for (uint64_t i = 0; i < nsec; i++) {
-					if (i + 1 < nsec) {
-						ld256(p + 32, nxt);
-					} else {
-#pragma unroll
-						for (int k = 0; k < 8; k++) nxt[k] = 0;
+				const uint32_t nsec = (uint32_t) ((end - pos) >> 5);       /* a chunk is shorter than 4 GiB */
+				const uint8_t *const pf_end = a.buf + end;
+				uint32_t A[8], B[8];
+				uint32_t i = 0;
+				bool stop = false;
+#define REP_WALK(X)                                                                             \
+	do {                                                                                        \
+		const uint32_t entry_ = st;                                                             \
+		_Pragma("unroll") for (int k = 0; k < 8; k++) REP_STEP4(st, X[k]);                      \
+		if (HAS_DEAD && st == deadK) {                                                          \
+			/* a byte of this sector had no edge: re-walk it to find which */                   \
+			st = entry_;                                                                        \
+			for (int k = 0; k < 32; k++) {                                                      \
+				const uint32_t nx = REP_STEP1(st, __ldg(p + k));                                \
+				if (nx == deadK) { died = true; from = st; pos += (uint64_t) k; break; }        \
+				st = nx;                                                                        \
+			}                                                                                   \
+			stop = true;                                                                        \
+		} else {                                                                                \
+			pos += 32; p += 32; i++;                                                            \
+		}                                                                                       \
+	} while (0)
+				if (nsec > 0) rep_ld256<HINT>(p, A);
+				while (i < nsec) {
+					if (a.pf_dist != 0 && (i & 7u) == 0 && p + a.pf_dist + 256 <= pf_end) {
+						prefetch_l2(p + a.pf_dist);
+						prefetch_l2(p + a.pf_dist + 128);
 					}
-					const uint32_t entry = st;
-#pragma unroll
-					for (int k = 0; k < 8; k++) REP_STEP4(st, cur[k]);
-					if (HAS_DEAD && st == deadK) {
-						/* a byte of this sector had no edge: re-walk it to find which */
-						st = entry;
-						for (int k = 0; k < 32; k++) {
-							const uint32_t nx = REP_STEP1(st, __ldg(p + k));
-							if (nx == deadK) { died = true; from = st; pos += (uint64_t) k; break; }
-							st = nx;
-						}
-						break;
-					}
-					pos += 32; p += 32;
-#pragma unroll
-					for (int k = 0; k < 8; k++) cur[k] = nxt[k];
+					if (i + 1 < nsec) rep_ld256<HINT>(p + 32, B);
+					REP_WALK(A);
+					if (stop || i >= nsec) break;
+					if (i + 1 < nsec) rep_ld256<HINT>(p + 32, A);
+					REP_WALK(B);
+					if (stop) break;
 				}
+#undef REP_WALK
 			}
 			if (!died) {
 				for (; pos < end; pos++) {
@@ -272,16 +313,42 @@ k1b_rep_kernel(const RepArgs a)
 			if (e >= REP_DIED_BODY) { dc = gw * 32u + l; ds = st; st = 0xFFu; break; }
 			st = e;
 		}
-		a.wmap[(size_t) gw * 16u + lane] = (uint8_t) st;
-		a.wdc[(size_t) gw * 16u + lane] = dc;
-		a.wds[(size_t) gw * 16u + lane] = (uint8_t) ds;
+		s_wmap[warp * 16u + lane] = (uint8_t) st;
+		s_wdc[warp * 16u + lane] = dc;
+		s_wds[warp * 16u + lane] = (uint8_t) ds;
+	}
+	/* the last warp of the CTA to get here folds the CTA's warp maps in order (no barrier: warps without
+	 * chunks have left, and nobody waits for the slowest walk) */
+	__syncwarp();
+	uint32_t last = 0;
+	if (lane == 0) {
+		__threadfence_block();
+		last = atomicAdd(s_done, 1u) == nactive - 1u ? 1u : 0u;
+		__threadfence_block();
+	}
+	last = __shfl_sync(0xFFFFFFFFu, last, 0);
+	if (last && lane < T) {
+		uint32_t st = lane, dc = 0xFFFFFFFFu, ds = 0;
+		for (uint32_t wv = 0; wv < nactive; wv++) {
+			const uint32_t e = *reinterpret_cast<volatile uint8_t *>(s_wmap + wv * 16u + st);
+			if (e == 0xFFu) {
+				dc = *reinterpret_cast<volatile uint32_t *>(s_wdc + wv * 16u + st);
+				ds = *reinterpret_cast<volatile uint8_t *>(s_wds + wv * 16u + st);
+				st = 0xFFu;
+				break;
+			}
+			st = e;
+		}
+		a.wmap[(size_t) blockIdx.x * 16u + lane] = (uint8_t) st;
+		a.wdc[(size_t) blockIdx.x * 16u + lane] = dc;
+		a.wds[(size_t) blockIdx.x * 16u + lane] = (uint8_t) ds;
 	}
 }
 
 #undef REP_STEP4
 #undef REP_STEP1
 
-/* Fold the warp maps in order (fan-in 32 per level, maps in shared memory), then turn a death on the path
+/* Fold the CTA maps in order (fan-in 32 per level, maps in shared memory), then turn a death on the path
  * of entry state s into (offset, state): the chunk it happened in is re-walked over its prefix; if the walk
  * survives that, the body walk from the image recorded where it died. */
 __global__ void __launch_bounds__(1024, 1)
@@ -289,8 +356,8 @@ k1b_rep_final_kernel(const RepArgs a)
 {
 	extern __shared__ __align__(16) uint8_t fm[];
 	const uint32_t T = a.T;
-	uint32_t n = a.nwarps;
-	uint8_t *A = fm, *B = fm + (size_t) a.nwarps * 16u;
+	uint32_t n = a.nmaps;
+	uint8_t *A = fm, *B = fm + (size_t) a.nmaps * 16u;
 	for (uint32_t i = threadIdx.x; i < n * 4u; i += blockDim.x) {
 		reinterpret_cast<uint32_t *>(A)[i] = reinterpret_cast<const uint32_t *>(a.wmap)[i];
 	}

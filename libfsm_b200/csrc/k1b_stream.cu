@@ -425,9 +425,12 @@ stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cuda
 	a.C = C;
 	a.nchunks = (uint32_t) ((len + a.mis + C - 1) / C);
 	a.nwarps = (a.nchunks + 31u) / 32u;
-	const uint32_t nlv = (a.nwarps + 31u) / 32u;
+	/* as many CTAs as there are SMs (or warps); CTA b walks the consecutive warps [b * wpc, b * wpc + wpc) */
+	a.wpc = (a.nwarps + (uint32_t) sms - 1u) / (uint32_t) sms;
+	a.nmaps = (a.nwarps + a.wpc - 1u) / a.wpc;
+	const uint32_t nlv = (a.nmaps + 31u) / 32u;
 
-	const size_t need = (size_t) a.nwarps * 16 * (1 + 4 + 1) + (size_t) a.nchunks * 16 * (8 + 1) +
+	const size_t need = (size_t) a.nmaps * 16 * (1 + 4 + 1) + (size_t) a.nchunks * 16 * (8 + 1) +
 	    (size_t) nlv * 16 * (4 + 1) * 2 + REP_MAX_ROWS * sizeof(StreamOut) + 16 * 256;
 	if (ss->rep_arena.cap < need) {
 		if (ss->rep_arena.base) cudaFree(ss->rep_arena.base);
@@ -439,9 +442,9 @@ stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cuda
 	}
 	Arena &ar = ss->rep_arena;
 	ar.used = 0;
-	a.wmap = ar.take<uint8_t>((size_t) a.nwarps * 16);
-	a.wdc = ar.take<uint32_t>((size_t) a.nwarps * 16);
-	a.wds = ar.take<uint8_t>((size_t) a.nwarps * 16);
+	a.wmap = ar.take<uint8_t>((size_t) a.nmaps * 16);
+	a.wdc = ar.take<uint32_t>((size_t) a.nmaps * 16);
+	a.wds = ar.take<uint8_t>((size_t) a.nmaps * 16);
 	a.body_off = ar.take<uint64_t>((size_t) a.nchunks * 16);
 	a.body_from = ar.take<uint8_t>((size_t) a.nchunks * 16);
 	for (int k = 0; k < 2; k++) {
@@ -452,16 +455,16 @@ stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cuda
 
 	/* [chunk maps 8 KiB][pad to a 16 KiB-aligned shared address][table]; the pad is at most 16 KiB */
 	const size_t smem = REP_MAPS_BYTES + 16384u + ((size_t) NT << REP_ROW_SHIFT);
-	const unsigned grid = (unsigned) (a.nwarps < (uint32_t) sms ? a.nwarps : (uint32_t) sms);
-	if (dfa->complete) {
-		FSMB_CUDA(cudaFuncSetAttribute(k1b_rep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), return -1);
-		k1b_rep_kernel<false><<<grid, 1024, smem, stream>>>(a);
-	} else {
-		FSMB_CUDA(cudaFuncSetAttribute(k1b_rep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), return -1);
-		k1b_rep_kernel<true><<<grid, 1024, smem, stream>>>(a);
-	}
+	const unsigned grid = a.nmaps;
+	int hint = 1;
+	if (const char *e = getenv("FSM_B200_REP_L2HINT")) hint = atoi(e) != 0;             /* tuning knobs */
+	if (const char *e = getenv("FSM_B200_REP_PREFETCH")) { const int v = atoi(e); if (v >= 0 && v <= 65536 && (v % 128) == 0) a.pf_dist = (uint32_t) v; }
+	void (*kern)(const RepArgs) = dfa->complete ? (hint ? k1b_rep_kernel<false, 1> : k1b_rep_kernel<false, 0>)
+	                                            : (hint ? k1b_rep_kernel<true, 1> : k1b_rep_kernel<true, 0>);
+	FSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), return -1);
+	kern<<<grid, 1024, smem, stream>>>(a);
 	count_launch();
-	const size_t smem2 = (size_t) a.nwarps * 16 + (size_t) nlv * 16 + 16;
+	const size_t smem2 = (size_t) a.nmaps * 16 + (size_t) nlv * 16 + 16;
 	FSMB_CUDA(cudaFuncSetAttribute(k1b_rep_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2), return -1);
 	k1b_rep_final_kernel<<<1, 1024, smem2, stream>>>(a);
 	count_launch();

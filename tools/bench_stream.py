@@ -20,16 +20,21 @@ for name in os.environ.get("DFAS", "utf8:,cfg2:uniform,cfg1:digits").split(","):
     else:
         dev = workloads.cfg2_device(nbytes // 1024, 1024, False, seed=1).reshape(-1)
     with L.Dfa(fsm) as dfa:
-        for chunk in os.environ.get("CHUNKS", "default").split(","):
-            if chunk == "default": os.environ.pop("FSM_B200_STREAM_CHUNK", None)
-            else: os.environ["FSM_B200_STREAM_CHUNK"] = chunk
-            for _ in range(2): r = dfa.exec_stream(dev)
-            torch.cuda.synchronize()
-            ts = []
-            for _ in range(5):
-                t0 = time.perf_counter(); r = dfa.exec_stream(dev); ts.append(time.perf_counter() - t0)
-            ms = float(np.median(ts)) * 1e3
-            gbs = dev.numel() / ms / 1e6
-            print(json.dumps({"dfa": name, "states": fsm.nstates, "bytes": int(dev.numel()), "chunk": chunk, "ms": round(ms, 3),
-                              "GBps": round(gbs, 1), "frac_hbm": round(gbs / peak, 4), "result": r}), flush=True)
+        # KNOBS: ';'-separated settings, each a ','-separated list of ENV=value pairs applied for that measurement
+        for knobs in os.environ.get("KNOBS", "").split(";"):
+            pairs = [kv.split("=", 1) for kv in knobs.split(",") if "=" in kv]
+            for k, v in pairs: os.environ[k] = v
+            for chunk in os.environ.get("CHUNKS", "default").split(","):
+                if chunk == "default": os.environ.pop("FSM_B200_STREAM_CHUNK", None)
+                else: os.environ["FSM_B200_STREAM_CHUNK"] = chunk
+                for _ in range(3): r = dfa.exec_stream(dev)
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(int(os.environ.get("REPS", 9))):
+                    t0 = time.perf_counter(); r = dfa.exec_stream(dev); ts.append(time.perf_counter() - t0)
+                ms = float(np.median(ts)) * 1e3
+                gbs = dev.numel() / ms / 1e6
+                print(json.dumps({"dfa": name, "states": fsm.nstates, "bytes": int(dev.numel()), "chunk": chunk, "knobs": knobs, "ms": round(ms, 4),
+                                  "GBps": round(gbs, 1), "frac_hbm": round(gbs / peak, 4), "result": r}), flush=True)
+            for k, _ in pairs: os.environ.pop(k, None)
     del dev
