@@ -69,6 +69,16 @@ stage_blob(uint8_t *smem, const uint8_t *blob, uint32_t blob_bytes, uint64_t *ba
 	mbar_wait(bar_a, 0);
 }
 
+/* the same with an L2 prefetch-size hint: a miss makes L2 fetch 256 B (SASS: LDG.E.ENL2.LTC256B.256) */
+__device__ __forceinline__ void
+ld256_l2_256(const uint8_t *p, uint32_t (&w)[8])
+{
+	asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]),
+	      "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+	    : "l"(p));
+}
+
 /* one full 32-byte DRAM sector per lane (SASS: LDG.E.ENL2.256) */
 __device__ __forceinline__ void
 ld256(const uint8_t *p, uint32_t (&w)[8])

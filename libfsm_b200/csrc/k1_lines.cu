@@ -64,6 +64,7 @@ struct LinesArgs {
 	uint64_t stride, len, n;
 	fsm_b200_result *out;
 	uint64_t *out_masks;          /* [n][W] */
+	uint32_t l2_hint;             /* tuning: sector loads ask L2 for 256 B around a miss (neighbouring lanes' lines) */
 };
 
 /* the staged blob; file scope so that the out-of-line re-walk addresses it as shared memory too */
@@ -184,7 +185,8 @@ k1_lines_kernel(const LinesArgs a)
 	};
 	auto load_sector = [&](uintptr_t saddr, uint32_t (&w)[8]) {
 		if (saddr >= lo_ptr && saddr + 32 <= hi_ptr) {
-			ld256(reinterpret_cast<const uint8_t *>(saddr), w);
+			if (a.l2_hint) ld256_l2_256(reinterpret_cast<const uint8_t *>(saddr), w);
+			else ld256(reinterpret_cast<const uint8_t *>(saddr), w);
 		} else {
 #pragma unroll
 			for (int k = 0; k < 8; k++) {
@@ -453,6 +455,7 @@ k1_lines_launch(const fsm_b200_dfa *dfa, const uint8_t *d_base, const uint64_t *
 	a.start = dfa->l_start;
 	a.perm_inv = dfa->d_lperm_inv;
 	a.absorb = getenv("FSM_B200_NO_ABSORB_SKIP") == nullptr ? dfa->d_labsorb : nullptr;
+	if (const char *e = getenv("FSM_B200_LINES_L2HINT")) a.l2_hint = atoi(e) != 0 ? 1u : 0u;   /* tuning knob */
 	a.masks = dfa->d_eager_masks;
 	a.ev_masks = dfa->d_lev_masks;
 	a.base = d_base; a.offsets = d_offsets; a.stride = stride; a.len = len; a.n = n;

@@ -60,7 +60,6 @@ struct RepArgs {
 	uint32_t wpc, nmaps;     /* warps per CTA in use; CTAs = maps the final kernel folds */
 	uint32_t T, ntable, dead;   /* dead = ntable - 1 for incomplete automata, else NO_EDGE */
 	uint32_t absorb_mask;    /* bit s: every byte loops state s back to itself */
-	uint32_t pf_dist;        /* tuning: explicit L2 prefetch this many bytes ahead of the walk, once per 256 B (0: none) */
 	const uint8_t *dense;    /* [ntable][256] next-state bytes (dead row included) */
 	/* CTA maps (each CTA folds the maps of its warps) */
 	uint8_t *wmap;           /* [nmaps][16]: exit state per entry state, 0xFF = died */
@@ -137,13 +136,7 @@ rep_ld256(const uint8_t *p, uint32_t (&w)[8])
 	}
 }
 
-__device__ __forceinline__ void
-prefetch_l2(const uint8_t *p)
-{
-	asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-}
-
-template <bool HAS_DEAD, int HINT>
+template <bool HAS_DEAD, int HINT, int NBUF>
 __global__ void __launch_bounds__(1024, 1)
 k1b_rep_kernel(const RepArgs a)
 {
@@ -237,11 +230,9 @@ k1b_rep_kernel(const RepArgs a)
 				st = nx; pos++;
 			}
 			if (!died) {
-				/* sectors: two buffers that swap roles (no register copies); the load of sector i + 1 is
-				 * issued before sector i is walked */
+				/* sectors: buffers that swap roles (no register copies), loads issued ahead of the walk */
 				const uint8_t *p = a.buf + pos;
 				const uint32_t nsec = (uint32_t) ((end - pos) >> 5);       /* a chunk is shorter than 4 GiB */
-				const uint8_t *const pf_end = a.buf + end;
 				uint32_t A[8], B[8];
 				uint32_t i = 0;
 				bool stop = false;
@@ -254,28 +245,64 @@ k1b_rep_kernel(const RepArgs a)
 			st = entry_;                                                                        \
 			for (int k = 0; k < 32; k++) {                                                      \
 				const uint32_t nx = REP_STEP1(st, __ldg(p + k));                                \
-				if (nx == deadK) { died = true; from = st; pos += (uint64_t) k; break; }        \
+				if (nx == deadK) { died = true; from = st; p += k; break; }                     \
 				st = nx;                                                                        \
 			}                                                                                   \
 			stop = true;                                                                        \
 		} else {                                                                                \
-			pos += 32; p += 32; i++;                                                            \
+			p += 32; i++;                                                                       \
 		}                                                                                       \
 	} while (0)
-				if (nsec > 0) rep_ld256<HINT>(p, A);
-				while (i < nsec) {
-					if (a.pf_dist != 0 && (i & 7u) == 0 && p + a.pf_dist + 256 <= pf_end) {
-						prefetch_l2(p + a.pf_dist);
-						prefetch_l2(p + a.pf_dist + 128);
+				if (NBUF == 4) {
+					uint32_t C[8], D[8];
+					if (nsec > 0) rep_ld256<HINT>(p, A);
+					if (nsec > 1) rep_ld256<HINT>(p + 32, B);
+					if (nsec > 2) rep_ld256<HINT>(p + 64, C);
+					while (i < nsec) {
+						if (i + 3 < nsec) rep_ld256<HINT>(p + 96, D);
+						REP_WALK(A);
+						if (stop || i >= nsec) break;
+						if (i + 3 < nsec) rep_ld256<HINT>(p + 96, A);
+						REP_WALK(B);
+						if (stop || i >= nsec) break;
+						if (i + 3 < nsec) rep_ld256<HINT>(p + 96, B);
+						REP_WALK(C);
+						if (stop || i >= nsec) break;
+						if (i + 3 < nsec) rep_ld256<HINT>(p + 96, C);
+						REP_WALK(D);
+						if (stop) break;
 					}
-					if (i + 1 < nsec) rep_ld256<HINT>(p + 32, B);
-					REP_WALK(A);
-					if (stop || i >= nsec) break;
-					if (i + 1 < nsec) rep_ld256<HINT>(p + 32, A);
-					REP_WALK(B);
-					if (stop) break;
+				} else if (NBUF == 3) {
+					/* three buffers: the load of sector i + 2 is issued before sector i is walked -- two
+					 * sectors per lane in flight (one is not enough to cover the loaded DRAM latency:
+					 * 31 % of the warp time sat on the first use of a loaded register) */
+					uint32_t C[8];
+					if (nsec > 0) rep_ld256<HINT>(p, A);
+					if (nsec > 1) rep_ld256<HINT>(p + 32, B);
+					while (i < nsec) {
+						if (i + 2 < nsec) rep_ld256<HINT>(p + 64, C);
+						REP_WALK(A);
+						if (stop || i >= nsec) break;
+						if (i + 2 < nsec) rep_ld256<HINT>(p + 64, A);
+						REP_WALK(B);
+						if (stop || i >= nsec) break;
+						if (i + 2 < nsec) rep_ld256<HINT>(p + 64, B);
+						REP_WALK(C);
+						if (stop) break;
+					}
+				} else {
+					if (nsec > 0) rep_ld256<HINT>(p, A);
+					while (i < nsec) {
+						if (i + 1 < nsec) rep_ld256<HINT>(p + 32, B);
+						REP_WALK(A);
+						if (stop || i >= nsec) break;
+						if (i + 1 < nsec) rep_ld256<HINT>(p + 32, A);
+						REP_WALK(B);
+						if (stop) break;
+					}
 				}
 #undef REP_WALK
+				pos = (uint64_t) (p - a.buf);
 			}
 			if (!died) {
 				for (; pos < end; pos++) {

@@ -456,11 +456,20 @@ stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cuda
 	/* [chunk maps 8 KiB][pad to a 16 KiB-aligned shared address][table]; the pad is at most 16 KiB */
 	const size_t smem = REP_MAPS_BYTES + 16384u + ((size_t) NT << REP_ROW_SHIFT);
 	const unsigned grid = a.nmaps;
-	int hint = 1;
+	int hint = 1, nbuf = 3;
 	if (const char *e = getenv("FSM_B200_REP_L2HINT")) hint = atoi(e) != 0;             /* tuning knobs */
-	if (const char *e = getenv("FSM_B200_REP_PREFETCH")) { const int v = atoi(e); if (v >= 0 && v <= 65536 && (v % 128) == 0) a.pf_dist = (uint32_t) v; }
-	void (*kern)(const RepArgs) = dfa->complete ? (hint ? k1b_rep_kernel<false, 1> : k1b_rep_kernel<false, 0>)
-	                                            : (hint ? k1b_rep_kernel<true, 1> : k1b_rep_kernel<true, 0>);
+	if (const char *e = getenv("FSM_B200_REP_NBUF")) { const int v = atoi(e); if (v >= 2 && v <= 4) nbuf = v; }
+	void (*kern)(const RepArgs);
+	if (nbuf == 4) {
+		kern = dfa->complete ? (hint ? k1b_rep_kernel<false, 1, 4> : k1b_rep_kernel<false, 0, 4>)
+		                     : (hint ? k1b_rep_kernel<true, 1, 4> : k1b_rep_kernel<true, 0, 4>);
+	} else if (nbuf == 3) {
+		kern = dfa->complete ? (hint ? k1b_rep_kernel<false, 1, 3> : k1b_rep_kernel<false, 0, 3>)
+		                     : (hint ? k1b_rep_kernel<true, 1, 3> : k1b_rep_kernel<true, 0, 3>);
+	} else {
+		kern = dfa->complete ? (hint ? k1b_rep_kernel<false, 1, 2> : k1b_rep_kernel<false, 0, 2>)
+		                     : (hint ? k1b_rep_kernel<true, 1, 2> : k1b_rep_kernel<true, 0, 2>);
+	}
 	FSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), return -1);
 	kern<<<grid, 1024, smem, stream>>>(a);
 	count_launch();
