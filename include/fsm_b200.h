@@ -43,7 +43,9 @@ extern "C" {
  *    determinise_ex and dfa_plan entry points were added.  Everything of version 1 is unchanged. */
 /* 3: struct fsm_b200_dfa_info grew (kclasses, krange*); fsm_exec_batch_eager of the shim copies the
  *    id list into caller storage.  Everything else of version 2 is unchanged. */
-#define FSM_B200_ABI_VERSION 3
+/* 4: fsm_b200_exec_stream_map_dev_async and struct fsm_b200_stream_map_entry were added.  Everything of
+ *    version 3 is unchanged. */
+#define FSM_B200_ABI_VERSION 4
 
 /* ------------------------------------------------------------------------------------
  * Flat description of a `struct fsm` (reference src/libfsm/internal.h:52-85).
@@ -265,6 +267,19 @@ int fsm_b200_exec_stream_map_dev(const fsm_b200_dfa *dfa, const uint8_t *d_buf, 
 	uint32_t *map_state /* host [ntable_states] */,
 	uint64_t *map_dead  /* host [ntable_states] */,
 	uint32_t *map_dead_state /* host [ntable_states] */, void *stream);
+
+/* The same map left ON THE DEVICE and nothing waited for: d_map (device memory, [nstates] records) is
+ * written by work queued on `stream`, so a collective queued behind it on that stream -- the all-gather
+ * of the ranks' maps (bench.py --config 4) -- needs no host round trip.  `state` is the exit state, or
+ * the state that had no edge when `died`; `dead_off` the shard offset of that byte (UINT64_MAX if none).
+ * Calls on one DFA must use one stream (they share scratch memory). */
+struct fsm_b200_stream_map_entry {
+	uint32_t state;
+	uint32_t died;
+	uint64_t dead_off;
+};
+int fsm_b200_exec_stream_map_dev_async(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len,
+	struct fsm_b200_stream_map_entry *d_map /* device [nstates] */, void *stream);
 
 /* --- determinisation: the subset-construction loop of fsm_determinise -----------------
  * (src/libfsm/determinise.c:23-335 incl. epsilon removal, epsilons.c:121-288).

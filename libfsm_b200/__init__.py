@@ -10,7 +10,7 @@ raises ImportError when the library has not been built."""
 from .desc import FlatFsm, RESULT_DTYPE
 
 _ENGINE = ("Dfa", "plan", "determinise", "determinise_stats", "minimise", "minimise_stats", "device_count",
-           "set_exec_variant", "launch_count", "results_from_torch", "StateLimitReached", "VARIANTS", "load_dfavm")
+           "set_exec_variant", "launch_count", "results_from_torch", "stream_map_arrays", "StateLimitReached", "VARIANTS", "load_dfavm")
 _NATIVE = ("FsmB200Error", "LIB_PATH", "ABI_SYMBOLS")
 
 __all__ = ["FlatFsm", "RESULT_DTYPE", *_ENGINE, *_NATIVE]

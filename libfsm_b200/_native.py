@@ -22,6 +22,7 @@ ABI_SYMBOLS = (
     "fsm_b200_ipc_export", "fsm_b200_ipc_open", "fsm_b200_ipc_close",
     "fsm_b200_set_exec_variant", "fsm_b200_get_exec_variant",
     "fsm_b200_exec_stream_host", "fsm_b200_exec_stream_dev", "fsm_b200_exec_stream_map_dev",
+    "fsm_b200_exec_stream_map_dev_async",
     "fsm_b200_determinise", "fsm_b200_determinise_ex", "fsm_b200_desc_free", "fsm_b200_determinise_stats",
     "fsm_b200_owned_desc_eager", "fsm_b200_dfa_eager_info",
     "fsm_b200_exec_batch_eager_host", "fsm_b200_exec_batch_eager_dev",
@@ -81,6 +82,8 @@ def _load() -> C.CDLL:
     lib.fsm_b200_exec_stream_host.argtypes = [vp, vp, u64, P(CResult)]
     lib.fsm_b200_exec_stream_dev.argtypes = [vp, vp, u64, P(CResult), vp]
     lib.fsm_b200_exec_stream_map_dev.argtypes = [vp, vp, u64, vp, vp, vp, vp]
+    lib.fsm_b200_exec_stream_map_dev_async.argtypes = [vp, vp, u64, vp, vp]
+    lib.fsm_b200_exec_stream_map_dev_async.restype = C.c_int
     lib.fsm_b200_determinise.argtypes = [P(CDesc), C.c_int, sz, P(COwnedDesc)]
     lib.fsm_b200_determinise_ex.argtypes = [P(CDesc), C.c_int, sz, C.c_uint, P(COwnedDesc)]
     lib.fsm_b200_owned_desc_eager.argtypes = [P(COwnedDesc), P(C.c_void_p), P(C.c_void_p)]

@@ -379,7 +379,7 @@ rep_eligible(const fsm_b200_dfa *dfa)
 
 int
 stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStream_t stream,
-	StreamScratch *ss, std::vector<StreamOut> &h_out)
+	StreamScratch *ss, std::vector<StreamOut> &h_out, StreamOut *d_user_out = nullptr)
 {
 	const uint32_t T = dfa->nstates, NT = dfa->ntable;
 	int sms = 0;
@@ -452,6 +452,7 @@ stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cuda
 		a.lv_ds[k] = ar.take<uint8_t>((size_t) nlv * 16);
 	}
 	a.out = ar.take<StreamOut>(REP_MAX_ROWS);
+	if (d_user_out != nullptr) a.out = d_user_out;       /* asynchronous form: the records stay on the device */
 
 	/* [chunk maps 8 KiB][pad to a 16 KiB-aligned shared address][table]; the pad is at most 16 KiB */
 	const size_t smem = REP_MAPS_BYTES + 16384u + ((size_t) NT << REP_ROW_SHIFT);
@@ -478,6 +479,7 @@ stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cuda
 	k1b_rep_final_kernel<<<1, 1024, smem2, stream>>>(a);
 	count_launch();
 	FSMB_CUDA(cudaGetLastError(), return -1);
+	if (d_user_out != nullptr) return 0;
 	FSMB_CUDA(cudaMemcpyAsync(ss->h_pinned, a.out, T * sizeof(StreamOut), cudaMemcpyDeviceToHost, stream), return -1);
 	FSMB_CUDA(cudaStreamSynchronize(stream), return -1);
 	h_out.assign(ss->h_pinned, ss->h_pinned + T);
@@ -487,9 +489,9 @@ stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cuda
 /* Run steps 1-5 over d_buf[0..len); leaves StreamOut[T] in h_out. */
 int
 stream_map(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStream_t stream,
-	StreamScratch *ss, std::vector<StreamOut> &h_out, StreamArgs *keep = nullptr)
+	StreamScratch *ss, std::vector<StreamOut> &h_out, StreamArgs *keep = nullptr, StreamOut *d_user_out = nullptr)
 {
-	if (keep == nullptr && rep_eligible(dfa)) return stream_map_rep(dfa, d_buf, len, stream, ss, h_out);
+	if (keep == nullptr && rep_eligible(dfa)) return stream_map_rep(dfa, d_buf, len, stream, ss, h_out, d_user_out);
 	const uint32_t T = dfa->nstates;
 	int sms = 0;
 	FSMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dfa->device), return -1);
@@ -574,6 +576,10 @@ stream_map(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cudaStre
 	}
 	FSMB_CUDA(cudaGetLastError(), return -1);
 	if (keep != nullptr) *keep = a;      /* the chunk maps stay in the arena until the next call on this DFA */
+	if (d_user_out != nullptr) {         /* asynchronous form: the records stay on the device, nobody waits */
+		FSMB_CUDA(cudaMemcpyAsync(d_user_out, d_out, T * sizeof(StreamOut), cudaMemcpyDeviceToDevice, stream), return -1);
+		return 0;
+	}
 	h_out.resize(T);
 	FSMB_CUDA(cudaMemcpyAsync(h_out.data(), d_out, T * sizeof(StreamOut), cudaMemcpyDeviceToHost, stream), return -1);
 	FSMB_CUDA(cudaStreamSynchronize(stream), return -1);
@@ -820,6 +826,57 @@ fsm_b200_exec_stream_map_dev(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint
 		map_state[dfa->dead] = dfa->dead; map_dead[dfa->dead] = 0; map_dead_state[dfa->dead] = dfa->dead;
 	}
 	return 0;
+}
+
+/* The shard map left ON THE DEVICE, nothing waited for: the [nstates] records are written by work queued on
+ * `stream`, so that a collective queued behind it on the same stream (the all-gather of the ranks' maps)
+ * needs no host round trip. */
+extern "C" int
+fsm_b200_exec_stream_map_dev_async(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len,
+	struct fsm_b200_stream_map_entry *d_map, void *stream)
+{
+	static_assert(sizeof(struct fsm_b200_stream_map_entry) == sizeof(StreamOut), "record layout");
+	if (dfa == nullptr || d_map == nullptr || (len > 0 && d_buf == nullptr)) {
+		set_error("exec_stream_map_dev_async: bad argument");
+		errno = EINVAL;
+		return -1;
+	}
+	if (dfa->nstates > K1B_MAX_STATES) {
+		set_error("exec_stream_map_dev_async: needs a table with at most %u states", K1B_MAX_STATES);
+		errno = ENOTSUP;
+		return -1;
+	}
+	FSMB_CUDA(cudaSetDevice(dfa->device), return -1);
+	StreamScratch *ss = ss_get(dfa);
+	if (ss == nullptr) { errno = ENOMEM; return -1; }
+	std::lock_guard<std::mutex> g(ss->mu);
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	const uint32_t T = dfa->nstates;
+	if (len == 0 || (!parallel_ok(dfa, len) && !rep_eligible(dfa))) {
+		/* nothing to cut into chunks: the synchronous form, then one copy (rare: empty or tiny shards) */
+		std::vector<StreamOut> m(T);
+		if (len == 0) {
+			for (uint32_t s = 0; s < T; s++) { m[s].state = s; m[s].died = 0; m[s].dead_off = UINT64_MAX; }
+		} else {
+			std::vector<uint8_t> h((size_t) len);
+			FSMB_CUDA(cudaMemcpyAsync(h.data(), d_buf, (size_t) len, cudaMemcpyDeviceToHost, st), return -1);
+			FSMB_CUDA(cudaStreamSynchronize(st), return -1);
+			for (uint32_t s = 0; s < T; s++) {
+				uint32_t cur = s; uint64_t k = 0; bool died = false;
+				for (; k < len; k++) {
+					const uint32_t nx = dfa->h_table32[(size_t) cur * 256 + h[k]];
+					if (nx == NO_EDGE) { died = true; break; }
+					cur = nx;
+				}
+				m[s].state = cur; m[s].died = died ? 1u : 0u; m[s].dead_off = died ? k : UINT64_MAX;
+			}
+		}
+		FSMB_CUDA(cudaMemcpyAsync(d_map, m.data(), T * sizeof(StreamOut), cudaMemcpyHostToDevice, st), return -1);
+		FSMB_CUDA(cudaStreamSynchronize(st), return -1);
+		return 0;
+	}
+	std::vector<StreamOut> unused;
+	return stream_map(dfa, d_buf, len, st, ss, unused, nullptr, reinterpret_cast<StreamOut *>(d_map));
 }
 
 extern "C" int

@@ -212,6 +212,24 @@ class Dfa:
                                                _stream_ptr()), "exec_stream_map_dev")
         return ms, md, mf
 
+    def exec_stream_map_async(self, dbuf, out):
+        """The shard map left on the device: ``out`` (torch CUDA int64 [nstates, 2]) receives one
+        fsm_b200_stream_map_entry per entry state, written by work queued on the current stream; nothing
+        waits.  Decode a (gathered) copy with stream_map_arrays()."""
+        assert out.is_cuda and out.is_contiguous() and out.numel() * out.element_size() >= 16 * self.info["nstates"]
+        check(lib.fsm_b200_exec_stream_map_dev_async(self._h, dbuf.data_ptr(), int(dbuf.numel()), out.data_ptr(),
+                                                     _stream_ptr()), "exec_stream_map_dev_async")
+
+
+def stream_map_arrays(records: np.ndarray):
+    """[..., nstates, 2] int64/uint64 view of fsm_b200_stream_map_entry records -> (map_state u32, map_dead u64,
+    map_dead_state u32) as Dfa.exec_stream_map returns them (minus the dead row)."""
+    a = np.ascontiguousarray(records).view(np.uint64)
+    state = (a[..., 0] & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    died = (a[..., 0] >> np.uint64(32)) != 0
+    dead = np.where(died, a[..., 1], np.uint64(0xFFFFFFFFFFFFFFFF))
+    return state, dead, np.where(died, state, np.uint32(0xFFFFFFFF)).astype(np.uint32)
+
 
 def results_from_torch(t) -> np.ndarray:
     """[n,16] uint8 CUDA/CPU tensor of result records -> numpy structured array."""

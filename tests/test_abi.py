@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_abi_version():
-    assert _native.lib.fsm_b200_abi_version() == 3
+    assert _native.lib.fsm_b200_abi_version() == 4
 
 
 def test_struct_layouts():

@@ -14,6 +14,9 @@ pytestmark = pytest.mark.gpu
 CASES = goldenio.load_exec_cases(os.path.join(goldenio.GOLDEN_DIR, "golden_exec.npz"))
 
 
+NODEATH = 0xFFFFFFFFFFFFFFFF
+
+
 def case(prefix):
     return next(c for c in CASES if c["name"].startswith(prefix))
 
@@ -156,6 +159,12 @@ def test_shard_maps_equal_bruteforce_and_compose(oracle, torch_cuda, chunk_env, 
         for lo, hi in ranges:
             a, b, c = dfa.exec_stream_map(dev[lo:hi])
             ms.append(a); md.append(b); mf.append(c)
+            rec = torch.zeros((fsm.nstates, 2), dtype=torch.int64, device="cuda")      # asynchronous form: same records
+            dfa.exec_stream_map_async(dev[lo:hi], rec)
+            torch.cuda.synchronize()
+            a2, b2, c2 = L.stream_map_arrays(rec.cpu().numpy())
+            n = fsm.nstates
+            assert (b2 == b[:n]).all() and (a2[b2 == NODEATH] == a[:n][b2 == NODEATH]).all() and (c2[b2 != NODEATH] == c[:n][b2 != NODEATH]).all()
             # brute force: the oracle from every entry state
             for s in range(0, fsm.nstates, max(1, fsm.nstates // 16)):
                 ret, end, cons = oracle.exec(with_start(fsm, s), data[lo:hi].tobytes(), validate=False)

@@ -57,6 +57,15 @@ def check_all_entries(oracle, dfa, fsm, dev, data):
     if data.size == 0:
         return
     ms, md, mf = dfa.exec_stream_map(dev)
+    # the asynchronous form leaves the same records on the device
+    import torch
+    rec = torch.zeros((fsm.nstates, 2), dtype=torch.int64, device=dev.device)
+    dfa.exec_stream_map_async(dev, rec)
+    torch.cuda.synchronize()
+    a_s, a_d, a_f = L.stream_map_arrays(rec.cpu().numpy())
+    n = fsm.nstates
+    assert (a_d == md[:n]).all() and (a_s[a_d == NODEATH] == ms[:n][a_d == NODEATH]).all() and \
+        (a_f[a_d != NODEATH] == mf[:n][a_d != NODEATH]).all()
     for s in range(fsm.nstates):
         ret, end, cons = oracle.exec(with_start(fsm, s), data.tobytes(), validate=False)
         if cons < data.size:

@@ -108,3 +108,18 @@ def test_shard_ranges_cover_and_balance():
         sizes = [int(offsets[h] - offsets[l]) for l, h in rs]
         assert max(sizes) - min(sizes) <= 300 * 2
     assert sharding.byte_ranges(1000, 3) == [(0, 320), (320, 656), (656, 1000)]
+
+
+def test_stream_map_records_decode_and_compose():
+    """fsm_b200_stream_map_entry records (state u32, died u32, dead_off u64) as gathered by bench.py --config 4:
+    decoded into the arrays compose_stream_maps folds (host logic only, no device)."""
+    from libfsm_b200.engine import stream_map_arrays
+    rec = np.zeros((2, 3, 2), dtype=np.uint64)                  # 2 shards, 3 entry states
+    rec[0, :, 0] = [1, 2, 0]; rec[0, :, 1] = 0xFFFFFFFFFFFFFFFF   # shard 0: 0->1, 1->2, 2->0, nobody dies
+    rec[1, 0, 0] = 2; rec[1, 0, 1] = 0xFFFFFFFFFFFFFFFF
+    rec[1, 1, 0] = 0 | (1 << 32); rec[1, 1, 1] = 7               # shard 1 from state 1: dies at offset 7, read in state 0
+    rec[1, 2, 0] = 1; rec[1, 2, 1] = 0xFFFFFFFFFFFFFFFF
+    S, D, F = stream_map_arrays(rec.view(np.int64))
+    assert S.dtype == np.uint32 and D.dtype == np.uint64
+    assert sharding.compose_stream_maps(0, 3, [100, 50], list(S), list(D), list(F)) == (0, 107, True)
+    assert sharding.compose_stream_maps(2, 3, [100, 50], list(S), list(D), list(F)) == (2, 150, False)
