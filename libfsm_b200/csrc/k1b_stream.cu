@@ -457,7 +457,7 @@ stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cuda
 	/* [chunk maps 8 KiB][pad to a 16 KiB-aligned shared address][table]; the pad is at most 16 KiB */
 	const size_t smem = REP_MAPS_BYTES + 16384u + ((size_t) NT << REP_ROW_SHIFT);
 	const unsigned grid = a.nmaps;
-	int hint = 1, nbuf = 3;
+	int hint = 1, nbuf = 4;      /* measured (profiles/r2_k1b_rep_knobs.jsonl): 2 buffers 0.60 ms, 3 0.56 ms, 4 0.50 ms per 2 GiB */
 	if (const char *e = getenv("FSM_B200_REP_L2HINT")) hint = atoi(e) != 0;             /* tuning knobs */
 	if (const char *e = getenv("FSM_B200_REP_NBUF")) { const int v = atoi(e); if (v >= 2 && v <= 4) nbuf = v; }
 	void (*kern)(const RepArgs);
