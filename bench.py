@@ -925,7 +925,8 @@ def run_cfg4(args):
                        "h2d_bytes_per_step": int(e2e_bytes), "d2h_bytes_per_step": 16, "entry": "fsm_b200_exec_stream_host, pinned host text",
                        "bytes": e2e_bytes}
         line["gpu_launches"] = int(launches)
-        line["roofline"] = roofline_record(nbytes, kms, "K1b: prefix + body (K1 lane / k-stride over the chunk jobs) + compose, whole device-side call")
+        line["roofline"] = roofline_record(nbytes, kms, "K1b, whole device-side call: k1b_rep_kernel (per-lane replicated table; prefix + body + warp/CTA fold in one single-wave kernel) + k1b_rep_final_kernel + read-back",
+                                           "r2_k1b_rep_traffic.json")
         line["parity"] = "valid text: (1, end, total); one 0xFF at a known offset of the last shard: (0, ., global offset); 4 MiB prefix vs the reference's fsm_exec"
         line["cpu_baseline"] = cpu_baseline_record(cpu, the_config(args)["reference_sample"])
         print(json.dumps(line), flush=True)
