@@ -37,6 +37,7 @@
 #include "common.h"
 #include "k1_exec_batch.h"
 #include "k1b_rep.cuh"
+#include "k1b_rep_tma.cuh"
 
 using namespace fsmb200;
 
@@ -369,6 +370,64 @@ pick_chunk(uint32_t T, uint32_t W, uint64_t len, int sms)
 
 /* ---- small automata: the fused form (k1b_rep.cuh) ------------------------------------------------ */
 
+typedef CUresult (*rep_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+rep_encode_tiled_fn
+rep_get_encode_tiled()
+{
+	static rep_encode_tiled_fn fn = nullptr;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+		    qres == cudaDriverEntryPointSuccess) {
+			fn = reinterpret_cast<rep_encode_tiled_fn>(p);
+		}
+	});
+	return fn;
+}
+
+/* The TMA-tile form (k1b_rep_tma.cuh): returns 1 when it launched, 0 when this call does not qualify (the
+ * caller then launches the 256-bit-load form), -1 on error. */
+int
+launch_rep_tma(const fsm_b200_dfa *dfa, const RepArgs &a, unsigned grid, cudaStream_t stream)
+{
+	if (const char *e = getenv("FSM_B200_REP_TMA")) { if (atoi(e) == 0) return 0; }
+	const uint64_t nfull64 = a.len / a.C;
+	if (a.mis != 0 || nfull64 < 32 || nfull64 > 0x7FFFFFFFull || a.C > 0x7FFFFFFFull) return 0;
+	int smem_optin = 0;
+	if (cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dfa->device) != cudaSuccess) return 0;
+	/* [maps + barriers][pad to an 8 KiB-aligned shared address (at most 8 KiB)][table][ring: 32 warps x NST KiB] */
+	const size_t ring_off = ((size_t) REPC_HEAD_BYTES + 8192u + ((size_t) a.ntable << REPC_ROW_SHIFT) + 1023u) & ~(size_t) 1023u;
+	int nst = (int) (((size_t) smem_optin - ring_off) / (32u * REPC_STAGE_BYTES));
+	if ((size_t) smem_optin < ring_off) nst = 0;
+	if (nst > 4) nst = 4;
+	if (const char *e = getenv("FSM_B200_REP_TMA_STAGES")) { const int v = atoi(e); if (v >= 2 && v < nst) nst = v; }   /* tuning knob */
+	if (nst < 2) return 0;
+	rep_encode_tiled_fn enc = rep_get_encode_tiled();
+	if (enc == nullptr) return 0;
+	CUtensorMap tmap;
+	const cuuint64_t gdim[2] = { (cuuint64_t) a.C, (cuuint64_t) nfull64 };
+	const cuuint64_t gstr[1] = { (cuuint64_t) a.C };
+	const cuuint32_t box[2] = { 32u, 32u };
+	const cuuint32_t estr[2] = { 1u, 1u };
+	const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(a.buf), gdim, gstr, box, estr,
+	    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) return 0;
+	const size_t smem = ring_off + (size_t) nst * 32u * REPC_STAGE_BYTES;
+	const bool dead = !dfa->complete;
+	void (*kern)(const RepArgs, const CUtensorMap, const uint32_t, const uint32_t);
+	if (nst == 4) kern = dead ? k1b_rep_tma_kernel<true, 4> : k1b_rep_tma_kernel<false, 4>;
+	else if (nst == 3) kern = dead ? k1b_rep_tma_kernel<true, 3> : k1b_rep_tma_kernel<false, 3>;
+	else kern = dead ? k1b_rep_tma_kernel<true, 2> : k1b_rep_tma_kernel<false, 2>;
+	FSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), return -1);
+	kern<<<grid, 1024, smem, stream>>>(a, tmap, (uint32_t) nfull64, (uint32_t) ring_off);
+	return 1;
+}
+
 bool
 rep_eligible(const fsm_b200_dfa *dfa)
 {
@@ -457,22 +516,27 @@ stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cuda
 	/* [chunk maps 8 KiB][pad to a 16 KiB-aligned shared address][table]; the pad is at most 16 KiB */
 	const size_t smem = REP_MAPS_BYTES + 16384u + ((size_t) NT << REP_ROW_SHIFT);
 	const unsigned grid = a.nmaps;
-	int hint = 1, nbuf = 4;      /* measured (profiles/r2_k1b_rep_knobs.jsonl): 2 buffers 0.60 ms, 3 0.56 ms, 4 0.50 ms per 2 GiB */
-	if (const char *e = getenv("FSM_B200_REP_L2HINT")) hint = atoi(e) != 0;             /* tuning knobs */
-	if (const char *e = getenv("FSM_B200_REP_NBUF")) { const int v = atoi(e); if (v >= 2 && v <= 4) nbuf = v; }
-	void (*kern)(const RepArgs);
-	if (nbuf == 4) {
-		kern = dfa->complete ? (hint ? k1b_rep_kernel<false, 1, 4> : k1b_rep_kernel<false, 0, 4>)
-		                     : (hint ? k1b_rep_kernel<true, 1, 4> : k1b_rep_kernel<true, 0, 4>);
-	} else if (nbuf == 3) {
-		kern = dfa->complete ? (hint ? k1b_rep_kernel<false, 1, 3> : k1b_rep_kernel<false, 0, 3>)
-		                     : (hint ? k1b_rep_kernel<true, 1, 3> : k1b_rep_kernel<true, 0, 3>);
-	} else {
-		kern = dfa->complete ? (hint ? k1b_rep_kernel<false, 1, 2> : k1b_rep_kernel<false, 0, 2>)
-		                     : (hint ? k1b_rep_kernel<true, 1, 2> : k1b_rep_kernel<true, 0, 2>);
+	/* aligned buffers with at least one warp of full chunks: input by TMA tiles (k1b_rep_tma.cuh) */
+	const int tma = launch_rep_tma(dfa, a, grid, stream);
+	if (tma < 0) return -1;
+	if (tma == 0) {
+		int hint = 1, nbuf = 4;      /* measured (profiles/r2_k1b_rep_knobs.jsonl): 2 buffers 0.60 ms, 3 0.56 ms, 4 0.50 ms per 2 GiB */
+		if (const char *e = getenv("FSM_B200_REP_L2HINT")) hint = atoi(e) != 0;             /* tuning knobs */
+		if (const char *e = getenv("FSM_B200_REP_NBUF")) { const int v = atoi(e); if (v >= 2 && v <= 4) nbuf = v; }
+		void (*kern)(const RepArgs);
+		if (nbuf == 4) {
+			kern = dfa->complete ? (hint ? k1b_rep_kernel<false, 1, 4> : k1b_rep_kernel<false, 0, 4>)
+			                     : (hint ? k1b_rep_kernel<true, 1, 4> : k1b_rep_kernel<true, 0, 4>);
+		} else if (nbuf == 3) {
+			kern = dfa->complete ? (hint ? k1b_rep_kernel<false, 1, 3> : k1b_rep_kernel<false, 0, 3>)
+			                     : (hint ? k1b_rep_kernel<true, 1, 3> : k1b_rep_kernel<true, 0, 3>);
+		} else {
+			kern = dfa->complete ? (hint ? k1b_rep_kernel<false, 1, 2> : k1b_rep_kernel<false, 0, 2>)
+			                     : (hint ? k1b_rep_kernel<true, 1, 2> : k1b_rep_kernel<true, 0, 2>);
+		}
+		FSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), return -1);
+		kern<<<grid, 1024, smem, stream>>>(a);
 	}
-	FSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), return -1);
-	kern<<<grid, 1024, smem, stream>>>(a);
 	count_launch();
 	const size_t smem2 = (size_t) a.nmaps * 16 + (size_t) nlv * 16 + 16;
 	FSMB_CUDA(cudaFuncSetAttribute(k1b_rep_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2), return -1);
