@@ -18,6 +18,14 @@
  * per word h = (w >> 3) & 0x1F1F1F1F and q = (w & 0x03030303) | ((w << 5) & 0x80808080) | lane bits: five
  * instructions per word instead of three (4.25 per byte instead of 3.75).
  *
+ * MEASURED (round 2, profiles/r2_k1b_rep_tma_ncu_full.txt, r2_k1b_rep_knobs.jsonl): slower than the 256-bit-load
+ * form -- 2 GiB of UTF-8 in 1.24 ms with 4 stages, 0.96 ms with 3, 0.59 ms with 2, against 0.50 ms.  The TMA
+ * unit delivers about one box ROW per 5 cycles per SM whatever the row's width (14.1 K tiles per SM in 2.39 M
+ * cycles = 169 cycles per 32-row tile), so 32-byte rows cap at 1.8 TB/s where the 128-byte rows of
+ * k1_krange_tile_kernel reach 6 TB/s; 65 % of all warp samples sit on the full barrier.  Wider rows would need
+ * 4 KiB per warp and stage.  Off by default (FSM_B200_REP_TMA=1 selects it); kept as the record of the
+ * experiment, parity-tested like every other variant.
+ *
  * Everything else -- chunking, prefix, distinct live images, chunk maps, warp / CTA folds, the final kernel --
  * is k1b_rep.cuh's.  Warps whose 32 chunks are not all full rows of the tensor (the last one) and unaligned
  * buffers read with 256-bit loads as before.

@@ -395,7 +395,12 @@ rep_get_encode_tiled()
 int
 launch_rep_tma(const fsm_b200_dfa *dfa, const RepArgs &a, unsigned grid, cudaStream_t stream)
 {
-	if (const char *e = getenv("FSM_B200_REP_TMA")) { if (atoi(e) == 0) return 0; }
+	/* Opt-in: measured SLOWER than the 256-bit-load form (2 GiB of UTF-8: 1.24 ms with 4 stages, 0.96 with 3,
+	 * 0.59 with 2, against 0.50 ms) -- the TMA unit serves about one box row per 5 cycles per SM whatever its
+	 * width, so 32-byte rows cap at 1.8 TB/s (65 % of the warp time sits on the full barrier;
+	 * profiles/r2_k1b_rep_tma_ncu_full.txt).  Kept selectable and parity-tested as the record of that. */
+	const char *tma_env = getenv("FSM_B200_REP_TMA");
+	if (tma_env == nullptr || atoi(tma_env) == 0) return 0;
 	const uint64_t nfull64 = a.len / a.C;
 	if (a.mis != 0 || nfull64 < 32 || nfull64 > 0x7FFFFFFFull || a.C > 0x7FFFFFFFull) return 0;
 	int smem_optin = 0;
@@ -516,7 +521,7 @@ stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cuda
 	/* [chunk maps 8 KiB][pad to a 16 KiB-aligned shared address][table]; the pad is at most 16 KiB */
 	const size_t smem = REP_MAPS_BYTES + 16384u + ((size_t) NT << REP_ROW_SHIFT);
 	const unsigned grid = a.nmaps;
-	/* aligned buffers with at least one warp of full chunks: input by TMA tiles (k1b_rep_tma.cuh) */
+	/* FSM_B200_REP_TMA=1: input by TMA tiles (k1b_rep_tma.cuh; aligned buffers with at least one warp of full chunks) */
 	const int tma = launch_rep_tma(dfa, a, grid, stream);
 	if (tma < 0) return -1;
 	if (tma == 0) {

@@ -186,3 +186,25 @@ def test_both_forms_agree_on_a_large_input(torch_cuda):
             else:
                 assert got[0] == 1 and got[2] == n
             assert got == want, pos
+
+
+def test_tma_tile_form_is_exact(oracle, torch_cuda):
+    """The opt-in TMA-tile form of the same kernel (k1b_rep_tma.cuh: compact table, input by 2-D TMA tiles;
+    measured slower, kept selectable): same records from every entry state, full and partial last warps, deaths."""
+    fsm = case("utf8:")["fsm"]
+    text = workloads.utf8_host(3000000, seed=13).copy()
+    os.environ["FSM_B200_REP_TMA"] = "1"
+    try:
+        with L.Dfa(fsm) as dfa:
+            dev = torch_cuda.from_numpy(text).cuda()
+            for n in (text.size, 2000003, 576 * 40, 576 * 32 + 5):
+                check_all_entries(oracle, dfa, fsm, dev[:n], text[:n])
+            for bad in (100, 70000, 2999990):
+                t2 = text.copy(); t2[bad] = 0xFF
+                check_all_entries(oracle, dfa, fsm, torch_cuda.from_numpy(t2).cuda(), t2)
+            for stages in ("2", "3"):
+                os.environ["FSM_B200_REP_TMA_STAGES"] = stages
+                assert dfa.exec_stream(dev) == oracle.exec(fsm, text.tobytes())
+    finally:
+        os.environ.pop("FSM_B200_REP_TMA", None)
+        os.environ.pop("FSM_B200_REP_TMA_STAGES", None)
