@@ -19,11 +19,11 @@
  * instructions per word instead of three (4.25 per byte instead of 3.75).
  *
  * MEASURED (round 2, profiles/r2_k1b_rep_tma_ncu_full.txt, r2_k1b_rep_knobs.jsonl): slower than the 256-bit-load
- * form -- 2 GiB of UTF-8 in 1.24 ms with 4 stages, 0.96 ms with 3, 0.59 ms with 2, against 0.50 ms.  The TMA
- * unit delivers about one box ROW per 5 cycles per SM whatever the row's width (14.1 K tiles per SM in 2.39 M
- * cycles = 169 cycles per 32-row tile), so 32-byte rows cap at 1.8 TB/s where the 128-byte rows of
- * k1_krange_tile_kernel reach 6 TB/s; 65 % of all warp samples sit on the full barrier.  Wider rows would need
- * 4 KiB per warp and stage.  Off by default (FSM_B200_REP_TMA=1 selects it); kept as the record of the
+ * form -- 2 GiB of UTF-8 in 1.24 ms with 4 stages, 0.96 ms with 3, 0.59 ms with 2, against 0.50 ms.  The more
+ * tiles are in flight the slower it gets; at 4 stages the TMA unit delivers one 32-byte box ROW per 5.3 cycles
+ * per SM (14.1 K tiles per SM in 2.39 M cycles = 169 cycles per 32-row tile: 1.8 TB/s) and 65 % of all warp
+ * samples sit on the full barrier -- skinny rows are the wrong shape for it (the 128-byte rows of
+ * k1_krange_tile_kernel reach 6 TB/s), and wider rows would need 4 KiB per warp and stage.  Off by default (FSM_B200_REP_TMA=1 selects it); kept as the record of the
  * experiment, parity-tested like every other variant.
  *
  * Everything else -- chunking, prefix, distinct live images, chunk maps, warp / CTA folds, the final kernel --

@@ -396,9 +396,8 @@ int
 launch_rep_tma(const fsm_b200_dfa *dfa, const RepArgs &a, unsigned grid, cudaStream_t stream)
 {
 	/* Opt-in: measured SLOWER than the 256-bit-load form (2 GiB of UTF-8: 1.24 ms with 4 stages, 0.96 with 3,
-	 * 0.59 with 2, against 0.50 ms) -- the TMA unit serves about one box row per 5 cycles per SM whatever its
-	 * width, so 32-byte rows cap at 1.8 TB/s (65 % of the warp time sits on the full barrier;
-	 * profiles/r2_k1b_rep_tma_ncu_full.txt).  Kept selectable and parity-tested as the record of that. */
+	 * 0.59 with 2, against 0.50 ms) -- tiles of 32-byte rows are the wrong shape for the TMA unit (at 4 stages one box row per
+	 * 5.3 cycles per SM = 1.8 TB/s, 65 % of the warp time on the full barrier; profiles/r2_k1b_rep_tma_ncu_full.txt).  Kept selectable and parity-tested as the record of that. */
 	const char *tma_env = getenv("FSM_B200_REP_TMA");
 	if (tma_env == nullptr || atoi(tma_env) == 0) return 0;
 	const uint64_t nfull64 = a.len / a.C;
