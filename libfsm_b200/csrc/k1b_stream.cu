@@ -312,6 +312,8 @@ struct StreamScratch {
 	uint32_t absorb_mask = 0;
 	Arena rep_arena;
 	StreamOut *h_pinned = nullptr;                    /* [REP_MAX_ROWS] read-back buffer */
+	int sms = 0;                                      /* per-call driver queries are a measurable share of a 1 MiB call */
+	const void *rep_kern = nullptr; size_t rep_kern_smem = 0;   /* kernel the shared-memory opt-in was last set for */
 };
 
 std::mutex g_ss_mu;
@@ -445,8 +447,10 @@ stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cuda
 	StreamScratch *ss, std::vector<StreamOut> &h_out, StreamOut *d_user_out = nullptr)
 {
 	const uint32_t T = dfa->nstates, NT = dfa->ntable;
-	int sms = 0;
-	FSMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dfa->device), return -1);
+	if (ss->sms == 0) {
+		FSMB_CUDA(cudaDeviceGetAttribute(&ss->sms, cudaDevAttrMultiProcessorCount, dfa->device), return -1);
+	}
+	const int sms = ss->sms;
 	if (ss->d_dense == nullptr) {
 		/* dense next-state bytes from the host copy of the table (missing edge -> dead row, which absorbs) */
 		std::vector<uint8_t> dense((size_t) NT * 256);
@@ -538,12 +542,17 @@ stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cuda
 			kern = dfa->complete ? (hint ? k1b_rep_kernel<false, 1, 2> : k1b_rep_kernel<false, 0, 2>)
 			                     : (hint ? k1b_rep_kernel<true, 1, 2> : k1b_rep_kernel<true, 0, 2>);
 		}
-		FSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), return -1);
+		if (ss->rep_kern != reinterpret_cast<const void *>(kern) || ss->rep_kern_smem != smem) {
+			FSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), return -1);
+			ss->rep_kern = reinterpret_cast<const void *>(kern); ss->rep_kern_smem = smem;
+		}
 		kern<<<grid, 1024, smem, stream>>>(a);
 	}
 	count_launch();
 	const size_t smem2 = (size_t) a.nmaps * 16 + (size_t) nlv * 16 + 16;
-	FSMB_CUDA(cudaFuncSetAttribute(k1b_rep_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2), return -1);
+	if (smem2 > 48u * 1024u) {       /* more than 3000 CTA maps: not on this hardware, but the opt-in is needed then */
+		FSMB_CUDA(cudaFuncSetAttribute(k1b_rep_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2), return -1);
+	}
 	k1b_rep_final_kernel<<<1, 1024, smem2, stream>>>(a);
 	count_launch();
 	FSMB_CUDA(cudaGetLastError(), return -1);
