@@ -313,8 +313,26 @@ struct StreamScratch {
 	Arena rep_arena;
 	StreamOut *h_pinned = nullptr;                    /* [REP_MAX_ROWS] read-back buffer */
 	int sms = 0;                                      /* per-call driver queries are a measurable share of a 1 MiB call */
-	const void *rep_kern = nullptr; size_t rep_kern_smem = 0;   /* kernel the shared-memory opt-in was last set for */
 };
+
+/* Opt a kernel in to the device's maximum dynamic shared memory ONCE per (device, kernel): the attribute is a
+ * per-function maximum, so it is set to the device limit (never to one automaton's need, which a smaller
+ * automaton would lower again) and remembered. */
+int
+ensure_max_smem(const void *kern, int device)
+{
+	static std::mutex mu;
+	static std::vector<std::pair<int, const void *>> done;
+	std::lock_guard<std::mutex> g(mu);
+	for (const auto &d : done) if (d.first == device && d.second == kern) return 0;
+	int optin = 0;
+	FSMB_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device), return -1);
+	FSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin), return -1);
+	done.emplace_back(device, kern);
+	return 0;
+}
+
+
 
 std::mutex g_ss_mu;
 
@@ -542,10 +560,7 @@ stream_map_rep(const fsm_b200_dfa *dfa, const uint8_t *d_buf, uint64_t len, cuda
 			kern = dfa->complete ? (hint ? k1b_rep_kernel<false, 1, 2> : k1b_rep_kernel<false, 0, 2>)
 			                     : (hint ? k1b_rep_kernel<true, 1, 2> : k1b_rep_kernel<true, 0, 2>);
 		}
-		if (ss->rep_kern != reinterpret_cast<const void *>(kern) || ss->rep_kern_smem != smem) {
-			FSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), return -1);
-			ss->rep_kern = reinterpret_cast<const void *>(kern); ss->rep_kern_smem = smem;
-		}
+		if (ensure_max_smem(reinterpret_cast<const void *>(kern), dfa->device) != 0) return -1;
 		kern<<<grid, 1024, smem, stream>>>(a);
 	}
 	count_launch();
