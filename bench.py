@@ -921,6 +921,8 @@ def run_cfg4(args):
                           "multi_gpu": "single GPU: fsm_b200_exec_stream_dev" if world == 1 else
                                        f"{world} byte-range shards; per rank K1b shard map left on the device (exit state / first dead offset per entry state), ONE NCCL all-gather of [nstates] x 16 B records on the same stream, one read-back, composed in rank order"}
         line["clocks"] = clocks
+        if world > 1:
+            line["untimed_settle_blocks_ms_per_step"] = c.settle
         line["e2e"] = {"value": world * e2e_bytes * e2e_steps / (e2e_ms / 1e3) / 1e9, "unit": "GB/s", "steps": e2e_steps,
                        "h2d_bytes_per_step": int(e2e_bytes), "d2h_bytes_per_step": 16, "entry": "fsm_b200_exec_stream_host, pinned host text",
                        "bytes": e2e_bytes}
