@@ -918,6 +918,8 @@ def run_cfg4(args):
         line = base_line(args, c, world * nbytes * args.steps / (ms_total / 1e3) / 1e9, ms_total / args.steps)
         line["engine"] = {"table": dfa.info, "dfa": "examples/utf8dfa 0..10FFFF starred, det + min: 8 states (fsm_equal with the PCRE-built validator)",
                           "bytes_per_gpu": nbytes,
+                          "stream_form": "fused small-automaton form (k1b_rep.cuh: per-lane replicated table, one single-wave kernel + final fold)"
+                                         if T <= 12 and os.environ.get("FSM_B200_STREAM_REP", "1") != "0" else "generic chunked K1b (prefix + K1 body + compose)",
                           "multi_gpu": "single GPU: fsm_b200_exec_stream_dev" if world == 1 else
                                        f"{world} byte-range shards; per rank K1b shard map left on the device (exit state / first dead offset per entry state), ONE NCCL all-gather of [nstates] x 16 B records on the same stream, one read-back, composed in rank order"}
         line["clocks"] = clocks
