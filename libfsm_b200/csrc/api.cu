@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <vector>
 
 #include "common.h"
 #include "k1_exec_batch.h"
@@ -30,6 +31,60 @@ void
 count_launch(uint64_t n)
 {
 	tl_launches += n;
+}
+
+
+/* ---- pinned host block pool (common.h) ---- */
+namespace {
+struct PoolBlock { void *p; size_t cap; };
+std::mutex g_pool_mu;
+std::vector<PoolBlock> g_pool_free;
+size_t g_pool_free_bytes = 0;
+constexpr size_t POOL_MAX_BLOCKS = 8, POOL_MAX_BYTES = 1ull << 30;
+}
+
+void *
+host_pool_get(size_t bytes, size_t *cap)
+{
+	if (bytes == 0) bytes = 1;
+	{
+		std::lock_guard<std::mutex> g(g_pool_mu);
+		size_t best = g_pool_free.size();
+		for (size_t i = 0; i < g_pool_free.size(); i++) {
+			if (g_pool_free[i].cap >= bytes && (best == g_pool_free.size() || g_pool_free[i].cap < g_pool_free[best].cap)) best = i;
+		}
+		if (best != g_pool_free.size() && g_pool_free[best].cap <= 4 * bytes + (1u << 20)) {
+			const PoolBlock b = g_pool_free[best];
+			g_pool_free.erase(g_pool_free.begin() + (long) best);
+			g_pool_free_bytes -= b.cap;
+			*cap = b.cap;
+			return b.p;
+		}
+	}
+	/* 12 % headroom, 1 MiB granules: the next result of about this size fits the same block */
+	const size_t want = (bytes + (bytes >> 3) + 0xFFFFFu) & ~(size_t) 0xFFFFFu;
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	*cap = want;
+	return p;
+}
+
+void
+host_pool_put(void *p, size_t cap)
+{
+	if (p == nullptr) return;
+	{
+		std::lock_guard<std::mutex> g(g_pool_mu);
+		if (g_pool_free.size() < POOL_MAX_BLOCKS && g_pool_free_bytes + cap <= POOL_MAX_BYTES) {
+			g_pool_free.push_back(PoolBlock{ p, cap });
+			g_pool_free_bytes += cap;
+			return;
+		}
+	}
+	cudaFreeHost(p);
 }
 
 /* Per-DFA scratch for the _host entry points: two slots (double buffering). */

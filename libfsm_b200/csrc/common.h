@@ -46,11 +46,50 @@ constexpr uint32_t CLASS_GLOBAL_MAX = 192;
 /* Largest lines-kernel blob (LUT + class rows + end bytes) staged into shared memory. */
 constexpr uint32_t SMEM_LINES_MAX = 224 * 1024;
 
+/* Pinned host blocks, cached between calls (api.cu).  The big outputs of determinise / minimise (config 5: 94 MB
+ * of edge groups) used to land in fresh std::vector storage: 36-50 ms of first-touch page faults per call,
+ * then a pageable device-to-host copy.  A block from this pool has its pages faulted in and pinned once; a
+ * freed description returns its blocks.  At most 8 free blocks / 1 GiB are kept. */
+void *host_pool_get(size_t bytes, size_t *cap);      /* nullptr when pinned memory cannot be had (callers fall back to vectors) */
+void host_pool_put(void *p, size_t cap);
+
+/* a pool block for the duration of a scope */
+struct PoolTemp {
+	void *p = nullptr; size_t cap = 0;
+	bool get(size_t bytes) { p = host_pool_get(bytes, &cap); return p != nullptr; }
+	~PoolTemp() { if (p != nullptr) host_pool_put(p, cap); }
+};
+
 /* Arrays behind a library-owned description (struct fsm_b200_owned_desc.owner). */
 struct Owner {
 	std::vector<uint8_t> is_end;
 	std::vector<uint64_t> group_off, group_sym, endid_off;
 	std::vector<uint32_t> group_to, endids;
+	/* edge groups in pool blocks instead of the two vectors above (large results) */
+	uint32_t *pin_gto = nullptr; size_t pin_gto_cap = 0;
+	uint64_t *pin_gsym = nullptr; size_t pin_gsym_cap = 0;
+	/* where the groups live: reserve `ng` groups, pool blocks first */
+	void groups_alloc(size_t ng) {
+		if (ng * 36 >= (1u << 20)) {
+			pin_gto = static_cast<uint32_t *>(host_pool_get(ng * 4, &pin_gto_cap));
+			pin_gsym = static_cast<uint64_t *>(host_pool_get(ng * 32, &pin_gsym_cap));
+			if (pin_gto != nullptr && pin_gsym != nullptr) return;
+			if (pin_gto != nullptr) host_pool_put(pin_gto, pin_gto_cap);
+			if (pin_gsym != nullptr) host_pool_put(pin_gsym, pin_gsym_cap);
+			pin_gto = nullptr; pin_gsym = nullptr;
+		}
+		group_to.resize(ng);
+		group_sym.resize(4 * ng);
+	}
+	uint32_t *gto() { return pin_gto != nullptr ? pin_gto : group_to.data(); }
+	uint64_t *gsym() { return pin_gsym != nullptr ? pin_gsym : group_sym.data(); }
+	Owner() = default;
+	Owner(const Owner &) = delete;
+	Owner &operator=(const Owner &) = delete;
+	~Owner() {
+		if (pin_gto != nullptr) host_pool_put(pin_gto, pin_gto_cap);
+		if (pin_gsym != nullptr) host_pool_put(pin_gsym, pin_gsym_cap);
+	}
 	/* eager-output sets of the result (fsm_b200_owned_desc_eager); empty when there are none */
 	std::vector<uint64_t> eager_off;
 	std::vector<uint32_t> eager_ids;

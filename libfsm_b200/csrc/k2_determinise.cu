@@ -778,17 +778,26 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 	const uint64_t NG = own->group_off[D];
 	if (d_ogto.reserve(NG + 1, false, st) || d_ogsym.reserve(4 * NG + 4, false, st)) return -1;
 	k2_emit_fill_kernel<<<blocks_for(D, 128), 128, 0, st>>>(trans_emit, D, K, d_cmask.p, d_ogoff.p, d_ogto.p, d_ogsym.p); count_launch();
-	own->group_to.resize(NG);
-	own->group_sym.resize(4 * NG);
-	std::vector<uint32_t> h_pooldata(pool_used);
-	std::vector<uint64_t> h_pooloff(D + 1);
+	/* the groups (config 5: 94 MB) and the state-set pool land in pinned pool blocks whose pages are already
+	 * faulted in: fresh vector storage cost 36-50 ms of page faults per call, more than every kernel together */
+	own->groups_alloc(NG);
+	PoolTemp t_pooldata, t_pooloff;
+	std::vector<uint32_t> v_pooldata;
+	std::vector<uint64_t> v_pooloff;
+	uint32_t *h_pooldata; uint64_t *h_pooloff;
+	if (t_pooldata.get((size_t) pool_used * 4 + 4) && t_pooloff.get((size_t) (D + 1) * 8)) {
+		h_pooldata = static_cast<uint32_t *>(t_pooldata.p); h_pooloff = static_cast<uint64_t *>(t_pooloff.p);
+	} else {
+		v_pooldata.resize(pool_used + 1); v_pooloff.resize(D + 1);
+		h_pooldata = v_pooldata.data(); h_pooloff = v_pooloff.data();
+	}
 	std::vector<uint8_t> h_aend(n);
 	if (NG) {
-		CK(cudaMemcpyAsync(own->group_to.data(), d_ogto.p, NG * 4, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(own->group_sym.data(), d_ogsym.p, NG * 32, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(own->gto(), d_ogto.p, NG * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(own->gsym(), d_ogsym.p, NG * 32, cudaMemcpyDeviceToHost, st));
 	}
-	CK(cudaMemcpyAsync(h_pooloff.data(), d_pooloff.p, (D + 1) * 8, cudaMemcpyDeviceToHost, st));
-	CK(cudaMemcpyAsync(h_pooldata.data(), d_pooldata.p, pool_used * 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(h_pooloff, d_pooloff.p, (D + 1) * 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(h_pooldata, d_pooldata.p, pool_used * 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(h_aend.data(), d_aend.p, n, cudaMemcpyDeviceToHost, st));
 	CK_SYNC(st);
 
@@ -837,7 +846,7 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 		}
 	}
 	if (has_eager && own->eager_ids.empty()) own->eager_off.clear();
-	if (own->group_to.empty()) { own->group_to.push_back(0); own->group_sym.resize(4, 0); }
+	if (NG == 0) { own->group_to.assign(1, 0); own->group_sym.assign(4, 0); }
 	if (own->endids.empty()) own->endids.push_back(0);
 	tl_stats.ms_emit = ms_since(t_emit);
 
@@ -846,8 +855,8 @@ determinise_impl(const struct fsm_b200_desc *nfa, int device, size_t state_limit
 	out->desc.hasstart = 1;
 	out->desc.is_end = own->is_end.data();
 	out->desc.group_off = own->group_off.data();
-	out->desc.group_symbols = own->group_sym.data();
-	out->desc.group_to = own->group_to.data();
+	out->desc.group_symbols = own->gsym();
+	out->desc.group_to = own->gto();
 	out->desc.eps_off = nullptr;
 	out->desc.eps_to = nullptr;
 	out->desc.endid_off = own->endid_off.data();

@@ -366,14 +366,13 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 	const uint64_t NG = own->group_off[D];
 	if (d_ogto.reserve(NG + 1, false, st) || d_ogsym.reserve(4 * NG + 4, false, st)) return -1;
 	k2_emit_fill_kernel<<<blocks_for(D, 128), 128, 0, st>>>(d_otrans.p, D, K, d_cmask.p, d_ogoff.p, d_ogto.p, d_ogsym.p); count_launch();
-	own->group_to.resize(NG);
-	own->group_sym.resize(4 * NG);
+	own->groups_alloc(NG);           /* pinned pool blocks for large results (common.h) */
 	std::vector<uint32_t> h_oorig(D);
 	uint32_t start_cls = 0;
 	uint64_t start_new = 0;
 	if (NG) {
-		CK(cudaMemcpyAsync(own->group_to.data(), d_ogto.p, NG * 4, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(own->group_sym.data(), d_ogsym.p, NG * 32, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(own->gto(), d_ogto.p, NG * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(own->gsym(), d_ogsym.p, NG * 32, cudaMemcpyDeviceToHost, st));
 	}
 	CK(cudaMemcpyAsync(h_oorig.data(), d_oorig.p, D * 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(&start_new, d_newid.p + dfa->start, 8, cudaMemcpyDeviceToHost, st));
@@ -413,7 +412,7 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 		}
 		if (own->eager_ids.empty()) own->eager_off.clear();
 	}
-	if (own->group_to.empty()) { own->group_to.push_back(0); own->group_sym.resize(4, 0); }
+	if (NG == 0) { own->group_to.assign(1, 0); own->group_sym.assign(4, 0); }
 	if (own->endids.empty()) own->endids.push_back(0);
 
 	out->desc.nstates = D;
@@ -421,8 +420,8 @@ fsm_b200_minimise(const struct fsm_b200_desc *dfa, int device, struct fsm_b200_o
 	out->desc.hasstart = 1;
 	out->desc.is_end = own->is_end.data();
 	out->desc.group_off = own->group_off.data();
-	out->desc.group_symbols = own->group_sym.data();
-	out->desc.group_to = own->group_to.data();
+	out->desc.group_symbols = own->gsym();
+	out->desc.group_to = own->gto();
 	out->desc.eps_off = nullptr;
 	out->desc.eps_to = nullptr;
 	out->desc.endid_off = own->endid_off.data();
