@@ -332,8 +332,6 @@ ensure_max_smem(const void *kern, int device)
 	return 0;
 }
 
-
-
 std::mutex g_ss_mu;
 
 StreamScratch *
