@@ -74,6 +74,18 @@ def _worker(rank, world, port, q):
             utf.start, dead, [h - l for l, h in br], allrec[:, 0].astype(np.uint32), allrec[:, 1], allrec[:, 2].astype(np.uint32))
         ret, end, cons = oracle.exec(utf, stream.tobytes())
         ok_stream = (cons == consumed) and (end == st) and ((ret == 1) == (not died and bool(utf.is_end[st])))
+        # the same exchange in the record layout bench.py --config 4 gathers (fsm_b200_stream_map_entry:
+        # state | died << 32, dead offset; [nstates] records left on the device by exec_stream_map_dev_async)
+        from libfsm_b200.engine import stream_map_arrays
+        dflag = md[:S] != sharding.NO_DEAD
+        rec2 = np.zeros((S, 2), dtype=np.uint64)
+        rec2[:, 0] = np.where(dflag, mf[:S], ms[:S]).astype(np.uint64) | (dflag.astype(np.uint64) << np.uint64(32))
+        rec2[:, 1] = md[:S]
+        all2 = torch.empty((world * S, 2), dtype=torch.int64)          # gloo wants the concatenated shape (NCCL also takes the stacked one)
+        dist.all_gather_into_tensor(all2, torch.from_numpy(rec2.view(np.int64)))
+        S2, D2, F2 = stream_map_arrays(all2.numpy().reshape(world, S, 2))
+        st2, consumed2, died2 = sharding.compose_stream_maps(utf.start, dead, [h - l for l, h in br], list(S2), list(D2), list(F2))
+        ok_stream = ok_stream and (st2, consumed2, died2) == (st, consumed, died)
         q.put((rank, ok_batch, ok_stream))
     finally:
         dist.destroy_process_group()
